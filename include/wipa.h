@@ -1,0 +1,125 @@
+/* libwipa — C ABI of the B200-native whisper-ipa hot path (log-mel -> encoder -> KV-cached decode -> PER).
+ *
+ * The reference (barathanaslan/whisper-ipa) has no FFI of its own: its two entry points call Python
+ * packages (mlx_whisper, editdistance).  Each entry point below names the reference call it replaces,
+ * so a maintainer can bind it from the scripts with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller (PyTorch allocation);
+ *     "host" pointers are ordinary host memory.  Nothing here takes or returns a torch type.
+ *   - every call takes the CUDA stream to enqueue on (a cudaStream_t passed as void*), returns
+ *     0 on success or a negative WIPA_E* code, and never throws.  wipa_last_error() gives detail.
+ *   - the library allocates only inside an explicit wipa_ctx (weights copy, workspaces, KV caches).
+ *   - one context per GPU / process; a context is not re-entrant.
+ */
+#ifndef WIPA_H_
+#define WIPA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WIPA_OK 0
+#define WIPA_EINVAL (-1)      /* bad argument / shape */
+#define WIPA_ECUDA (-2)       /* CUDA runtime or driver error */
+#define WIPA_ENOMEM (-3)
+#define WIPA_ESTATE (-4)      /* call out of order (e.g. decode before encode, weights missing) */
+#define WIPA_EUNSUPPORTED (-5)
+
+#define WIPA_DTYPE_F32 0      /* "fp32 path": true fp32 FMA everywhere, greedy ids bit-exact vs the oracle */
+#define WIPA_DTYPE_BF16 1     /* "bf16 path": bf16 weights / GEMM operands / KV, fp32 accumulate + residual */
+
+typedef struct wipa_ctx wipa_ctx;
+
+/* Architecture of the Whisper checkpoint (what `load_model(base_model)` fixes in
+ * ref:scripts/evaluate_model.py:33-37 / ref:scripts/transcribe_single.py:12). head_dim must be 64. */
+typedef struct wipa_arch {
+    int32_t d_model, enc_layers, dec_layers, heads, ffn, n_mels, vocab;
+    int32_t dtype;            /* WIPA_DTYPE_* */
+} wipa_arch;
+
+/* One named fp32 tensor of an HF-named Whisper state_dict, resident on the device. */
+typedef struct wipa_tensor_desc {
+    const char* name;         /* e.g. "model.decoder.layers.3.encoder_attn.k_proj.weight" */
+    const float* data;        /* device, contiguous fp32 */
+    int64_t numel;
+} wipa_tensor_desc;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* Replaces: mlx_whisper.load_models.load_model + model.set_dtype (ref:scripts/evaluate_model.py:33-37). */
+int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_beams, wipa_ctx** out);
+/* Replaces: model.update(tree_unflatten(...)) weight overlay (ref:scripts/evaluate_model.py:58-73).
+ * May be called repeatedly (base weights, then the "decoder." overlay); unknown names -> WIPA_EINVAL. */
+int wipa_ctx_load_weights(wipa_ctx*, const wipa_tensor_desc* tensors, int n, void* stream);
+int wipa_ctx_destroy(wipa_ctx*);
+
+/* ---- (a) log-mel front end ------------------------------------------------------------------ */
+/* Replaces: mlx_whisper.audio.log_mel_spectrogram(audio, n_mels) (ref:scripts/evaluate_model.py:189,
+ * ref:scripts/transcribe_single.py:45, ref:scripts/ipa_data_loader.py:82) on already pad_or_trim'ed audio.
+ * audio: device f32[B, 480000];  mel: device f32[B, n_mels, 3000] (HF layout).  Context-free. */
+int wipa_logmel(const float* audio, int B, int n_mels, float* mel, void* stream);
+
+/* ---- (b) encoder ---------------------------------------------------------------------------- */
+/* Replaces: model.encoder(mel) (ref:scripts/evaluate_model.py:197, ref:scripts/transcribe_single.py:54).
+ * mel: device f32[B, n_mels, 3000]; enc_out: device f32[B,1500,d] or NULL.  Also projects and stores the
+ * per-layer cross-attention K/V of the B utterances inside the context, ready for wipa_decode_*. */
+int wipa_encode(wipa_ctx*, const float* mel, int B, float* enc_out, void* stream);
+/* Same, from an externally supplied encoder output (the scripts pass `audio_features` to decode()). */
+int wipa_set_audio_features(wipa_ctx*, const float* enc_out /* device f32[B,1500,d] */, int B, void* stream);
+
+/* ---- (c) decoder ---------------------------------------------------------------------------- */
+typedef struct wipa_decode_opts {
+    const int32_t* prompt;        /* host int32[P]: e.g. <|sot|><|en|><|transcribe|><|notimestamps|> */
+    int32_t prompt_len;
+    int32_t max_new;              /* sample_len (224 - P in the reference's DecodingOptions default) */
+    int32_t eot;                  /* end-of-text id; rows that emit it are padded with it afterwards */
+    const int32_t* suppress;      /* host: ids masked at every step (may be NULL) */
+    int32_t n_suppress;
+    const int32_t* begin_suppress;/* host: ids masked at the first sampled position only */
+    int32_t n_begin_suppress;
+} wipa_decode_opts;
+
+/* Replaces: mlx_whisper.decoding.decode(model, audio_features, DecodingOptions(...)) greedy path
+ * (ref:scripts/evaluate_model.py:200, ref:scripts/transcribe_single.py:55, ref:scripts/train_whisper_ipa.py:356).
+ * out_ids: device int32[B, max_new] (EOT-padded), out_len: device int32[B] (tokens before EOT). */
+int wipa_decode_greedy(wipa_ctx*, int B, const wipa_decode_opts*, int32_t* out_ids, int32_t* out_len, void* stream);
+/* Beam search with HF `_beam_search` semantics (early_stopping=False); same outputs (best hypothesis). */
+int wipa_decode_beam(wipa_ctx*, int B, int beams, float length_penalty, const wipa_decode_opts*,
+                     int32_t* out_ids, int32_t* out_len, void* stream);
+/* Diagnostics for the parity tests: teacher-forced logits.  tokens: host int32[B,T]; logits: device f32[B,T,V]. */
+int wipa_decode_logits(wipa_ctx*, int B, const int32_t* tokens, int T, float* logits, void* stream);
+
+/* ---- (d) PER scorer ------------------------------------------------------------------------- */
+/* Replaces: editdistance.eval(ref_phones, hyp_phones) (ref:scripts/evaluate_ipa.py:100) for N pairs at once.
+ * CSR packing: pair i = ref[ref_off[i]:ref_off[i+1]] vs hyp[hyp_off[i]:hyp_off[i+1]]; all device int32.
+ * dist_len: device int32[N,2] = (edit distance, ref length) — the pair layout the multi-GPU gather moves.
+ * The percentage (d/len)*100.0 and mean/std stay on the host in float64 (ref:scripts/evaluate_ipa.py:103,370). */
+int wipa_per_batch(const int32_t* ref, const int32_t* ref_off, const int32_t* hyp, const int32_t* hyp_off,
+                   int N, int max_ref_len, int32_t* dist_len, void* stream);
+
+/* ---- introspection -------------------------------------------------------------------------- */
+const char* wipa_strerror(int code);
+const char* wipa_last_error(void);
+/* Number of kernels of this library launched since the last reset (bench.py's "gpu_launches"). */
+int64_t wipa_launch_count(int reset);
+/* Timing of one named kernel family on its own launch stream: bench.py brackets with these. */
+int wipa_ctx_get_info(wipa_ctx*, int what, int64_t* out);
+#define WIPA_INFO_WORKSPACE_BYTES 0
+#define WIPA_INFO_CROSSKV_BYTES 1
+#define WIPA_INFO_DECODE_STEPS 2
+
+/* Standalone kernel entry points used by tests/ and bench.py's roofline section. */
+/* C[M,N] = A[M,K] * W[N,K]^T (+bias) in bf16 on tcgen05, fp32 accumulate, fp32 out. All device pointers. */
+int wipa_test_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, float* C,
+                        int M, int N, int K, int block_n, void* stream);
+int wipa_test_gemm_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, void* stream);
+/* One decode-step cross-attention sweep over the context's cached encoder K/V (the dominant HBM kernel):
+ * q: device f32[B, d] (pre-scaled), out: device f32[B, d]; layer selects which cached K/V. */
+int wipa_test_cross_attn(wipa_ctx*, int B, int layer, const float* q, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WIPA_H_ */

@@ -1,0 +1,380 @@
+"""CPU restatement of the Whisper hot path (log-mel -> encoder -> KV-cached greedy / beam decode).
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``whisper_ipa_b200/`` may import this module; it is
+imported by ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` /
+``--impl reference`` legs as the *checker*, never as the product.
+
+What it restates
+----------------
+The reference scripts (``ref:scripts/evaluate_model.py:187-201``, ``ref:scripts/transcribe_single.py:43-56``)
+delegate every arithmetic step to ``mlx-whisper==0.4.3`` (``ref:requirements.txt:23``), which is NOT vendored
+under /root/reference and cannot be installed here (needs Apple Metal).  BASELINE.json names the
+HF ``WhisperForConditionalGeneration.generate`` path as the parity oracle, so this file restates
+*that* published algorithm in plain fp32 torch-CPU tensor code, function by function:
+
+* ``mel_filter_bank``      <- HF:audio_utils.py:453-544 (slaney scale, slaney norm)
+* ``log_mel_spectrogram``  <- HF:models/whisper/feature_extraction_whisper.py:135-164
+* ``sinusoids``            <- HF:models/whisper/modeling_whisper.py:55-65
+* ``encoder_forward``      <- HF:models/whisper/modeling_whisper.py:593-647 (+ layer :361-414, attention :284-357)
+* ``decoder_step``         <- HF:models/whisper/modeling_whisper.py:449-506, 691-796, 1081
+* ``greedy_decode``        <- HF:generation/utils.py:2658-2841 with the begin-suppress processor
+                              HF:generation/logits_process.py:1855-1902
+* ``beam_decode``          <- HF:generation/utils.py:3076-3400 (length_penalty 1.0, early_stopping False)
+
+Pinning: ``tests/test_oracle_whisper.py`` checks every function here against the real HF
+implementation (importable in this image) and against ``tests/golden/*.npz`` fixtures generated
+from HF by ``oracle/make_golden.py``.  Parity is therefore pinned to HF 5.5.0; the reference tree
+itself holds no golden tensor for this path ("parity unpinned" on the reference side).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+N_FFT = 400
+HOP = 160
+N_SAMPLES = 480000
+N_FRAMES = 3000
+N_AUDIO_CTX = 1500
+
+ARCHS: Dict[str, Dict[str, int]] = {
+    # HF WhisperConfig kwargs for the five named architectures
+    "tiny": dict(d_model=384, encoder_layers=4, decoder_layers=4, encoder_attention_heads=6,
+                 decoder_attention_heads=6, encoder_ffn_dim=1536, decoder_ffn_dim=1536,
+                 num_mel_bins=80, vocab_size=51865),
+    "base": dict(d_model=512, encoder_layers=6, decoder_layers=6, encoder_attention_heads=8,
+                 decoder_attention_heads=8, encoder_ffn_dim=2048, decoder_ffn_dim=2048,
+                 num_mel_bins=80, vocab_size=51865),
+    "small": dict(d_model=768, encoder_layers=12, decoder_layers=12, encoder_attention_heads=12,
+                  decoder_attention_heads=12, encoder_ffn_dim=3072, decoder_ffn_dim=3072,
+                  num_mel_bins=80, vocab_size=51865),
+    "medium": dict(d_model=1024, encoder_layers=24, decoder_layers=24, encoder_attention_heads=16,
+                   decoder_attention_heads=16, encoder_ffn_dim=4096, decoder_ffn_dim=4096,
+                   num_mel_bins=80, vocab_size=51865),
+    "large-v3": dict(d_model=1280, encoder_layers=32, decoder_layers=32, encoder_attention_heads=20,
+                     decoder_attention_heads=20, encoder_ffn_dim=5120, decoder_ffn_dim=5120,
+                     num_mel_bins=128, vocab_size=51866),
+}
+
+PROMPT_PRE_V3 = [50258, 50259, 50359, 50363]   # <|sot|><|en|><|transcribe|><|notimestamps|>
+PROMPT_V3 = [50258, 50259, 50360, 50364]
+EOT = 50257
+BEGIN_SUPPRESS = [220, 50257]
+
+
+def prompt_for(arch: str) -> List[int]:
+    return PROMPT_V3 if arch == "large-v3" else PROMPT_PRE_V3
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs
+# --------------------------------------------------------------------------------------
+def synthetic_audio(n_clips: int, first: int = 0) -> np.ndarray:
+    """30 s clips of 0.1-scaled Gaussian noise, seed 1234 + clip index."""
+    out = np.empty((n_clips, N_SAMPLES), dtype=np.float32)
+    for i in range(n_clips):
+        out[i] = np.random.default_rng(1234 + first + i).standard_normal(N_SAMPLES).astype(np.float32) * 0.1
+    return out
+
+
+def synthetic_references(n_clips: int, first: int = 0) -> List[np.ndarray]:
+    """PER reference id sequences: one rng(4321) stream, consumed in clip order."""
+    rng = np.random.default_rng(4321)
+    seqs = []
+    for _ in range(first + n_clips):
+        n = int(rng.integers(20, 120))
+        seqs.append(rng.integers(0, 50257, size=n).astype(np.int32))
+    return seqs[first:]
+
+
+# --------------------------------------------------------------------------------------
+# log-mel front end
+# --------------------------------------------------------------------------------------
+def _hz_to_mel_slaney(f: np.ndarray) -> np.ndarray:
+    f = np.asarray(f, dtype=np.float64)
+    mels = 3.0 * f / 200.0
+    logstep = 27.0 / np.log(6.4)
+    big = f >= 1000.0
+    mels = np.where(big, 15.0 + np.log(np.maximum(f, 1e-30) / 1000.0) * logstep, mels)
+    return mels
+
+
+def _mel_to_hz_slaney(m: np.ndarray) -> np.ndarray:
+    m = np.asarray(m, dtype=np.float64)
+    f = 200.0 * m / 3.0
+    logstep = np.log(6.4) / 27.0
+    big = m >= 15.0
+    return np.where(big, 1000.0 * np.exp(logstep * (m - 15.0)), f)
+
+
+def mel_filter_bank(n_mels: int, n_freq: int = 201, sr: int = 16000, fmax: float = 8000.0) -> np.ndarray:
+    """[n_freq, n_mels] float64 triangular slaney filterbank (HF:audio_utils.py:453-544)."""
+    mel_pts = np.linspace(_hz_to_mel_slaney(0.0), _hz_to_mel_slaney(fmax), n_mels + 2)
+    hz_pts = _mel_to_hz_slaney(mel_pts)
+    fft_freqs = np.linspace(0, sr // 2, n_freq)
+    diff = np.diff(hz_pts)
+    slopes = hz_pts[None, :] - fft_freqs[:, None]
+    down = -slopes[:, :-2] / diff[:-1]
+    up = slopes[:, 2:] / diff[1:]
+    fb = np.maximum(0.0, np.minimum(down, up))
+    enorm = 2.0 / (hz_pts[2:n_mels + 2] - hz_pts[:n_mels])
+    return fb * enorm[None, :]
+
+
+def log_mel_spectrogram(audio: torch.Tensor, n_mels: int = 80) -> torch.Tensor:
+    """audio f32[B, 480000] -> f32[B, n_mels, 3000]  (HF:...feature_extraction_whisper.py:135-164)."""
+    audio = torch.as_tensor(audio, dtype=torch.float32)
+    if audio.dim() == 1:
+        audio = audio[None]
+    B = audio.shape[0]
+    window = torch.hann_window(N_FFT, periodic=True, dtype=torch.float32)
+    padded = F.pad(audio[:, None, :], (N_FFT // 2, N_FFT // 2), mode="reflect")[:, 0]
+    frames = padded.unfold(-1, N_FFT, HOP)                      # [B, 3001, 400]
+    spec = torch.fft.rfft(frames * window, dim=-1)              # [B, 3001, 201]
+    power = (spec.real ** 2 + spec.imag ** 2)[:, :-1, :]         # drop last frame -> [B, 3000, 201]
+    fb = torch.from_numpy(mel_filter_bank(n_mels)).to(torch.float32)    # [201, n_mels]
+    mel = torch.matmul(power, fb).transpose(1, 2)               # [B, n_mels, 3000]
+    log_spec = torch.clamp(mel, min=1e-10).log10()
+    mx = log_spec.reshape(B, -1).max(dim=1).values.view(B, 1, 1)
+    log_spec = torch.maximum(log_spec, mx - 8.0)
+    return (log_spec + 4.0) / 4.0
+
+
+# --------------------------------------------------------------------------------------
+# model restatement (functional, keyed by the HF state_dict names)
+# --------------------------------------------------------------------------------------
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    inc = math.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(channels // 2))
+    t = torch.arange(length).view(-1, 1) * inv.view(1, -1)
+    return torch.cat([t.sin(), t.cos()], dim=1)
+
+
+@dataclass
+class Dims:
+    d: int
+    n_enc: int
+    n_dec: int
+    heads: int
+    ffn: int
+    n_mels: int
+    vocab: int
+
+    @staticmethod
+    def from_arch(arch: str) -> "Dims":
+        a = ARCHS[arch]
+        return Dims(a["d_model"], a["encoder_layers"], a["decoder_layers"], a["encoder_attention_heads"],
+                    a["encoder_ffn_dim"], a["num_mel_bins"], a["vocab_size"])
+
+
+def _lin(x, sd, name, bias=True):
+    return F.linear(x, sd[name + ".weight"], sd[name + ".bias"] if bias else None)
+
+
+def _ln(x, sd, name):
+    return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], 1e-5)
+
+
+def _heads(x, H):
+    B, T, D = x.shape
+    return x.view(B, T, H, D // H).transpose(1, 2)         # [B,H,T,hd]
+
+
+def _attend(q, k, v, causal_offset: Optional[int] = None):
+    """softmax(q k^T) v with NO extra scaling (q is pre-scaled, HF:...modeling_whisper.py:310,349)."""
+    s = torch.matmul(q, k.transpose(-1, -2))
+    if causal_offset is not None:
+        Tq, Tk = s.shape[-2:]
+        i = torch.arange(Tq).view(-1, 1) + causal_offset
+        j = torch.arange(Tk).view(1, -1)
+        s = s.masked_fill(j > i, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    o = torch.matmul(p, v)                                   # [B,H,Tq,hd]
+    B, H, Tq, hd = o.shape
+    return o.transpose(1, 2).reshape(B, Tq, H * hd)
+
+
+def encoder_forward(sd: Dict[str, torch.Tensor], dims: Dims, mel: torch.Tensor,
+                    taps: Optional[dict] = None) -> torch.Tensor:
+    """mel f32[B, n_mels, 3000] -> f32[B, 1500, d]."""
+    p = "model.encoder."
+    x = F.gelu(F.conv1d(mel, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1))
+    x = F.gelu(F.conv1d(x, sd[p + "conv2.weight"], sd[p + "conv2.bias"], stride=2, padding=1))
+    x = x.permute(0, 2, 1) + sd[p + "embed_positions.weight"]
+    if taps is not None:
+        taps["stem"] = x.clone()
+    scale = (dims.d // dims.heads) ** -0.5
+    for l in range(dims.n_enc):
+        lp = f"{p}layers.{l}."
+        h = _ln(x, sd, lp + "self_attn_layer_norm")
+        q = _heads(_lin(h, sd, lp + "self_attn.q_proj") * scale, dims.heads)
+        k = _heads(_lin(h, sd, lp + "self_attn.k_proj", bias=False), dims.heads)
+        v = _heads(_lin(h, sd, lp + "self_attn.v_proj"), dims.heads)
+        x = x + _lin(_attend(q, k, v), sd, lp + "self_attn.out_proj")
+        h = _ln(x, sd, lp + "final_layer_norm")
+        x = x + _lin(F.gelu(_lin(h, sd, lp + "fc1")), sd, lp + "fc2")
+        if taps is not None:
+            taps[f"layer{l}"] = x.clone()
+    return _ln(x, sd, p + "layer_norm")
+
+
+def cross_kv(sd, dims: Dims, enc: torch.Tensor) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+    """Per decoder layer (K, V) as [B,H,1500,hd] (HF:...modeling_whisper.py:326-336)."""
+    out = []
+    for l in range(dims.n_dec):
+        lp = f"model.decoder.layers.{l}.encoder_attn."
+        k = _heads(_lin(enc, sd, lp + "k_proj", bias=False), dims.heads)
+        v = _heads(_lin(enc, sd, lp + "v_proj"), dims.heads)
+        out.append((k, v))
+    return out
+
+
+def decoder_forward(sd, dims: Dims, tokens: torch.Tensor, pos0: int, xkv, self_kv: list) -> torch.Tensor:
+    """tokens int64[B,T] at positions pos0.. -> logits f32[B,T,V]; appends to self_kv in place."""
+    p = "model.decoder."
+    B, T = tokens.shape
+    x = sd[p + "embed_tokens.weight"][tokens] + sd[p + "embed_positions.weight"][pos0:pos0 + T]
+    scale = (dims.d // dims.heads) ** -0.5
+    for l in range(dims.n_dec):
+        lp = f"{p}layers.{l}."
+        h = _ln(x, sd, lp + "self_attn_layer_norm")
+        q = _heads(_lin(h, sd, lp + "self_attn.q_proj") * scale, dims.heads)
+        k = _heads(_lin(h, sd, lp + "self_attn.k_proj", bias=False), dims.heads)
+        v = _heads(_lin(h, sd, lp + "self_attn.v_proj"), dims.heads)
+        if self_kv[l] is None:
+            self_kv[l] = (k, v)
+        else:
+            self_kv[l] = (torch.cat([self_kv[l][0], k], dim=2), torch.cat([self_kv[l][1], v], dim=2))
+        x = x + _lin(_attend(q, self_kv[l][0], self_kv[l][1], causal_offset=pos0), sd, lp + "self_attn.out_proj")
+        h = _ln(x, sd, lp + "encoder_attn_layer_norm")
+        q = _heads(_lin(h, sd, lp + "encoder_attn.q_proj") * scale, dims.heads)
+        x = x + _lin(_attend(q, xkv[l][0], xkv[l][1]), sd, lp + "encoder_attn.out_proj")
+        h = _ln(x, sd, lp + "final_layer_norm")
+        x = x + _lin(F.gelu(_lin(h, sd, lp + "fc1")), sd, lp + "fc2")
+    x = _ln(x, sd, p + "layer_norm")
+    return F.linear(x, sd[p + "embed_tokens.weight"])       # tied head, no bias (:966,1081)
+
+
+def greedy_decode(sd, dims: Dims, enc: torch.Tensor, prompt: Sequence[int], max_new: int,
+                  eot: int = EOT, begin_suppress: Sequence[int] = BEGIN_SUPPRESS,
+                  suppress: Sequence[int] = (), return_logits: bool = False):
+    """HF greedy semantics: returns int64[B, max_new] right-padded with ``eot`` (= pad id) after EOS,
+    and the per-row count of tokens before EOS."""
+    B = enc.shape[0]
+    xkv = cross_kv(sd, dims, enc)
+    self_kv = [None] * dims.n_dec
+    toks = torch.tensor([list(prompt)] * B, dtype=torch.long)
+    logits = decoder_forward(sd, dims, toks, 0, xkv, self_kv)[:, -1].float()
+    out = torch.full((B, max_new), eot, dtype=torch.long)
+    lens = torch.full((B,), max_new, dtype=torch.long)
+    done = torch.zeros(B, dtype=torch.bool)
+    all_logits = []
+    pos = len(prompt)
+    for i in range(max_new):
+        logits = logits.clone()
+        if len(suppress):
+            logits[:, list(suppress)] = float("-inf")
+        if i == 0 and len(begin_suppress):
+            logits[:, list(begin_suppress)] = float("-inf")
+        if return_logits:
+            all_logits.append(logits.clone())
+        nxt = logits.argmax(dim=-1)
+        nxt = torch.where(done, torch.full_like(nxt, eot), nxt)
+        newly = (~done) & (nxt == eot)
+        lens = torch.where(newly, torch.full_like(lens, i), lens)
+        done = done | newly
+        out[:, i] = nxt
+        if bool(done.all()) or i == max_new - 1:
+            break
+        logits = decoder_forward(sd, dims, nxt[:, None], pos, xkv, self_kv)[:, -1].float()
+        pos += 1
+    if return_logits:
+        return out, lens, all_logits
+    return out, lens
+
+
+def beam_decode(sd, dims: Dims, enc: torch.Tensor, prompt: Sequence[int], max_new: int, beams: int,
+                length_penalty: float = 1.0, eot: int = EOT,
+                begin_suppress: Sequence[int] = BEGIN_SUPPRESS):
+    """Beam search with HF `_beam_search` semantics (HF:generation/utils.py:3076-3400) for
+    early_stopping=False, num_return_sequences=1: keep 2*beams candidates per step, finished
+    hypotheses scored sum_logprob / (cur_len ** length_penalty) with cur_len counting prompt + generated
+    (including EOS); stop when no running beam can beat the worst finished one.
+    Returns int64[B, max_new] (best hypothesis, EOS stripped, right-padded with eot) and lengths."""
+    B = enc.shape[0]
+    P = len(prompt)
+    xkv1 = cross_kv(sd, dims, enc)
+    xkv = [(k.repeat_interleave(beams, 0), v.repeat_interleave(beams, 0)) for k, v in xkv1]
+    self_kv = [None] * dims.n_dec
+    toks = torch.tensor([list(prompt)] * (B * beams), dtype=torch.long)
+    logits = decoder_forward(sd, dims, toks, 0, xkv, self_kv)[:, -1].float()
+    V = logits.shape[-1]
+    running = toks.view(B, beams, P).clone()
+    run_lp = torch.zeros(B, beams)
+    run_lp[:, 1:] = -1e9
+    fin_seq = [[] for _ in range(B)]         # list of (score, tokens list)
+    fin_done = torch.zeros(B, dtype=torch.bool)
+    pos = P
+    for i in range(max_new):
+        logits = logits.clone()
+        lp = torch.log_softmax(logits, dim=-1)
+        if i == 0 and len(begin_suppress):
+            lp[:, list(begin_suppress)] = float("-inf")
+        lp = lp.view(B, beams, V) + run_lp[:, :, None]
+        top_lp, top_idx = torch.topk(lp.view(B, beams * V), 2 * beams, dim=1)
+        src = top_idx // V
+        tok = top_idx % V
+        cur_len = P + i + 1
+        new_running = torch.zeros(B, beams, cur_len, dtype=torch.long)
+        new_lp = torch.full((B, beams), -1e9)
+        reorder = torch.zeros(B, beams, dtype=torch.long)
+        for b in range(B):
+            n = 0
+            for c in range(2 * beams):
+                s, t, sc = int(src[b, c]), int(tok[b, c]), float(top_lp[b, c])
+                if t == eot:
+                    # HF only admits an EOS candidate into the finished set if it ranks in the top `beams`
+                    if c < beams and not fin_done[b]:
+                        fin_seq[b].append((sc / (cur_len ** length_penalty),
+                                           running[b, s].tolist() + [t]))
+                    continue
+                if n < beams:
+                    new_running[b, n, :-1] = running[b, s]
+                    new_running[b, n, -1] = t
+                    new_lp[b, n] = sc
+                    reorder[b, n] = b * beams + s
+                    n += 1
+            fin_seq[b] = sorted(fin_seq[b], key=lambda z: -z[0])[:beams]
+            if len(fin_seq[b]) >= beams and not fin_done[b]:
+                # early_stopping=False: best possible running score uses the current length
+                best_running = float(new_lp[b].max()) / (cur_len ** length_penalty) if length_penalty <= 0 \
+                    else float(new_lp[b].max()) / ((P + max_new) ** length_penalty)
+                worst_fin = fin_seq[b][-1][0]
+                if worst_fin >= best_running:
+                    fin_done[b] = True
+        running, run_lp = new_running, new_lp
+        if bool(fin_done.all()) or i == max_new - 1:
+            break
+        flat = reorder.view(-1)
+        self_kv = [(k[flat], v[flat]) for k, v in self_kv]
+        logits = decoder_forward(sd, dims, running[:, :, -1].reshape(-1, 1), pos, xkv, self_kv)[:, -1].float()
+        pos += 1
+    out = torch.full((B, max_new), eot, dtype=torch.long)
+    lens = torch.zeros(B, dtype=torch.long)
+    for b in range(B):
+        cur_len = running.shape[-1]
+        cands = list(fin_seq[b])
+        if not fin_done[b]:
+            for k in range(beams):
+                cands.append((float(run_lp[b, k]) / (cur_len ** length_penalty), running[b, k].tolist()))
+        best = max(cands, key=lambda z: z[0])[1][P:]
+        if best and best[-1] == eot:
+            best = best[:-1]
+        out[b, :len(best)] = torch.tensor(best, dtype=torch.long)
+        lens[b] = len(best)
+    return out, lens

@@ -1,0 +1,441 @@
+// Attention kernels.
+//   enc_attention_kernel   : encoder self-attention (non-causal, 1500 x 1500 x 64 per head), flash-style
+//                            online softmax, fp32 math on CUDA cores.  This is the fp32-path kernel
+//                            (HF:models/whisper/modeling_whisper.py:284-357 with scaling folded into q).
+//   self_attention_kernel  : one decode step of decoder self-attention over the paged KV cache.
+//   cross_attention_kernel : one decode step of cross-attention against the cached encoder K/V —
+//                            the dominant HBM stream of the whole decode.
+#include "common.cuh"
+
+// ================================================================================================
+// encoder self-attention, SIMT
+// ================================================================================================
+#define EA_BQ 64
+#define EA_BK 64
+#define EA_LD (64 + 4)
+
+template <typename T>
+__device__ __forceinline__ void load16_as_float(const T* p, float* out);   // 16 consecutive elements
+template <>
+__device__ __forceinline__ void load16_as_float<float>(const float* p, float* out) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float4 v = *reinterpret_cast<const float4*>(p + 4 * i);
+        out[4 * i] = v.x; out[4 * i + 1] = v.y; out[4 * i + 2] = v.z; out[4 * i + 3] = v.w;
+    }
+}
+template <>
+__device__ __forceinline__ void load16_as_float<bf16>(const bf16* p, float* out) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        uint4 u = *reinterpret_cast<const uint4*>(p + 8 * i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = __bfloat1622float2(h[j]);
+            out[8 * i + 2 * j] = f.x; out[8 * i + 2 * j + 1] = f.y;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+enc_attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ out,
+                     int H, int Tq) {
+    extern __shared__ __align__(16) float ea_smem[];
+    float* Qt = ea_smem;                        // [64 e][EA_LD q]
+    float* Kt = Qt + 64 * EA_LD;                // [64 e][EA_LD key]
+    float* Vs = Kt + 64 * EA_LD;                // [64 key][EA_LD e]
+    float* Pt = Vs + 64 * EA_LD;                // [64 key][EA_LD q]
+
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int bh = blockIdx.y;
+    const int q0 = blockIdx.x * EA_BQ;
+    const T* qb = q + (size_t)bh * Tq * 64;
+    const T* kb = k + (size_t)bh * Tq * 64;
+    const T* vb = v + (size_t)bh * Tq * 64;
+
+    const int lr = tid >> 2;                    // row within a 64-row tile
+    const int le = (tid & 3) * 16;              // 16-element chunk
+    {
+        float tmp[16];
+        const int t = q0 + lr;
+        if (t < Tq) load16_as_float<T>(qb + (size_t)t * 64 + le, tmp);
+        else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tmp[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) Qt[(le + i) * EA_LD + lr] = tmp[i];
+    }
+
+    float m_run[4], l_run[4], o[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        m_run[i] = -INFINITY; l_run[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+    }
+
+    for (int k0 = 0; k0 < Tq; k0 += EA_BK) {
+        __syncthreads();                         // previous tile fully consumed (also covers the Q store)
+        {
+            float tk[16], tv[16];
+            const int t = k0 + lr;
+            if (t < Tq) {
+                load16_as_float<T>(kb + (size_t)t * 64 + le, tk);
+                load16_as_float<T>(vb + (size_t)t * 64 + le, tv);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { tk[i] = 0.f; tv[i] = 0.f; }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Kt[(le + i) * EA_LD + lr] = tk[i];
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+                *reinterpret_cast<float4*>(&Vs[lr * EA_LD + le + i]) = make_float4(tv[i], tv[i + 1], tv[i + 2], tv[i + 3]);
+        }
+        __syncthreads();
+
+        float s[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll 8
+        for (int e = 0; e < 64; ++e) {
+            const float4 qv = *reinterpret_cast<const float4*>(&Qt[e * EA_LD + ty * 4]);
+            const float4 kv = *reinterpret_cast<const float4*>(&Kt[e * EA_LD + tx * 4]);
+            const float qa[4] = {qv.x, qv.y, qv.z, qv.w};
+            const float ka[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) s[i][j] = fmaf(qa[i], ka[j], s[i][j]);
+        }
+        // mask the key tail, online softmax over the 16 lanes that share a query row
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (k0 + tx * 4 + j >= Tq) s[i][j] = -INFINITY;
+                mx = fmaxf(mx, s[i][j]);
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+            const float m_new = fmaxf(m_run[i], mx);
+            const float alpha = expf(m_run[i] - m_new);          // exp(-inf) = 0 on the first tile
+            float rs = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float p = expf(s[i][j] - m_new);
+                s[i][j] = p;
+                rs += p;
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, off);
+            l_run[i] = l_run[i] * alpha + rs;
+            m_run[i] = m_new;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[i][j] *= alpha;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(&Pt[(tx * 4 + j) * EA_LD + ty * 4]) = make_float4(s[0][j], s[1][j], s[2][j], s[3][j]);
+        __syncthreads();
+#pragma unroll 8
+        for (int kk = 0; kk < EA_BK; ++kk) {
+            const float4 pv = *reinterpret_cast<const float4*>(&Pt[kk * EA_LD + ty * 4]);
+            const float4 vv = *reinterpret_cast<const float4*>(&Vs[kk * EA_LD + tx * 4]);
+            const float pa[4] = {pv.x, pv.y, pv.z, pv.w};
+            const float va[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o[i][j] = fmaf(pa[i], va[j], o[i][j]);
+        }
+    }
+    const int b = bh / H, h = bh - b * H;
+    const int d = H * 64;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int t = q0 + ty * 4 + i;
+        if (t < Tq) {
+            const float inv = 1.0f / l_run[i];
+            float r[4] = {o[i][0] * inv, o[i][1] * inv, o[i][2] * inv, o[i][3] * inv};
+            store_group<4>(out, sizeof(T) == 2, ((size_t)b * Tq + t) * d + h * 64 + tx * 4, r, true);
+        }
+    }
+}
+
+template <typename T>
+int launch_enc_attention(const T* q, const T* k, const T* v, T* out, int B, int H, int Tq, cudaStream_t st) {
+    const size_t smem = sizeof(float) * 4 * 64 * EA_LD;
+    static bool configured = false;
+    if (!configured) {
+        WIPA_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid(cdiv(Tq, EA_BQ), B * H);
+    enc_attention_kernel<T><<<grid, 256, smem, st>>>(q, k, v, out, H, Tq);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+template int launch_enc_attention<float>(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
+template int launch_enc_attention<bf16>(const bf16*, const bf16*, const bf16*, bf16*, int, int, int, cudaStream_t);
+
+// ================================================================================================
+// decoder self-attention, one new token per sequence, paged KV
+// ================================================================================================
+template <typename T>
+__device__ __forceinline__ float dot64(const T* kp, const float* qs);
+template <>
+__device__ __forceinline__ float dot64<float>(const float* kp, const float* qs) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; i += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(kp + i);
+        acc = fmaf(kv.x, qs[i], acc); acc = fmaf(kv.y, qs[i + 1], acc);
+        acc = fmaf(kv.z, qs[i + 2], acc); acc = fmaf(kv.w, qs[i + 3], acc);
+    }
+    return acc;
+}
+template <>
+__device__ __forceinline__ float dot64<bf16>(const bf16* kp, const float* qs) {
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < 64; i += 8) {
+        const uint4 u = *reinterpret_cast<const uint4*>(kp + i);
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(h[j]);
+            acc = fmaf(f.x, qs[i + 2 * j], acc);
+            acc = fmaf(f.y, qs[i + 2 * j + 1], acc);
+        }
+    }
+    return acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, const T* __restrict__ vpool,
+                      const int* __restrict__ block_table, int bt_stride, const int* __restrict__ pos_ptr,
+                      T* __restrict__ out, int H) {
+    __shared__ float qs[64];
+    __shared__ float sc[WIPA_MAX_TGT];
+    __shared__ float red[4];
+    __shared__ float part[2][64];
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = H * 64;
+    const int len = *pos_ptr + 1;
+    const int* bt = block_table + (size_t)b * bt_stride;
+    if (tid < 64) qs[tid] = q[(size_t)b * d + h * 64 + tid];
+    __syncthreads();
+
+    float mx = -INFINITY;
+    for (int j = tid; j < len; j += 128) {
+        const int page = bt[j / WIPA_PAGE];
+        const T* kp = kpool + (((size_t)page * H + h) * WIPA_PAGE + (j % WIPA_PAGE)) * 64;
+        const float s = dot64<T>(kp, qs);
+        sc[j] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = tid; j < len; j += 128) {
+        const float p = expf(sc[j] - mx);
+        sc[j] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = red[0] + red[1] + red[2] + red[3];
+    const float inv = 1.0f / sum;
+
+    const int e = tid & 63, half = tid >> 6;
+    float acc = 0.f;
+    for (int j = half; j < len; j += 2) {
+        const int page = bt[j / WIPA_PAGE];
+        const T* vp = vpool + (((size_t)page * H + h) * WIPA_PAGE + (j % WIPA_PAGE)) * 64;
+        acc = fmaf(sc[j], to_f32(vp[e]), acc);
+    }
+    part[half][e] = acc;
+    __syncthreads();
+    if (tid < 64) out[(size_t)b * d + h * 64 + tid] = from_f32<T>((part[0][tid] + part[1][tid]) * inv);
+}
+
+template <typename T>
+int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
+                          const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st) {
+    dim3 grid(H, Bs);
+    self_attention_kernel<T><<<grid, 128, 0, st>>>(q, kpool, vpool, block_table, bt_stride, pos_ptr, out, H);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+template int launch_self_attention<float>(const float*, const float*, const float*, const int*, int, const int*, float*, int, int, cudaStream_t);
+template int launch_self_attention<bf16>(const float*, const bf16*, const bf16*, const int*, int, const int*, bf16*, int, int, cudaStream_t);
+
+// ================================================================================================
+// decoder cross-attention, one query per (sequence, head) against 1500 cached encoder keys/values
+// ================================================================================================
+// K/V for one (utterance, head) are contiguous [1500][64].  A key row is 64 * sizeof(T) bytes; LPK lanes
+// each read one 16-byte vector of it, so a warp covers KPW = 32 / LPK consecutive keys (512 contiguous
+// bytes) per load instruction; loads are issued 4 deep before any use to keep enough bytes in flight.
+#define CA_THREADS 256
+#define CA_WARPS (CA_THREADS / 32)
+
+template <typename T> struct CaCfg;
+template <> struct CaCfg<float> { static constexpr int VEC = 4, LPK = 16, KPW = 2; };
+template <> struct CaCfg<bf16> { static constexpr int VEC = 8, LPK = 8, KPW = 4; };
+
+template <typename T>
+__device__ __forceinline__ void unpack16(const uint4& u, float* f);
+template <>
+__device__ __forceinline__ void unpack16<float>(const uint4& u, float* f) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+}
+template <>
+__device__ __forceinline__ void unpack16<bf16>(const uint4& u, float* f) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 t = __bfloat1622float2(h[j]);
+        f[2 * j] = t.x; f[2 * j + 1] = t.y;
+    }
+}
+
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(CA_THREADS)
+cross_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc,
+                       const int* __restrict__ utt_of_seq, T* __restrict__ out, int H) {
+    using C = CaCfg<T>;
+    constexpr int UNROLL = 4;
+    constexpr int KSTEP = CA_WARPS * C::KPW;                 // keys covered by the CTA per load wave
+    __shared__ float sc[WIPA_T_ENC + 4];
+    __shared__ float red[CA_WARPS];
+    __shared__ float part[CA_WARPS][64];
+
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = H * 64;
+    const int utt = utt_of_seq ? utt_of_seq[b] : b;
+    const T* kb = kc + ((size_t)utt * H + h) * WIPA_T_ENC * 64;
+    const T* vb = vc + ((size_t)utt * H + h) * WIPA_T_ENC * 64;
+    const int sub = lane / C::LPK;                           // which of the warp's KPW keys
+    const int li = lane % C::LPK;                            // which 16-byte chunk of the row
+
+    float qv[C::VEC];
+#pragma unroll
+    for (int i = 0; i < C::VEC; ++i) qv[i] = q[(size_t)b * d + h * 64 + li * C::VEC + i];
+
+    // ---- phase 1: scores --------------------------------------------------------------------
+    float mx = -INFINITY;
+    for (int base = warp * C::KPW; base < WIPA_T_ENC; base += KSTEP * UNROLL) {
+        uint4 u[UNROLL];
+#pragma unroll
+        for (int r = 0; r < UNROLL; ++r) {
+            const int key = base + r * KSTEP + sub;
+            u[r] = key < WIPA_T_ENC ? ld_stream16(kb + (size_t)key * 64 + li * C::VEC) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < UNROLL; ++r) {
+            const int key = base + r * KSTEP + sub;
+            float f[C::VEC];
+            unpack16<T>(u[r], f);
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < C::VEC; ++i) s = fmaf(f[i], qv[i], s);
+#pragma unroll
+            for (int off = C::LPK / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+            if (key < WIPA_T_ENC) {
+                if (li == 0) sc[key] = s;
+                mx = fmaxf(mx, s);
+            }
+        }
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+#pragma unroll
+    for (int w = 1; w < CA_WARPS; ++w) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+
+    // ---- phase 2: softmax numerators and their sum -----------------------------------------------
+    float sum = 0.f;
+    for (int j = tid; j < WIPA_T_ENC; j += CA_THREADS) {
+        const float p = expf(sc[j] - mx);
+        sc[j] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < CA_WARPS; ++w) sum += red[w];
+    const float inv = 1.0f / sum;
+
+    // ---- phase 3: weighted sum of values ---------------------------------------------------------
+    float acc[C::VEC];
+#pragma unroll
+    for (int i = 0; i < C::VEC; ++i) acc[i] = 0.f;
+    for (int base = warp * C::KPW; base < WIPA_T_ENC; base += KSTEP * UNROLL) {
+        uint4 u[UNROLL];
+#pragma unroll
+        for (int r = 0; r < UNROLL; ++r) {
+            const int key = base + r * KSTEP + sub;
+            u[r] = key < WIPA_T_ENC ? ld_stream16(vb + (size_t)key * 64 + li * C::VEC) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int r = 0; r < UNROLL; ++r) {
+            const int key = base + r * KSTEP + sub;
+            const float p = key < WIPA_T_ENC ? sc[key] : 0.f;
+            float f[C::VEC];
+            unpack16<T>(u[r], f);
+#pragma unroll
+            for (int i = 0; i < C::VEC; ++i) acc[i] = fmaf(p, f[i], acc[i]);
+        }
+    }
+#pragma unroll
+    for (int off = C::LPK; off < 32; off <<= 1)
+#pragma unroll
+        for (int i = 0; i < C::VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+    if (lane < C::LPK) {
+#pragma unroll
+        for (int i = 0; i < C::VEC; ++i) part[warp][li * C::VEC + i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float r = 0.f;
+#pragma unroll
+        for (int w = 0; w < CA_WARPS; ++w) r += part[w][tid];
+        out[(size_t)b * d + h * 64 + tid] = from_f32<T>(r * inv);
+    }
+}
+
+template <typename T>
+int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, int Bs, int H,
+                           cudaStream_t st) {
+    dim3 grid(H, Bs);
+    cross_attention_kernel<T><<<grid, CA_THREADS, 0, st>>>(q, k, v, utt_of_seq, out, H);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+template int launch_cross_attention<float>(const float*, const float*, const float*, const int*, float*, int, int, cudaStream_t);
+template int launch_cross_attention<bf16>(const float*, const bf16*, const bf16*, const int*, bf16*, int, int, cudaStream_t);

@@ -1,0 +1,318 @@
+// Shared declarations for libwipa (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/wipa.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libwipa is written for sm_100a only"
+#endif
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+void wipa_set_error(const char* fmt, ...);
+extern int64_t g_wipa_launches;
+
+#define WIPA_CUDA_CHECK(expr)                                                                   \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            wipa_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return WIPA_ECUDA;                                                                  \
+        }                                                                                       \
+    } while (0)
+
+#define WIPA_CHECK(cond, code, ...)                   \
+    do {                                              \
+        if (!(cond)) {                                \
+            wipa_set_error(__VA_ARGS__);              \
+            return (code);                            \
+        }                                             \
+    } while (0)
+
+#define WIPA_TRY(expr)              \
+    do {                            \
+        int _r = (expr);            \
+        if (_r != WIPA_OK) return _r; \
+    } while (0)
+
+// every kernel launch of the library goes through this so bench.py can report "gpu_launches"
+#define WIPA_LAUNCHED()                                                                        \
+    do {                                                                                       \
+        ++g_wipa_launches;                                                                     \
+        cudaError_t _e = cudaPeekAtLastError();                                                \
+        if (_e != cudaSuccess) {                                                               \
+            wipa_set_error("%s:%d: launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return WIPA_ECUDA;                                                                 \
+        }                                                                                      \
+    } while (0)
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// model constants
+// ------------------------------------------------------------------------------------------------
+#define WIPA_N_FFT 400
+#define WIPA_HOP 160
+#define WIPA_N_SAMPLES 480000
+#define WIPA_N_FRAMES 3000
+#define WIPA_N_FREQ 201
+#define WIPA_T_ENC 1500
+#define WIPA_T_ENC_PAD 1504      // V^T rows padded so TMA strides are multiples of 16 bytes
+#define WIPA_HEAD_DIM 64
+#define WIPA_MAX_TGT 448
+#define WIPA_PAGE 16             // tokens per self-KV page
+
+// ------------------------------------------------------------------------------------------------
+// epilogue description shared by the SIMT-fp32 and tcgen05-bf16 GEMM kernels
+// ------------------------------------------------------------------------------------------------
+enum EpiMode : int {
+    EPI_STORE = 0,      // out[m, n] = acc + bias
+    EPI_GELU = 1,       // out = gelu(acc + bias)
+    EPI_RESADD = 2,     // out_f32 = resid + acc + bias
+    EPI_GELU_POS = 3,   // out_f32 = gelu(acc + bias) + pos[m % T, n]      (conv2 + positional embedding)
+    EPI_HEADS = 4,      // split N into (q|k|v) x heads, write [B,H,T,64] (or V^T [B,H,64,Tpad])
+    EPI_QKV_DEC = 5,    // decoder self-attn projection: q -> f32 [M,d]; k,v -> paged cache at *pos_ptr
+    EPI_ARGMAX = 6      // per-(row, n-tile) running (max, argmax) with suppress masks, nothing else stored
+};
+
+struct EpiParams {
+    int mode;
+    int out_bf16;            // element type of out/out1/out2 (0 = f32, 1 = bf16)
+    int vec_ok;              // 8-wide vector stores legal (alignment + N % 8 == 0)
+    int M_rows;              // valid rows per batch (rows beyond are padding of the M tile)
+    int N;                   // valid columns
+    const float* bias;       // [N] or nullptr
+    void* out;
+    void* out1;
+    void* out2;
+    long long ldo;           // elements between consecutive output rows
+    int o_rpb;               // output rows per batch  (row m -> batch m / o_rpb, t = m % o_rpb)
+    long long o_bstride;     // elements between batches of the output
+    const float* resid;      // EPI_RESADD (same addressing as out)
+    const float* pos;        // EPI_GELU_POS: [T, N]
+    int T;                   // rows per clip (EPI_HEADS / EPI_GELU_POS)
+    int H;                   // heads
+    int d;                   // d_model
+    int n_which;             // EPI_HEADS: how many of (q,k,v) N spans; first maps to out, then out1, out2
+    int v_transposed;        // EPI_HEADS: last "which" written transposed [B,H,64,Tpad]
+    int Tpad;
+    // EPI_QKV_DEC
+    const int* pos_ptr;      // device scalar: position being written
+    const int* block_table;  // [M, bt_stride] page ids
+    int bt_stride;
+    int n_pages;             // pages per layer pool (unused by addressing, kept for asserts)
+    // EPI_ARGMAX
+    float* pmax;             // [M, n_tiles]
+    int* pidx;               // [M, n_tiles]
+    int n_tiles;
+    const uint32_t* mask_always;   // vocab bitmask, bit set = suppressed (may be nullptr)
+    const uint32_t* mask_begin;    // applied when *step_ptr == 0 (may be nullptr)
+    const int* step_ptr;
+};
+
+// A-operand addressing shared by both GEMM kernels: row m of the logical [M, K] matrix lives at
+//   A + (m / a_rpb) * a_bstride + (m % a_rpb) * lda        (elements)
+// Rows may overlap (lda < K): that is how conv1d(k=3) over a channels-last, zero-padded signal becomes a GEMM.
+struct AOperand {
+    const void* ptr;
+    long long lda;
+    int a_rpb;               // rows per batch
+    long long a_bstride;
+    int n_batch;
+};
+
+// ------------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float gelu_erf(float x) {
+    // exact-erf GELU (HF activation_function="gelu", HF:models/whisper/configuration_whisper.py:140)
+    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&t);
+}
+
+// store W consecutive values starting at element index `idx` of a f32 or bf16 array
+template <int W>
+__device__ __forceinline__ void store_group(void* base, int is_bf16, long long idx, const float* v, bool vec) {
+    if (is_bf16) {
+        bf16* p = reinterpret_cast<bf16*>(base) + idx;
+        if (vec) {
+            if (W == 8) {
+                uint4 u;
+                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                *reinterpret_cast<uint4*>(p) = u;
+            } else {
+                uint2 u;
+                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                *reinterpret_cast<uint2*>(p) = u;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < W; ++i) p[i] = __float2bfloat16_rn(v[i]);
+        }
+    } else {
+        float* p = reinterpret_cast<float*>(base) + idx;
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < W; i += 4)
+                *reinterpret_cast<float4*>(p + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < W; ++i) p[i] = v[i];
+        }
+    }
+}
+
+// Apply the epilogue to W (4 or 8) consecutive accumulator columns n0..n0+W-1 of logical row m.
+// n0 is a multiple of W.  Columns >= ep.N are dropped.
+template <int W>
+__device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, float* v) {
+    if (n0 >= ep.N) return;
+    const bool full = (n0 + W <= ep.N);
+    const bool vec = ep.vec_ok && full;
+    if (ep.bias != nullptr) {
+        if (vec) {
+#pragma unroll
+            for (int i = 0; i < W; i += 4) {
+                float4 b = *reinterpret_cast<const float4*>(ep.bias + n0 + i);
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < W; ++i) if (n0 + i < ep.N) v[i] += ep.bias[n0 + i];
+        }
+    }
+    const int ob = m / ep.o_rpb;
+    const int ot = m - ob * ep.o_rpb;
+    const long long row = (long long)ob * ep.o_bstride + (long long)ot * ep.ldo;
+    switch (ep.mode) {
+        case EPI_GELU:
+#pragma unroll
+            for (int i = 0; i < W; ++i) v[i] = gelu_erf(v[i]);
+            // fallthrough
+        case EPI_STORE: {
+            if (full) store_group<W>(ep.out, ep.out_bf16, row + n0, v, vec);
+            else {
+                for (int i = 0; i < W && n0 + i < ep.N; ++i) store_group<1>(ep.out, ep.out_bf16, row + n0 + i, v + i, false);
+            }
+            break;
+        }
+        case EPI_RESADD: {
+            const float* r = ep.resid + row + n0;
+            float* o = reinterpret_cast<float*>(ep.out) + row + n0;
+            if (vec) {
+#pragma unroll
+                for (int i = 0; i < W; i += 4) {
+                    float4 x = *reinterpret_cast<const float4*>(r + i);
+                    *reinterpret_cast<float4*>(o + i) = make_float4(x.x + v[i], x.y + v[i + 1], x.z + v[i + 2], x.w + v[i + 3]);
+                }
+            } else {
+                for (int i = 0; i < W && n0 + i < ep.N; ++i) o[i] = r[i] + v[i];
+            }
+            break;
+        }
+        case EPI_GELU_POS: {
+            const int t = m % ep.T;
+            const float* pp = ep.pos + (long long)t * ep.N + n0;
+            float* o = reinterpret_cast<float*>(ep.out) + row + n0;
+#pragma unroll
+            for (int i = 0; i < W; ++i) if (n0 + i < ep.N) o[i] = gelu_erf(v[i]) + pp[i];
+            break;
+        }
+        case EPI_HEADS: {
+            const int which = n0 / ep.d;
+            const int c = n0 - which * ep.d;
+            const int h = c / WIPA_HEAD_DIM;
+            const int e = c - h * WIPA_HEAD_DIM;
+            const int b = m / ep.T;
+            const int t = m - b * ep.T;
+            void* dst = which == 0 ? ep.out : (which == 1 ? ep.out1 : ep.out2);
+            if (ep.v_transposed && which == ep.n_which - 1) {
+                const long long base = ((long long)(b * ep.H + h) * WIPA_HEAD_DIM + e) * ep.Tpad + t;
+#pragma unroll
+                for (int i = 0; i < W; ++i) store_group<1>(dst, ep.out_bf16, base + (long long)i * ep.Tpad, v + i, false);
+            } else {
+                const long long base = ((long long)(b * ep.H + h) * ep.T + t) * WIPA_HEAD_DIM + e;
+                store_group<W>(dst, ep.out_bf16, base, v, true);
+            }
+            break;
+        }
+        case EPI_QKV_DEC: {
+            const int which = n0 / ep.d;
+            const int c = n0 - which * ep.d;
+            if (which == 0) {
+                store_group<W>(ep.out, 0, (long long)m * ep.d + c, v, true);
+            } else {
+                const int h = c / WIPA_HEAD_DIM;
+                const int e = c - h * WIPA_HEAD_DIM;
+                const int p = *ep.pos_ptr;
+                const int page = ep.block_table[(long long)m * ep.bt_stride + p / WIPA_PAGE];
+                const long long base = (((long long)page * ep.H + h) * WIPA_PAGE + (p % WIPA_PAGE)) * WIPA_HEAD_DIM + e;
+                store_group<W>(which == 1 ? ep.out1 : ep.out2, ep.out_bf16, base, v, true);
+            }
+            break;
+        }
+        default:
+            break;
+    }
+}
+
+__device__ __forceinline__ bool vocab_masked(const EpiParams& ep, int n, bool begin) {
+    bool m = false;
+    if (ep.mask_always != nullptr) m = (ep.mask_always[n >> 5] >> (n & 31)) & 1u;
+    if (begin && ep.mask_begin != nullptr) m = m || ((ep.mask_begin[n >> 5] >> (n & 31)) & 1u);
+    return m;
+}
+
+// warp-level helpers
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernel launch entry points implemented across the .cu files (host side)
+// ------------------------------------------------------------------------------------------------
+int launch_gemm_f32(const AOperand& a, const float* W, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
+int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep, int block_n,
+                     cudaStream_t st);
+int wipa_init_tma();   // resolves cuTensorMapEncodeTiled through the runtime; idempotent
+
+template <typename T>
+int launch_layernorm(const float* x, const float* w, const float* b, T* out, int M, int d, cudaStream_t st);
+template <typename T>
+int launch_enc_attention(const T* q, const T* k, const T* v, T* out, int B, int H, int Tq, cudaStream_t st);
+int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, int B, int H, cudaStream_t st);
+template <typename T>
+int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
+                          const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st);
+template <typename T>
+int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, int Bs, int H,
+                           cudaStream_t st);

@@ -1,0 +1,233 @@
+// bf16 path GEMM on the 5th-generation tensor cores:  C[M,N] = A[M,K] * W[N,K]^T, fp32 accumulate in TMEM.
+//
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of A (128 x 64) and W (BN x 64), 128B-swizzled,
+//               into a STAGES-deep shared-memory ring guarded by full/empty mbarriers
+//   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x 4 per k-block and
+//               tcgen05.commit's the stage back to the producer; the last commit signals the epilogue
+//   warps 2-5   epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one row per thread) and apply the shared
+//               epilogue (bias / GELU / residual / head split / paged-KV scatter / fused vocab argmax)
+//
+// The A operand is described by a 3-D tensor map (K, rows-per-batch, batches) whose row stride may be smaller than
+// K: a k=3 conv1d over a channels-last, zero-row-padded signal is then exactly this GEMM (no im2col buffer),
+// and out-of-range rows / K tails are zero-filled by TMA.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
+
+template <int BN> struct TcCfg {
+    static constexpr int W_BYTES = BN * TC_BK * 2;
+    static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
+    static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+    static constexpr int SMEM = STAGES * (TC_A_BYTES + W_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+template <int BN>
+__global__ void __launch_bounds__(192)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
+                    int tiles_per_batch, int a_rpb, EpiParams ep) {
+    using Cfg = TcCfg<BN>;
+    extern __shared__ uint8_t tc_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sW = smem + Cfg::STAGES * TC_A_BYTES;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sW + Cfg::STAGES * Cfg::W_BYTES);
+    uint64_t* empty = full + Cfg::STAGES;
+    uint64_t* tmem_full = empty + Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN;
+    const int batch = blockIdx.y / tiles_per_batch;
+    const int t0 = (blockIdx.y - batch * tiles_per_batch) * TC_BM;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmW);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+            ptx::mbar_init(tmem_full, 1);
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+                ptx::mbar_wait(&empty[s], ph ^ 1);
+                ptx::mbar_arrive_expect_tx(&full[s], TC_A_BYTES + Cfg::W_BYTES);
+                ptx::tma_load_3d(sA + s * TC_A_BYTES, &tmA, &full[s], kb * TC_BK, t0, batch);
+                ptx::tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, &full[s], kb * TC_BK, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::idesc_bf16_f32(TC_BM, BN);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % Cfg::STAGES;
+                const uint32_t ph = (kb / Cfg::STAGES) & 1;
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
+                const uint32_t w_addr = ptx::smem_u32(sW + s * Cfg::W_BYTES);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k) {
+                    const uint64_t da = ptx::smem_desc_sw128_kmajor(a_addr + k * 32);
+                    const uint64_t db = ptx::smem_desc_sw128_kmajor(w_addr + k * 32);
+                    ptx::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
+            }
+            ptx::umma_commit(tmem_full);                     // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // epilogue warps: TMEM lane quarter is fixed by warp id % 4
+        const int quarter = warp & 3;
+        const int t = t0 + quarter * 32 + lane;
+        const bool row_ok = t < ep.M_rows;
+        const int m = batch * a_rpb + t;
+        ptx::mbar_wait(tmem_full, 0);
+        ptx::tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        if (ep.mode == EPI_ARGMAX) {
+            const bool begin = (ep.step_ptr != nullptr) && (*ep.step_ptr == 0);
+            float best = -INFINITY;
+            int best_n = 0x7fffffff;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                ptx::tmem_ld16(taddr + c0, v);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int n = n0 + c0 + i;
+                    if (n < ep.N && !vocab_masked(ep, n, begin) && v[i] > best) { best = v[i]; best_n = n; }
+                }
+            }
+            if (row_ok) {
+                ep.pmax[(long long)m * ep.n_tiles + blockIdx.x] = best;
+                ep.pidx[(long long)m * ep.n_tiles + blockIdx.x] = best_n;
+            }
+        } else {
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                float v[16];
+                ptx::tmem_ld16(taddr + c0, v);
+                ptx::tmem_ld_wait();
+                if (row_ok) {
+                    epi_group<8>(ep, m, n0 + c0, v);
+                    epi_group<8>(ep, m, n0 + c0 + 8, v + 8);
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                          strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        wipa_set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims %llu,%llu,%llu strides %llu,%llu box %u,%u", (int)r,
+                       rank, (unsigned long long)dims[0], (unsigned long long)dims[1],
+                       (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)strides_bytes[0],
+                       (unsigned long long)(rank > 2 ? strides_bytes[1] : 0), box[0], box[1]);
+        return WIPA_ECUDA;
+    }
+    return WIPA_OK;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int tiles_per_batch, int n_batch, int a_rpb,
+              int N, EpiParams ep, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             TcCfg<BN>::SMEM));
+        configured = true;
+    }
+    dim3 grid(cdiv(N, BN), tiles_per_batch * n_batch);
+    if (ep.mode == EPI_ARGMAX) ep.n_tiles = grid.x;
+    gemm_bf16_tc_kernel<BN><<<grid, 192, TcCfg<BN>::SMEM, st>>>(tmA, tmW, num_kb, tiles_per_batch, a_rpb, ep);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
+}  // namespace
+
+int wipa_init_tma() {
+    if (g_encode != nullptr) return WIPA_OK;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    WIPA_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    WIPA_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, WIPA_ECUDA,
+               "cuTensorMapEncodeTiled not available from the driver");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    return WIPA_OK;
+}
+
+int gemm_bf16_num_tiles(int N, int block_n) { return cdiv(N, block_n); }
+
+int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep_in, int block_n,
+                     cudaStream_t st) {
+    WIPA_TRY(wipa_init_tma());
+    WIPA_CHECK(K % 8 == 0 && a.lda % 8 == 0 && a.a_bstride % 8 == 0, WIPA_EINVAL,
+               "gemm_bf16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");
+    WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_bf16: M != rows_per_batch * batches");
+    WIPA_CHECK((reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, WIPA_EINVAL,
+               "gemm_bf16: operands must be 16-byte aligned");
+    CUtensorMap tmA, tmW;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a.a_rpb, (cuuint64_t)a.n_batch};
+        cuuint64_t bstride = a.n_batch > 1 ? (cuuint64_t)a.a_bstride : (cuuint64_t)a.a_rpb * (cuuint64_t)a.lda;
+        cuuint64_t strides[2] = {(cuuint64_t)a.lda * 2, bstride * 2};
+        cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+        WIPA_TRY(make_map(&tmA, a.ptr, 3, dims, strides, box));
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {TC_BK, (cuuint32_t)block_n};
+        WIPA_TRY(make_map(&tmW, W, 2, dims, strides, box));
+    }
+    EpiParams ep = ep_in;
+    ep.M_rows = a.a_rpb;
+    const int num_kb = cdiv(K, TC_BK);
+    const int tpb = cdiv(a.a_rpb, TC_BM);
+    switch (block_n) {
+        case 32: return launch_bn<32>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 64: return launch_bn<64>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 128: return launch_bn<128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 256: return launch_bn<256>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        default: break;
+    }
+    wipa_set_error("gemm_bf16: unsupported block_n %d", block_n);
+    return WIPA_EINVAL;
+}
