@@ -115,6 +115,13 @@ int wipa_ctx_get_info(wipa_ctx*, int what, int64_t* out);
 int wipa_test_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, float* C,
                         int M, int N, int K, int block_n, void* stream);
 int wipa_test_gemm_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, void* stream);
+/* conv1d-as-GEMM addressing: logical row (batch, t) of A starts at A + batch*bstride + t*lda and spans K >= lda
+ * elements (rows overlap); A/W are bf16 (tcgen05 kernel) when is_bf16 else fp32 (SIMT kernel); C fp32 [M, N]. */
+int wipa_test_gemm_rows(const void* A, int is_bf16, long long lda, int rows_per_batch, long long bstride, int n_batch,
+                        const void* W, float* C, int N, int K, int block_n, void* stream);
+/* Encoder self-attention alone: q,k,v device f32 [B,H,T,64] (q pre-scaled) -> out device f32 [B,T,H*64]. */
+int wipa_test_enc_attention(const float* q, const float* k, const float* v, float* out, int B, int H, int T,
+                            int use_bf16, void* stream);
 /* One decode-step cross-attention sweep over the context's cached encoder K/V (the dominant HBM kernel):
  * q: device f32[B, d] (pre-scaled), out: device f32[B, d]; layer selects which cached K/V. */
 int wipa_test_cross_attn(wipa_ctx*, int B, int layer, const float* q, float* out, void* stream);

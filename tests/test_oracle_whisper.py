@@ -1,0 +1,76 @@
+"""Pins the CPU restatement of the Whisper path (oracle/whisper_oracle.py) to the real oracle: HF transformers, live and
+through the committed golden vectors (oracle/make_golden.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hf_reference as hf
+from oracle import whisper_oracle as wo
+
+
+@pytest.fixture(scope="module")
+def tiny():
+    m = hf.build_hf_model("tiny", seed=0)
+    return m, hf.state_dict_f32(m), wo.Dims.from_arch("tiny")
+
+
+@pytest.mark.parametrize("n_mels", [80, 128])
+def test_logmel_matches_hf_and_golden(n_mels, golden_dir):
+    audio = wo.synthetic_audio(2)
+    mine = wo.log_mel_spectrogram(torch.from_numpy(audio), n_mels).numpy()
+    g = np.load(os.path.join(golden_dir, f"logmel_{n_mels}.npz"))
+    assert np.abs(mine[:, :, ::25] - g["mel_sub"]).max() < 2e-4
+    assert np.abs(mine.reshape(2, -1).max(1) - g["mel_max"]).max() < 1e-4
+    live = hf.hf_log_mel(audio[:1], n_mels).numpy()
+    assert np.abs(mine[:1] - live).max() < 2e-4
+
+
+def test_mel_filter_bank_matches_hf():
+    from transformers.audio_utils import mel_filter_bank
+    for n in (80, 128):
+        ref = mel_filter_bank(num_frequency_bins=201, num_mel_filters=n, min_frequency=0.0, max_frequency=8000.0,
+                              sampling_rate=16000, norm="slaney", mel_scale="slaney")
+        assert np.abs(wo.mel_filter_bank(n) - ref).max() < 1e-12
+
+
+def test_encoder_and_logits_match_golden(tiny, golden_dir):
+    _, sd, dims = tiny
+    g = np.load(os.path.join(golden_dir, "tiny_fp32.npz"))
+    feats = wo.log_mel_spectrogram(torch.from_numpy(wo.synthetic_audio(4)), 80)
+    enc = wo.encoder_forward(sd, dims, feats)
+    assert np.abs(enc[:, ::50].numpy() - g["enc_rows"]).max() < 2e-4
+    xkv = wo.cross_kv(sd, dims, enc)
+    logits = wo.decoder_forward(sd, dims, torch.tensor([wo.PROMPT_PRE_V3] * 4), 0, xkv, [None] * dims.n_dec)[:, -1]
+    assert np.abs(logits[:, ::97].numpy() - g["logits0_slice"]).max() < 2e-4
+    assert (logits.argmax(-1).numpy() == g["logits0_argmax"]).all()
+
+
+@pytest.mark.parametrize("name,gain", [("tiny_fp32", 1.0), ("tiny_gain_fp32", 3.0)])
+def test_greedy_ids_match_golden(name, gain, golden_dir):
+    sd = hf.state_dict_f32(hf.build_hf_model("tiny", seed=0, init_gain=gain))
+    dims = wo.Dims.from_arch("tiny")
+    g = np.load(os.path.join(golden_dir, f"{name}.npz"))
+    feats = wo.log_mel_spectrogram(torch.from_numpy(wo.synthetic_audio(4)), 80)
+    enc = wo.encoder_forward(sd, dims, feats)
+    ids, lens = wo.greedy_decode(sd, dims, enc, wo.PROMPT_PRE_V3, 24)
+    assert (ids.numpy() == g["greedy_ids"]).all()
+
+
+def test_greedy_matches_hf_generate_live(tiny):
+    model, sd, dims = tiny
+    feats = hf.hf_log_mel(wo.synthetic_audio(2, first=7), 80)
+    want = hf.hf_generate(model, feats, "tiny", max_new=12)
+    enc = wo.encoder_forward(sd, dims, feats)
+    ids, _ = wo.greedy_decode(sd, dims, enc, wo.PROMPT_PRE_V3, 12)
+    assert torch.equal(ids, want)
+
+
+def test_beam_matches_hf_generate_live(tiny):
+    model, sd, dims = tiny
+    feats = hf.hf_log_mel(wo.synthetic_audio(2, first=3), 80)
+    want = hf.hf_generate(model, feats, "tiny", max_new=8, num_beams=3)
+    enc = wo.encoder_forward(sd, dims, feats)
+    ids, lens = wo.beam_decode(sd, dims, enc, wo.PROMPT_PRE_V3, 8, beams=3)
+    assert torch.equal(ids[:, :want.shape[1]], want)

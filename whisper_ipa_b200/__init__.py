@@ -1,0 +1,14 @@
+"""whisper_ipa_b200 — B200-native (sm_100a) hot path of barathanaslan/whisper-ipa: batched Whisper transcription + PER.
+
+Importing the package does not need a GPU; every compute entry point goes through libwipa.so (CUDA) and raises when the
+library or a B200 is missing — there is no CPU fallback."""
+from .archs import ARCHS, WhisperArch, arch_from_name
+from .audio import FeatureExtractor, load_audio, log_mel_features, log_mel_spectrogram, pad_or_trim
+from .decoding import DecodingOptions, DecodingResult, decode
+from .metrics import (evaluate_batch, normalize_ipa_for_comparison, phone_error_rate, phone_error_rates, tokenize_ipa)
+from .model import WhisperIPA, load_model
+
+__all__ = ["ARCHS", "WhisperArch", "arch_from_name", "FeatureExtractor", "load_audio", "log_mel_features",
+           "log_mel_spectrogram", "pad_or_trim", "DecodingOptions", "DecodingResult", "decode", "evaluate_batch",
+           "normalize_ipa_for_comparison", "phone_error_rate", "phone_error_rates", "tokenize_ipa", "WhisperIPA",
+           "load_model"]

@@ -6,6 +6,7 @@
 //   cross_attention_kernel : one decode step of cross-attention against the cached encoder K/V —
 //                            the dominant HBM stream of the whole decode.
 #include "common.cuh"
+#include "ptx.cuh"
 
 // ================================================================================================
 // encoder self-attention, SIMT
@@ -286,15 +287,21 @@ template int launch_self_attention<bf16>(const float*, const bf16*, const bf16*,
 // ================================================================================================
 // decoder cross-attention, one query per (sequence, head) against 1500 cached encoder keys/values
 // ================================================================================================
-// K/V for one (utterance, head) are contiguous [1500][64].  A key row is 64 * sizeof(T) bytes; LPK lanes
-// each read one 16-byte vector of it, so a warp covers KPW = 32 / LPK consecutive keys (512 contiguous
-// bytes) per load instruction; loads are issued 4 deep before any use to keep enough bytes in flight.
+// This kernel moves ~92 % of the decode step's bytes at batch 64, so it is built as a pure
+// HBM streamer.  K/V of one (utterance, head) are contiguous [1500][64].  The 1500 keys are split into n_split
+// chunks; CTA (chunk, head, seq) issues two cp.async.bulk copies (its K chunk and its V chunk, each one contiguous
+// block) into shared memory behind two mbarriers and only then computes: scores + local softmax from the K
+// buffer while V is still landing, then P.V.  Several CTAs are resident per SM (24-48 KB of loads in flight
+// each), which is what keeps HBM busy; nothing is read twice.  Each CTA emits a flash-decoding partial
+// (max, sum, o[64]); the last CTA to finish a (seq, head) — found with one atomic ticket — merges the partials in
+// chunk order (deterministic) and writes the head's output.
 #define CA_THREADS 256
 #define CA_WARPS (CA_THREADS / 32)
+#define CA_PART 66                     // floats per partial: m, l, o[64]
 
 template <typename T> struct CaCfg;
-template <> struct CaCfg<float> { static constexpr int VEC = 4, LPK = 16, KPW = 2; };
-template <> struct CaCfg<bf16> { static constexpr int VEC = 8, LPK = 8, KPW = 4; };
+template <> struct CaCfg<float> { static constexpr int VEC = 4, LPK = 16; };   // lanes per key row (16 B each)
+template <> struct CaCfg<bf16> { static constexpr int VEC = 8, LPK = 8; };
 
 template <typename T>
 __device__ __forceinline__ void unpack16(const uint4& u, float* f);
@@ -312,61 +319,64 @@ __device__ __forceinline__ void unpack16<bf16>(const uint4& u, float* f) {
     }
 }
 
-__device__ __forceinline__ uint4 ld_stream16(const void* p) {
-    uint4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
+__device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
+__device__ __forceinline__ float2 ld_pair(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
 
 template <typename T>
 __global__ void __launch_bounds__(CA_THREADS)
 cross_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc,
-                       const int* __restrict__ utt_of_seq, T* __restrict__ out, int H) {
+                       const int* __restrict__ utt_of_seq, T* __restrict__ out, float* __restrict__ part,
+                       int* __restrict__ counters, int H, int chunk) {
     using C = CaCfg<T>;
-    constexpr int UNROLL = 4;
-    constexpr int KSTEP = CA_WARPS * C::KPW;                 // keys covered by the CTA per load wave
-    __shared__ float sc[WIPA_T_ENC + 4];
+    extern __shared__ __align__(128) uint8_t ca_smem[];
+    T* sK = reinterpret_cast<T*>(ca_smem);                        // [chunk][64]
+    T* sV = sK + (size_t)chunk * 64;                              // [chunk][64]
+    float* sc = reinterpret_cast<float*>(sV + (size_t)chunk * 64);   // [chunk]
+    __shared__ __align__(8) uint64_t bar[2];
     __shared__ float red[CA_WARPS];
-    __shared__ float part[CA_WARPS][64];
+    __shared__ float opart[CA_WARPS][64];
+    __shared__ int s_last;
 
-    const int h = blockIdx.x, b = blockIdx.y;
+    const int split = blockIdx.x, n_split = gridDim.x, h = blockIdx.y, b = blockIdx.z;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = H * 64;
+    const int k0 = split * chunk;
+    const int nk = min(chunk, WIPA_T_ENC - k0);                   // >= 1 by construction of chunk
     const int utt = utt_of_seq ? utt_of_seq[b] : b;
-    const T* kb = kc + ((size_t)utt * H + h) * WIPA_T_ENC * 64;
-    const T* vb = vc + ((size_t)utt * H + h) * WIPA_T_ENC * 64;
-    const int sub = lane / C::LPK;                           // which of the warp's KPW keys
-    const int li = lane % C::LPK;                            // which 16-byte chunk of the row
+    const size_t head_off = ((size_t)utt * H + h) * WIPA_T_ENC * 64 + (size_t)k0 * 64;
 
+    if (tid == 0) {
+        ptx::mbar_init(&bar[0], 1);
+        ptx::mbar_init(&bar[1], 1);
+        ptx::fence_barrier_init();
+        const uint32_t bytes = (uint32_t)nk * 64u * (uint32_t)sizeof(T);
+        ptx::mbar_arrive_expect_tx(&bar[0], bytes);
+        ptx::bulk_load_1d(sK, kc + head_off, bytes, &bar[0]);
+        ptx::mbar_arrive_expect_tx(&bar[1], bytes);
+        ptx::bulk_load_1d(sV, vc + head_off, bytes, &bar[1]);
+    }
+    const int sub = tid / C::LPK;                                  // key slot of this lane group
+    const int li = tid % C::LPK;                                   // 16-byte chunk of the row
+    constexpr int KPI = CA_THREADS / C::LPK;                       // keys per iteration of the CTA
     float qv[C::VEC];
 #pragma unroll
     for (int i = 0; i < C::VEC; ++i) qv[i] = q[(size_t)b * d + h * 64 + li * C::VEC + i];
+    __syncthreads();                                               // barrier init visible to all waiters
 
-    // ---- phase 1: scores --------------------------------------------------------------------
+    // ---- phase 1: scores from the K buffer ----------------------------------------------------------
+    ptx::mbar_wait(&bar[0], 0);
     float mx = -INFINITY;
-    for (int base = warp * C::KPW; base < WIPA_T_ENC; base += KSTEP * UNROLL) {
-        uint4 u[UNROLL];
+    for (int key = sub; key < nk; key += KPI) {
+        const uint4 u = *reinterpret_cast<const uint4*>(sK + (size_t)key * 64 + li * C::VEC);
+        float f[C::VEC];
+        unpack16<T>(u, f);
+        float s = 0.f;
 #pragma unroll
-        for (int r = 0; r < UNROLL; ++r) {
-            const int key = base + r * KSTEP + sub;
-            u[r] = key < WIPA_T_ENC ? ld_stream16(kb + (size_t)key * 64 + li * C::VEC) : make_uint4(0, 0, 0, 0);
-        }
+        for (int i = 0; i < C::VEC; ++i) s = fmaf(f[i], qv[i], s);
 #pragma unroll
-        for (int r = 0; r < UNROLL; ++r) {
-            const int key = base + r * KSTEP + sub;
-            float f[C::VEC];
-            unpack16<T>(u[r], f);
-            float s = 0.f;
-#pragma unroll
-            for (int i = 0; i < C::VEC; ++i) s = fmaf(f[i], qv[i], s);
-#pragma unroll
-            for (int off = C::LPK / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-            if (key < WIPA_T_ENC) {
-                if (li == 0) sc[key] = s;
-                mx = fmaxf(mx, s);
-            }
-        }
+        for (int off = C::LPK / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (li == 0) sc[key] = s;
+        mx = fmaxf(mx, s);
     }
     mx = warp_max(mx);
     if (lane == 0) red[warp] = mx;
@@ -375,10 +385,8 @@ cross_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc, co
 #pragma unroll
     for (int w = 1; w < CA_WARPS; ++w) mx = fmaxf(mx, red[w]);
     __syncthreads();
-
-    // ---- phase 2: softmax numerators and their sum -----------------------------------------------
     float sum = 0.f;
-    for (int j = tid; j < WIPA_T_ENC; j += CA_THREADS) {
+    for (int j = tid; j < nk; j += CA_THREADS) {
         const float p = expf(sc[j] - mx);
         sc[j] = p;
         sum += p;
@@ -389,53 +397,77 @@ cross_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc, co
     sum = 0.f;
 #pragma unroll
     for (int w = 0; w < CA_WARPS; ++w) sum += red[w];
-    const float inv = 1.0f / sum;
 
-    // ---- phase 3: weighted sum of values ---------------------------------------------------------
-    float acc[C::VEC];
-#pragma unroll
-    for (int i = 0; i < C::VEC; ++i) acc[i] = 0.f;
-    for (int base = warp * C::KPW; base < WIPA_T_ENC; base += KSTEP * UNROLL) {
-        uint4 u[UNROLL];
-#pragma unroll
-        for (int r = 0; r < UNROLL; ++r) {
-            const int key = base + r * KSTEP + sub;
-            u[r] = key < WIPA_T_ENC ? ld_stream16(vb + (size_t)key * 64 + li * C::VEC) : make_uint4(0, 0, 0, 0);
-        }
-#pragma unroll
-        for (int r = 0; r < UNROLL; ++r) {
-            const int key = base + r * KSTEP + sub;
-            const float p = key < WIPA_T_ENC ? sc[key] : 0.f;
-            float f[C::VEC];
-            unpack16<T>(u[r], f);
-#pragma unroll
-            for (int i = 0; i < C::VEC; ++i) acc[i] = fmaf(p, f[i], acc[i]);
-        }
+    // ---- phase 2: P.V from the V buffer; lane owns two output dims, warps stride over keys -----------
+    ptx::mbar_wait(&bar[1], 0);
+    float a0 = 0.f, a1 = 0.f;
+    for (int key = warp; key < nk; key += CA_WARPS) {
+        const float p = sc[key];
+        const float2 v2 = ld_pair(sV + (size_t)key * 64 + lane * 2);
+        a0 = fmaf(p, v2.x, a0);
+        a1 = fmaf(p, v2.y, a1);
     }
-#pragma unroll
-    for (int off = C::LPK; off < 32; off <<= 1)
-#pragma unroll
-        for (int i = 0; i < C::VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-    if (lane < C::LPK) {
-#pragma unroll
-        for (int i = 0; i < C::VEC; ++i) part[warp][li * C::VEC + i] = acc[i];
-    }
+    opart[warp][lane * 2] = a0;
+    opart[warp][lane * 2 + 1] = a1;
     __syncthreads();
+    const size_t bh = (size_t)b * H + h;
+    float* my_part = part + (bh * n_split + split) * CA_PART;
     if (tid < 64) {
         float r = 0.f;
 #pragma unroll
-        for (int w = 0; w < CA_WARPS; ++w) r += part[w][tid];
-        out[(size_t)b * d + h * 64 + tid] = from_f32<T>(r * inv);
+        for (int w = 0; w < CA_WARPS; ++w) r += opart[w][tid];
+        my_part[2 + tid] = r;
+        if (tid == 0) { my_part[0] = mx; my_part[1] = sum; }
+    }
+    // ---- ticket: the last chunk of this (seq, head) merges ---------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const int ticket = atomicAdd(&counters[bh], 1);
+        s_last = (ticket == n_split - 1);
+        if (s_last) counters[bh] = 0;                               // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (tid < 64) {
+        const float* pp = part + bh * n_split * CA_PART;
+        float M = -INFINITY;
+        for (int s = 0; s < n_split; ++s) M = fmaxf(M, __ldcg(pp + s * CA_PART));
+        float L = 0.f, o = 0.f;
+        for (int s = 0; s < n_split; ++s) {
+            const float wgt = expf(__ldcg(pp + s * CA_PART) - M);
+            L = fmaf(__ldcg(pp + s * CA_PART + 1), wgt, L);
+            o = fmaf(__ldcg(pp + s * CA_PART + 2 + tid), wgt, o);
+        }
+        out[(size_t)b * d + h * 64 + tid] = from_f32<T>(o / L);
     }
 }
 
+int cross_attention_default_split(int elem_bytes, int Bs, int H) {
+    // chunk sized for ~48 KB of K+V per CTA (4 CTAs / SM resident): 188 keys in bf16, 94 in fp32
+    (void)Bs; (void)H;
+    return elem_bytes == 2 ? 8 : 16;
+}
+
 template <typename T>
-int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, int Bs, int H,
-                           cudaStream_t st) {
-    dim3 grid(H, Bs);
-    cross_attention_kernel<T><<<grid, CA_THREADS, 0, st>>>(q, k, v, utt_of_seq, out, H);
+int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
+                           int* counters, int Bs, int H, int n_split, cudaStream_t st) {
+    WIPA_CHECK(n_split >= 1 && n_split <= 64, WIPA_EINVAL, "cross_attention: n_split %d out of range", n_split);
+    int chunk = cdiv(WIPA_T_ENC, n_split);
+    chunk = (chunk + 3) & ~3;                                       // keeps every chunk's byte count a multiple of 16
+    WIPA_CHECK((n_split - 1) * chunk < WIPA_T_ENC, WIPA_EINVAL, "cross_attention: n_split %d leaves an empty chunk", n_split);
+    const size_t smem = (size_t)chunk * 64 * sizeof(T) * 2 + (size_t)chunk * sizeof(float);
+    static size_t configured[2] = {0, 0};
+    size_t& cfg = configured[sizeof(T) == 2];
+    if (smem > 48 * 1024 && smem > cfg) {
+        WIPA_CUDA_CHECK(cudaFuncSetAttribute(cross_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg = smem;
+    }
+    dim3 grid(n_split, H, Bs);
+    cross_attention_kernel<T><<<grid, CA_THREADS, smem, st>>>(q, k, v, utt_of_seq, out, part, counters, H, chunk);
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
-template int launch_cross_attention<float>(const float*, const float*, const float*, const int*, float*, int, int, cudaStream_t);
-template int launch_cross_attention<bf16>(const float*, const bf16*, const bf16*, const int*, bf16*, int, int, cudaStream_t);
+template int launch_cross_attention<float>(const float*, const float*, const float*, const int*, float*, float*, int*, int, int, int, cudaStream_t);
+template int launch_cross_attention<bf16>(const float*, const bf16*, const bf16*, const int*, bf16*, float*, int*, int, int, int, cudaStream_t);

@@ -103,8 +103,8 @@ struct EpiParams {
     int T;                   // rows per clip (EPI_HEADS / EPI_GELU_POS)
     int H;                   // heads
     int d;                   // d_model
-    int n_which;             // EPI_HEADS: how many of (q,k,v) N spans; first maps to out, then out1, out2
-    int v_transposed;        // EPI_HEADS: last "which" written transposed [B,H,64,Tpad]
+    long long which_stride;  // EPI_HEADS: N is split in blocks of d columns; block w is written at out + w * which_stride
+    int vt_which;            // EPI_HEADS: this block (-1 = none) is written transposed, [B,H,64,Tpad]
     int Tpad;
     // EPI_QKV_DEC
     const int* pos_ptr;      // device scalar: position being written
@@ -247,14 +247,14 @@ __device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, fl
             const int e = c - h * WIPA_HEAD_DIM;
             const int b = m / ep.T;
             const int t = m - b * ep.T;
-            void* dst = which == 0 ? ep.out : (which == 1 ? ep.out1 : ep.out2);
-            if (ep.v_transposed && which == ep.n_which - 1) {
-                const long long base = ((long long)(b * ep.H + h) * WIPA_HEAD_DIM + e) * ep.Tpad + t;
+            const long long wbase = (long long)which * ep.which_stride;
+            if (which == ep.vt_which) {
+                const long long base = wbase + ((long long)(b * ep.H + h) * WIPA_HEAD_DIM + e) * ep.Tpad + t;
 #pragma unroll
-                for (int i = 0; i < W; ++i) store_group<1>(dst, ep.out_bf16, base + (long long)i * ep.Tpad, v + i, false);
+                for (int i = 0; i < W; ++i) store_group<1>(ep.out, ep.out_bf16, base + (long long)i * ep.Tpad, v + i, false);
             } else {
-                const long long base = ((long long)(b * ep.H + h) * ep.T + t) * WIPA_HEAD_DIM + e;
-                store_group<W>(dst, ep.out_bf16, base, v, true);
+                const long long base = wbase + ((long long)(b * ep.H + h) * ep.T + t) * WIPA_HEAD_DIM + e;
+                store_group<W>(ep.out, ep.out_bf16, base, v, true);
             }
             break;
         }
@@ -313,6 +313,34 @@ int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* 
 template <typename T>
 int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
                           const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st);
+// split-K cross-attention: part = f32 [Bs*H, n_split, 66] scratch, counters = int [Bs*H] (zero, self-resetting)
 template <typename T>
-int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, int Bs, int H,
-                           cudaStream_t st);
+int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
+                           int* counters, int Bs, int H, int n_split, cudaStream_t st);
+int cross_attention_default_split(int elem_bytes, int Bs, int H);
+
+// elementwise.cu
+template <typename T>
+int launch_mel_to_rows(const float* mel, T* rows, int B, int C, cudaStream_t st);       // [B,C,3000] -> [B,3002,C] (rows 1..3000)
+template <typename T>
+int launch_embed(const T* tok_emb, const float* pos_emb, const int* tok, const int* pos_ptr, float* x, int Bs, int d,
+                 cudaStream_t st);
+int launch_convert(const float* src, void* dst, long long n, float scale, int to_bf16, cudaStream_t st);
+int launch_conv_weight(const float* src, void* dst, int N, int C, int to_bf16, cudaStream_t st);   // [N,C,3] -> [N,3*C]
+int launch_row_argmax(const float* logits, int Bs, int V, const uint32_t* mask_always, const uint32_t* mask_begin,
+                      const int* step_ptr, float* pmax, int* pidx, cudaStream_t st);
+
+struct DecodeState {       // all device pointers, owned by the context
+    int* pos;              // position of the token being consumed this step
+    int* step;             // index of the token being sampled (pos - (n_forced - 1)); < 0 while forcing
+    int* cur_tok;          // [Bs]
+    int* done;             // [Bs]
+    int* n_done;           // count of finished rows
+    const int* forced;     // [Bs, n_forced] teacher-forced tokens (the prompt)
+    int n_forced;
+    int* out_ids;          // [Bs, max_new]
+    int* out_len;          // [Bs]
+    int max_new;
+    int eot;
+};
+int launch_greedy_finalize(const float* pmax, const int* pidx, int n_tiles, DecodeState ds, int Bs, cudaStream_t st);

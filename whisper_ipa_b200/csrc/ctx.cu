@@ -1,0 +1,834 @@
+// wipa_ctx: weights, workspaces, cross-/self-KV caches and the encoder / decoder schedules built from the kernels.
+//
+// HBM layout (T = float on the fp32 path, bf16 on the bf16 path; residual stream always fp32):
+//   weights      one arena of T (GEMM operands, [N, K] K-major, q/k/v fused to [3d, d] with q pre-scaled by the
+//                exact power of two 64^-0.5) + one fp32 arena (biases, LayerNorm, position tables)
+//   cross-KV     [dec layer][K|V][utterance][head][1500][64] T — one contiguous 1500x64 block per (utt, head), the
+//                unit the cross-attention kernel streams with cp.async.bulk; indexed by utterance, so beams share it
+//   self-KV      per layer a pool of pages [page][head][16][64] T addressed through a block table [seq][28]
+//   activations  encoder micro-batch buffers sized for enc_mb clips; decoder buffers sized for max_batch*max_beams rows
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+#include "common.cuh"
+#include "logmel.cuh"
+
+namespace {
+
+enum SlotKind { SLOT_F32 = 0, SLOT_T = 1, SLOT_CONV = 2 };
+struct Slot {
+    void* dst;
+    int kind;
+    float scale;
+    int64_t numel;
+    int N, C;            // SLOT_CONV
+    std::string canon;   // canonical name (aliases share it)
+};
+
+struct EncLayer {
+    float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+    void *qkv_w, *o_w, *fc1_w, *fc2_w;
+    float *qkv_b, *o_b, *fc1_b, *fc2_b;
+};
+struct DecLayer {
+    float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
+    void *qkv_w, *o_w, *cq_w, *co_w, *fc1_w, *fc2_w;
+    float *qkv_b, *o_b, *cq_b, *co_b, *fc1_b, *fc2_b;
+};
+
+struct GraphEntry {
+    cudaGraphExec_t exec = nullptr;
+    int nodes = 0;
+};
+
+}  // namespace
+
+struct wipa_ctx {
+    wipa_arch a;
+    int max_batch, max_beams, max_seqs;
+    bool bf;
+    size_t esz;
+    int enc_mb;
+    int pages_per_seq;
+
+    std::vector<void*> allocs;
+    std::unordered_map<std::string, Slot> slots;
+    std::unordered_set<std::string> loaded;
+    size_t n_required = 0;
+
+    // weights
+    void *conv1_w, *conv2_w, *tok_emb, *xkv_w;
+    float *conv1_b, *conv2_b, *enc_pos, *enc_ln_w, *enc_ln_b, *dec_pos, *dec_ln_w, *dec_ln_b, *xkv_b;
+    std::vector<EncLayer> enc;
+    std::vector<DecLayer> dec;
+
+    // encoder workspaces
+    void *mel_rows, *conv1_out, *eh, *eqkv, *eattn, *effn, *enc_T;
+    float* ex;
+    // caches
+    void* xkv;
+    size_t xkv_which_stride;       // elements between consecutive (layer, K|V) blocks
+    int n_utts = 0;
+    void *kpool, *vpool;
+    size_t pool_layer_stride;      // elements per layer pool
+    // decoder workspaces
+    float *dx, *dq, *ca_part, *pmax, *logits;
+    void *dh, *dattn, *dffn;
+    int *block_table, *utt_of_seq, *ca_counters, *pidx;
+    int *d_pos, *d_step, *d_cur_tok, *d_done, *d_n_done, *d_forced, *d_out_ids, *d_out_len;
+    uint32_t *mask_always, *mask_begin;
+    int* h_pinned = nullptr;       // pinned host scratch (n_done)
+    int n_logit_tiles;
+    int bn_enc, bn_dec, bn_logits, ca_split;
+    int64_t decode_steps = 0;
+    size_t workspace_bytes = 0, xkv_bytes = 0;
+    LogmelTables mel_tables;
+    float* mel_clipmax;
+
+    std::unordered_map<long long, GraphEntry> graphs;
+};
+
+namespace {
+
+int ctx_alloc(wipa_ctx* c, void** p, size_t bytes, bool zero) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    if (bytes == 0) bytes = 256;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) {
+        wipa_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+        cudaGetLastError();
+        return WIPA_ENOMEM;
+    }
+    c->allocs.push_back(*p);
+    c->workspace_bytes += bytes;
+    if (zero) WIPA_CUDA_CHECK(cudaMemset(*p, 0, bytes));
+    return WIPA_OK;
+}
+
+struct Carver {
+    char* base;
+    size_t off = 0;
+    size_t esz;
+    void* take(size_t elems) {
+        void* p = base ? base + off : nullptr;
+        off += ((elems * esz + 255) & ~(size_t)255);
+        return p;
+    }
+};
+
+// Lays out both arenas and the name table.  Called twice: once with null bases to measure, once to assign.
+void layout_weights(wipa_ctx* c, char* tbase, char* fbase, size_t* tbytes, size_t* fbytes) {
+    const wipa_arch& a = c->a;
+    const int d = a.d_model, ffn = a.ffn, V = a.vocab;
+    Carver T{tbase, 0, c->esz}, F{fbase, 0, 4};
+    const bool assign = tbase != nullptr;
+    auto reg = [&](const std::string& name, void* dst, int kind, int64_t numel, float scale = 1.f, int N = 0, int C = 0,
+                   const char* canon = nullptr) {
+        if (!assign) return;
+        Slot s{dst, kind, scale, numel, N, C, canon ? std::string(canon) : name};
+        c->slots[name] = s;
+    };
+    auto ln = [&](const std::string& p, float*& w, float*& b) {
+        w = (float*)F.take(d); b = (float*)F.take(d);
+        reg(p + ".weight", w, SLOT_F32, d); reg(p + ".bias", b, SLOT_F32, d);
+    };
+    auto lin = [&](const std::string& p, void*& w, float*& b, int N, int K) {
+        w = T.take((size_t)N * K); b = (float*)F.take(N);
+        reg(p + ".weight", w, SLOT_T, (int64_t)N * K); reg(p + ".bias", b, SLOT_F32, N);
+    };
+    // q|k|v fused: q (and its bias) carry the 64^-0.5 = 0.125 scaling (exact), k has no bias (stays zero)
+    auto qkv = [&](const std::string& p, void*& w, float*& b) {
+        w = T.take((size_t)3 * d * d); b = (float*)F.take(3 * d);
+        char* wb = (char*)w;
+        const size_t blk = (size_t)d * d * c->esz;
+        reg(p + ".q_proj.weight", wb, SLOT_T, (int64_t)d * d, 0.125f);
+        reg(p + ".k_proj.weight", wb ? wb + blk : nullptr, SLOT_T, (int64_t)d * d);
+        reg(p + ".v_proj.weight", wb ? wb + 2 * blk : nullptr, SLOT_T, (int64_t)d * d);
+        reg(p + ".q_proj.bias", b, SLOT_F32, d, 0.125f);
+        reg(p + ".v_proj.bias", b ? b + 2 * d : nullptr, SLOT_F32, d);
+    };
+    if (assign) { c->enc.resize(a.enc_layers); c->dec.resize(a.dec_layers); }
+    std::vector<EncLayer> enc_tmp(a.enc_layers);
+    std::vector<DecLayer> dec_tmp(a.dec_layers);
+    std::vector<EncLayer>& E = assign ? c->enc : enc_tmp;
+    std::vector<DecLayer>& D = assign ? c->dec : dec_tmp;
+
+    const std::string pe = "model.encoder.", pd = "model.decoder.";
+    c->conv1_w = T.take((size_t)d * 3 * a.n_mels); c->conv1_b = (float*)F.take(d);
+    reg(pe + "conv1.weight", c->conv1_w, SLOT_CONV, (int64_t)d * 3 * a.n_mels, 1.f, d, a.n_mels);
+    reg(pe + "conv1.bias", c->conv1_b, SLOT_F32, d);
+    c->conv2_w = T.take((size_t)d * 3 * d); c->conv2_b = (float*)F.take(d);
+    reg(pe + "conv2.weight", c->conv2_w, SLOT_CONV, (int64_t)d * 3 * d, 1.f, d, d);
+    reg(pe + "conv2.bias", c->conv2_b, SLOT_F32, d);
+    c->enc_pos = (float*)F.take((size_t)WIPA_T_ENC * d);
+    reg(pe + "embed_positions.weight", c->enc_pos, SLOT_F32, (int64_t)WIPA_T_ENC * d);
+    for (int l = 0; l < a.enc_layers; ++l) {
+        const std::string p = pe + "layers." + std::to_string(l) + ".";
+        ln(p + "self_attn_layer_norm", E[l].ln1_w, E[l].ln1_b);
+        qkv(p + "self_attn", E[l].qkv_w, E[l].qkv_b);
+        lin(p + "self_attn.out_proj", E[l].o_w, E[l].o_b, d, d);
+        ln(p + "final_layer_norm", E[l].ln2_w, E[l].ln2_b);
+        lin(p + "fc1", E[l].fc1_w, E[l].fc1_b, ffn, d);
+        lin(p + "fc2", E[l].fc2_w, E[l].fc2_b, d, ffn);
+    }
+    ln(pe + "layer_norm", c->enc_ln_w, c->enc_ln_b);
+
+    c->tok_emb = T.take((size_t)V * d);
+    reg(pd + "embed_tokens.weight", c->tok_emb, SLOT_T, (int64_t)V * d);
+    reg("proj_out.weight", c->tok_emb, SLOT_T, (int64_t)V * d, 1.f, 0, 0, "model.decoder.embed_tokens.weight");   // tied head
+    c->dec_pos = (float*)F.take((size_t)WIPA_MAX_TGT * d);
+    reg(pd + "embed_positions.weight", c->dec_pos, SLOT_F32, (int64_t)WIPA_MAX_TGT * d);
+    c->xkv_w = T.take((size_t)a.dec_layers * 2 * d * d);
+    c->xkv_b = (float*)F.take((size_t)a.dec_layers * 2 * d);
+    for (int l = 0; l < a.dec_layers; ++l) {
+        const std::string p = pd + "layers." + std::to_string(l) + ".";
+        ln(p + "self_attn_layer_norm", D[l].ln1_w, D[l].ln1_b);
+        qkv(p + "self_attn", D[l].qkv_w, D[l].qkv_b);
+        lin(p + "self_attn.out_proj", D[l].o_w, D[l].o_b, d, d);
+        ln(p + "encoder_attn_layer_norm", D[l].ln2_w, D[l].ln2_b);
+        // cross-attention: q scaled like self-attention; k / v of all layers fused into one [L*2*d, d] operand
+        D[l].cq_w = T.take((size_t)d * d); D[l].cq_b = (float*)F.take(d);
+        reg(p + "encoder_attn.q_proj.weight", D[l].cq_w, SLOT_T, (int64_t)d * d, 0.125f);
+        reg(p + "encoder_attn.q_proj.bias", D[l].cq_b, SLOT_F32, d, 0.125f);
+        char* xw = (char*)c->xkv_w;
+        const size_t blk = (size_t)d * d * c->esz;
+        reg(p + "encoder_attn.k_proj.weight", xw ? xw + (size_t)(2 * l) * blk : nullptr, SLOT_T, (int64_t)d * d);
+        reg(p + "encoder_attn.v_proj.weight", xw ? xw + (size_t)(2 * l + 1) * blk : nullptr, SLOT_T, (int64_t)d * d);
+        reg(p + "encoder_attn.v_proj.bias", c->xkv_b ? c->xkv_b + (size_t)(2 * l + 1) * d : nullptr, SLOT_F32, d);
+        lin(p + "encoder_attn.out_proj", D[l].co_w, D[l].co_b, d, d);
+        ln(p + "final_layer_norm", D[l].ln3_w, D[l].ln3_b);
+        lin(p + "fc1", D[l].fc1_w, D[l].fc1_b, ffn, d);
+        lin(p + "fc2", D[l].fc2_w, D[l].fc2_b, d, ffn);
+    }
+    ln(pd + "layer_norm", c->dec_ln_w, c->dec_ln_b);
+    *tbytes = T.off;
+    *fbytes = F.off;
+}
+
+AOperand plainA(const void* p, int M, int K) {
+    AOperand a;
+    a.ptr = p; a.lda = K; a.a_rpb = M; a.a_bstride = (long long)M * K; a.n_batch = 1;
+    return a;
+}
+
+EpiParams epi(int mode, int M, int N) {
+    EpiParams e;
+    memset(&e, 0, sizeof(e));
+    e.mode = mode;
+    e.N = N;
+    e.vec_ok = (N % 8 == 0) ? 1 : 0;
+    e.o_rpb = M > 0 ? M : 1;
+    e.ldo = N;
+    e.vt_which = -1;
+    e.T = 1;
+    return e;
+}
+
+int gemm(wipa_ctx* c, const AOperand& a, const void* W, int M, int N, int K, const EpiParams& ep, int bn, cudaStream_t st) {
+    if (c->bf) return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, bn, st);
+    return launch_gemm_f32(a, (const float*)W, M, N, K, ep, st);
+}
+
+template <typename T>
+int ln_t(const float* x, const float* w, const float* b, void* out, int M, int d, cudaStream_t st) {
+    return launch_layernorm<T>(x, w, b, (T*)out, M, d, st);
+}
+int ln(wipa_ctx* c, const float* x, const float* w, const float* b, void* out, int M, cudaStream_t st) {
+    return c->bf ? ln_t<bf16>(x, w, b, out, M, c->a.d_model, st) : ln_t<float>(x, w, b, out, M, c->a.d_model, st);
+}
+
+__global__ void to_f32_kernel(const void* __restrict__ src, int is_bf16, float* __restrict__ dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride)
+        dst[i] = is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
+}
+int launch_to_f32(const void* src, int is_bf16, float* dst, long long n, cudaStream_t st) {
+    if (n == 0) return WIPA_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    to_f32_kernel<<<(int)blocks, 256, 0, st>>>(src, is_bf16, dst, n);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
+__global__ void decode_init_kernel(DecodeState ds, int* block_table, int* utt_of_seq, int Bs, int beams, int pages_per_seq,
+                                   int* ca_counters, int n_counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        *ds.pos = 0;
+        *ds.step = -(ds.n_forced - 1);
+        *ds.n_done = 0;
+    }
+    if (i < Bs) {
+        ds.cur_tok[i] = ds.forced[(size_t)i * ds.n_forced];
+        ds.done[i] = 0;
+        ds.out_len[i] = ds.max_new;
+        utt_of_seq[i] = i / beams;
+    }
+    if (i < Bs * pages_per_seq) block_table[i] = i;          // sequence b owns pages [b*pps, (b+1)*pps)
+    if (i < Bs * ds.max_new) ds.out_ids[i] = ds.eot;
+    if (i < n_counters) ca_counters[i] = 0;
+}
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+int require_weights(wipa_ctx* c) {
+    WIPA_CHECK(c->loaded.size() >= c->n_required, WIPA_ESTATE, "weights missing: %zu of %zu tensors loaded", c->loaded.size(),
+               c->n_required);
+    return WIPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoder over clips [u0, u0 + nb) of the current batch; fills enc_T rows and the cross-KV of those utterances
+// ------------------------------------------------------------------------------------------------
+int cross_kv_project(wipa_ctx* c, int u0, int nb, cudaStream_t st) {
+    const wipa_arch& a = c->a;
+    const int d = a.d_model, H = a.heads, M = nb * WIPA_T_ENC, N = a.dec_layers * 2 * d;
+    EpiParams ep = epi(EPI_HEADS, M, N);
+    ep.bias = c->xkv_b;
+    ep.out = (char*)c->xkv + (size_t)u0 * H * WIPA_T_ENC * 64 * c->esz;
+    ep.out_bf16 = c->bf;
+    ep.T = WIPA_T_ENC; ep.H = H; ep.d = d;
+    ep.which_stride = (long long)c->xkv_which_stride;
+    return gemm(c, plainA(c->enc_T, M, d), c->xkv_w, M, N, d, ep, c->bn_enc, st);
+}
+
+int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, cudaStream_t st) {
+    const wipa_arch& a = c->a;
+    const int d = a.d_model, H = a.heads, ffn = a.ffn, C = a.n_mels;
+    const int T3 = WIPA_N_FRAMES, T = WIPA_T_ENC, M = nb * T;
+    if (c->bf) WIPA_TRY(launch_mel_to_rows<bf16>(mel, (bf16*)c->mel_rows, nb, C, st));
+    else WIPA_TRY(launch_mel_to_rows<float>(mel, (float*)c->mel_rows, nb, C, st));
+    {   // conv1 (k3, p1) + GELU -> rows 1..3000 of the zero-padded [nb, 3002, d] buffer
+        AOperand A; A.ptr = c->mel_rows; A.lda = C; A.a_rpb = T3; A.a_bstride = (long long)(T3 + 2) * C; A.n_batch = nb;
+        EpiParams ep = epi(EPI_GELU, nb * T3, d);
+        ep.bias = c->conv1_b;
+        ep.out = (char*)c->conv1_out + (size_t)d * c->esz; ep.out_bf16 = c->bf;
+        ep.ldo = d; ep.o_rpb = T3; ep.o_bstride = (long long)(T3 + 2) * d;
+        WIPA_TRY(gemm(c, A, c->conv1_w, nb * T3, d, 3 * C, ep, c->bn_enc, st));
+    }
+    {   // conv2 (k3, s2, p1) + GELU + sinusoidal positions -> residual stream x f32 [nb*1500, d]
+        AOperand A; A.ptr = c->conv1_out; A.lda = 2 * d; A.a_rpb = T; A.a_bstride = (long long)(T3 + 2) * d; A.n_batch = nb;
+        EpiParams ep = epi(EPI_GELU_POS, M, d);
+        ep.bias = c->conv2_b; ep.out = c->ex; ep.pos = c->enc_pos; ep.T = T;
+        ep.ldo = d; ep.o_rpb = T; ep.o_bstride = (long long)T * d;
+        WIPA_TRY(gemm(c, A, c->conv2_w, M, d, 3 * d, ep, c->bn_enc, st));
+    }
+    const size_t hq = (size_t)nb * H * T * 64;             // elements of one of q / k / v in [B,H,T,64]
+    for (int l = 0; l < a.enc_layers; ++l) {
+        const EncLayer& L = c->enc[l];
+        WIPA_TRY(ln(c, c->ex, L.ln1_w, L.ln1_b, c->eh, M, st));
+        {
+            EpiParams ep = epi(EPI_HEADS, M, 3 * d);
+            ep.bias = L.qkv_b; ep.out = c->eqkv; ep.out_bf16 = c->bf;
+            ep.T = T; ep.H = H; ep.d = d; ep.which_stride = (long long)hq;
+            WIPA_TRY(gemm(c, plainA(c->eh, M, d), L.qkv_w, M, 3 * d, d, ep, c->bn_enc, st));
+        }
+        if (c->bf) {
+            const bf16* q = (const bf16*)c->eqkv;
+            WIPA_TRY(launch_enc_attention<bf16>(q, q + hq, q + 2 * hq, (bf16*)c->eattn, nb, H, T, st));
+        } else {
+            const float* q = (const float*)c->eqkv;
+            WIPA_TRY(launch_enc_attention<float>(q, q + hq, q + 2 * hq, (float*)c->eattn, nb, H, T, st));
+        }
+        {
+            EpiParams ep = epi(EPI_RESADD, M, d);
+            ep.bias = L.o_b; ep.out = c->ex; ep.resid = c->ex;
+            WIPA_TRY(gemm(c, plainA(c->eattn, M, d), L.o_w, M, d, d, ep, c->bn_enc, st));
+        }
+        WIPA_TRY(ln(c, c->ex, L.ln2_w, L.ln2_b, c->eh, M, st));
+        {
+            EpiParams ep = epi(EPI_GELU, M, ffn);
+            ep.bias = L.fc1_b; ep.out = c->effn; ep.out_bf16 = c->bf;
+            WIPA_TRY(gemm(c, plainA(c->eh, M, d), L.fc1_w, M, ffn, d, ep, c->bn_enc, st));
+        }
+        {
+            EpiParams ep = epi(EPI_RESADD, M, d);
+            ep.bias = L.fc2_b; ep.out = c->ex; ep.resid = c->ex;
+            WIPA_TRY(gemm(c, plainA(c->effn, M, ffn), L.fc2_w, M, d, ffn, ep, c->bn_enc, st));
+        }
+    }
+    WIPA_TRY(ln(c, c->ex, c->enc_ln_w, c->enc_ln_b, c->enc_T, M, st));
+    if (enc_out != nullptr) WIPA_TRY(launch_layernorm<float>(c->ex, c->enc_ln_w, c->enc_ln_b, enc_out, M, d, st));
+    return cross_kv_project(c, u0, nb, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one decoder step for S sequences: consumes cur_tok at *pos, appends self-KV, leaves the next token in cur_tok
+//   logits_mode 0: skip the vocabulary projection (teacher-forced prompt positions)
+//               1: fused / fp32 argmax with the suppress masks
+//               2: store fp32 logits rows at logits_out (row stride ldo)
+// ------------------------------------------------------------------------------------------------
+DecodeState make_state(wipa_ctx* c, int n_forced, int max_new, int eot) {
+    DecodeState ds;
+    ds.pos = c->d_pos; ds.step = c->d_step; ds.cur_tok = c->d_cur_tok; ds.done = c->d_done; ds.n_done = c->d_n_done;
+    ds.forced = c->d_forced; ds.n_forced = n_forced; ds.out_ids = c->d_out_ids; ds.out_len = c->d_out_len;
+    ds.max_new = max_new; ds.eot = eot;
+    return ds;
+}
+
+int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, float* logits_out, long long ldo, cudaStream_t st) {
+    const wipa_arch& a = c->a;
+    const int d = a.d_model, H = a.heads, ffn = a.ffn, V = a.vocab;
+    if (c->bf) WIPA_TRY(launch_embed<bf16>((const bf16*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
+    else WIPA_TRY(launch_embed<float>((const float*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
+    for (int l = 0; l < a.dec_layers; ++l) {
+        const DecLayer& L = c->dec[l];
+        char* kp = (char*)c->kpool + (size_t)l * c->pool_layer_stride * c->esz;
+        char* vp = (char*)c->vpool + (size_t)l * c->pool_layer_stride * c->esz;
+        WIPA_TRY(ln(c, c->dx, L.ln1_w, L.ln1_b, c->dh, S, st));
+        {
+            EpiParams ep = epi(EPI_QKV_DEC, S, 3 * d);
+            ep.bias = L.qkv_b; ep.out = c->dq; ep.out1 = kp; ep.out2 = vp; ep.out_bf16 = c->bf;
+            ep.H = H; ep.d = d; ep.pos_ptr = c->d_pos; ep.block_table = c->block_table; ep.bt_stride = c->pages_per_seq;
+            WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.qkv_w, S, 3 * d, d, ep, c->bn_dec, st));
+        }
+        if (c->bf) WIPA_TRY(launch_self_attention<bf16>(c->dq, (const bf16*)kp, (const bf16*)vp, c->block_table, c->pages_per_seq,
+                                                        c->d_pos, (bf16*)c->dattn, S, H, st));
+        else WIPA_TRY(launch_self_attention<float>(c->dq, (const float*)kp, (const float*)vp, c->block_table, c->pages_per_seq,
+                                                   c->d_pos, (float*)c->dattn, S, H, st));
+        {
+            EpiParams ep = epi(EPI_RESADD, S, d);
+            ep.bias = L.o_b; ep.out = c->dx; ep.resid = c->dx;
+            WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.o_w, S, d, d, ep, c->bn_dec, st));
+        }
+        WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
+        {
+            EpiParams ep = epi(EPI_STORE, S, d);
+            ep.bias = L.cq_b; ep.out = c->dq; ep.out_bf16 = 0;
+            WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.cq_w, S, d, d, ep, c->bn_dec, st));
+        }
+        {
+            const char* xk = (const char*)c->xkv + (size_t)(2 * l) * c->xkv_which_stride * c->esz;
+            const char* xv = (const char*)c->xkv + (size_t)(2 * l + 1) * c->xkv_which_stride * c->esz;
+            if (c->bf) WIPA_TRY(launch_cross_attention<bf16>(c->dq, (const bf16*)xk, (const bf16*)xv, c->utt_of_seq, (bf16*)c->dattn,
+                                                             c->ca_part, c->ca_counters, S, H, c->ca_split, st));
+            else WIPA_TRY(launch_cross_attention<float>(c->dq, (const float*)xk, (const float*)xv, c->utt_of_seq, (float*)c->dattn,
+                                                        c->ca_part, c->ca_counters, S, H, c->ca_split, st));
+        }
+        {
+            EpiParams ep = epi(EPI_RESADD, S, d);
+            ep.bias = L.co_b; ep.out = c->dx; ep.resid = c->dx;
+            WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.co_w, S, d, d, ep, c->bn_dec, st));
+        }
+        WIPA_TRY(ln(c, c->dx, L.ln3_w, L.ln3_b, c->dh, S, st));
+        {
+            EpiParams ep = epi(EPI_GELU, S, ffn);
+            ep.bias = L.fc1_b; ep.out = c->dffn; ep.out_bf16 = c->bf;
+            WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.fc1_w, S, ffn, d, ep, c->bn_dec, st));
+        }
+        {
+            EpiParams ep = epi(EPI_RESADD, S, d);
+            ep.bias = L.fc2_b; ep.out = c->dx; ep.resid = c->dx;
+            WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, c->bn_dec, st));
+        }
+    }
+    int n_tiles = 1;
+    if (logits_mode != 0) {
+        WIPA_TRY(ln(c, c->dx, c->dec_ln_w, c->dec_ln_b, c->dh, S, st));
+        if (logits_mode == 1 && c->bf) {
+            // fused vocabulary projection + running argmax: the [S, V] logits never reach HBM
+            EpiParams ep = epi(EPI_ARGMAX, S, V);
+            ep.pmax = c->pmax; ep.pidx = c->pidx;
+            ep.mask_always = c->mask_always; ep.mask_begin = c->mask_begin; ep.step_ptr = c->d_step;
+            n_tiles = c->n_logit_tiles;
+            WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits, st));
+        } else {
+            float* dst = logits_mode == 2 ? logits_out : c->logits;
+            EpiParams ep = epi(EPI_STORE, S, V);
+            ep.out = dst; ep.out_bf16 = 0; ep.vec_ok = 0;
+            ep.ldo = logits_mode == 2 ? ldo : V;
+            ep.o_rpb = 1; ep.o_bstride = ep.ldo;                 // row m -> m * ldo
+            WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits, st));
+            if (logits_mode == 1)
+                WIPA_TRY(launch_row_argmax(dst, S, V, c->mask_always, c->mask_begin, c->d_step, c->pmax, c->pidx, st));
+        }
+    }
+    WIPA_TRY(launch_greedy_finalize(c->pmax, c->pidx, n_tiles, ds, S, st));
+    return WIPA_OK;
+}
+
+int upload_mask(wipa_ctx* c, uint32_t* dmask, const int32_t* ids, int n, cudaStream_t st) {
+    const int words = (c->a.vocab + 31) / 32;
+    std::vector<uint32_t> m(words, 0u);
+    for (int i = 0; i < n; ++i) {
+        WIPA_CHECK(ids[i] >= 0 && ids[i] < c->a.vocab, WIPA_EINVAL, "suppress id %d outside the vocabulary", ids[i]);
+        m[ids[i] >> 5] |= 1u << (ids[i] & 31);
+    }
+    WIPA_CUDA_CHECK(cudaMemcpyAsync(dmask, m.data(), words * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    WIPA_CUDA_CHECK(cudaStreamSynchronize(st));     // m is a stack-owned pageable buffer
+    return WIPA_OK;
+}
+
+int decode_setup(wipa_ctx* c, int S, int beams, const std::vector<int32_t>& forced, int n_forced, int max_new, int eot,
+                 DecodeState* ds_out, cudaStream_t st) {
+    WIPA_CUDA_CHECK(cudaMemcpyAsync(c->d_forced, forced.data(), forced.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    WIPA_CUDA_CHECK(cudaStreamSynchronize(st));
+    DecodeState ds = make_state(c, n_forced, max_new, eot);
+    int n = S * c->pages_per_seq;
+    if (S * max_new > n) n = S * max_new;
+    const int n_counters = c->max_seqs * c->a.heads;
+    if (n_counters > n) n = n_counters;
+    decode_init_kernel<<<cdiv(n, 256), 256, 0, st>>>(ds, c->block_table, c->utt_of_seq, S, beams, c->pages_per_seq,
+                                                      c->ca_counters, n_counters);
+    WIPA_LAUNCHED();
+    *ds_out = ds;
+    return WIPA_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_beams, wipa_ctx** out) {
+    WIPA_CHECK(arch && out, WIPA_EINVAL, "wipa_ctx_create: null argument");
+    WIPA_CHECK(arch->d_model % 128 == 0 && arch->d_model <= 1280, WIPA_EUNSUPPORTED, "d_model %d must be 128*k <= 1280", arch->d_model);
+    WIPA_CHECK(arch->heads * WIPA_HEAD_DIM == arch->d_model, WIPA_EUNSUPPORTED, "head_dim must be 64 (d_model %d, heads %d)",
+               arch->d_model, arch->heads);
+    WIPA_CHECK(arch->ffn % 64 == 0 && arch->n_mels % 16 == 0 && arch->vocab > 0, WIPA_EINVAL, "bad ffn / n_mels / vocab");
+    WIPA_CHECK(arch->dtype == WIPA_DTYPE_F32 || arch->dtype == WIPA_DTYPE_BF16, WIPA_EINVAL, "bad dtype %d", arch->dtype);
+    WIPA_CHECK(max_batch >= 1 && max_beams >= 1 && max_batch * max_beams <= 4096, WIPA_EINVAL, "bad max_batch / max_beams");
+    int dev = 0, major = 0;
+    WIPA_CUDA_CHECK(cudaGetDevice(&dev));
+    WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    WIPA_CHECK(major == 10, WIPA_EUNSUPPORTED, "libwipa needs an sm_100a device (found compute capability major %d)", major);
+
+    wipa_ctx* c = new wipa_ctx();
+    c->a = *arch;
+    c->max_batch = max_batch; c->max_beams = max_beams; c->max_seqs = max_batch * max_beams;
+    c->bf = arch->dtype == WIPA_DTYPE_BF16;
+    c->esz = c->bf ? 2 : 4;
+    c->enc_mb = env_int("WIPA_ENC_MB", 32);
+    if (c->enc_mb > max_batch) c->enc_mb = max_batch;
+    c->pages_per_seq = WIPA_MAX_TGT / WIPA_PAGE;
+    c->bn_enc = env_int("WIPA_BN_ENC", 128);
+    c->bn_dec = env_int("WIPA_BN_DEC", 32);
+    c->bn_logits = env_int("WIPA_BN_LOGITS", 128);
+    c->ca_split = env_int("WIPA_CA_SPLIT", cross_attention_default_split((int)c->esz, max_batch, arch->heads));
+    c->n_logit_tiles = cdiv(arch->vocab, c->bn_logits);
+    memset(&c->mel_tables, 0, sizeof(c->mel_tables));
+
+    const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
+    size_t tbytes = 0, fbytes = 0;
+    layout_weights(c, nullptr, nullptr, &tbytes, &fbytes);
+    void *tbase = nullptr, *fbase = nullptr;
+    int r = WIPA_OK;
+#define CTX_TRY(expr) do { r = (expr); if (r != WIPA_OK) { wipa_ctx_destroy(c); return r; } } while (0)
+    CTX_TRY(ctx_alloc(c, &tbase, tbytes, true));
+    CTX_TRY(ctx_alloc(c, &fbase, fbytes, true));
+    layout_weights(c, (char*)tbase, (char*)fbase, &tbytes, &fbytes);
+    {
+        std::unordered_set<std::string> canon;
+        for (auto& kv : c->slots) canon.insert(kv.second.canon);
+        c->n_required = canon.size();
+    }
+    const size_t e = c->esz;
+    const size_t T3 = WIPA_N_FRAMES, T = WIPA_T_ENC;
+    CTX_TRY(ctx_alloc(c, &c->mel_rows, (size_t)mb * (T3 + 2) * arch->n_mels * e, true));
+    CTX_TRY(ctx_alloc(c, &c->conv1_out, (size_t)mb * (T3 + 2) * d * e, true));      // rows 0 / 3001 stay zero
+    CTX_TRY(ctx_alloc(c, (void**)&c->ex, (size_t)mb * T * d * 4, false));
+    CTX_TRY(ctx_alloc(c, &c->eh, (size_t)mb * T * d * e, false));
+    CTX_TRY(ctx_alloc(c, &c->eqkv, (size_t)3 * mb * T * d * e, false));
+    CTX_TRY(ctx_alloc(c, &c->eattn, (size_t)mb * T * d * e, false));
+    CTX_TRY(ctx_alloc(c, &c->effn, (size_t)mb * T * ffn * e, false));
+    CTX_TRY(ctx_alloc(c, &c->enc_T, (size_t)mb * T * d * e, false));
+    c->xkv_which_stride = (size_t)max_batch * H * T * 64;
+    c->xkv_bytes = (size_t)arch->dec_layers * 2 * c->xkv_which_stride * e;
+    CTX_TRY(ctx_alloc(c, &c->xkv, c->xkv_bytes, false));
+    c->pool_layer_stride = (size_t)S * c->pages_per_seq * H * WIPA_PAGE * 64;
+    CTX_TRY(ctx_alloc(c, &c->kpool, (size_t)arch->dec_layers * c->pool_layer_stride * e, false));
+    CTX_TRY(ctx_alloc(c, &c->vpool, (size_t)arch->dec_layers * c->pool_layer_stride * e, false));
+    CTX_TRY(ctx_alloc(c, (void**)&c->dx, (size_t)S * d * 4, false));
+    CTX_TRY(ctx_alloc(c, (void**)&c->dq, (size_t)S * d * 4, false));
+    CTX_TRY(ctx_alloc(c, &c->dh, (size_t)S * d * e, false));
+    CTX_TRY(ctx_alloc(c, &c->dattn, (size_t)S * d * e, false));
+    CTX_TRY(ctx_alloc(c, &c->dffn, (size_t)S * ffn * e, false));
+    CTX_TRY(ctx_alloc(c, (void**)&c->ca_part, (size_t)S * H * 64 * 66 * 4, false));
+    CTX_TRY(ctx_alloc(c, (void**)&c->ca_counters, (size_t)S * H * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->pmax, (size_t)S * c->n_logit_tiles * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->pidx, (size_t)S * c->n_logit_tiles * 4, true));
+    if (!c->bf) CTX_TRY(ctx_alloc(c, (void**)&c->logits, (size_t)S * V * 4, false));
+    else c->logits = nullptr;
+    CTX_TRY(ctx_alloc(c, (void**)&c->block_table, (size_t)S * c->pages_per_seq * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->utt_of_seq, (size_t)S * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->d_pos, 256, true));
+    c->d_step = c->d_pos + 1; c->d_n_done = c->d_pos + 2;
+    CTX_TRY(ctx_alloc(c, (void**)&c->d_cur_tok, (size_t)S * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->d_done, (size_t)S * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->d_forced, (size_t)S * (WIPA_MAX_TGT + 1) * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->d_out_ids, (size_t)S * WIPA_MAX_TGT * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->d_out_len, (size_t)S * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->mask_always, (size_t)((V + 31) / 32) * 4, true));
+    CTX_TRY(ctx_alloc(c, (void**)&c->mask_begin, (size_t)((V + 31) / 32) * 4, true));
+    if (cudaMallocHost((void**)&c->h_pinned, 256) != cudaSuccess) {
+        wipa_set_error("cudaMallocHost failed");
+        wipa_ctx_destroy(c);
+        return WIPA_ENOMEM;
+    }
+#undef CTX_TRY
+    *out = c;
+    return WIPA_OK;
+}
+
+extern "C" int wipa_ctx_destroy(wipa_ctx* c) {
+    if (!c) return WIPA_OK;
+    cudaDeviceSynchronize();
+    for (auto& g : c->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+    for (void* p : c->allocs) cudaFree(p);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    delete c;
+    return WIPA_OK;
+}
+
+extern "C" int wipa_ctx_load_weights(wipa_ctx* c, const wipa_tensor_desc* tensors, int n, void* stream) {
+    WIPA_CHECK(c && (tensors || n == 0), WIPA_EINVAL, "wipa_ctx_load_weights: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < n; ++i) {
+        const wipa_tensor_desc& t = tensors[i];
+        WIPA_CHECK(t.name && t.data, WIPA_EINVAL, "tensor %d: null name or data", i);
+        auto it = c->slots.find(t.name);
+        WIPA_CHECK(it != c->slots.end(), WIPA_EINVAL, "unknown tensor name '%s'", t.name);
+        const Slot& s = it->second;
+        WIPA_CHECK(t.numel == s.numel, WIPA_EINVAL, "tensor '%s': %lld elements, expected %lld", t.name, (long long)t.numel,
+                   (long long)s.numel);
+        if (s.kind == SLOT_CONV) WIPA_TRY(launch_conv_weight(t.data, s.dst, s.N, s.C, c->bf, st));
+        else WIPA_TRY(launch_convert(t.data, s.dst, s.numel, s.scale, s.kind == SLOT_T ? (int)c->bf : 0, st));
+        c->loaded.insert(s.canon);
+    }
+    // the weights changed: graphs stay valid (same buffers), cached cross-KV does not
+    c->n_utts = 0;
+    return WIPA_OK;
+}
+
+extern "C" int wipa_logmel(const float* audio, int B, int n_mels, float* mel, void* stream) {
+    WIPA_CHECK(B >= 0 && (n_mels == 80 || n_mels == 128), WIPA_EINVAL, "wipa_logmel: B=%d n_mels=%d (80 or 128)", B, n_mels);
+    if (B == 0) return WIPA_OK;
+    WIPA_CHECK(audio && mel, WIPA_EINVAL, "wipa_logmel: null pointer");
+    // constant tables (windowed DFT matrix, banded filterbank) are built once per (device, n_mels)
+    struct Cached { LogmelTables t; float* clipmax; int cap; bool ok; };
+    static Cached cache[16][2];
+    int dev = 0;
+    WIPA_CUDA_CHECK(cudaGetDevice(&dev));
+    WIPA_CHECK(dev < 16, WIPA_EUNSUPPORTED, "device index %d", dev);
+    Cached& cc = cache[dev][n_mels == 128];
+    if (!cc.ok) {
+        WIPA_TRY(logmel_tables_create(n_mels, &cc.t));
+        cc.clipmax = nullptr; cc.cap = 0; cc.ok = true;
+    }
+    if (cc.cap < B) {
+        if (cc.clipmax) { WIPA_CUDA_CHECK(cudaDeviceSynchronize()); cudaFree(cc.clipmax); }
+        WIPA_CUDA_CHECK(cudaMalloc(&cc.clipmax, sizeof(float) * (size_t)B));
+        cc.cap = B;
+    }
+    return launch_logmel(cc.t, audio, B, mel, cc.clipmax, (cudaStream_t)stream);
+}
+
+extern "C" int wipa_encode(wipa_ctx* c, const float* mel, int B, float* enc_out, void* stream) {
+    WIPA_CHECK(c && mel, WIPA_EINVAL, "wipa_encode: null argument");
+    WIPA_CHECK(B >= 1 && B <= c->max_batch, WIPA_EINVAL, "wipa_encode: B=%d outside 1..%d", B, c->max_batch);
+    WIPA_TRY(require_weights(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t mel_clip = (size_t)c->a.n_mels * WIPA_N_FRAMES, enc_clip = (size_t)WIPA_T_ENC * c->a.d_model;
+    for (int u0 = 0; u0 < B; u0 += c->enc_mb) {
+        const int nb = (B - u0) < c->enc_mb ? (B - u0) : c->enc_mb;
+        WIPA_TRY(encode_chunk(c, mel + u0 * mel_clip, u0, nb, enc_out ? enc_out + u0 * enc_clip : nullptr, st));
+    }
+    c->n_utts = B;
+    return WIPA_OK;
+}
+
+extern "C" int wipa_set_audio_features(wipa_ctx* c, const float* enc_out, int B, void* stream) {
+    WIPA_CHECK(c && enc_out, WIPA_EINVAL, "wipa_set_audio_features: null argument");
+    WIPA_CHECK(B >= 1 && B <= c->max_batch, WIPA_EINVAL, "wipa_set_audio_features: B=%d outside 1..%d", B, c->max_batch);
+    WIPA_TRY(require_weights(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t enc_clip = (size_t)WIPA_T_ENC * c->a.d_model;
+    for (int u0 = 0; u0 < B; u0 += c->enc_mb) {
+        const int nb = (B - u0) < c->enc_mb ? (B - u0) : c->enc_mb;
+        WIPA_TRY(launch_convert(enc_out + u0 * enc_clip, c->enc_T, (long long)nb * enc_clip, 1.0f, c->bf, st));
+        WIPA_TRY(cross_kv_project(c, u0, nb, st));
+    }
+    c->n_utts = B;
+    return WIPA_OK;
+}
+
+static int check_decode_args(wipa_ctx* c, int B, const wipa_decode_opts* o, int32_t* out_ids, int32_t* out_len) {
+    WIPA_CHECK(c && o && out_ids && out_len, WIPA_EINVAL, "decode: null argument");
+    WIPA_CHECK(c->n_utts > 0, WIPA_ESTATE, "decode before wipa_encode / wipa_set_audio_features");
+    WIPA_CHECK(B == c->n_utts, WIPA_EINVAL, "decode: B=%d but %d utterances are encoded", B, c->n_utts);
+    WIPA_CHECK(o->prompt && o->prompt_len >= 1, WIPA_EINVAL, "decode: empty prompt");
+    WIPA_CHECK(o->max_new >= 1 && o->prompt_len + o->max_new <= WIPA_MAX_TGT, WIPA_EINVAL,
+               "decode: prompt_len %d + max_new %d exceeds %d target positions", o->prompt_len, o->max_new, WIPA_MAX_TGT);
+    WIPA_CHECK(o->eot >= 0 && o->eot < c->a.vocab, WIPA_EINVAL, "decode: eot %d outside the vocabulary", o->eot);
+    WIPA_CHECK((o->n_suppress == 0 || o->suppress) && (o->n_begin_suppress == 0 || o->begin_suppress), WIPA_EINVAL,
+               "decode: suppress list pointer missing");
+    for (int i = 0; i < o->prompt_len; ++i)
+        WIPA_CHECK(o->prompt[i] >= 0 && o->prompt[i] < c->a.vocab, WIPA_EINVAL, "decode: prompt id %d outside the vocabulary", o->prompt[i]);
+    return WIPA_OK;
+}
+
+extern "C" int wipa_decode_greedy(wipa_ctx* c, int B, const wipa_decode_opts* o, int32_t* out_ids, int32_t* out_len, void* stream) {
+    WIPA_TRY(check_decode_args(c, B, o, out_ids, out_len));
+    WIPA_TRY(require_weights(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = B, P = o->prompt_len, max_new = o->max_new;
+    WIPA_TRY(upload_mask(c, c->mask_always, o->suppress, o->n_suppress, st));
+    WIPA_TRY(upload_mask(c, c->mask_begin, o->begin_suppress, o->n_begin_suppress, st));
+    std::vector<int32_t> forced((size_t)S * P);
+    for (int b = 0; b < S; ++b) memcpy(&forced[(size_t)b * P], o->prompt, sizeof(int32_t) * P);
+    DecodeState ds;
+    WIPA_TRY(decode_setup(c, S, 1, forced, P, max_new, o->eot, &ds, st));
+
+    const int total_steps = P - 1 + max_new;           // P-1 forced positions, then max_new sampled tokens
+    int s = 0;
+    for (; s < P - 1; ++s) WIPA_TRY(decode_step(c, S, ds, 0, nullptr, 0, st));
+    // first sampled step eagerly (also settles every lazily-set function attribute), the rest as graph replays
+    WIPA_TRY(decode_step(c, S, ds, 1, nullptr, 0, st));
+    ++s;
+    const bool use_graph = env_int("WIPA_NO_GRAPH", 0) == 0 && total_steps - s >= 2;
+    GraphEntry* ge = nullptr;
+    if (use_graph) {
+        const long long key = ((long long)S << 40) | ((long long)P << 20) | (long long)max_new | ((long long)(o->eot & 0xffff) << 48);
+        ge = &c->graphs[key];
+        if (ge->exec == nullptr) {
+            cudaGraph_t g = nullptr;
+            const int64_t before = g_wipa_launches;
+            WIPA_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const int r = decode_step(c, S, ds, 1, nullptr, 0, st);
+            cudaError_t e = cudaStreamEndCapture(st, &g);
+            if (r != WIPA_OK) { if (g) cudaGraphDestroy(g); return r; }
+            WIPA_CUDA_CHECK(e);
+            ge->nodes = (int)(g_wipa_launches - before);
+            g_wipa_launches = before;                    // capture launched nothing
+            WIPA_CUDA_CHECK(cudaGraphInstantiate(&ge->exec, g, 0));
+            cudaGraphDestroy(g);
+        }
+    }
+    int* h_done = c->h_pinned;
+    *h_done = 0;
+    while (s < total_steps) {
+        int burst = total_steps - s < 8 ? total_steps - s : 8;
+        for (int i = 0; i < burst; ++i) {
+            if (ge) { WIPA_CUDA_CHECK(cudaGraphLaunch(ge->exec, st)); g_wipa_launches += ge->nodes; }
+            else WIPA_TRY(decode_step(c, S, ds, 1, nullptr, 0, st));
+        }
+        s += burst;
+        if (s < total_steps) {       // all rows finished? (HF stops as soon as every row has emitted EOS)
+            WIPA_CUDA_CHECK(cudaMemcpyAsync(h_done, c->d_n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            WIPA_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (*h_done >= S) break;
+        }
+    }
+    c->decode_steps += s;
+    WIPA_CUDA_CHECK(cudaMemcpyAsync(out_ids, c->d_out_ids, sizeof(int32_t) * (size_t)S * max_new, cudaMemcpyDeviceToDevice, st));
+    WIPA_CUDA_CHECK(cudaMemcpyAsync(out_len, c->d_out_len, sizeof(int32_t) * (size_t)S, cudaMemcpyDeviceToDevice, st));
+    return WIPA_OK;
+}
+
+extern "C" int wipa_decode_logits(wipa_ctx* c, int B, const int32_t* tokens, int T, float* logits, void* stream) {
+    WIPA_CHECK(c && tokens && logits, WIPA_EINVAL, "wipa_decode_logits: null argument");
+    WIPA_CHECK(c->n_utts > 0 && B == c->n_utts, WIPA_ESTATE, "wipa_decode_logits: %d utterances encoded, B=%d", c->n_utts, B);
+    WIPA_CHECK(T >= 1 && T <= WIPA_MAX_TGT, WIPA_EINVAL, "wipa_decode_logits: T=%d", T);
+    WIPA_TRY(require_weights(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = c->a.vocab;
+    // T forced tokens + one dummy so that every step stays on the teacher-forced branch of the finalize kernel
+    std::vector<int32_t> forced((size_t)B * (T + 1), 0);
+    for (int b = 0; b < B; ++b)
+        for (int t = 0; t < T; ++t) {
+            const int32_t id = tokens[(size_t)b * T + t];
+            WIPA_CHECK(id >= 0 && id < V, WIPA_EINVAL, "wipa_decode_logits: token %d outside the vocabulary", id);
+            forced[(size_t)b * (T + 1) + t] = id;
+        }
+    DecodeState ds;
+    WIPA_TRY(decode_setup(c, B, 1, forced, T + 1, 0, 0, &ds, st));
+    for (int t = 0; t < T; ++t)
+        WIPA_TRY(decode_step(c, B, ds, 2, logits + (size_t)t * V, (long long)T * V, st));
+    c->decode_steps += T;
+    return WIPA_OK;
+}
+
+extern "C" int wipa_decode_beam(wipa_ctx* c, int B, int beams, float length_penalty, const wipa_decode_opts* o,
+                                int32_t* out_ids, int32_t* out_len, void* stream) {
+    (void)c; (void)B; (void)beams; (void)length_penalty; (void)o; (void)out_ids; (void)out_len; (void)stream;
+    wipa_set_error("wipa_decode_beam: beam search is not built yet");
+    return WIPA_EUNSUPPORTED;
+}
+
+extern "C" int wipa_ctx_get_info(wipa_ctx* c, int what, int64_t* out) {
+    WIPA_CHECK(c && out, WIPA_EINVAL, "wipa_ctx_get_info: null argument");
+    switch (what) {
+        case WIPA_INFO_WORKSPACE_BYTES: *out = (int64_t)c->workspace_bytes; return WIPA_OK;
+        case WIPA_INFO_CROSSKV_BYTES: *out = (int64_t)c->xkv_bytes; return WIPA_OK;
+        case WIPA_INFO_DECODE_STEPS: *out = c->decode_steps; return WIPA_OK;
+        default: break;
+    }
+    wipa_set_error("wipa_ctx_get_info: unknown selector %d", what);
+    return WIPA_EINVAL;
+}
+
+// ---- standalone kernel entry points (tests / roofline) ----------------------------------------------
+extern "C" int wipa_test_gemm_bf16(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int block_n,
+                                   void* stream) {
+    EpiParams ep = epi(EPI_STORE, M, N);
+    ep.bias = bias; ep.out = C; ep.out_bf16 = 0;
+    return launch_gemm_bf16(plainA(A, M, K), (const bf16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
+}
+
+extern "C" int wipa_test_gemm_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, void* stream) {
+    EpiParams ep = epi(EPI_STORE, M, N);
+    ep.bias = bias; ep.out = C; ep.out_bf16 = 0;
+    return launch_gemm_f32(plainA(A, M, K), W, M, N, K, ep, (cudaStream_t)stream);
+}
+
+// conv-as-GEMM addressing check: row m = (batch, t) of A starts at A + batch*bstride + t*lda and spans K >= lda elements
+extern "C" int wipa_test_gemm_rows(const void* A, int is_bf16, long long lda, int rows_per_batch, long long bstride, int n_batch,
+                                   const void* W, float* C, int N, int K, int block_n, void* stream) {
+    const int M = rows_per_batch * n_batch;
+    EpiParams ep = epi(EPI_STORE, M, N);
+    ep.out = C; ep.out_bf16 = 0;
+    AOperand a; a.ptr = A; a.lda = lda; a.a_rpb = rows_per_batch; a.a_bstride = bstride; a.n_batch = n_batch;
+    if (is_bf16) return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
+    return launch_gemm_f32(a, (const float*)W, M, N, K, ep, (cudaStream_t)stream);
+}
+
+extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* q, float* out, void* stream) {
+    WIPA_CHECK(c && q, WIPA_EINVAL, "wipa_test_cross_attn: null argument");
+    WIPA_CHECK(B >= 1 && B <= c->max_seqs && layer >= 0 && layer < c->a.dec_layers, WIPA_EINVAL, "wipa_test_cross_attn: bad B / layer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* xk = (const char*)c->xkv + (size_t)(2 * layer) * c->xkv_which_stride * c->esz;
+    const char* xv = (const char*)c->xkv + (size_t)(2 * layer + 1) * c->xkv_which_stride * c->esz;
+    if (c->bf) WIPA_TRY(launch_cross_attention<bf16>(q, (const bf16*)xk, (const bf16*)xv, nullptr, (bf16*)c->dattn, c->ca_part,
+                                                     c->ca_counters, B, c->a.heads, c->ca_split, st));
+    else WIPA_TRY(launch_cross_attention<float>(q, (const float*)xk, (const float*)xv, nullptr, (float*)c->dattn, c->ca_part,
+                                                c->ca_counters, B, c->a.heads, c->ca_split, st));
+    if (out) WIPA_TRY(launch_to_f32(c->dattn, c->bf, out, (long long)B * c->a.d_model, st));
+    return WIPA_OK;
+}
+
+// encoder self-attention alone: q,k,v f32 [B,H,T,64] (q pre-scaled) -> out f32 [B,T,H*64]; use_bf16 selects the kernel family
+extern "C" int wipa_test_enc_attention(const float* q, const float* k, const float* v, float* out, int B, int H, int T,
+                                       int use_bf16, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!use_bf16) return launch_enc_attention<float>(q, k, v, out, B, H, T, st);
+    const long long n = (long long)B * H * T * 64;
+    bf16* buf = nullptr;
+    WIPA_CUDA_CHECK(cudaMalloc(&buf, sizeof(bf16) * (size_t)n * 4));
+    int r = launch_convert(q, buf, n, 1.f, 1, st);
+    if (r == WIPA_OK) r = launch_convert(k, buf + n, n, 1.f, 1, st);
+    if (r == WIPA_OK) r = launch_convert(v, buf + 2 * n, n, 1.f, 1, st);
+    if (r == WIPA_OK) r = launch_enc_attention<bf16>(buf, buf + n, buf + 2 * n, buf + 3 * n, B, H, T, st);
+    if (r == WIPA_OK) r = launch_to_f32(buf + 3 * n, 1, out, n, st);
+    cudaStreamSynchronize(st);
+    cudaFree(buf);
+    return r;
+}
