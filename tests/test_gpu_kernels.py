@@ -1,0 +1,116 @@
+"""GPU parity of the standalone kernels through the C ABI: both GEMM families (incl. the conv-as-GEMM overlapping-row
+addressing), encoder attention, and the split-K cross-attention streamer."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.fixture(scope="module")
+def lib(built_lib):
+    from whisper_ipa_b200 import _lib
+    torch.backends.cuda.matmul.allow_tf32 = False
+    return _lib
+
+
+@pytest.mark.parametrize("M,N,K", [(64, 64, 64), (200, 136, 240), (1500, 384, 384), (37, 51865 // 50, 384)])
+def test_gemm_f32(lib, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    A = torch.randn(M, K, device="cuda", generator=g)
+    W = torch.randn(N, K, device="cuda", generator=g)
+    b = torch.randn(N, device="cuda", generator=g)
+    Cc = torch.empty(M, N, device="cuda")
+    lib.check(lib.lib().wipa_test_gemm_f32(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cc.data_ptr(), M, N, K, _st()), "gemm_f32")
+    ref = (A.double() @ W.double().T + b.double()).float()
+    assert (Cc - ref).abs().max().item() < 1e-4 * max(1.0, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("bn", [32, 64, 128, 256])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (64, 768, 768), (300, 1000, 384), (1500, 384, 1536), (256, 51865 // 25, 384)])
+def test_gemm_bf16_tcgen05(lib, bn, M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N + bn)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g)
+    Cc = torch.full((M, N), float("nan"), device="cuda")
+    lib.check(lib.lib().wipa_test_gemm_bf16(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cc.data_ptr(), M, N, K, bn, _st()),
+              "gemm_bf16")
+    ref = (A.double() @ W.double().T + b.double()).float()          # exact products of the bf16 operands
+    err = (Cc - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.parametrize("is_bf16", [0, 1])
+@pytest.mark.parametrize("C_in,stride,T_out", [(80, 1, 3000), (128, 1, 3000), (384, 2, 1500)])
+def test_gemm_conv_rows(lib, is_bf16, C_in, stride, T_out):
+    """conv1d(k=3, p=1, stride) as a GEMM over overlapping rows of a zero-row-padded channels-last signal."""
+    B, N, T_in = 2, 128, 3000
+    g = torch.Generator(device="cuda").manual_seed(C_in + stride)
+    x = torch.randn(B, C_in, T_in, device="cuda", generator=g)
+    w = torch.randn(N, C_in, 3, device="cuda", generator=g) * 0.1
+    dt = torch.bfloat16 if is_bf16 else torch.float32
+    rows = torch.zeros(B, T_in + 2, C_in, device="cuda", dtype=dt)
+    rows[:, 1:-1] = x.transpose(1, 2).to(dt)
+    wg = w.permute(0, 2, 1).reshape(N, 3 * C_in).contiguous().to(dt)           # k = tap * C + c
+    out = torch.full((B * T_out, N), float("nan"), device="cuda")
+    lib.check(lib.lib().wipa_test_gemm_rows(rows.data_ptr(), is_bf16, stride * C_in, T_out, (T_in + 2) * C_in, B,
+                                            wg.data_ptr(), out.data_ptr(), N, 3 * C_in, 128, _st()), "gemm_rows")
+    ref = torch.nn.functional.conv1d(rows[:, 1:-1].transpose(1, 2).double(), wg.double().reshape(N, 3, C_in).permute(0, 2, 1),
+                                     stride=stride, padding=1).transpose(1, 2).reshape(B * T_out, N).float()
+    err = (out - ref).abs().max().item()
+    assert err < 2e-4 * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.parametrize("use_bf16,tol", [(0, 2e-5), (1, 2e-2)])
+@pytest.mark.parametrize("T", [1500, 200])
+def test_enc_attention(lib, use_bf16, tol, T):
+    B, H = 2, 3
+    g = torch.Generator(device="cuda").manual_seed(T)
+    q = torch.randn(B, H, T, 64, device="cuda", generator=g) * 0.3
+    k = torch.randn(B, H, T, 64, device="cuda", generator=g)
+    v = torch.randn(B, H, T, 64, device="cuda", generator=g)
+    out = torch.empty(B, T, H * 64, device="cuda")
+    lib.check(lib.lib().wipa_test_enc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, T, use_bf16, _st()),
+              "enc_attention")
+    if use_bf16:
+        q, k, v = (t.to(torch.bfloat16).float() for t in (q, k, v))
+    p = torch.softmax(q.double() @ k.double().transpose(-1, -2), -1)
+    ref = (p @ v.double()).transpose(1, 2).reshape(B, T, H * 64).float()
+    assert (out - ref).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("dtype,tol", [("float32", 2e-5), ("bfloat16", 2e-2)])
+def test_cross_attention_streamer(lib, tiny_sd, dtype, tol):
+    import whisper_ipa_b200 as w
+    B = 5
+    m = w.WhisperIPA("tiny", dtype=dtype, max_batch=B)
+    m.load_state_dict(tiny_sd)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    enc = torch.randn(B, 1500, 384, device="cuda", generator=g)
+    m.set_audio_features(enc)
+    H, d = 6, 384
+    for layer in (0, 3):
+        q = torch.randn(B, d, device="cuda", generator=g)
+        out = torch.empty(B, d, device="cuda")
+        lib.check(lib.lib().wipa_test_cross_attn(m._ctx, B, layer, q.data_ptr(), out.data_ptr(), _st()), "cross_attn")
+        lp = f"model.decoder.layers.{layer}.encoder_attn."
+        wk, wv, bv = (tiny_sd[lp + n].cuda() for n in ("k_proj.weight", "v_proj.weight", "v_proj.bias"))
+        e = enc
+        if dtype == "bfloat16":
+            e, wk, wv = (t.to(torch.bfloat16).float() for t in (e, wk, wv))
+        K = (e.double() @ wk.double().T).view(B, 1500, H, 64).transpose(1, 2)
+        V = (e.double() @ wv.double().T + bv.double()).view(B, 1500, H, 64).transpose(1, 2)
+        if dtype == "bfloat16":
+            K, V = K.float().to(torch.bfloat16).double(), V.float().to(torch.bfloat16).double()
+        qh = q.double().view(B, H, 1, 64)
+        ref = (torch.softmax(qh @ K.transpose(-1, -2), -1) @ V).reshape(B, d).float()
+        err = (out - ref).abs().max().item()
+        assert err < tol, f"layer {layer}: max err {err}"
+    m.close()

@@ -460,7 +460,7 @@ int launch_cross_attention(const float* q, const T* k, const T* v, const int* ut
     const size_t smem = (size_t)chunk * 64 * sizeof(T) * 2 + (size_t)chunk * sizeof(float);
     static size_t configured[2] = {0, 0};
     size_t& cfg = configured[sizeof(T) == 2];
-    if (smem > 48 * 1024 && smem > cfg) {
+    if (smem + 4096 > 48 * 1024 && smem > cfg) {      // + static shared memory of the kernel
         WIPA_CUDA_CHECK(cudaFuncSetAttribute(cross_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg = smem;
     }

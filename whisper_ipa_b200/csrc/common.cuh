@@ -26,6 +26,7 @@ extern int64_t g_wipa_launches;
         cudaError_t _e = (expr);                                                                \
         if (_e != cudaSuccess) {                                                                \
             wipa_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            cudaGetLastError(); /* clear the (non-sticky) error so later calls are not blamed */  \
             return WIPA_ECUDA;                                                                  \
         }                                                                                       \
     } while (0)
@@ -51,6 +52,7 @@ extern int64_t g_wipa_launches;
         cudaError_t _e = cudaPeekAtLastError();                                                \
         if (_e != cudaSuccess) {                                                               \
             wipa_set_error("%s:%d: launch failed: %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            cudaGetLastError();                                                                \
             return WIPA_ECUDA;                                                                 \
         }                                                                                      \
     } while (0)

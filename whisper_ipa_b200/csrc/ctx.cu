@@ -82,6 +82,7 @@ struct wipa_ctx {
     int *d_pos, *d_step, *d_cur_tok, *d_done, *d_n_done, *d_forced, *d_out_ids, *d_out_len;
     uint32_t *mask_always, *mask_begin;
     int* h_pinned = nullptr;       // pinned host scratch (n_done)
+    cudaStream_t cap_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy default stream)
     int n_logit_tiles;
     int bn_enc, bn_dec, bn_logits, ca_split;
     int64_t decode_steps = 0;
@@ -569,8 +570,10 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     CTX_TRY(ctx_alloc(c, (void**)&c->d_out_len, (size_t)S * 4, true));
     CTX_TRY(ctx_alloc(c, (void**)&c->mask_always, (size_t)((V + 31) / 32) * 4, true));
     CTX_TRY(ctx_alloc(c, (void**)&c->mask_begin, (size_t)((V + 31) / 32) * 4, true));
-    if (cudaMallocHost((void**)&c->h_pinned, 256) != cudaSuccess) {
-        wipa_set_error("cudaMallocHost failed");
+    if (cudaMallocHost((void**)&c->h_pinned, 256) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        wipa_set_error("cudaMallocHost / cudaStreamCreate failed");
+        cudaGetLastError();
         wipa_ctx_destroy(c);
         return WIPA_ENOMEM;
     }
@@ -585,6 +588,7 @@ extern "C" int wipa_ctx_destroy(wipa_ctx* c) {
     for (auto& g : c->graphs) if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
     for (void* p : c->allocs) cudaFree(p);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
     delete c;
     return WIPA_OK;
 }
@@ -702,9 +706,9 @@ extern "C" int wipa_decode_greedy(wipa_ctx* c, int B, const wipa_decode_opts* o,
         if (ge->exec == nullptr) {
             cudaGraph_t g = nullptr;
             const int64_t before = g_wipa_launches;
-            WIPA_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-            const int r = decode_step(c, S, ds, 1, nullptr, 0, st);
-            cudaError_t e = cudaStreamEndCapture(st, &g);
+            WIPA_CUDA_CHECK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const int r = decode_step(c, S, ds, 1, nullptr, 0, c->cap_stream);
+            cudaError_t e = cudaStreamEndCapture(c->cap_stream, &g);
             if (r != WIPA_OK) { if (g) cudaGraphDestroy(g); return r; }
             WIPA_CUDA_CHECK(e);
             ge->nodes = (int)(g_wipa_launches - before);
