@@ -164,6 +164,7 @@ def main():
     ap.add_argument("--ref-clips", type=int, default=2)
     ap.add_argument("--cpu-baseline-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -225,11 +226,15 @@ def main():
     _lib.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     for _ in range(K):
         ids, lens, counts = device_step()
     e1.record()
     sync_all()
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     launches = torch.tensor([_lib.launch_count()], device=dev, dtype=torch.int64)
     if world > 1:

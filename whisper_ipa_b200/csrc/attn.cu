@@ -231,6 +231,8 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
     const int h = blockIdx.x, b = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int d = H * 64;
+    pdl_launch_dependents();
+    pdl_wait();
     const int len = *pos_ptr + 1;
     const int* bt = block_table + (size_t)b * bt_stride;
     if (tid < 64) qs[tid] = q[(size_t)b * d + h * 64 + tid];
@@ -277,7 +279,7 @@ template <typename T>
 int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
                           const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st) {
     dim3 grid(H, Bs);
-    self_attention_kernel<T><<<grid, 128, 0, st>>>(q, kpool, vpool, block_table, bt_stride, pos_ptr, out, H);
+    WIPA_CUDA_CHECK(wipa_launch(self_attention_kernel<T>, grid, dim3(128), (size_t)0, st, q, kpool, vpool, block_table, bt_stride, pos_ptr, out, H));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

@@ -5,6 +5,7 @@
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <string>
 
 #include "../../include/wipa.h"
@@ -58,6 +59,31 @@ extern int64_t g_wipa_launches;
     } while (0)
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// ------------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): kernels of the decode step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, signal `launch_dependents` as soon as they start, prefetch
+// their STATIC operands (weights, cached encoder K/V) and only then `griddepcontrol.wait` for the previous kernel.
+// Launch latency, prologues and the first HBM loads of kernel N+1 therefore overlap the tail of kernel N.
+// RULE: every kernel launched through wipa_launch must execute pdl_wait() before it reads anything a previous
+// kernel wrote and before it writes anything a previous kernel may still read.
+// ------------------------------------------------------------------------------------------------
+extern int g_wipa_pdl;       // 1 (default) or 0 (env WIPA_PDL=0): attach the PDL attribute to launches
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t wipa_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                      Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_wipa_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------------

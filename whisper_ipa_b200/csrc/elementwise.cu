@@ -12,6 +12,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
                  T* __restrict__ out, int M) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     if (row >= M) return;
     constexpr int d = NV * 128;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
@@ -47,7 +49,7 @@ int launch_layernorm(const float* x, const float* w, const float* b, T* out, int
     if (M == 0) return WIPA_OK;
     const int grid = cdiv(M, 8);
     switch (d / 128) {
-#define LN_CASE(NV) case NV: layernorm_kernel<T, NV><<<grid, 256, 0, st>>>(x, w, b, out, M); break;
+#define LN_CASE(NV) case NV: WIPA_CUDA_CHECK(wipa_launch(layernorm_kernel<T, NV>, dim3(grid), dim3(256), (size_t)0, st, x, w, b, out, M)); break;
         LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8) LN_CASE(9) LN_CASE(10)
 #undef LN_CASE
     }
@@ -103,6 +105,8 @@ template <typename T>
 __global__ void embed_kernel(const T* __restrict__ tok_emb, const float* __restrict__ pos_emb,
                              const int* __restrict__ tok, const int* __restrict__ pos_ptr, float* __restrict__ x, int d) {
     const int b = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const int p = *pos_ptr;
     const T* te = tok_emb + (size_t)tok[b] * d;
     const float* pe = pos_emb + (size_t)p * d;
@@ -112,7 +116,7 @@ __global__ void embed_kernel(const T* __restrict__ tok_emb, const float* __restr
 template <typename T>
 int launch_embed(const T* tok_emb, const float* pos_emb, const int* tok, const int* pos_ptr, float* x, int Bs, int d,
                  cudaStream_t st) {
-    embed_kernel<T><<<Bs, 256, 0, st>>>(tok_emb, pos_emb, tok, pos_ptr, x, d);
+    WIPA_CUDA_CHECK(wipa_launch(embed_kernel<T>, dim3(Bs), dim3(256), (size_t)0, st, tok_emb, pos_emb, tok, pos_ptr, x, d));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
@@ -174,6 +178,8 @@ row_argmax_kernel(const float* __restrict__ logits, int V, const uint32_t* __res
     __shared__ float smax[8];
     __shared__ int sidx[8];
     const int b = blockIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     const float* row = logits + (size_t)b * V;
     const bool begin = (step_ptr != nullptr) && (*step_ptr == 0);
     float best = -INFINITY;
@@ -203,7 +209,7 @@ row_argmax_kernel(const float* __restrict__ logits, int V, const uint32_t* __res
 
 int launch_row_argmax(const float* logits, int Bs, int V, const uint32_t* mask_always, const uint32_t* mask_begin,
                       const int* step_ptr, float* pmax, int* pidx, cudaStream_t st) {
-    row_argmax_kernel<<<Bs, 256, 0, st>>>(logits, V, mask_always, mask_begin, step_ptr, pmax, pidx);
+    WIPA_CUDA_CHECK(wipa_launch(row_argmax_kernel, dim3(Bs), dim3(256), (size_t)0, st, logits, V, mask_always, mask_begin, step_ptr, pmax, pidx));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
@@ -217,6 +223,8 @@ int launch_row_argmax(const float* logits, int Bs, int V, const uint32_t* mask_a
 __global__ void __launch_bounds__(1024)
 greedy_finalize_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int n_tiles, DecodeState ds, int Bs) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     const int pos = *ds.pos;
     const int i = pos - (ds.n_forced - 1);            // index of the token sampled at this step
     for (int b = warp; b < Bs; b += 32) {
@@ -257,7 +265,7 @@ greedy_finalize_kernel(const float* __restrict__ pmax, const int* __restrict__ p
 }
 
 int launch_greedy_finalize(const float* pmax, const int* pidx, int n_tiles, DecodeState ds, int Bs, cudaStream_t st) {
-    greedy_finalize_kernel<<<1, 1024, 0, st>>>(pmax, pidx, n_tiles, ds, Bs);
+    WIPA_CUDA_CHECK(wipa_launch(greedy_finalize_kernel, dim3(1), dim3(1024), (size_t)0, st, pmax, pidx, n_tiles, ds, Bs));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

@@ -1,9 +1,12 @@
 // Error plumbing and launch accounting of libwipa.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 int64_t g_wipa_launches = 0;
+static int init_pdl() { const char* v = getenv("WIPA_PDL"); return (v && *v) ? atoi(v) != 0 : 1; }
+int g_wipa_pdl = init_pdl();
 static thread_local char g_wipa_err[1024] = "";
 
 void wipa_set_error(const char* fmt, ...) {

@@ -17,6 +17,8 @@ gemm_f32_kernel(AOperand a, const float* __restrict__ W, int M, int N, int K, Ep
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // global->smem mapping: each thread moves one float4 of A and one of W per k-block
     const int lr = tid >> 2;            // 0..63 row within tile
@@ -76,7 +78,7 @@ int launch_gemm_f32(const AOperand& a, const float* W, int M, int N, int K, cons
     WIPA_CHECK(a.lda % 4 == 0 && a.a_bstride % 4 == 0, WIPA_EINVAL, "gemm_f32: A rows must be 16-byte aligned");
     WIPA_CHECK(ep.mode != EPI_ARGMAX, WIPA_EINVAL, "gemm_f32: fused argmax is a tcgen05-path epilogue");
     dim3 grid(cdiv(N, SG_BN), cdiv(M, SG_BM));
-    gemm_f32_kernel<<<grid, 256, 0, st>>>(a, W, M, N, K, ep);
+    WIPA_CUDA_CHECK(wipa_launch(gemm_f32_kernel, grid, dim3(256), (size_t)0, st, a, W, M, N, K, ep));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

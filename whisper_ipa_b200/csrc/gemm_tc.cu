@@ -17,13 +17,17 @@ namespace {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;
 
-template <int BN> struct TcCfg {
+// BOXM = rows of A fetched per k-block: 128, or 64 when the whole problem has <= 64 rows (decode steps at batch <= 64).
+// With BOXM = 64 the MMA still reads a 128-row operand: rows 64..127 alias the next ring slot, produce garbage
+// accumulator lanes 64..127, and are never loaded by the epilogue (row_ok), so the ring can be twice as deep.
+template <int BN, int BOXM> struct TcCfg {
+    static constexpr int A_BYTES = BOXM * TC_BK * 2;
     static constexpr int W_BYTES = BN * TC_BK * 2;
-    static constexpr int STAGES = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
+    // ring depth: small-N tiles are the latency-bound decode GEMMs -> keep (nearly) all of K in flight
+    static constexpr int STAGES = BN == 32 ? (BOXM == 64 ? 12 : 8) : (BN == 64 ? 6 : (BN == 128 ? 3 : 4));
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-    static constexpr int SMEM = STAGES * (TC_A_BYTES + W_BYTES) + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int SMEM = STAGES * (A_BYTES + W_BYTES) + (TC_BM - BOXM) * TC_BK * 2 /*over-read*/ + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -31,15 +35,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 
-template <int BN>
+template <int BN, int BOXM>
 __global__ void __launch_bounds__(192)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
                     int tiles_per_batch, int a_rpb, EpiParams ep) {
-    using Cfg = TcCfg<BN>;
+    using Cfg = TcCfg<BN, BOXM>;
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
-    uint8_t* sW = smem + Cfg::STAGES * TC_A_BYTES;
+    uint8_t* sW = smem + Cfg::STAGES * Cfg::A_BYTES + (TC_BM - BOXM) * TC_BK * 2;
     uint64_t* full = reinterpret_cast<uint64_t*>(sW + Cfg::STAGES * Cfg::W_BYTES);
     uint64_t* empty = full + Cfg::STAGES;
     uint64_t* tmem_full = empty + Cfg::STAGES;
@@ -50,6 +54,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int batch = blockIdx.y / tiles_per_batch;
     const int t0 = (blockIdx.y - batch * tiles_per_batch) * TC_BM;
 
+    pdl_launch_dependents();                                  // the next kernel may start its own prologue now
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmW);
@@ -71,12 +76,21 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
+            // weights are static: fill the ring with W tiles BEFORE waiting for the previous kernel, then the A tiles
+            const int pre = num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES;
+            for (int kb = 0; kb < pre; ++kb) {
+                ptx::mbar_arrive_expect_tx(&full[kb], Cfg::A_BYTES + Cfg::W_BYTES);
+                ptx::tma_load_2d(sW + kb * Cfg::W_BYTES, &tmW, &full[kb], kb * TC_BK, n0);
+            }
+            pdl_wait();
+            for (int kb = 0; kb < pre; ++kb)
+                ptx::tma_load_3d(sA + kb * Cfg::A_BYTES, &tmA, &full[kb], kb * TC_BK, t0, batch);
+            for (int kb = pre; kb < num_kb; ++kb) {
                 const int s = kb % Cfg::STAGES;
                 const uint32_t ph = (kb / Cfg::STAGES) & 1;
                 ptx::mbar_wait(&empty[s], ph ^ 1);
-                ptx::mbar_arrive_expect_tx(&full[s], TC_A_BYTES + Cfg::W_BYTES);
-                ptx::tma_load_3d(sA + s * TC_A_BYTES, &tmA, &full[s], kb * TC_BK, t0, batch);
+                ptx::mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::W_BYTES);
+                ptx::tma_load_3d(sA + s * Cfg::A_BYTES, &tmA, &full[s], kb * TC_BK, t0, batch);
                 ptx::tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, &full[s], kb * TC_BK, n0);
             }
         }
@@ -89,7 +103,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const uint32_t ph = (kb / Cfg::STAGES) & 1;
                 ptx::mbar_wait(&full[s], ph);
                 ptx::tc_fence_after();
-                const uint32_t a_addr = ptx::smem_u32(sA + s * TC_A_BYTES);
+                const uint32_t a_addr = ptx::smem_u32(sA + s * Cfg::A_BYTES);
                 const uint32_t w_addr = ptx::smem_u32(sW + s * Cfg::W_BYTES);
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k) {
@@ -108,10 +122,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int t = t0 + quarter * 32 + lane;
         const bool row_ok = t < ep.M_rows;
         const int m = batch * a_rpb + t;
+        pdl_wait();                                          // the epilogue reads / writes activations of earlier kernels
         ptx::mbar_wait(tmem_full, 0);
         ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        if (ep.mode == EPI_ARGMAX) {
+        if (BOXM == 64 && quarter >= 2) {
+            // lanes 64..127 hold garbage (see TcCfg); nothing to do
+        } else if (ep.mode == EPI_ARGMAX) {
             const bool begin = (ep.step_ptr != nullptr) && (*ep.step_ptr == 0);
             float best = -INFINITY;
             int best_n = 0x7fffffff;
@@ -164,18 +181,19 @@ int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dim
     return WIPA_OK;
 }
 
-template <int BN>
+template <int BN, int BOXM>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int tiles_per_batch, int n_batch, int a_rpb,
               int N, EpiParams ep, cudaStream_t st) {
+    using Cfg = TcCfg<BN, BOXM>;
     static bool configured = false;
     if (!configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             TcCfg<BN>::SMEM));
+        WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, BOXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
     dim3 grid(cdiv(N, BN), tiles_per_batch * n_batch);
     if (ep.mode == EPI_ARGMAX) ep.n_tiles = grid.x;
-    gemm_bf16_tc_kernel<BN><<<grid, 192, TcCfg<BN>::SMEM, st>>>(tmA, tmW, num_kb, tiles_per_batch, a_rpb, ep);
+    WIPA_CUDA_CHECK(wipa_launch(gemm_bf16_tc_kernel<BN, BOXM>, grid, dim3(192), (size_t)Cfg::SMEM, st, tmA, tmW, num_kb,
+                                tiles_per_batch, a_rpb, ep));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
@@ -203,12 +221,13 @@ int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, cons
     WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_bf16: M != rows_per_batch * batches");
     WIPA_CHECK((reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, WIPA_EINVAL,
                "gemm_bf16: operands must be 16-byte aligned");
+    const int box_m = (a.a_rpb <= 64 && block_n == 32) ? 64 : 128;
     CUtensorMap tmA, tmW;
     {
         cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a.a_rpb, (cuuint64_t)a.n_batch};
         cuuint64_t bstride = a.n_batch > 1 ? (cuuint64_t)a.a_bstride : (cuuint64_t)a.a_rpb * (cuuint64_t)a.lda;
         cuuint64_t strides[2] = {(cuuint64_t)a.lda * 2, bstride * 2};
-        cuuint32_t box[3] = {TC_BK, TC_BM, 1};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_m, 1};
         WIPA_TRY(make_map(&tmA, a.ptr, 3, dims, strides, box));
     }
     {
@@ -222,10 +241,12 @@ int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, cons
     const int num_kb = cdiv(K, TC_BK);
     const int tpb = cdiv(a.a_rpb, TC_BM);
     switch (block_n) {
-        case 32: return launch_bn<32>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-        case 64: return launch_bn<64>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-        case 128: return launch_bn<128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-        case 256: return launch_bn<256>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 32:
+            if (box_m == 64) return launch_bn<32, 64>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+            return launch_bn<32, 128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 64: return launch_bn<64, 128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 128: return launch_bn<128, 128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 256: return launch_bn<256, 128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
         default: break;
     }
     wipa_set_error("gemm_bf16: unsupported block_n %d", block_n);
