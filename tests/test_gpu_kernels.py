@@ -68,8 +68,8 @@ def test_gemm_conv_rows(lib, is_bf16, C_in, stride, T_out):
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), f"max err {err}"
 
 
-@pytest.mark.parametrize("use_bf16,tol", [(0, 2e-5), (1, 2e-2)])
-@pytest.mark.parametrize("T", [1500, 200])
+@pytest.mark.parametrize("use_bf16,tol", [(0, 2e-5), (1, 2e-2), (2, 2e-2)])      # 2 = tcgen05 flash kernel
+@pytest.mark.parametrize("T", [1500, 200, 128, 37])
 def test_enc_attention(lib, use_bf16, tol, T):
     B, H = 2, 3
     g = torch.Generator(device="cuda").manual_seed(T)

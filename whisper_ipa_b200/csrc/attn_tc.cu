@@ -1,0 +1,282 @@
+// Encoder self-attention on the 5th-generation tensor cores (bf16 path).
+//
+// Non-causal attention over T = 1500 frames, head_dim 64 (HF:models/whisper/modeling_whisper.py:284-357; the 64^-0.5
+// scaling is folded into the q projection).  One CTA owns a 128-query tile of one (clip, head) and walks the keys in
+// blocks of 128:
+//
+//   warp 0      TMA producer: Q tile once, then K / V blocks ([128 keys][64] each, 128B-swizzled) into a 3-deep ring
+//   warp 1      tcgen05 issuer:  S_j = Q K_j^T   (M128 x N128 x K64, fp32 in TMEM, double-buffered)
+//                                O_j = P_j V_j   (M128 x N64 x K128; P_j is the bf16 tile the softmax warps left in
+//                                                 shared memory, V_j is consumed as an MN-major B operand straight
+//                                                 from its TMA image — no transpose anywhere)
+//   warps 2-5   softmax, one query row per thread: tcgen05.ld S_j, running max / sum in fp32 (exp2 with log2e folded
+//               into one FFMA), P_j -> bf16 -> swizzled shared memory, then fold the PREVIOUS block's O_{j-1} from TMEM
+//               into the fp32 register accumulator (o = o * alpha + O_{j-1}).  The tensor pipe therefore never waits
+//               for a rescale: every P V product starts from zero in its own TMEM buffer.
+//
+// Tail handling: key indices >= T get -inf scores (their K/V rows are zero-filled by TMA), query rows >= T are
+// computed on zero-filled Q and never stored.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int FA_BQ = 128;
+constexpr int FA_BK = 128;
+constexpr int FA_STAGES = 3;
+constexpr int FA_TILE_BYTES = 128 * 64 * 2;                   // one [128][64] bf16 tile
+constexpr int FA_P_BYTES = 2 * FA_TILE_BYTES;                 // [128 q][128 keys] as two K-chunks of 64 keys
+constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 2 * FA_P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int FA_TMEM_COLS = 512;                             // S: 2 x 128 columns, O: 2 x 64 columns
+constexpr float LOG2E = 1.4426950408889634f;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_fa = nullptr;
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// MN-major B operand with the 128-byte swizzle: rows are K indices (keys), 128 bytes = 64 N elements per row, 8-row
+// groups 1024 bytes apart (cute/atom/mma_traits_sm100.hpp: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), m = 1 here).
+__device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)(1024u >> 4) << 16;                     // LBO: next 64-element block along N (unused, N = 64)
+    d |= (uint64_t)(1024u >> 4) << 32;                     // SBO: next group of 8 keys
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(192, 1)
+enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                        const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int H, int T) {
+    extern __shared__ uint8_t fa_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + FA_TILE_BYTES;                          // [stage]
+    uint8_t* sV = sK + FA_STAGES * FA_TILE_BYTES;              // [stage]
+    uint8_t* sP = sV + FA_STAGES * FA_TILE_BYTES;              // [2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
+    uint64_t* q_full = bars;                                   // 1
+    uint64_t* kv_full = bars + 1;                              // FA_STAGES
+    uint64_t* kv_empty = kv_full + FA_STAGES;                  // FA_STAGES
+    uint64_t* s_full = kv_empty + FA_STAGES;                   // 2
+    uint64_t* p_ready = s_full + 2;                            // 2
+    uint64_t* o_full = p_ready + 2;                            // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q0 = blockIdx.x * FA_BQ;
+    const int bh = blockIdx.y;
+    const int nb = (T + FA_BK - 1) / FA_BK;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmQ);
+        ptx::prefetch_tensormap(&tmK);
+        ptx::prefetch_tensormap(&tmV);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            ptx::mbar_init(q_full, 1);
+            for (int s = 0; s < FA_STAGES; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
+            for (int s = 0; s < 2; ++s) { ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&p_ready[s], 128); ptx::mbar_init(&o_full[s], 1); }
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, FA_TMEM_COLS);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_S = tmem_base;                         // + 128 * buf
+    const uint32_t tmem_O = tmem_base + 256;                   // + 64 * buf
+
+    if (warp == 0) {
+        if (lane == 0) {
+            ptx::mbar_arrive_expect_tx(q_full, FA_TILE_BYTES);
+            ptx::tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
+            for (int j = 0; j < nb; ++j) {
+                const int s = j % FA_STAGES;
+                if (j >= FA_STAGES) ptx::mbar_wait(&kv_empty[s], ((j / FA_STAGES) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
+                ptx::tma_load_3d(sK + s * FA_TILE_BYTES, &tmK, &kv_full[s], 0, j * FA_BK, bh);
+                ptx::tma_load_3d(sV + s * FA_TILE_BYTES, &tmV, &kv_full[s], 0, j * FA_BK, bh);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = idesc_bf16(128, 128, 0);
+            constexpr uint32_t idesc_o = idesc_bf16(128, 64, 1);
+            const uint32_t q_addr = ptx::smem_u32(sQ);
+            auto issue_qk = [&](int j) {
+                const int s = j % FA_STAGES;
+                ptx::mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
+                ptx::tc_fence_after();
+                const uint32_t k_addr = ptx::smem_u32(sK + s * FA_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::umma_bf16(tmem_S + (uint32_t)(j & 1) * 128u, ptx::smem_desc_sw128_kmajor(q_addr + k * 32),
+                                   ptx::smem_desc_sw128_kmajor(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+                ptx::umma_commit(&s_full[j & 1]);
+            };
+            ptx::mbar_wait(q_full, 0);
+            issue_qk(0);
+            for (int j = 0; j < nb; ++j) {
+                if (j + 1 < nb) issue_qk(j + 1);
+                ptx::mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+                ptx::tc_fence_after();
+                const uint32_t p_addr = ptx::smem_u32(sP + (j & 1) * FA_P_BYTES);
+                const uint32_t v_addr = ptx::smem_u32(sV + (j % FA_STAGES) * FA_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                   // 16 keys per MMA
+                    const uint64_t da = ptx::smem_desc_sw128_kmajor(p_addr + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32);
+                    const uint64_t db = smem_desc_sw128_mnmajor(v_addr + k * 2048);
+                    ptx::umma_bf16(tmem_O + (uint32_t)(j & 1) * 64u, da, db, idesc_o, k != 0 ? 1u : 0u);
+                }
+                ptx::umma_commit(&o_full[j & 1]);
+                ptx::umma_commit(&kv_empty[j % FA_STAGES]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;                        // query row of this thread within the tile
+        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        float o[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) o[i] = 0.f;
+        float m = -INFINITY, l = 0.f, alpha_prev = 0.f;
+        const uint32_t p_row = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const uint32_t sw = (uint32_t)(r & 7);
+
+        auto fold_o = [&](int j, float alpha) {                   // o = o * alpha + O_j
+            ptx::mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            float t[64];
+            ptx::tmem_ld32(tmem_O + (uint32_t)(j & 1) * 64u + lane_off, t);
+            ptx::tmem_ld32(tmem_O + (uint32_t)(j & 1) * 64u + 32u + lane_off, t + 32);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 64; ++i) o[i] = fmaf(o[i], alpha, t[i]);
+        };
+
+        for (int j = 0; j < nb; ++j) {
+            ptx::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            float s[128];
+            const uint32_t ts = tmem_S + (uint32_t)(j & 1) * 128u + lane_off;
+            ptx::tmem_ld32(ts, s);
+            ptx::tmem_ld32(ts + 32, s + 32);
+            ptx::tmem_ld32(ts + 64, s + 64);
+            ptx::tmem_ld32(ts + 96, s + 96);
+            ptx::tmem_ld_wait();
+            const int kbase = j * FA_BK;
+            if (kbase + FA_BK > T) {
+#pragma unroll
+                for (int c = 0; c < 128; ++c) if (kbase + c >= T) s[c] = -INFINITY;
+            }
+            float mx = s[0];
+#pragma unroll
+            for (int c = 1; c < 128; ++c) mx = fmaxf(mx, s[c]);
+            const float m_new = fmaxf(m, mx);
+            const float alpha = ex2((m - m_new) * LOG2E);         // 0 on the first block (m = -inf)
+            const float nm = -m_new * LOG2E;
+            m = m_new;
+            float sum = 0.f;
+            uint8_t* prow = sP + (j & 1) * FA_P_BYTES + p_row;
+#pragma unroll
+            for (int c8 = 0; c8 < 16; ++c8) {                      // 8 keys = one 16-byte piece of the swizzled row
+                float p[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    p[i] = ex2(fmaf(s[c8 * 8 + i], LOG2E, nm));
+                    sum += p[i];
+                }
+                uint4 u;
+                u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
+                u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+                const uint32_t chunk = (uint32_t)(c8 >> 3), piece = (uint32_t)(c8 & 7);
+                *reinterpret_cast<uint4*>(prow + chunk * FA_TILE_BYTES + ((piece ^ sw) << 4)) = u;
+            }
+            l = fmaf(l, alpha, sum);
+            ptx::fence_proxy_async();                             // P visible to the tensor core's async proxy
+            ptx::tc_fence_before();                               // our TMEM reads of S_j are complete
+            ptx::mbar_arrive(&p_ready[j & 1]);
+            if (j > 0) fold_o(j - 1, alpha_prev);
+            alpha_prev = alpha;
+        }
+        fold_o(nb - 1, alpha_prev);
+        const int t = q0 + r;
+        if (t < T) {
+            const float inv = 1.0f / l;
+            const int b = bh / H, h = bh - b * H;
+            bf16* dst = out + ((size_t)b * T + t) * ((size_t)H * 64) + (size_t)h * 64;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+                uint4 u;
+                u.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv); u.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
+                u.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv); u.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+                *reinterpret_cast<uint4*>(dst + i) = u;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, FA_TMEM_COLS);
+}
+
+int make_map_3d(CUtensorMap* map, const void* base, int T, int BH) {
+    cuuint64_t dims[3] = {64, (cuuint64_t)T, (cuuint64_t)BH};
+    cuuint64_t strides[2] = {128, (cuuint64_t)T * 128};
+    cuuint32_t box[3] = {64, 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_fa(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        wipa_set_error("enc_attention_tc: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return WIPA_ECUDA;
+    }
+    return WIPA_OK;
+}
+
+}  // namespace
+
+// q, k, v: bf16 [B, H, T, 64] (q pre-scaled); out: bf16 [B, T, H*64]
+int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, int B, int H, int T, cudaStream_t st) {
+    if (g_encode_fa == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        WIPA_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        WIPA_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, WIPA_ECUDA, "cuTensorMapEncodeTiled not available");
+        g_encode_fa = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    WIPA_CHECK(T >= 1 && B >= 1 && H >= 1, WIPA_EINVAL, "enc_attention_tc: bad shape");
+    CUtensorMap tmQ, tmK, tmV;
+    WIPA_TRY(make_map_3d(&tmQ, q, T, B * H));
+    WIPA_TRY(make_map_3d(&tmK, k, T, B * H));
+    WIPA_TRY(make_map_3d(&tmV, v, T, B * H));
+    static bool configured = false;
+    if (!configured) {
+        WIPA_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+        configured = true;
+    }
+    dim3 grid(cdiv(T, FA_BQ), B * H);
+    enc_attention_tc_kernel<<<grid, 192, FA_SMEM, st>>>(tmQ, tmK, tmV, out, H, T);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}

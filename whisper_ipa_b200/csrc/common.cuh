@@ -337,7 +337,7 @@ template <typename T>
 int launch_layernorm(const float* x, const float* w, const float* b, T* out, int M, int d, cudaStream_t st);
 template <typename T>
 int launch_enc_attention(const T* q, const T* k, const T* v, T* out, int B, int H, int Tq, cudaStream_t st);
-int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* vt, bf16* out, int B, int H, cudaStream_t st);
+int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, int B, int H, int T, cudaStream_t st);   // attn_tc.cu
 template <typename T>
 int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
                           const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st);

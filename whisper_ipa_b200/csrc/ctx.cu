@@ -85,6 +85,7 @@ struct wipa_ctx {
     cudaStream_t cap_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy default stream)
     int n_logit_tiles;
     int bn_enc, bn_dec, bn_logits, ca_split;
+    int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (bf16 path)
     int64_t decode_steps = 0;
     size_t workspace_bytes = 0, xkv_bytes = 0;
     LogmelTables mel_tables;
@@ -335,7 +336,8 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
         }
         if (c->bf) {
             const bf16* q = (const bf16*)c->eqkv;
-            WIPA_TRY(launch_enc_attention<bf16>(q, q + hq, q + 2 * hq, (bf16*)c->eattn, nb, H, T, st));
+            if (c->enc_attn_simt) WIPA_TRY(launch_enc_attention<bf16>(q, q + hq, q + 2 * hq, (bf16*)c->eattn, nb, H, T, st));
+            else WIPA_TRY(launch_enc_attention_tc(q, q + hq, q + 2 * hq, (bf16*)c->eattn, nb, H, T, st));
         } else {
             const float* q = (const float*)c->eqkv;
             WIPA_TRY(launch_enc_attention<float>(q, q + hq, q + 2 * hq, (float*)c->eattn, nb, H, T, st));
@@ -516,6 +518,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->bn_logits = env_int("WIPA_BN_LOGITS", 128);
     c->ca_split = env_int("WIPA_CA_SPLIT", cross_attention_default_split((int)c->esz, max_batch, arch->heads));
     c->n_logit_tiles = cdiv(arch->vocab, c->bn_logits);
+    c->enc_attn_simt = env_int("WIPA_ENC_ATTN_SIMT", 0);
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
@@ -830,7 +833,8 @@ extern "C" int wipa_test_enc_attention(const float* q, const float* k, const flo
     int r = launch_convert(q, buf, n, 1.f, 1, st);
     if (r == WIPA_OK) r = launch_convert(k, buf + n, n, 1.f, 1, st);
     if (r == WIPA_OK) r = launch_convert(v, buf + 2 * n, n, 1.f, 1, st);
-    if (r == WIPA_OK) r = launch_enc_attention<bf16>(buf, buf + n, buf + 2 * n, buf + 3 * n, B, H, T, st);
+    if (r == WIPA_OK) r = use_bf16 == 2 ? launch_enc_attention_tc(buf, buf + n, buf + 2 * n, buf + 3 * n, B, H, T, st)
+                                        : launch_enc_attention<bf16>(buf, buf + n, buf + 2 * n, buf + 3 * n, B, H, T, st);
     if (r == WIPA_OK) r = launch_to_f32(buf + 3 * n, 1, out, n, st);
     cudaStreamSynchronize(st);
     cudaFree(buf);
