@@ -275,6 +275,28 @@ def main():
             dist.destroy_process_group()
         return
 
+    # ---- where the pass goes: each phase timed on its own (CUDA events, device-resident inputs) --------------------
+    from whisper_ipa_b200.audio import log_mel_features
+
+    def timed(fn, reps=2):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            out = fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps, out
+
+    t_mel, mel_dev = timed(lambda: log_mel_features(audio_dev, arch.n_mels))
+    t_enc, _ = timed(lambda: model.encoder(mel_dev, return_features=False))
+    t_dec, (ids_d, lens_d) = timed(lambda: model.decode_tokens(tr.prompt, args.max_new))
+    t_per, _ = timed(lambda: tr.score_device(ids_d, lens_d, rf_d, ro_d, max_ref))
+    phases = {"logmel_ms": t_mel, "encoder_ms": t_enc, "decode_ms": t_dec, "per_ms": t_per,
+              "decode_us_per_step": 1000.0 * t_dec / (PROMPT_LEN - 1 + args.max_new)}
+    del mel_dev
+
     # ---- roofline of the dominant kernel: cross-attention streamer timed alone -------------------------------------
     import ctypes as C
     esz = 2 if args.dtype == "bfloat16" else 4
@@ -329,6 +351,7 @@ def main():
         "gpu_launches": int(launches.item()),
         "clocks": clocks,
         "roofline": roofline,
+        "phases": phases,
         "cpu_baseline": cpu_baseline,
         "per_mean": float(np.mean([metrics.per_from_counts(int(c[0]), int(c[1]), int(l)) for c, l in zip(counts_h.tolist(), lens_h.tolist())])),
     }

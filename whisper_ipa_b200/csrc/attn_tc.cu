@@ -41,18 +41,9 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-// MN-major B operand with the 128-byte swizzle: rows are K indices (keys), 128 bytes = 64 N elements per row, 8-row
-// groups 1024 bytes apart (cute/atom/mma_traits_sm100.hpp: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)), m = 1 here).
-__device__ __forceinline__ uint64_t smem_desc_sw128_mnmajor(uint32_t smem_addr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
-    d |= (uint64_t)(1024u >> 4) << 16;                     // LBO: next 64-element block along N (unused, N = 64)
-    d |= (uint64_t)(1024u >> 4) << 32;                     // SBO: next group of 8 keys
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-
+// V_j is consumed as an MN-major B operand with the 128-byte swizzle: rows are K indices (keys), 128 bytes = 64 N
+// elements per row, 8-row groups 1024 bytes apart (cute/atom/mma_traits_sm100.hpp: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)),
+// m = 1 here), i.e. exactly the TMA image of a [128 keys][64] tile; 16 keys per MMA = 2048 bytes per K step.
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
@@ -104,54 +95,69 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     const uint32_t tmem_S = tmem_base;                         // + 128 * buf
     const uint32_t tmem_O = tmem_base + 256;                   // + 64 * buf
 
+    // role warps run warp-uniformly and elect one lane per issue (bare UTMALDG / UTCHMMA in SASS, descriptors in
+    // uniform registers)
     if (warp == 0) {
-        if (lane == 0) {
+        if (ptx::elect_one()) {
             ptx::mbar_arrive_expect_tx(q_full, FA_TILE_BYTES);
             ptx::tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
-            for (int j = 0; j < nb; ++j) {
-                const int s = j % FA_STAGES;
-                if (j >= FA_STAGES) ptx::mbar_wait(&kv_empty[s], ((j / FA_STAGES) & 1) ^ 1);
+        }
+        __syncwarp();
+        int s = 0;
+        uint32_t ph = 1;                                        // first pass over the ring: slots are free
+        for (int j = 0; j < nb; ++j) {
+            if (j >= FA_STAGES) ptx::mbar_wait(&kv_empty[s], ph);
+            if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
                 ptx::tma_load_3d(sK + s * FA_TILE_BYTES, &tmK, &kv_full[s], 0, j * FA_BK, bh);
                 ptx::tma_load_3d(sV + s * FA_TILE_BYTES, &tmV, &kv_full[s], 0, j * FA_BK, bh);
             }
+            __syncwarp();
+            if (++s == FA_STAGES) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = idesc_bf16(128, 128, 0);
-            constexpr uint32_t idesc_o = idesc_bf16(128, 64, 1);
-            const uint32_t q_addr = ptx::smem_u32(sQ);
-            auto issue_qk = [&](int j) {
-                const int s = j % FA_STAGES;
-                ptx::mbar_wait(&kv_full[s], (j / FA_STAGES) & 1);
-                ptx::tc_fence_after();
-                const uint32_t k_addr = ptx::smem_u32(sK + s * FA_TILE_BYTES);
+        constexpr uint32_t idesc_s = idesc_bf16(128, 128, 0);
+        constexpr uint32_t idesc_o = idesc_bf16(128, 64, 1);
+        const uint32_t q_lo = ptx::smem_desc_lo(ptx::smem_u32(sQ));
+        const uint32_t k_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sK));
+        const uint32_t p_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sP));
+        const uint32_t v_lo0 = ((ptx::smem_u32(sV) & 0x3FFFFu) >> 4) | ((1024u >> 4) << 16);     // MN-major: LBO field = 1024 B
+        auto issue_qk = [&](int j, int s, uint32_t ph) {          // S_j = Q K_j^T
+            ptx::mbar_wait(&kv_full[s], ph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                const uint32_t k_lo = k_lo0 + (uint32_t)s * (FA_TILE_BYTES >> 4);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    ptx::umma_bf16(tmem_S + (uint32_t)(j & 1) * 128u, ptx::smem_desc_sw128_kmajor(q_addr + k * 32),
-                                   ptx::smem_desc_sw128_kmajor(k_addr + k * 32), idesc_s, k != 0 ? 1u : 0u);
+                    ptx::umma_bf16(tmem_S + (uint32_t)(j & 1) * 128u, ptx::smem_desc_sw128(q_lo + 2 * k),
+                                   ptx::smem_desc_sw128(k_lo + 2 * k), idesc_s, k != 0 ? 1u : 0u);
                 ptx::umma_commit(&s_full[j & 1]);
-            };
-            ptx::mbar_wait(q_full, 0);
-            issue_qk(0);
-            for (int j = 0; j < nb; ++j) {
-                if (j + 1 < nb) issue_qk(j + 1);
-                ptx::mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
-                ptx::tc_fence_after();
-                const uint32_t p_addr = ptx::smem_u32(sP + (j & 1) * FA_P_BYTES);
-                const uint32_t v_addr = ptx::smem_u32(sV + (j % FA_STAGES) * FA_TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {                   // 16 keys per MMA
-                    const uint64_t da = ptx::smem_desc_sw128_kmajor(p_addr + (k >> 2) * FA_TILE_BYTES + (k & 3) * 32);
-                    const uint64_t db = smem_desc_sw128_mnmajor(v_addr + k * 2048);
-                    ptx::umma_bf16(tmem_O + (uint32_t)(j & 1) * 64u, da, db, idesc_o, k != 0 ? 1u : 0u);
-                }
-                ptx::umma_commit(&o_full[j & 1]);
-                ptx::umma_commit(&kv_empty[j % FA_STAGES]);
             }
+            __syncwarp();
+        };
+        ptx::mbar_wait(q_full, 0);
+        issue_qk(0, 0, 0);
+        int s = 0, s1 = 1 % FA_STAGES;                           // ring slots of blocks j and j + 1
+        uint32_t ph1 = (1 / FA_STAGES) & 1;
+        for (int j = 0; j < nb; ++j) {
+            if (j + 1 < nb) issue_qk(j + 1, s1, ph1);
+            ptx::mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {                               // O_j = P_j V_j, 16 keys per MMA
+                const uint32_t p_lo = p_lo0 + (uint32_t)(j & 1) * (FA_P_BYTES >> 4);
+                const uint32_t v_lo = v_lo0 + (uint32_t)s * (FA_TILE_BYTES >> 4);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    ptx::umma_bf16(tmem_O + (uint32_t)(j & 1) * 64u,
+                                   ptx::smem_desc_sw128(p_lo + (uint32_t)(k >> 2) * (FA_TILE_BYTES >> 4) + (uint32_t)(k & 3) * 2u),
+                                   ptx::smem_desc_sw128(v_lo + (uint32_t)k * (2048u >> 4)), idesc_o, k != 0 ? 1u : 0u);
+                ptx::umma_commit(&o_full[j & 1]);
+                ptx::umma_commit(&kv_empty[s]);
+            }
+            __syncwarp();
+            s = s1;
+            if (++s1 == FA_STAGES) { s1 = 0; ph1 ^= 1; }
         }
-        __syncwarp();
     } else {
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;                        // query row of this thread within the tile

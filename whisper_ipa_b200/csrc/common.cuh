@@ -214,12 +214,12 @@ __device__ __forceinline__ void store_group(void* base, int is_bf16, long long i
 
 // Apply the epilogue to W (4 or 8) consecutive accumulator columns n0..n0+W-1 of logical row m.
 // n0 is a multiple of W.  Columns >= ep.N are dropped.
-template <int W>
+template <int W, bool SKIP_BIAS = false>
 __device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, float* v) {
     if (n0 >= ep.N) return;
     const bool full = (n0 + W <= ep.N);
     const bool vec = ep.vec_ok && full;
-    if (ep.bias != nullptr) {
+    if (!SKIP_BIAS && ep.bias != nullptr) {
         if (vec) {
 #pragma unroll
             for (int i = 0; i < W; i += 4) {

@@ -35,6 +35,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
 
+#ifdef WIPA_GEMM_DBG
+__device__ unsigned long long g_gemm_dbg[4096 * 8];
+#define DBG_STAMP(i) do { g_gemm_dbg[(blockIdx.y * gridDim.x + blockIdx.x) % 4096 * 8 + (i)] = clock64(); } while (0)
+#else
+#define DBG_STAMP(i) do { } while (0)
+#endif
+
 template <int BN, int BOXM>
 __global__ void __launch_bounds__(192)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
@@ -55,6 +62,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int t0 = (blockIdx.y - batch * tiles_per_batch) * TC_BM;
 
     pdl_launch_dependents();                                  // the next kernel may start its own prologue now
+    if (threadIdx.x == 0) DBG_STAMP(0);
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmW);
@@ -74,45 +82,63 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Role warps run warp-uniformly and elect one lane per issue: ptxas then keeps descriptors and barrier addresses
+    // in uniform registers and emits bare UTMALDG / UTCHMMA (under `if (lane == 0)` every such instruction is wrapped
+    // in an ELECT / BRA.U.ANY loop plus R2UR moves, ~135 cycles per MMA issue as measured with clock stamps).
     if (warp == 0) {
-        if (lane == 0) {
-            // weights are static: fill the ring with W tiles BEFORE waiting for the previous kernel, then the A tiles
-            const int pre = num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES;
+        // weights are static: fill the ring with W tiles BEFORE waiting for the previous kernel, then the A tiles
+        const int pre = num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES;
+        if (ptx::elect_one()) {
             for (int kb = 0; kb < pre; ++kb) {
                 ptx::mbar_arrive_expect_tx(&full[kb], Cfg::A_BYTES + Cfg::W_BYTES);
                 ptx::tma_load_2d(sW + kb * Cfg::W_BYTES, &tmW, &full[kb], kb * TC_BK, n0);
             }
-            pdl_wait();
+            DBG_STAMP(1);
+        }
+        __syncwarp();
+        pdl_wait();
+        if (ptx::elect_one()) {
+            DBG_STAMP(2);
             for (int kb = 0; kb < pre; ++kb)
                 ptx::tma_load_3d(sA + kb * Cfg::A_BYTES, &tmA, &full[kb], kb * TC_BK, t0, batch);
-            for (int kb = pre; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (kb / Cfg::STAGES) & 1;
-                ptx::mbar_wait(&empty[s], ph ^ 1);
+        }
+        __syncwarp();
+        int s = 0;
+        uint32_t ph = 0;                                       // parity of the ring pass that filled slot s last
+        for (int kb = pre; kb < num_kb; ++kb) {
+            ptx::mbar_wait(&empty[s], ph);
+            if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::W_BYTES);
                 ptx::tma_load_3d(sA + s * Cfg::A_BYTES, &tmA, &full[s], kb * TC_BK, t0, batch);
                 ptx::tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, &full[s], kb * TC_BK, n0);
             }
+            __syncwarp();
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
-        __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = ptx::idesc_bf16_f32(TC_BM, BN);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % Cfg::STAGES;
-                const uint32_t ph = (kb / Cfg::STAGES) & 1;
-                ptx::mbar_wait(&full[s], ph);
-                ptx::tc_fence_after();
-                const uint32_t a_addr = ptx::smem_u32(sA + s * Cfg::A_BYTES);
-                const uint32_t w_addr = ptx::smem_u32(sW + s * Cfg::W_BYTES);
+        constexpr uint32_t idesc = ptx::idesc_bf16_f32(TC_BM, BN);
+        const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sA));
+        const uint32_t w_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sW));
+        int s = 0;
+        uint32_t ph = 0;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            ptx::mbar_wait(&full[s], ph);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+                if (kb == 0) DBG_STAMP(3);
+                const uint32_t a_lo = a_lo0 + (uint32_t)s * (Cfg::A_BYTES >> 4);
+                const uint32_t w_lo = w_lo0 + (uint32_t)s * (Cfg::W_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k) {
-                    const uint64_t da = ptx::smem_desc_sw128_kmajor(a_addr + k * 32);
-                    const uint64_t db = ptx::smem_desc_sw128_kmajor(w_addr + k * 32);
-                    ptx::umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-                }
+                for (int k = 0; k < TC_BK / 16; ++k)
+                    ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(a_lo + 2 * k), ptx::smem_desc_sw128(w_lo + 2 * k), idesc,
+                                   (kb | k) != 0 ? 1u : 0u);
                 ptx::umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
             }
+            __syncwarp();
+            if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        if (ptx::elect_one()) {
+            DBG_STAMP(4);
             ptx::umma_commit(tmem_full);                     // accumulator complete
         }
         __syncwarp();
@@ -123,9 +149,63 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool row_ok = t < ep.M_rows;
         const int m = batch * a_rpb + t;
         pdl_wait();                                          // the epilogue reads / writes activations of earlier kernels
-        ptx::mbar_wait(tmem_full, 0);
-        ptx::tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        if (BN == 32 && ep.mode != EPI_ARGMAX) {
+            // Latency-bound decode tiles: fetch bias and residual for the whole 32-column row segment BEFORE the
+            // accumulator is ready, so that after the last MMA only tcgen05.ld + adds + stores remain.
+            const bool active = row_ok && !(BOXM == 64 && quarter >= 2);
+            const bool fast = ep.vec_ok && (n0 + 32 <= ep.N);
+            float add[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) add[i] = 0.f;
+            long long row = 0;
+            if (active && fast) {
+                if (ep.bias != nullptr) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 b = *reinterpret_cast<const float4*>(ep.bias + n0 + i);
+                        add[i] = b.x; add[i + 1] = b.y; add[i + 2] = b.z; add[i + 3] = b.w;
+                    }
+                }
+                if (ep.mode == EPI_RESADD) {
+                    const int ob = m / ep.o_rpb;
+                    row = (long long)ob * ep.o_bstride + (long long)(m - ob * ep.o_rpb) * ep.ldo + n0;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        const float4 x = *reinterpret_cast<const float4*>(ep.resid + row + i);
+                        add[i] += x.x; add[i + 1] += x.y; add[i + 2] += x.z; add[i + 3] += x.w;
+                    }
+                }
+            }
+            ptx::mbar_wait(tmem_full, 0);
+            if (threadIdx.x == 64) DBG_STAMP(5);
+            ptx::tc_fence_after();
+            if (!(BOXM == 64 && quarter >= 2)) {                 // warp-uniform: tcgen05.ld is a warp-collective
+                float v[32];
+                ptx::tmem_ld32(taddr, v);
+                ptx::tmem_ld_wait();
+                if (!active) {
+                    // padding row of the M tile: nothing to store
+                } else if (fast) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] += add[i];
+                    if (ep.mode == EPI_RESADD) {
+                        float* o = reinterpret_cast<float*>(ep.out) + row;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 8) epi_group<8, true>(ep, m, n0 + i, v + i);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 8) epi_group<8>(ep, m, n0 + i, v + i);
+                }
+            }
+        } else {
+        ptx::mbar_wait(tmem_full, 0);
+        if (threadIdx.x == 64) DBG_STAMP(5);
+        ptx::tc_fence_after();
         if (BOXM == 64 && quarter >= 2) {
             // lanes 64..127 hold garbage (see TcCfg); nothing to do
         } else if (ep.mode == EPI_ARGMAX) {
@@ -159,10 +239,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
         }
+        }
     }
+    if (threadIdx.x == 64) DBG_STAMP(6);
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (threadIdx.x == 0) DBG_STAMP(7);
 }
 
 int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
@@ -212,6 +295,15 @@ int wipa_init_tma() {
 }
 
 int gemm_bf16_num_tiles(int N, int block_n) { return cdiv(N, block_n); }
+
+extern "C" int wipa_debug_gemm_stamps(unsigned long long* host_out, int n) {
+#ifdef WIPA_GEMM_DBG
+    return cudaMemcpyFromSymbol(host_out, g_gemm_dbg, sizeof(unsigned long long) * (size_t)n) == cudaSuccess ? 0 : -2;
+#else
+    (void)host_out; (void)n;
+    return WIPA_EUNSUPPORTED;
+#endif
+}
 
 int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep_in, int block_n,
                      cudaStream_t st) {

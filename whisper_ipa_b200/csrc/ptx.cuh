@@ -150,6 +150,14 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_kmajor(uint32_t smem_addr) {
     return d;
 }
 
+// The same descriptor split so that the per-MMA work is one add: lo = (addr >> 4) | LBO field, advanced by (bytes >> 4)
+// (the 14-bit address field cannot carry: shared memory is < 256 KB); hi is constant.
+__device__ __forceinline__ uint32_t smem_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t lo) {
+    constexpr uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);      // SBO | version 1 (bit 46) | SWIZZLE_128B (bits 61-63)
+    return ((uint64_t)hi << 32) | lo;
+}
+
 // Instruction descriptor for kind::f16, A/B = bf16 K-major, D = fp32, M x N tile
 __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
