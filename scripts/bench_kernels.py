@@ -50,7 +50,7 @@ def main():
             A = torch.randn(M, K, device="cuda").to(torch.bfloat16)
             W = torch.randn(N, K, device="cuda").to(torch.bfloat16)
             Cc = torch.empty(M, N, device="cuda")
-            for bn in (128, 256):
+            for bn in (128, 0):
                 us = timeit(lambda: _lib.check(lib.wipa_test_gemm_bf16(A.data_ptr(), W.data_ptr(), None, Cc.data_ptr(), M, N, K, bn, st), "g"), reps=5)
                 print(f"gemm_bf16 M={M} N={N} K={K} bn={bn} (f32 out): {us:9.1f} us  {2.0 * M * N * K / us / 1e6:7.1f} TFLOP/s")
             del A, W, Cc

@@ -47,9 +47,23 @@ def test_gemm_bf16_tcgen05(lib, bn, M, N, K):
     assert err < 2e-4 * max(1.0, ref.abs().max().item()), f"max err {err}"
 
 
-@pytest.mark.parametrize("is_bf16", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (3000, 768, 768), (1500, 1000, 1536), (40000, 520, 384)])
+def test_gemm_bf16_persistent(lib, M, N, K):
+    """block_n = 0 selects the persistent 128 x 256 kernel (double-buffered TMEM accumulators, staged epilogue)."""
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    W = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g)
+    Cc = torch.full((M, N), float("nan"), device="cuda")
+    lib.check(lib.lib().wipa_test_gemm_bf16(A.data_ptr(), W.data_ptr(), b.data_ptr(), Cc.data_ptr(), M, N, K, 0, _st()), "gemm_bf16")
+    ref = (A.float() @ W.float().T + b)
+    err = (Cc - ref).abs().max().item()
+    assert err < 5e-4 * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.parametrize("is_bf16,bn", [(0, 128), (1, 128), (1, 0)])
 @pytest.mark.parametrize("C_in,stride,T_out", [(80, 1, 3000), (128, 1, 3000), (384, 2, 1500)])
-def test_gemm_conv_rows(lib, is_bf16, C_in, stride, T_out):
+def test_gemm_conv_rows(lib, is_bf16, bn, C_in, stride, T_out):
     """conv1d(k=3, p=1, stride) as a GEMM over overlapping rows of a zero-row-padded channels-last signal."""
     B, N, T_in = 2, 128, 3000
     g = torch.Generator(device="cuda").manual_seed(C_in + stride)
@@ -61,7 +75,7 @@ def test_gemm_conv_rows(lib, is_bf16, C_in, stride, T_out):
     wg = w.permute(0, 2, 1).reshape(N, 3 * C_in).contiguous().to(dt)           # k = tap * C + c
     out = torch.full((B * T_out, N), float("nan"), device="cuda")
     lib.check(lib.lib().wipa_test_gemm_rows(rows.data_ptr(), is_bf16, stride * C_in, T_out, (T_in + 2) * C_in, B,
-                                            wg.data_ptr(), out.data_ptr(), N, 3 * C_in, 128, _st()), "gemm_rows")
+                                            wg.data_ptr(), out.data_ptr(), N, 3 * C_in, bn, _st()), "gemm_rows")
     ref = torch.nn.functional.conv1d(rows[:, 1:-1].transpose(1, 2).double(), wg.double().reshape(N, 3, C_in).permute(0, 2, 1),
                                      stride=stride, padding=1).transpose(1, 2).reshape(B * T_out, N).float()
     err = (out - ref).abs().max().item()

@@ -2,7 +2,7 @@
 //   enc_attention_kernel   : encoder self-attention (non-causal, 1500 x 1500 x 64 per head), flash-style
 //                            online softmax, fp32 math on CUDA cores.  This is the fp32-path kernel
 //                            (HF:models/whisper/modeling_whisper.py:284-357 with scaling folded into q).
-//   self_attention_kernel  : one decode step of decoder self-attention over the paged KV cache.
+//   self_attention_kernel  : one decode step of decoder self-attention over the paged KV cache (warp per (seq, head)).
 //   cross_attention_kernel : one decode step of cross-attention against the cached encoder K/V —
 //                            the dominant HBM stream of the whole decode.
 #include "common.cuh"
@@ -219,67 +219,98 @@ __device__ __forceinline__ float dot64<bf16>(const bf16* kp, const float* qs) {
     return acc;
 }
 
+// One warp per (sequence, head), four independent warps per CTA, no block-level synchronisation:
+//   scores   lane-per-key: lane l owns keys l, l+32, ... (<= 14 of them at 448 positions); it reads the whole 64-element
+//            K row (one full 128 / 256-byte line per lane) and dots it with q held in registers -> no shuffles per key
+//   softmax  one warp max + one warp sum; probabilities parked in shared memory (keeps the code small: the fully
+//            unrolled register version was 125 KB of SASS and thrashed the instruction cache)
+//   P.V      lane-per-dim: lane l owns output dims 2l, 2l+1; p_j is a shared-memory broadcast and the V row is one
+//            coalesced line per key, a whole page (16 keys) of loads in flight at a time
+template <typename T>
+__device__ __forceinline__ float2 ld_v2(const T* p);
+template <> __device__ __forceinline__ float2 ld_v2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
+template <> __device__ __forceinline__ float2 ld_v2<bf16>(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+__device__ __forceinline__ void st_v2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st_v2(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+
 template <typename T>
 __global__ void __launch_bounds__(128)
 self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, const T* __restrict__ vpool,
                       const int* __restrict__ block_table, int bt_stride, const int* __restrict__ pos_ptr,
-                      T* __restrict__ out, int H) {
-    __shared__ float qs[64];
-    __shared__ float sc[WIPA_MAX_TGT];
-    __shared__ float red[4];
-    __shared__ float part[2][64];
-    const int h = blockIdx.x, b = blockIdx.y;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int d = H * 64;
+                      T* __restrict__ out, int H, int n_pairs) {
+    __shared__ float sc_all[4][WIPA_MAX_TGT];                      // scores / probabilities of this warp's keys
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = blockIdx.x * 4 + warp;
     pdl_launch_dependents();
     pdl_wait();
+    if (pair >= n_pairs) return;
+    float* sc = sc_all[warp];
+    const int b = pair / H, h = pair - b * H;
+    const int d = H * 64;
     const int len = *pos_ptr + 1;
     const int* bt = block_table + (size_t)b * bt_stride;
-    if (tid < 64) qs[tid] = q[(size_t)b * d + h * 64 + tid];
-    __syncthreads();
-
+    float qr[64];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 t = qp[i];
+            qr[4 * i] = t.x; qr[4 * i + 1] = t.y; qr[4 * i + 2] = t.z; qr[4 * i + 3] = t.w;
+        }
+    }
     float mx = -INFINITY;
-    for (int j = tid; j < len; j += 128) {
+#pragma unroll 2
+    for (int j = lane; j < len; j += 32) {
         const int page = bt[j / WIPA_PAGE];
         const T* kp = kpool + (((size_t)page * H + h) * WIPA_PAGE + (j % WIPA_PAGE)) * 64;
-        const float s = dot64<T>(kp, qs);
+        const float s = dot64<T>(kp, qr);
         sc[j] = s;
         mx = fmaxf(mx, s);
     }
     mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    __syncthreads();
     float sum = 0.f;
-    for (int j = tid; j < len; j += 128) {
+    for (int j = lane; j < len; j += 32) {
         const float p = expf(sc[j] - mx);
         sc[j] = p;
         sum += p;
     }
     sum = warp_sum(sum);
-    if (lane == 0) red[warp] = sum;
-    __syncthreads();
-    sum = red[0] + red[1] + red[2] + red[3];
-    const float inv = 1.0f / sum;
-
-    const int e = tid & 63, half = tid >> 6;
-    float acc = 0.f;
-    for (int j = half; j < len; j += 2) {
-        const int page = bt[j / WIPA_PAGE];
-        const T* vp = vpool + (((size_t)page * H + h) * WIPA_PAGE + (j % WIPA_PAGE)) * 64;
-        acc = fmaf(sc[j], to_f32(vp[e]), acc);
+    __syncwarp();
+    float a0 = 0.f, a1 = 0.f;
+    const size_t hoff = (size_t)h * WIPA_PAGE * 64 + 2 * lane;
+#pragma unroll 1
+    for (int pg = 0; pg * WIPA_PAGE < len; ++pg) {                 // one page (16 keys) per iteration: 16 loads in flight
+        const T* vp = vpool + (size_t)bt[pg] * H * WIPA_PAGE * 64 + hoff;
+        const int n = min(WIPA_PAGE, len - pg * WIPA_PAGE);
+        if (n == WIPA_PAGE) {
+            float2 v2[WIPA_PAGE];
+#pragma unroll
+            for (int jj = 0; jj < WIPA_PAGE; ++jj) v2[jj] = ld_v2<T>(vp + jj * 64);
+#pragma unroll
+            for (int jj = 0; jj < WIPA_PAGE; ++jj) {
+                const float p = sc[pg * WIPA_PAGE + jj];
+                a0 = fmaf(p, v2[jj].x, a0);
+                a1 = fmaf(p, v2[jj].y, a1);
+            }
+        } else {
+            for (int jj = 0; jj < n; ++jj) {
+                const float p = sc[pg * WIPA_PAGE + jj];
+                const float2 v2 = ld_v2<T>(vp + jj * 64);
+                a0 = fmaf(p, v2.x, a0);
+                a1 = fmaf(p, v2.y, a1);
+            }
+        }
     }
-    part[half][e] = acc;
-    __syncthreads();
-    if (tid < 64) out[(size_t)b * d + h * 64 + tid] = from_f32<T>((part[0][tid] + part[1][tid]) * inv);
+    const float inv = 1.0f / sum;
+    st_v2(out + (size_t)b * d + h * 64 + 2 * lane, a0 * inv, a1 * inv);
 }
 
 template <typename T>
 int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
                           const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st) {
-    dim3 grid(H, Bs);
-    WIPA_CUDA_CHECK(wipa_launch(self_attention_kernel<T>, grid, dim3(128), (size_t)0, st, q, kpool, vpool, block_table, bt_stride, pos_ptr, out, H));
+    const int n_pairs = Bs * H;
+    WIPA_CUDA_CHECK(wipa_launch(self_attention_kernel<T>, dim3(cdiv(n_pairs, 4)), dim3(128), (size_t)0, st, q, kpool, vpool,
+                                block_table, bt_stride, pos_ptr, out, H, n_pairs));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

@@ -331,6 +331,7 @@ __device__ __forceinline__ float warp_max(float v) {
 int launch_gemm_f32(const AOperand& a, const float* W, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
 int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep, int block_n,
                      cudaStream_t st);
+int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep, cudaStream_t st);   // gemm_tc2.cu
 int wipa_init_tma();   // resolves cuTensorMapEncodeTiled through the runtime; idempotent
 
 template <typename T>

@@ -85,6 +85,7 @@ struct wipa_ctx {
     cudaStream_t cap_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy default stream)
     int n_logit_tiles;
     int bn_enc, bn_dec, bn_logits, ca_split;
+    int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
     int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (bf16 path)
     int64_t decode_steps = 0;
     size_t workspace_bytes = 0, xkv_bytes = 0;
@@ -231,7 +232,11 @@ EpiParams epi(int mode, int M, int N) {
 }
 
 int gemm(wipa_ctx* c, const AOperand& a, const void* W, int M, int N, int K, const EpiParams& ep, int bn, cudaStream_t st) {
-    if (c->bf) return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, bn, st);
+    if (c->bf) {
+        // bn == 0: the persistent 128 x 256 kernel when there are at least two waves of its tiles, else 128 x 128 tiles
+        if (bn == 0 && (long long)cdiv(M, 128) * cdiv(N, 256) < 2 * 148) bn = 128;
+        return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, bn, st);
+    }
     return launch_gemm_f32(a, (const float*)W, M, N, K, ep, st);
 }
 
@@ -381,38 +386,41 @@ DecodeState make_state(wipa_ctx* c, int n_forced, int max_new, int eot) {
 int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, float* logits_out, long long ldo, cudaStream_t st) {
     const wipa_arch& a = c->a;
     const int d = a.d_model, H = a.heads, ffn = a.ffn, V = a.vocab;
+    const int skip = c->skip_mask;       // ablation bits: 1 LN, 2 self-attn, 4 cross-attn, 8 qkv, 16 d x d GEMMs, 32 fc1, 64 fc2, 128 logits
     if (c->bf) WIPA_TRY(launch_embed<bf16>((const bf16*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
     else WIPA_TRY(launch_embed<float>((const float*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
     for (int l = 0; l < a.dec_layers; ++l) {
         const DecLayer& L = c->dec[l];
         char* kp = (char*)c->kpool + (size_t)l * c->pool_layer_stride * c->esz;
         char* vp = (char*)c->vpool + (size_t)l * c->pool_layer_stride * c->esz;
-        WIPA_TRY(ln(c, c->dx, L.ln1_w, L.ln1_b, c->dh, S, st));
+        if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln1_w, L.ln1_b, c->dh, S, st));
         {
             EpiParams ep = epi(EPI_QKV_DEC, S, 3 * d);
             ep.bias = L.qkv_b; ep.out = c->dq; ep.out1 = kp; ep.out2 = vp; ep.out_bf16 = c->bf;
             ep.H = H; ep.d = d; ep.pos_ptr = c->d_pos; ep.block_table = c->block_table; ep.bt_stride = c->pages_per_seq;
-            WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.qkv_w, S, 3 * d, d, ep, c->bn_dec, st));
+            if (!(skip & 8)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.qkv_w, S, 3 * d, d, ep, c->bn_dec, st));
         }
-        if (c->bf) WIPA_TRY(launch_self_attention<bf16>(c->dq, (const bf16*)kp, (const bf16*)vp, c->block_table, c->pages_per_seq,
+        if (skip & 2) {}
+        else if (c->bf) WIPA_TRY(launch_self_attention<bf16>(c->dq, (const bf16*)kp, (const bf16*)vp, c->block_table, c->pages_per_seq,
                                                         c->d_pos, (bf16*)c->dattn, S, H, st));
         else WIPA_TRY(launch_self_attention<float>(c->dq, (const float*)kp, (const float*)vp, c->block_table, c->pages_per_seq,
                                                    c->d_pos, (float*)c->dattn, S, H, st));
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.o_b; ep.out = c->dx; ep.resid = c->dx;
-            WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.o_w, S, d, d, ep, c->bn_dec, st));
+            if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.o_w, S, d, d, ep, c->bn_dec, st));
         }
-        WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
+        if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
         {
             EpiParams ep = epi(EPI_STORE, S, d);
             ep.bias = L.cq_b; ep.out = c->dq; ep.out_bf16 = 0;
-            WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.cq_w, S, d, d, ep, c->bn_dec, st));
+            if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.cq_w, S, d, d, ep, c->bn_dec, st));
         }
         {
             const char* xk = (const char*)c->xkv + (size_t)(2 * l) * c->xkv_which_stride * c->esz;
             const char* xv = (const char*)c->xkv + (size_t)(2 * l + 1) * c->xkv_which_stride * c->esz;
-            if (c->bf) WIPA_TRY(launch_cross_attention<bf16>(c->dq, (const bf16*)xk, (const bf16*)xv, c->utt_of_seq, (bf16*)c->dattn,
+            if (skip & 4) {}
+            else if (c->bf) WIPA_TRY(launch_cross_attention<bf16>(c->dq, (const bf16*)xk, (const bf16*)xv, c->utt_of_seq, (bf16*)c->dattn,
                                                              c->ca_part, c->ca_counters, S, H, c->ca_split, st));
             else WIPA_TRY(launch_cross_attention<float>(c->dq, (const float*)xk, (const float*)xv, c->utt_of_seq, (float*)c->dattn,
                                                         c->ca_part, c->ca_counters, S, H, c->ca_split, st));
@@ -420,18 +428,19 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.co_b; ep.out = c->dx; ep.resid = c->dx;
-            WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.co_w, S, d, d, ep, c->bn_dec, st));
+            if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.co_w, S, d, d, ep, c->bn_dec, st));
         }
-        WIPA_TRY(ln(c, c->dx, L.ln3_w, L.ln3_b, c->dh, S, st));
+        if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln3_w, L.ln3_b, c->dh, S, st));
         {
             EpiParams ep = epi(EPI_GELU, S, ffn);
             ep.bias = L.fc1_b; ep.out = c->dffn; ep.out_bf16 = c->bf;
-            WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.fc1_w, S, ffn, d, ep, c->bn_dec, st));
+            // N = ffn tiles of 32 columns would not fit one wave once S needs two M tiles: use 64-wide tiles then
+            if (!(skip & 32)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.fc1_w, S, ffn, d, ep, (S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec, st));
         }
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.fc2_b; ep.out = c->dx; ep.resid = c->dx;
-            WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, c->bn_dec, st));
+            if (!(skip & 64)) WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, c->bn_dec, st));
         }
     }
     int n_tiles = 1;
@@ -443,7 +452,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             ep.pmax = c->pmax; ep.pidx = c->pidx;
             ep.mask_always = c->mask_always; ep.mask_begin = c->mask_begin; ep.step_ptr = c->d_step;
             n_tiles = c->n_logit_tiles;
-            WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits, st));
+            if (!(skip & 128)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits, st));
         } else {
             float* dst = logits_mode == 2 ? logits_out : c->logits;
             EpiParams ep = epi(EPI_STORE, S, V);
@@ -513,12 +522,13 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->enc_mb = env_int("WIPA_ENC_MB", 32);
     if (c->enc_mb > max_batch) c->enc_mb = max_batch;
     c->pages_per_seq = WIPA_MAX_TGT / WIPA_PAGE;
-    c->bn_enc = env_int("WIPA_BN_ENC", 128);
+    c->bn_enc = env_int("WIPA_BN_ENC", 0);
     c->bn_dec = env_int("WIPA_BN_DEC", 32);
     c->bn_logits = env_int("WIPA_BN_LOGITS", 128);
     c->ca_split = env_int("WIPA_CA_SPLIT", cross_attention_default_split((int)c->esz, max_batch, arch->heads));
     c->n_logit_tiles = cdiv(arch->vocab, c->bn_logits);
     c->enc_attn_simt = env_int("WIPA_ENC_ATTN_SIMT", 0);
+    c->skip_mask = env_int("WIPA_SKIP_MASK", 0);
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
@@ -723,7 +733,7 @@ extern "C" int wipa_decode_greedy(wipa_ctx* c, int B, const wipa_decode_opts* o,
     int* h_done = c->h_pinned;
     *h_done = 0;
     while (s < total_steps) {
-        int burst = total_steps - s < 8 ? total_steps - s : 8;
+        int burst = total_steps - s < 32 ? total_steps - s : 32;
         for (int i = 0; i < burst; ++i) {
             if (ge) { WIPA_CUDA_CHECK(cudaGraphLaunch(ge->exec, st)); g_wipa_launches += ge->nodes; }
             else WIPA_TRY(decode_step(c, S, ds, 1, nullptr, 0, st));

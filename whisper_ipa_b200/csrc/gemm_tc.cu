@@ -1,7 +1,7 @@
 // bf16 path GEMM on the 5th-generation tensor cores:  C[M,N] = A[M,K] * W[N,K]^T, fp32 accumulate in TMEM.
 //
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles of A (128 x 64) and W (BN x 64), 128B-swizzled,
-//               into a STAGES-deep shared-memory ring guarded by full/empty mbarriers
+//               into a STAGES-deep shared-memory ring guarded by full/empty mbarriers (KPB k-blocks per ring slot)
 //   warp 1      allocates TMEM, then one elected lane issues tcgen05.mma (M=128, N=BN, K=16) x 4 per k-block and
 //               tcgen05.commit's the stage back to the producer; the last commit signals the epilogue
 //   warps 2-5   epilogue: tcgen05.ld the 128 x BN fp32 accumulator (one row per thread) and apply the shared
@@ -24,10 +24,15 @@ constexpr int TC_BK = 64;
 template <int BN, int BOXM> struct TcCfg {
     static constexpr int A_BYTES = BOXM * TC_BK * 2;
     static constexpr int W_BYTES = BN * TC_BK * 2;
-    // ring depth: small-N tiles are the latency-bound decode GEMMs -> keep (nearly) all of K in flight
-    static constexpr int STAGES = BN == 32 ? (BOXM == 64 ? 12 : 8) : (BN == 64 ? 6 : (BN == 128 ? 3 : 4));
+    // A ring slot holds KPB consecutive k-blocks behind ONE full/empty barrier pair.  The narrow tiles are the
+    // latency-bound decode GEMMs: their MMAs are short (32 cycles each, bound by the A read from shared memory), so a
+    // barrier round trip per 64-wide k-block (~150 cycles of try_wait + commit) would dominate the issue loop.
+    static constexpr int KPB = BN == 32 ? (BOXM == 64 ? 4 : 2) : (BN == 64 ? 2 : 1);
+    static constexpr int STAGES = BN == 32 ? (BOXM == 64 ? 3 : 4) : (BN == 64 ? 3 : (BN == 128 ? 3 : 4));
+    static constexpr int STAGE_A = KPB * A_BYTES;
+    static constexpr int STAGE_W = KPB * W_BYTES;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-    static constexpr int SMEM = STAGES * (A_BYTES + W_BYTES) + (TC_BM - BOXM) * TC_BK * 2 /*over-read*/ + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int SMEM = STAGES * (STAGE_A + STAGE_W) + (TC_BM - BOXM) * TC_BK * 2 /*over-read*/ + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -50,8 +55,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
-    uint8_t* sW = smem + Cfg::STAGES * Cfg::A_BYTES + (TC_BM - BOXM) * TC_BK * 2;
-    uint64_t* full = reinterpret_cast<uint64_t*>(sW + Cfg::STAGES * Cfg::W_BYTES);
+    uint8_t* sW = smem + Cfg::STAGES * Cfg::STAGE_A + (TC_BM - BOXM) * TC_BK * 2;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sW + Cfg::STAGES * Cfg::STAGE_W);
     uint64_t* empty = full + Cfg::STAGES;
     uint64_t* tmem_full = empty + Cfg::STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
@@ -87,11 +92,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // in an ELECT / BRA.U.ANY loop plus R2UR moves, ~135 cycles per MMA issue as measured with clock stamps).
     if (warp == 0) {
         // weights are static: fill the ring with W tiles BEFORE waiting for the previous kernel, then the A tiles
-        const int pre = num_kb < Cfg::STAGES ? num_kb : Cfg::STAGES;
+        constexpr int KPB = Cfg::KPB;
+        const int num_g = (num_kb + KPB - 1) / KPB;               // ring slots to fill in total
+        const int pre = num_g < Cfg::STAGES ? num_g : Cfg::STAGES;
         if (ptx::elect_one()) {
-            for (int kb = 0; kb < pre; ++kb) {
-                ptx::mbar_arrive_expect_tx(&full[kb], Cfg::A_BYTES + Cfg::W_BYTES);
-                ptx::tma_load_2d(sW + kb * Cfg::W_BYTES, &tmW, &full[kb], kb * TC_BK, n0);
+            for (int g = 0; g < pre; ++g) {
+                const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
+                ptx::mbar_arrive_expect_tx(&full[g], (uint32_t)nk * (Cfg::A_BYTES + Cfg::W_BYTES));
+                for (int i = 0; i < nk; ++i)
+                    ptx::tma_load_2d(sW + g * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[g], (g * KPB + i) * TC_BK, n0);
             }
             DBG_STAMP(1);
         }
@@ -99,40 +108,55 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         pdl_wait();
         if (ptx::elect_one()) {
             DBG_STAMP(2);
-            for (int kb = 0; kb < pre; ++kb)
-                ptx::tma_load_3d(sA + kb * Cfg::A_BYTES, &tmA, &full[kb], kb * TC_BK, t0, batch);
+            for (int g = 0; g < pre; ++g) {
+                const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
+                for (int i = 0; i < nk; ++i)
+                    ptx::tma_load_3d(sA + g * Cfg::STAGE_A + i * Cfg::A_BYTES, &tmA, &full[g], (g * KPB + i) * TC_BK, t0, batch);
+            }
         }
         __syncwarp();
         int s = 0;
         uint32_t ph = 0;                                       // parity of the ring pass that filled slot s last
-        for (int kb = pre; kb < num_kb; ++kb) {
+        for (int g = pre; g < num_g; ++g) {
             ptx::mbar_wait(&empty[s], ph);
             if (ptx::elect_one()) {
-                ptx::mbar_arrive_expect_tx(&full[s], Cfg::A_BYTES + Cfg::W_BYTES);
-                ptx::tma_load_3d(sA + s * Cfg::A_BYTES, &tmA, &full[s], kb * TC_BK, t0, batch);
-                ptx::tma_load_2d(sW + s * Cfg::W_BYTES, &tmW, &full[s], kb * TC_BK, n0);
+                const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
+                ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)nk * (Cfg::A_BYTES + Cfg::W_BYTES));
+                for (int i = 0; i < nk; ++i) {
+                    ptx::tma_load_3d(sA + s * Cfg::STAGE_A + i * Cfg::A_BYTES, &tmA, &full[s], (g * KPB + i) * TC_BK, t0, batch);
+                    ptx::tma_load_2d(sW + s * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[s], (g * KPB + i) * TC_BK, n0);
+                }
             }
             __syncwarp();
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = ptx::idesc_bf16_f32(TC_BM, BN);
+        constexpr int KPB = Cfg::KPB;
+        const int num_g = (num_kb + KPB - 1) / KPB;
         const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sA));
         const uint32_t w_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sW));
         int s = 0;
         uint32_t ph = 0;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int g = 0; g < num_g; ++g) {
             ptx::mbar_wait(&full[s], ph);
             ptx::tc_fence_after();
             if (ptx::elect_one()) {
-                if (kb == 0) DBG_STAMP(3);
-                const uint32_t a_lo = a_lo0 + (uint32_t)s * (Cfg::A_BYTES >> 4);
-                const uint32_t w_lo = w_lo0 + (uint32_t)s * (Cfg::W_BYTES >> 4);
+                if (g == 0) DBG_STAMP(3);
+                const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
+                const uint32_t a_lo = a_lo0 + (uint32_t)s * (Cfg::STAGE_A >> 4);
+                const uint32_t w_lo = w_lo0 + (uint32_t)s * (Cfg::STAGE_W >> 4);
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)
-                    ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(a_lo + 2 * k), ptx::smem_desc_sw128(w_lo + 2 * k), idesc,
-                                   (kb | k) != 0 ? 1u : 0u);
-                ptx::umma_commit(&empty[s]);                 // frees the smem stage when these MMAs retire
+                for (int i = 0; i < KPB; ++i) {
+                    if (i < nk) {
+#pragma unroll
+                        for (int k = 0; k < TC_BK / 16; ++k)
+                            ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(a_lo + (uint32_t)i * (Cfg::A_BYTES >> 4) + 2 * k),
+                                           ptx::smem_desc_sw128(w_lo + (uint32_t)i * (Cfg::W_BYTES >> 4) + 2 * k), idesc,
+                                           (g | i | k) != 0 ? 1u : 0u);
+                    }
+                }
+                ptx::umma_commit(&empty[s]);                 // frees the ring slot when these MMAs retire
             }
             __syncwarp();
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -307,6 +331,7 @@ extern "C" int wipa_debug_gemm_stamps(unsigned long long* host_out, int n) {
 
 int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep_in, int block_n,
                      cudaStream_t st) {
+    if (block_n == 0) return launch_gemm_bf16_persistent(a, W, M, N, K, ep_in, st);     // 128 x 256 persistent kernel
     WIPA_TRY(wipa_init_tma());
     WIPA_CHECK(K % 8 == 0 && a.lda % 8 == 0 && a.a_bstride % 8 == 0, WIPA_EINVAL,
                "gemm_bf16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");

@@ -1,0 +1,239 @@
+// Encoder-side bf16 GEMM on tcgen05: persistent, warp-specialised, double-buffered accumulators.
+//
+//   C[M,N] = A[M,K] * W[N,K]^T with M in the tens of thousands (32 clips x 1500 frames per encoder micro-batch).
+//
+//   grid        one CTA per SM; CTA i walks tiles i, i + grid, ... in n-fastest order (CTAs that run together share
+//               the A tile and all of W in L2)
+//   warp 0      TMA producer: A (128 x 64) and W (256 x 64) k-blocks, 128B-swizzled, 3-deep ring across tile boundaries
+//   warp 1      tcgen05 issuer: M128 x N256 x K16 MMAs (128 cycles each, 96 B/cycle of operand reads - under the 128
+//               B/cycle shared-memory limit that caps N = 128 tiles) into one of TWO 256-column TMEM accumulators
+//   warps 2-9   epilogue, overlapped with the next tile's main loop: tcgen05.ld (lane = row) -> fp32 staging tile in
+//               shared memory -> re-read as (row, 8-column) items so that bias / residual loads and the output stores
+//               are coalesced 128..256-byte row segments -> shared epilogue (bias, GELU, residual, head split, ...)
+//
+// The A operand is the same 3-D tensor map as in gemm_tc.cu (rows may overlap: conv1d(k=3) as a GEMM).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+constexpr int G2_BM = 128;
+constexpr int G2_BN = 256;
+constexpr int G2_BK = 64;
+constexpr int G2_STAGES = 3;
+constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;                 // 16 KB
+constexpr int G2_W_BYTES = G2_BN * G2_BK * 2;                 // 32 KB
+constexpr int G2_LDS = 68;                                    // staging row pitch in floats (64 + 4: conflict-free float4 rows)
+constexpr int G2_STAGE_F = G2_BM * G2_LDS;                    // floats per staging tile (128 rows x 64 columns)
+constexpr int G2_SMEM = G2_STAGES * (G2_A_BYTES + G2_W_BYTES) + 2 * G2_STAGE_F * 4 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int G2_THREADS = 64 + 256;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g2_encode = nullptr;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
+                            int tiles_per_batch, int n_mtiles, int n_ntiles, int a_rpb, EpiParams ep) {
+    extern __shared__ uint8_t g2_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA = smem;
+    uint8_t* sW = sA + G2_STAGES * G2_A_BYTES;
+    float* stage_f = reinterpret_cast<float*>(sW + G2_STAGES * G2_W_BYTES);       // [2 halves][128][G2_LDS]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage_f + 2 * G2_STAGE_F);
+    uint64_t* empty = full + G2_STAGES;
+    uint64_t* tmem_full = empty + G2_STAGES;                  // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                     // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = n_mtiles * n_ntiles;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmW);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < G2_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+            for (int b = 0; b < 2; ++b) { ptx::mbar_init(&tmem_full[b], 1); ptx::mbar_init(&tmem_empty[b], 8); }
+            ptx::fence_barrier_init();
+        }
+        __syncwarp();
+        ptx::tmem_alloc(tmem_slot, 512);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int mt = tile / n_ntiles, nt = tile - mt * n_ntiles;
+            const int batch = mt / tiles_per_batch;
+            const int t0 = (mt - batch * tiles_per_batch) * G2_BM;
+            const int n0 = nt * G2_BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(&empty[s], ph ^ 1);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&full[s], G2_A_BYTES + G2_W_BYTES);
+                    ptx::tma_load_3d(sA + s * G2_A_BYTES, &tmA, &full[s], kb * G2_BK, t0, batch);
+                    ptx::tma_load_2d(sW + s * G2_W_BYTES, &tmW, &full[s], kb * G2_BK, n0);
+                }
+                __syncwarp();
+                if (++s == G2_STAGES) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = ptx::idesc_bf16_f32(G2_BM, G2_BN);
+        const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sA));
+        const uint32_t w_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sW));
+        int s = 0;
+        uint32_t ph = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int buf = it & 1;
+            ptx::mbar_wait(&tmem_empty[buf], ((it >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+            ptx::tc_fence_after();
+            const uint32_t acc = tmem_base + (uint32_t)buf * G2_BN;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                ptx::mbar_wait(&full[s], ph);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                    const uint32_t a_lo = a_lo0 + (uint32_t)s * (G2_A_BYTES >> 4);
+                    const uint32_t w_lo = w_lo0 + (uint32_t)s * (G2_W_BYTES >> 4);
+#pragma unroll
+                    for (int k = 0; k < G2_BK / 16; ++k)
+                        ptx::umma_bf16(acc, ptx::smem_desc_sw128(a_lo + 2 * k), ptx::smem_desc_sw128(w_lo + 2 * k), idesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+                    ptx::umma_commit(&empty[s]);
+                }
+                __syncwarp();
+                if (++s == G2_STAGES) { s = 0; ph ^= 1; }
+            }
+            if (ptx::elect_one()) ptx::umma_commit(&tmem_full[buf]);
+            __syncwarp();
+        }
+    } else {
+        const int ew = warp - 2;                               // 0..7
+        const int half = ew >> 2;                              // which 128 columns of the accumulator
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may read
+        const int r = quarter * 32 + lane;                     // row of the tile held by this thread after tcgen05.ld
+        const int tih = (ew & 3) * 32 + lane;                  // thread index within the half-group (0..127)
+        float* st = stage_f + half * G2_STAGE_F;
+        const int bar_id = 1 + half;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int mt = tile / n_ntiles, nt = tile - mt * n_ntiles;
+            const int batch = mt / tiles_per_batch;
+            const int t0 = (mt - batch * tiles_per_batch) * G2_BM;
+            const int n0 = nt * G2_BN + half * 128;
+            const int buf = it & 1;
+            ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t)buf * G2_BN + (uint32_t)half * 128u + ((uint32_t)(quarter * 32) << 16);
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {                      // 64 columns at a time
+                float v[64];
+                ptx::tmem_ld32(taddr + c * 64, v);
+                ptx::tmem_ld32(taddr + c * 64 + 32, v + 32);
+                ptx::tmem_ld_wait();
+                if (c == 1) {                                  // accumulator fully read by this warp
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+                }
+                named_bar_sync(bar_id, 128);                   // previous chunk's readers are done with the staging tile
+                float* row = st + r * G2_LDS;
+#pragma unroll
+                for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(row + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                named_bar_sync(bar_id, 128);
+#pragma unroll 2
+                for (int j = 0; j < 8; ++j) {
+                    const int idx = tih + j * 128;
+                    const int rr = idx >> 3, c8 = idx & 7;
+                    const int t = t0 + rr;
+                    if (t < ep.M_rows) {
+                        float w[8];
+                        const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
+                        const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                        w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
+                        epi_group<8>(ep, batch * a_rpb + t, n0 + c * 64 + c8 * 8, w);
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+int g2_make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                const cuuint32_t* box) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g2_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+                           strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        wipa_set_error("gemm_bf16_persistent: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return WIPA_ECUDA;
+    }
+    return WIPA_OK;
+}
+
+}  // namespace
+
+int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep_in, cudaStream_t st) {
+    if (g2_encode == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        WIPA_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        WIPA_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, WIPA_ECUDA, "cuTensorMapEncodeTiled not available");
+        g2_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    WIPA_CHECK(K % 8 == 0 && a.lda % 8 == 0 && a.a_bstride % 8 == 0, WIPA_EINVAL,
+               "gemm_bf16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");
+    WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_bf16: M != rows_per_batch * batches");
+    WIPA_CHECK(ep_in.mode != EPI_ARGMAX && ep_in.mode != EPI_QKV_DEC, WIPA_EINVAL, "gemm_bf16_persistent: decode-only epilogue");
+    CUtensorMap tmA, tmW;
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a.a_rpb, (cuuint64_t)a.n_batch};
+        cuuint64_t bstride = a.n_batch > 1 ? (cuuint64_t)a.a_bstride : (cuuint64_t)a.a_rpb * (cuuint64_t)a.lda;
+        cuuint64_t strides[2] = {(cuuint64_t)a.lda * 2, bstride * 2};
+        cuuint32_t box[3] = {G2_BK, G2_BM, 1};
+        WIPA_TRY(g2_make_map(&tmA, a.ptr, 3, dims, strides, box));
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+        cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+        cuuint32_t box[2] = {G2_BK, G2_BN};
+        WIPA_TRY(g2_make_map(&tmW, W, 2, dims, strides, box));
+    }
+    EpiParams ep = ep_in;
+    ep.M_rows = a.a_rpb;
+    static bool configured = false;
+    static int n_sm = 148;
+    if (!configured) {
+        WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+        int dev = 0;
+        WIPA_CUDA_CHECK(cudaGetDevice(&dev));
+        WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const int tpb = cdiv(a.a_rpb, G2_BM);
+    const int n_mtiles = tpb * a.n_batch, n_ntiles = cdiv(N, G2_BN);
+    const int n_tiles = n_mtiles * n_ntiles;
+    const int grid = n_tiles < n_sm ? n_tiles : n_sm;
+    gemm_bf16_persistent_kernel<<<grid, G2_THREADS, G2_SMEM, st>>>(tmA, tmW, cdiv(K, G2_BK), tpb, n_mtiles, n_ntiles, a.a_rpb, ep);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
