@@ -122,6 +122,8 @@ int wipa_test_gemm_rows(const void* A, int is_bf16, long long lda, int rows_per_
 /* Encoder self-attention alone: q,k,v device f32 [B,H,T,64] (q pre-scaled) -> out device f32 [B,T,H*64]. */
 int wipa_test_enc_attention(const float* q, const float* k, const float* v, float* out, int B, int H, int T,
                             int use_bf16, void* stream);
+/* Same on bf16 device buffers without conversions (kernel timing): tc = 1 tcgen05 kernel, 0 SIMT kernel. */
+int wipa_test_enc_attention_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int T, int tc, void* stream);
 /* One decode-step cross-attention sweep over the context's cached encoder K/V (the dominant HBM kernel):
  * q: device f32[B, d] (pre-scaled), out: device f32[B, d]; layer selects which cached K/V. */
 int wipa_test_cross_attn(wipa_ctx*, int B, int layer, const float* q, float* out, void* stream);

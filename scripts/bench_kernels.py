@@ -33,17 +33,16 @@ def main():
     what = args.what.split(",")
 
     if "attn" in what:
-        B, H, T = 8, 12, 1500
-        q = torch.randn(B, H, T, 64, device="cuda") * 0.3
-        k = torch.randn(B, H, T, 64, device="cuda")
-        v = torch.randn(B, H, T, 64, device="cuda")
-        out = torch.empty(B, T, H * 64, device="cuda")
+        B, H, T = 32, 12, 1500
+        q = (torch.randn(B, H, T, 64, device="cuda") * 0.3).to(torch.bfloat16)
+        k = torch.randn(B, H, T, 64, device="cuda").to(torch.bfloat16)
+        v = torch.randn(B, H, T, 64, device="cuda").to(torch.bfloat16)
+        out = torch.empty(B, T, H * 64, device="cuda", dtype=torch.bfloat16)
         flops = 4.0 * T * T * 64 * B * H
-        for mode, name in ((1, "simt bf16"), (2, "tcgen05")):
-            us = timeit(lambda: _lib.check(lib.wipa_test_enc_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
-                                                                       B, H, T, mode, st), "attn"), reps=5)
-            print(f"enc_attention {name:10s} B={B} (incl. f32<->bf16 conversion + malloc of the test wrapper): {us:9.1f} us  "
-                  f"{flops / us / 1e6:7.1f} TFLOP/s")
+        for tc, name in ((1, "tcgen05"),):
+            us = timeit(lambda: _lib.check(lib.wipa_test_enc_attention_bf16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(),
+                                                                            B, H, T, tc, st), "attn"), reps=10)
+            print(f"enc_attention {name:10s} B={B} H={H} T={T}: {us:9.1f} us  {flops / us / 1e6:7.1f} TFLOP/s")
 
     if "gemm_enc" in what:
         for (M, N, K) in ((48000, 768, 768), (48000, 2304, 768), (48000, 3072, 768), (48000, 768, 3072), (48000, 18432, 768)):

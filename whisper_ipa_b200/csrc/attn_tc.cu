@@ -1,16 +1,18 @@
 // Encoder self-attention on the 5th-generation tensor cores (bf16 path).
 //
 // Non-causal attention over T = 1500 frames, head_dim 64 (HF:models/whisper/modeling_whisper.py:284-357; the 64^-0.5
-// scaling is folded into the q projection).  One CTA owns a 128-query tile of one (clip, head) and walks the keys in
-// blocks of 128:
+// scaling is folded into the q projection).  One CTA owns TWO 128-query tiles of one (clip, head) and walks the keys
+// in blocks of 128; the two tiles share every K / V block (half the L2 traffic) and keep the MUFU pipe busy in turns:
 //
-//   warp 0      TMA producer: Q tile once, then K / V blocks ([128 keys][64] each, 128B-swizzled) into a 3-deep ring
-//   warp 1      tcgen05 issuer:  S_j = Q K_j^T   (M128 x N128 x K64, fp32 in TMEM, double-buffered)
-//                                O_j = P_j V_j   (M128 x N64 x K128; P_j is the bf16 tile the softmax warps left in
-//                                                 shared memory, V_j is consumed as an MN-major B operand straight
-//                                                 from its TMA image — no transpose anywhere)
-//   warps 2-5   softmax, one query row per thread: tcgen05.ld S_j, running max / sum in fp32 (exp2 with log2e folded
-//               into one FFMA), P_j -> bf16 -> swizzled shared memory, then fold the PREVIOUS block's O_{j-1} from TMEM
+//   warp 0      TMA producer: both Q tiles once, then K / V blocks ([128 keys][64] each, 128B-swizzled), 2-deep ring
+//   warp 1      tcgen05 issuer, per key block j and tile g:
+//                   S_g   = Q_g K_j^T        (M128 x N128 x K64, fp32 in TMEM, one buffer per tile)
+//                   O_g,j = P_g,j V_j        (M128 x N64 x K128; P is the bf16 tile the softmax warps left in shared
+//                                             memory, V_j is consumed as an MN-major B operand straight from its TMA
+//                                             image - no transpose anywhere; double-buffered in TMEM)
+//   warps 2-5   softmax of tile 0, warps 6-9 softmax of tile 1, one query row per thread: a max pass and an exp pass
+//               over S in TMEM (64 columns in registers at a time), running max / sum in fp32 (exp2 with log2e folded
+//               into one FFMA), P -> bf16 -> swizzled shared memory, then fold the PREVIOUS block's O_{j-1} from TMEM
 //               into the fp32 register accumulator (o = o * alpha + O_{j-1}).  The tensor pipe therefore never waits
 //               for a rescale: every P V product starts from zero in its own TMEM buffer.
 //
@@ -21,13 +23,14 @@
 
 namespace {
 
-constexpr int FA_BQ = 128;
+constexpr int FA_BQ = 256;                                    // two 128-row tiles per CTA
 constexpr int FA_BK = 128;
-constexpr int FA_STAGES = 3;
+constexpr int FA_STAGES = 2;
 constexpr int FA_TILE_BYTES = 128 * 64 * 2;                   // one [128][64] bf16 tile
 constexpr int FA_P_BYTES = 2 * FA_TILE_BYTES;                 // [128 q][128 keys] as two K-chunks of 64 keys
-constexpr int FA_SMEM = FA_TILE_BYTES * (1 + 2 * FA_STAGES) + 2 * FA_P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-constexpr int FA_TMEM_COLS = 512;                             // S: 2 x 128 columns, O: 2 x 64 columns
+constexpr int FA_SMEM = FA_TILE_BYTES * (2 + 2 * FA_STAGES) + 4 * FA_P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int FA_TMEM_COLS = 512;                             // S: 2 tiles x 128 columns, O: 2 tiles x 2 x 64 columns
+constexpr int FA_THREADS = 64 + 256;
 constexpr float LOG2E = 1.4426950408889634f;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -49,23 +52,23 @@ __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn_major) 
            ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(FA_THREADS, 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                         const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int H, int T) {
     extern __shared__ uint8_t fa_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + FA_TILE_BYTES;                          // [stage]
+    uint8_t* sQ = smem;                                        // [2 tiles]
+    uint8_t* sK = sQ + 2 * FA_TILE_BYTES;                      // [stage]
     uint8_t* sV = sK + FA_STAGES * FA_TILE_BYTES;              // [stage]
-    uint8_t* sP = sV + FA_STAGES * FA_TILE_BYTES;              // [2]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * FA_P_BYTES);
+    uint8_t* sP = sV + FA_STAGES * FA_TILE_BYTES;              // [tile][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * FA_P_BYTES);
     uint64_t* q_full = bars;                                   // 1
     uint64_t* kv_full = bars + 1;                              // FA_STAGES
     uint64_t* kv_empty = kv_full + FA_STAGES;                  // FA_STAGES
-    uint64_t* s_full = kv_empty + FA_STAGES;                   // 2
-    uint64_t* p_ready = s_full + 2;                            // 2
-    uint64_t* o_full = p_ready + 2;                            // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 2);
+    uint64_t* s_full = kv_empty + FA_STAGES;                   // [tile]
+    uint64_t* p_ready = s_full + 2;                            // [tile]
+    uint64_t* o_full = p_ready + 2;                            // [tile][2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * FA_BQ;
@@ -81,7 +84,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (lane == 0) {
             ptx::mbar_init(q_full, 1);
             for (int s = 0; s < FA_STAGES; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
-            for (int s = 0; s < 2; ++s) { ptx::mbar_init(&s_full[s], 1); ptx::mbar_init(&p_ready[s], 128); ptx::mbar_init(&o_full[s], 1); }
+            for (int g = 0; g < 2; ++g) { ptx::mbar_init(&s_full[g], 1); ptx::mbar_init(&p_ready[g], 128); }
+            for (int i = 0; i < 4; ++i) ptx::mbar_init(&o_full[i], 1);
             ptx::fence_barrier_init();
         }
         __syncwarp();
@@ -92,76 +96,84 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_S = tmem_base;                         // + 128 * buf
-    const uint32_t tmem_O = tmem_base + 256;                   // + 64 * buf
+    const uint32_t tmem_S = tmem_base;                         // + 128 * tile
+    const uint32_t tmem_O = tmem_base + 256;                   // + 128 * tile + 64 * buf
 
     // role warps run warp-uniformly and elect one lane per issue (bare UTMALDG / UTCHMMA in SASS, descriptors in
     // uniform registers)
     if (warp == 0) {
         if (ptx::elect_one()) {
-            ptx::mbar_arrive_expect_tx(q_full, FA_TILE_BYTES);
+            ptx::mbar_arrive_expect_tx(q_full, 2 * FA_TILE_BYTES);
             ptx::tma_load_3d(sQ, &tmQ, q_full, 0, q0, bh);
+            ptx::tma_load_3d(sQ + FA_TILE_BYTES, &tmQ, q_full, 0, q0 + 128, bh);
         }
         __syncwarp();
-        int s = 0;
-        uint32_t ph = 1;                                        // first pass over the ring: slots are free
         for (int j = 0; j < nb; ++j) {
-            if (j >= FA_STAGES) ptx::mbar_wait(&kv_empty[s], ph);
+            const int s = j & 1;
+            if (j >= FA_STAGES) ptx::mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
             if (ptx::elect_one()) {
                 ptx::mbar_arrive_expect_tx(&kv_full[s], 2 * FA_TILE_BYTES);
                 ptx::tma_load_3d(sK + s * FA_TILE_BYTES, &tmK, &kv_full[s], 0, j * FA_BK, bh);
                 ptx::tma_load_3d(sV + s * FA_TILE_BYTES, &tmV, &kv_full[s], 0, j * FA_BK, bh);
             }
             __syncwarp();
-            if (++s == FA_STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc_s = idesc_bf16(128, 128, 0);
         constexpr uint32_t idesc_o = idesc_bf16(128, 64, 1);
-        const uint32_t q_lo = ptx::smem_desc_lo(ptx::smem_u32(sQ));
+        const uint32_t q_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sQ));
         const uint32_t k_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sK));
         const uint32_t p_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sP));
         const uint32_t v_lo0 = ((ptx::smem_u32(sV) & 0x3FFFFu) >> 4) | ((1024u >> 4) << 16);     // MN-major: LBO field = 1024 B
-        auto issue_qk = [&](int j, int s, uint32_t ph) {          // S_j = Q K_j^T
-            ptx::mbar_wait(&kv_full[s], ph);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-                const uint32_t k_lo = k_lo0 + (uint32_t)s * (FA_TILE_BYTES >> 4);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::umma_bf16(tmem_S + (uint32_t)(j & 1) * 128u, ptx::smem_desc_sw128(q_lo + 2 * k),
-                                   ptx::smem_desc_sw128(k_lo + 2 * k), idesc_s, k != 0 ? 1u : 0u);
-                ptx::umma_commit(&s_full[j & 1]);
-            }
-            __syncwarp();
-        };
         ptx::mbar_wait(q_full, 0);
-        issue_qk(0, 0, 0);
-        int s = 0, s1 = 1 % FA_STAGES;                           // ring slots of blocks j and j + 1
-        uint32_t ph1 = (1 / FA_STAGES) & 1;
-        for (int j = 0; j < nb; ++j) {
-            if (j + 1 < nb) issue_qk(j + 1, s1, ph1);
-            ptx::mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {                               // O_j = P_j V_j, 16 keys per MMA
-                const uint32_t p_lo = p_lo0 + (uint32_t)(j & 1) * (FA_P_BYTES >> 4);
-                const uint32_t v_lo = v_lo0 + (uint32_t)s * (FA_TILE_BYTES >> 4);
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    ptx::umma_bf16(tmem_O + (uint32_t)(j & 1) * 64u,
-                                   ptx::smem_desc_sw128(p_lo + (uint32_t)(k >> 2) * (FA_TILE_BYTES >> 4) + (uint32_t)(k & 3) * 2u),
-                                   ptx::smem_desc_sw128(v_lo + (uint32_t)k * (2048u >> 4)), idesc_o, k != 0 ? 1u : 0u);
-                ptx::umma_commit(&o_full[j & 1]);
-                ptx::umma_commit(&kv_empty[s]);
+        for (int j = 0; j <= nb; ++j) {                           // iteration nb only drains the last P V products
+            if (j < nb) {
+                ptx::mbar_wait(&kv_full[j & 1], (j >> 1) & 1);
+                ptx::tc_fence_after();
             }
-            __syncwarp();
-            s = s1;
-            if (++s1 == FA_STAGES) { s1 = 0; ph1 ^= 1; }
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                if (j > 0) {                                      // P_g(j-1) is in shared memory and S_g has been drained
+                    ptx::mbar_wait(&p_ready[g], (j - 1) & 1);
+                    ptx::tc_fence_after();
+                }
+                if (ptx::elect_one()) {
+                    if (j < nb) {                                 // S_g = Q_g K_j^T
+                        const uint32_t q_lo = q_lo0 + (uint32_t)g * (FA_TILE_BYTES >> 4);
+                        const uint32_t k_lo = k_lo0 + (uint32_t)(j & 1) * (FA_TILE_BYTES >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_bf16(tmem_S + (uint32_t)g * 128u, ptx::smem_desc_sw128(q_lo + 2 * k),
+                                           ptx::smem_desc_sw128(k_lo + 2 * k), idesc_s, k != 0 ? 1u : 0u);
+                        ptx::umma_commit(&s_full[g]);
+                    }
+                    if (j > 0) {                                  // O_g(j-1) = P_g(j-1) V_{j-1}, 16 keys per MMA
+                        const int jp = j - 1;
+                        const uint32_t p_lo = p_lo0 + (uint32_t)(g * 2 + (jp & 1)) * (FA_P_BYTES >> 4);
+                        const uint32_t v_lo = v_lo0 + (uint32_t)(jp & 1) * (FA_TILE_BYTES >> 4);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            ptx::umma_bf16(tmem_O + (uint32_t)g * 128u + (uint32_t)(jp & 1) * 64u,
+                                           ptx::smem_desc_sw128(p_lo + (uint32_t)(k >> 2) * (FA_TILE_BYTES >> 4) + (uint32_t)(k & 3) * 2u),
+                                           ptx::smem_desc_sw128(v_lo + (uint32_t)k * (2048u >> 4)), idesc_o, k != 0 ? 1u : 0u);
+                        ptx::umma_commit(&o_full[g * 2 + (jp & 1)]);
+                        if (g == 1) ptx::umma_commit(&kv_empty[jp & 1]);
+                    }
+                }
+                __syncwarp();
+            }
         }
     } else {
-        const int quarter = warp & 3;
+        const int g = (warp - 2) >> 2;                            // which query tile
+        const int quarter = warp & 3;                             // TMEM lane quarter this warp may touch
         const int r = quarter * 32 + lane;                        // query row of this thread within the tile
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+        const uint32_t ts = tmem_S + (uint32_t)g * 128u + lane_off;
+        const uint32_t to = tmem_O + (uint32_t)g * 128u + lane_off;
+        uint64_t* my_s_full = &s_full[g];
+        uint64_t* my_p_ready = &p_ready[g];
+        uint64_t* my_o_full = &o_full[g * 2];
+        uint8_t* myP = sP + g * 2 * FA_P_BYTES;
         float o[64];
 #pragma unroll
         for (int i = 0; i < 64; ++i) o[i] = 0.f;
@@ -170,63 +182,78 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         const uint32_t sw = (uint32_t)(r & 7);
 
         auto fold_o = [&](int j, float alpha) {                   // o = o * alpha + O_j
-            ptx::mbar_wait(&o_full[j & 1], (j >> 1) & 1);
+            ptx::mbar_wait(&my_o_full[j & 1], (j >> 1) & 1);
             ptx::tc_fence_after();
             float t[64];
-            ptx::tmem_ld32(tmem_O + (uint32_t)(j & 1) * 64u + lane_off, t);
-            ptx::tmem_ld32(tmem_O + (uint32_t)(j & 1) * 64u + 32u + lane_off, t + 32);
+            ptx::tmem_ld32(to + (uint32_t)(j & 1) * 64u, t);
+            ptx::tmem_ld32(to + (uint32_t)(j & 1) * 64u + 32u, t + 32);
             ptx::tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 64; ++i) o[i] = fmaf(o[i], alpha, t[i]);
         };
 
         for (int j = 0; j < nb; ++j) {
-            ptx::mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+            ptx::mbar_wait(my_s_full, j & 1);
             ptx::tc_fence_after();
-            float s[128];
-            const uint32_t ts = tmem_S + (uint32_t)(j & 1) * 128u + lane_off;
-            ptx::tmem_ld32(ts, s);
-            ptx::tmem_ld32(ts + 32, s + 32);
-            ptx::tmem_ld32(ts + 64, s + 64);
-            ptx::tmem_ld32(ts + 96, s + 96);
-            ptx::tmem_ld_wait();
             const int kbase = j * FA_BK;
-            if (kbase + FA_BK > T) {
+            const bool tail = kbase + FA_BK > T;
+            float s[64];
+            // ---- pass 1: row max over the 128 scores ------------------------------------------------------------
+            float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
-                for (int c = 0; c < 128; ++c) if (kbase + c >= T) s[c] = -INFINITY;
+            for (int hf = 0; hf < 2; ++hf) {
+                ptx::tmem_ld32(ts + hf * 64, s);
+                ptx::tmem_ld32(ts + hf * 64 + 32, s + 32);
+                ptx::tmem_ld_wait();
+                if (tail) {
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) if (kbase + hf * 64 + c >= T) s[c] = -INFINITY;
+                }
+#pragma unroll
+                for (int c = 0; c < 64; c += 4) {
+                    mx0 = fmaxf(mx0, s[c]); mx1 = fmaxf(mx1, s[c + 1]); mx2 = fmaxf(mx2, s[c + 2]); mx3 = fmaxf(mx3, s[c + 3]);
+                }
             }
-            float mx = s[0];
-#pragma unroll
-            for (int c = 1; c < 128; ++c) mx = fmaxf(mx, s[c]);
+            const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
             const float m_new = fmaxf(m, mx);
             const float alpha = ex2((m - m_new) * LOG2E);         // 0 on the first block (m = -inf)
             const float nm = -m_new * LOG2E;
             m = m_new;
-            float sum = 0.f;
-            uint8_t* prow = sP + (j & 1) * FA_P_BYTES + p_row;
+            // ---- pass 2: p = exp(s - m), bf16 P tile into swizzled shared memory ---------------------------------------
+            float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
+            uint8_t* prow = myP + (j & 1) * FA_P_BYTES + p_row;
 #pragma unroll
-            for (int c8 = 0; c8 < 16; ++c8) {                      // 8 keys = one 16-byte piece of the swizzled row
-                float p[8];
+            for (int hf = 1; hf >= 0; --hf) {                      // second half first: it is already in registers
+                if (hf == 0) {
+                    ptx::tmem_ld32(ts, s);
+                    ptx::tmem_ld32(ts + 32, s + 32);
+                    ptx::tmem_ld_wait();
+                    if (tail) {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    p[i] = ex2(fmaf(s[c8 * 8 + i], LOG2E, nm));
-                    sum += p[i];
+                        for (int c = 0; c < 64; ++c) if (kbase + c >= T) s[c] = -INFINITY;
+                    }
                 }
-                uint4 u;
-                u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
-                u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
-                const uint32_t chunk = (uint32_t)(c8 >> 3), piece = (uint32_t)(c8 & 7);
-                *reinterpret_cast<uint4*>(prow + chunk * FA_TILE_BYTES + ((piece ^ sw) << 4)) = u;
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8) {                   // 8 keys = one 16-byte piece of the swizzled row
+                    float p[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) p[i] = ex2(fmaf(s[c8 * 8 + i], LOG2E, nm));
+                    sum0 += p[0] + p[4]; sum1 += p[1] + p[5]; sum2 += p[2] + p[6]; sum3 += p[3] + p[7];
+                    uint4 u;
+                    u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
+                    u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+                    *reinterpret_cast<uint4*>(prow + hf * FA_TILE_BYTES + (((uint32_t)c8 ^ sw) << 4)) = u;
+                }
             }
-            l = fmaf(l, alpha, sum);
+            l = fmaf(l, alpha, (sum0 + sum1) + (sum2 + sum3));
             ptx::fence_proxy_async();                             // P visible to the tensor core's async proxy
-            ptx::tc_fence_before();                               // our TMEM reads of S_j are complete
-            ptx::mbar_arrive(&p_ready[j & 1]);
+            ptx::tc_fence_before();                               // our TMEM reads of S are complete
+            ptx::mbar_arrive(my_p_ready);
             if (j > 0) fold_o(j - 1, alpha_prev);
             alpha_prev = alpha;
         }
         fold_o(nb - 1, alpha_prev);
-        const int t = q0 + r;
+        const int t = q0 + g * 128 + r;
         if (t < T) {
             const float inv = 1.0f / l;
             const int b = bh / H, h = bh - b * H;
@@ -282,7 +309,7 @@ int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o
         configured = true;
     }
     dim3 grid(cdiv(T, FA_BQ), B * H);
-    enc_attention_tc_kernel<<<grid, 192, FA_SMEM, st>>>(tmQ, tmK, tmV, out, H, T);
+    enc_attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, out, H, T);
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

@@ -832,6 +832,13 @@ extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* 
     return WIPA_OK;
 }
 
+// encoder self-attention on bf16 device buffers, no conversions (timing): q,k,v bf16 [B,H,T,64] -> out bf16 [B,T,H*64]
+extern "C" int wipa_test_enc_attention_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int T, int tc,
+                                            void* stream) {
+    if (tc) return launch_enc_attention_tc((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, B, H, T, (cudaStream_t)stream);
+    return launch_enc_attention<bf16>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, B, H, T, (cudaStream_t)stream);
+}
+
 // encoder self-attention alone: q,k,v f32 [B,H,T,64] (q pre-scaled) -> out f32 [B,T,H*64]; use_bf16 selects the kernel family
 extern "C" int wipa_test_enc_attention(const float* q, const float* k, const float* v, float* out, int B, int H, int T,
                                        int use_bf16, void* stream) {
