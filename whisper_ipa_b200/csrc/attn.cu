@@ -5,6 +5,8 @@
 //   self_attention_kernel  : one decode step of decoder self-attention over the paged KV cache (warp per (seq, head)).
 //   cross_attention_kernel : one decode step of cross-attention against the cached encoder K/V —
 //                            the dominant HBM stream of the whole decode.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -477,6 +479,254 @@ cross_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc, co
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// persistent streamer (default): one CTA per SM, 8 consumer warps + 1 producer warp.
+//
+// The K/V of all (sequence, head) pairs form one long stream of UNITS: 12 chunks of CS_CK = 125 keys per pair (K chunk
+// + V chunk = one ring slot, filled by two cp.async.bulk copies behind one mbarrier).  The stream is cut into
+// contiguous, equally long unit ranges, one per CTA ("stream-K"): perfect balance at any batch size, and every CTA
+// reads one long sequential HBM region.  A range covers whole pairs in its middle (result written directly) and at
+// most two partial pairs at its ends; a partial pair leaves a flash-decoding partial (m, l, o[64], next chunk) in the
+// slot of its first chunk and adds its chunk count to the pair's counter — whoever completes the count of 12 walks
+// the slots in chunk order (deterministic) and writes the head's output.
+//
+// The producer warp runs ahead over pair boundaries, so the ring (6 x 32 KB in bf16) always holds ~190 KB of loads in
+// flight per SM; K/V are static inside a decode step, so under PDL the first slots are requested BEFORE
+// griddepcontrol.wait and HBM does not idle between the layers' launches.  Every consumer warp owns 1/8 of each
+// chunk's keys and carries a warp-local online softmax (m, l, o) across the chunks of a pair; the 8 warp partials are
+// merged through shared memory at the end of the pair.  The next pair's q is prefetched one pair ahead.
+// ------------------------------------------------------------------------------------------------
+#define CS_CK 125                      // keys per chunk: 1500 = 12 x 125, every chunk is full
+#define CS_NCH (WIPA_T_ENC / CS_CK)
+#define CS_CONSUMERS 8
+#define CS_THREADS (32 * (1 + CS_CONSUMERS))
+#define CS_PART 68                     // floats per global partial: m, l, next chunk, pad, o[64]
+
+template <typename T> struct CsCfg {
+    static constexpr int CHUNK_BYTES = CS_CK * 64 * (int)sizeof(T);              // 16000 (bf16) / 32000 (fp32)
+    static constexpr int SLOT_BYTES = 2 * CHUNK_BYTES;
+    static constexpr int STAGES = sizeof(T) == 2 ? 6 : 3;
+    static constexpr int KPW = 32 / CaCfg<T>::LPK;                               // keys per warp per iteration
+    static constexpr int ITERS = (CS_CK + CS_CONSUMERS * KPW - 1) / (CS_CONSUMERS * KPW);
+    static constexpr int SMEM = STAGES * SLOT_BYTES + 2 * CS_CONSUMERS * CA_PART * 4 + 2 * STAGES * 8 + 64;
+};
+
+template <typename T> __device__ __forceinline__ float ca_exp(float x);
+template <> __device__ __forceinline__ float ca_exp<float>(float x) { return expf(x); }
+template <> __device__ __forceinline__ float ca_exp<bf16>(float x) { return __expf(x); }
+
+template <typename T>
+__global__ void __launch_bounds__(CS_THREADS, 1)
+cross_attention_stream_kernel(const float* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc,
+                              const int* __restrict__ utt_of_seq, T* __restrict__ out, float* __restrict__ part,
+                              int* __restrict__ counters, int H, long long n_units, int kv_static) {
+    using C = CaCfg<T>;
+    using S = CsCfg<T>;
+    extern __shared__ __align__(128) uint8_t cs_smem[];
+    uint8_t* ring = cs_smem;
+    float* wpart = reinterpret_cast<float*>(ring + S::STAGES * S::SLOT_BYTES);   // [2][8][CA_PART]
+    uint64_t* full = reinterpret_cast<uint64_t*>(wpart + 2 * CS_CONSUMERS * CA_PART);
+    uint64_t* empty = full + S::STAGES;
+    __shared__ int s_total;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = H * 64;
+    const int u0 = (int)(n_units * blockIdx.x / gridDim.x);
+    const int u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
+
+    pdl_launch_dependents();
+    if (tid == 0) {
+        for (int s = 0; s < S::STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CS_CONSUMERS); }
+        ptx::fence_barrier_init();
+    }
+    __syncthreads();
+
+    if (warp == CS_CONSUMERS) {
+        // ---- producer ------------------------------------------------------------------------------------------
+        // inside a decode step utt_of_seq and the cached K/V were completed by kernels far upstream: no dependency wait
+        if (!kv_static) pdl_wait();
+        int s = 0;
+        uint32_t ph = 1;                                           // first ring pass: every slot is free
+        int pair = u0 / CS_NCH, ch = u0 - pair * CS_NCH;
+        size_t base = 0;
+        bool fresh = true;
+        for (int u = u0; u < u1; ++u) {
+            if (fresh) {
+                const int b = pair / H, h = pair - b * H;
+                const int utt = utt_of_seq ? utt_of_seq[b] : b;
+                base = ((size_t)utt * H + h) * WIPA_T_ENC * 64;
+                fresh = false;
+            }
+            ptx::mbar_wait(&empty[s], ph);
+            if (ptx::elect_one()) {
+                uint8_t* slot = ring + s * S::SLOT_BYTES;
+                ptx::mbar_arrive_expect_tx(&full[s], S::SLOT_BYTES);
+                ptx::bulk_load_1d(slot, kc + base + (size_t)ch * CS_CK * 64, S::CHUNK_BYTES, &full[s]);
+                ptx::bulk_load_1d(slot + S::CHUNK_BYTES, vc + base + (size_t)ch * CS_CK * 64, S::CHUNK_BYTES, &full[s]);
+            }
+            __syncwarp();
+            if (++s == S::STAGES) { s = 0; ph ^= 1; }
+            if (++ch == CS_NCH) { ch = 0; ++pair; fresh = true; }
+        }
+    } else {
+        // ---- consumers -----------------------------------------------------------------------------------------
+        const int grp = lane / C::LPK;                             // key slot of this lane group within the warp
+        const int li = lane % C::LPK;                              // 16-byte piece of the key row
+        pdl_wait();                                                // q comes from the previous kernel
+        int s = 0;
+        uint32_t ph = 0;
+        int parity = 0;
+        const int n_pairs_total = (int)(n_units / CS_NCH);
+        auto load_q = [&](int pair, float* dst) {
+            const int b = pair / H, h = pair - b * H;
+            const float4* qp = reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64 + li * C::VEC);
+#pragma unroll
+            for (int i = 0; i < C::VEC / 4; ++i) {
+                const float4 t = qp[i];
+                dst[4 * i] = t.x; dst[4 * i + 1] = t.y; dst[4 * i + 2] = t.z; dst[4 * i + 3] = t.w;
+            }
+        };
+        float qn[C::VEC];
+        if (u0 < u1) load_q(u0 / CS_NCH, qn);
+        for (int u = u0; u < u1; parity ^= 1) {
+            const int pair = u / CS_NCH;
+            const int ch0 = u - pair * CS_NCH;
+            const int ch1 = min(CS_NCH, ch0 + (u1 - u));
+            const int b = pair / H, h = pair - b * H;
+            float qv[C::VEC];
+#pragma unroll
+            for (int i = 0; i < C::VEC; ++i) qv[i] = qn[i];
+            if (pair + 1 < n_pairs_total) load_q(pair + 1, qn);     // lands while this pair is being processed
+            float m_run = -INFINITY, l_run = 0.f, a0 = 0.f, a1 = 0.f;
+            for (int ch = ch0; ch < ch1; ++ch) {
+                ptx::mbar_wait(&full[s], ph);
+                const T* sK = reinterpret_cast<const T*>(ring + s * S::SLOT_BYTES);
+                const T* sV = reinterpret_cast<const T*>(ring + s * S::SLOT_BYTES + S::CHUNK_BYTES);
+                float sc[S::ITERS];
+                float mw = -INFINITY;
+#pragma unroll
+                for (int it = 0; it < S::ITERS; ++it) {
+                    const int key = (it * CS_CONSUMERS + warp) * S::KPW + grp;
+                    float v = -INFINITY;
+                    if (key < CS_CK) {
+                        const uint4 u4 = *reinterpret_cast<const uint4*>(sK + (size_t)key * 64 + li * C::VEC);
+                        float f[C::VEC];
+                        unpack16<T>(u4, f);
+                        v = 0.f;
+#pragma unroll
+                        for (int i = 0; i < C::VEC; ++i) v = fmaf(f[i], qv[i], v);
+                    }
+#pragma unroll
+                    for (int off = C::LPK / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    sc[it] = v;                                    // -inf for absent keys (whole lane group absent)
+                    mw = fmaxf(mw, v);
+                }
+#pragma unroll
+                for (int off = C::LPK; off < 32; off <<= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, off));
+                const float m_new = fmaxf(m_run, mw);              // finite: every warp owns >= 1 key of every chunk
+                const float alpha = ca_exp<T>(m_run - m_new);      // 0 on the first chunk
+                float lsum = 0.f;
+#pragma unroll
+                for (int it = 0; it < S::ITERS; ++it) {
+                    sc[it] = ca_exp<T>(sc[it] - m_new);
+                    lsum += sc[it];
+                }
+#pragma unroll
+                for (int off = C::LPK; off < 32; off <<= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+                l_run = fmaf(l_run, alpha, lsum);
+                a0 *= alpha; a1 *= alpha;
+                m_run = m_new;
+#pragma unroll
+                for (int it = 0; it < S::ITERS; ++it) {
+#pragma unroll
+                    for (int gg = 0; gg < S::KPW; ++gg) {
+                        const int key = (it * CS_CONSUMERS + warp) * S::KPW + gg;
+                        const float p = __shfl_sync(0xffffffffu, sc[it], gg * C::LPK);
+                        if (key < CS_CK) {
+                            const float2 v2 = ld_pair(sV + (size_t)key * 64 + lane * 2);
+                            a0 = fmaf(p, v2.x, a0);
+                            a1 = fmaf(p, v2.y, a1);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&empty[s]);        // this warp is done with the slot
+                if (++s == S::STAGES) { s = 0; ph ^= 1; }
+            }
+            u += ch1 - ch0;
+            // ---- merge the 8 warp partials of this pair (or part of a pair) -------------------------------------------
+            float* wp = wpart + (parity * CS_CONSUMERS + warp) * CA_PART;
+            wp[2 + lane * 2] = a0;
+            wp[3 + lane * 2] = a1;
+            if (lane == 0) { wp[0] = m_run; wp[1] = l_run; }
+            asm volatile("bar.sync 1, %0;" ::"n"(CS_CONSUMERS * 32) : "memory");
+            if (warp < 2) {
+                const int e = warp * 32 + lane;
+                const float* pp = wpart + parity * CS_CONSUMERS * CA_PART;
+                float M = pp[0];
+#pragma unroll
+                for (int w = 1; w < CS_CONSUMERS; ++w) M = fmaxf(M, pp[w * CA_PART]);
+                float L = 0.f, o = 0.f;
+#pragma unroll
+                for (int w = 0; w < CS_CONSUMERS; ++w) {
+                    const float wgt = ca_exp<T>(pp[w * CA_PART] - M);
+                    L = fmaf(pp[w * CA_PART + 1], wgt, L);
+                    o = fmaf(pp[w * CA_PART + 2 + e], wgt, o);
+                }
+                if (ch1 - ch0 == CS_NCH) {
+                    out[(size_t)b * d + h * 64 + e] = from_f32<T>(o / L);
+                } else {
+                    float* gp = part + ((size_t)pair * CS_NCH + ch0) * CS_PART;
+                    gp[4 + e] = o;
+                    if (e == 0) { gp[0] = M; gp[1] = L; gp[2] = (float)ch1; }
+                    __threadfence();
+                    asm volatile("bar.sync 2, 64;" ::: "memory");    // both merging warps have published their halves
+                    if (e == 0) {
+                        const int before = atomicAdd(&counters[pair], ch1 - ch0);
+                        s_total = before + (ch1 - ch0);
+                        if (before + (ch1 - ch0) == CS_NCH) counters[pair] = 0;   // ready for the next launch
+                    }
+                    asm volatile("bar.sync 2, 64;" ::: "memory");
+                    if (s_total == CS_NCH) {                        // all 12 chunks of this pair are in: walk the slots in order
+                        __threadfence();
+                        const float* g0 = part + (size_t)pair * CS_NCH * CS_PART;
+                        float GM = -INFINITY;
+                        for (int sl = 0; sl < CS_NCH; sl = (int)__ldcg(g0 + sl * CS_PART + 2)) GM = fmaxf(GM, __ldcg(g0 + sl * CS_PART));
+                        float GL = 0.f, go = 0.f;
+                        for (int sl = 0; sl < CS_NCH; sl = (int)__ldcg(g0 + sl * CS_PART + 2)) {
+                            const float wgt = ca_exp<T>(__ldcg(g0 + sl * CS_PART) - GM);
+                            GL = fmaf(__ldcg(g0 + sl * CS_PART + 1), wgt, GL);
+                            go = fmaf(__ldcg(g0 + sl * CS_PART + 4 + e), wgt, go);
+                        }
+                        out[(size_t)b * d + h * 64 + e] = from_f32<T>(go / GL);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+static int launch_cross_attention_stream(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
+                                         int* counters, int Bs, int H, int kv_static, cudaStream_t st) {
+    using S = CsCfg<T>;
+    static bool configured = false;
+    static int n_sm = 148;
+    if (!configured) {
+        WIPA_CUDA_CHECK(cudaFuncSetAttribute(cross_attention_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+        int dev = 0;
+        WIPA_CUDA_CHECK(cudaGetDevice(&dev));
+        WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        configured = true;
+    }
+    const long long n_units = (long long)Bs * H * CS_NCH;
+    const int grid = n_units < n_sm ? (int)n_units : n_sm;
+    WIPA_CUDA_CHECK(wipa_launch(cross_attention_stream_kernel<T>, dim3(grid), dim3(CS_THREADS), (size_t)S::SMEM, st, q, k, v,
+                                utt_of_seq, out, part, counters, H, n_units, kv_static));
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
 int cross_attention_default_split(int elem_bytes, int Bs, int H) {
     // chunk sized for ~48 KB of K+V per CTA (4 CTAs / SM resident): 188 keys in bf16, 94 in fp32
     (void)Bs; (void)H;
@@ -485,7 +735,9 @@ int cross_attention_default_split(int elem_bytes, int Bs, int H) {
 
 template <typename T>
 int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
-                           int* counters, int Bs, int H, int n_split, cudaStream_t st) {
+                           int* counters, int Bs, int H, int n_split, int kv_static, cudaStream_t st) {
+    static const int legacy = [] { const char* e = getenv("WIPA_CA_LEGACY"); return (e && *e) ? atoi(e) : 0; }();
+    if (!legacy) return launch_cross_attention_stream<T>(q, k, v, utt_of_seq, out, part, counters, Bs, H, kv_static, st);
     WIPA_CHECK(n_split >= 1 && n_split <= 64, WIPA_EINVAL, "cross_attention: n_split %d out of range", n_split);
     int chunk = cdiv(WIPA_T_ENC, n_split);
     chunk = (chunk + 3) & ~3;                                       // keeps every chunk's byte count a multiple of 16
@@ -502,5 +754,5 @@ int launch_cross_attention(const float* q, const T* k, const T* v, const int* ut
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
-template int launch_cross_attention<float>(const float*, const float*, const float*, const int*, float*, float*, int*, int, int, int, cudaStream_t);
-template int launch_cross_attention<bf16>(const float*, const bf16*, const bf16*, const int*, bf16*, float*, int*, int, int, int, cudaStream_t);
+template int launch_cross_attention<float>(const float*, const float*, const float*, const int*, float*, float*, int*, int, int, int, int, cudaStream_t);
+template int launch_cross_attention<bf16>(const float*, const bf16*, const bf16*, const int*, bf16*, float*, int*, int, int, int, int, cudaStream_t);

@@ -345,7 +345,7 @@ int launch_self_attention(const float* q, const T* kpool, const T* vpool, const 
 // split-K cross-attention: part = f32 [Bs*H, n_split, 66] scratch, counters = int [Bs*H] (zero, self-resetting)
 template <typename T>
 int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
-                           int* counters, int Bs, int H, int n_split, cudaStream_t st);
+                           int* counters, int Bs, int H, int n_split, int kv_static, cudaStream_t st);
 int cross_attention_default_split(int elem_bytes, int Bs, int H);
 
 // elementwise.cu

@@ -421,9 +421,9 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             const char* xv = (const char*)c->xkv + (size_t)(2 * l + 1) * c->xkv_which_stride * c->esz;
             if (skip & 4) {}
             else if (c->bf) WIPA_TRY(launch_cross_attention<bf16>(c->dq, (const bf16*)xk, (const bf16*)xv, c->utt_of_seq, (bf16*)c->dattn,
-                                                             c->ca_part, c->ca_counters, S, H, c->ca_split, st));
+                                                             c->ca_part, c->ca_counters, S, H, c->ca_split, 1, st));
             else WIPA_TRY(launch_cross_attention<float>(c->dq, (const float*)xk, (const float*)xv, c->utt_of_seq, (float*)c->dattn,
-                                                        c->ca_part, c->ca_counters, S, H, c->ca_split, st));
+                                                        c->ca_part, c->ca_counters, S, H, c->ca_split, 1, st));
         }
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
@@ -825,9 +825,9 @@ extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* 
     const char* xk = (const char*)c->xkv + (size_t)(2 * layer) * c->xkv_which_stride * c->esz;
     const char* xv = (const char*)c->xkv + (size_t)(2 * layer + 1) * c->xkv_which_stride * c->esz;
     if (c->bf) WIPA_TRY(launch_cross_attention<bf16>(q, (const bf16*)xk, (const bf16*)xv, nullptr, (bf16*)c->dattn, c->ca_part,
-                                                     c->ca_counters, B, c->a.heads, c->ca_split, st));
+                                                     c->ca_counters, B, c->a.heads, c->ca_split, 0, st));
     else WIPA_TRY(launch_cross_attention<float>(q, (const float*)xk, (const float*)xv, nullptr, (float*)c->dattn, c->ca_part,
-                                                c->ca_counters, B, c->a.heads, c->ca_split, st));
+                                                c->ca_counters, B, c->a.heads, c->ca_split, 0, st));
     if (out) WIPA_TRY(launch_to_f32(c->dattn, c->bf, out, (long long)B * c->a.d_model, st));
     return WIPA_OK;
 }
