@@ -6,7 +6,7 @@ log-mel -> encoder (+ cross-K/V projection) -> 220 greedy decode steps (4-token 
 `value`  : device-timed (CUDA events, max over ranks), audio already resident in HBM.
 `e2e`    : the same pass through the public API (pipeline.Transcriber.evaluate_ids) from pinned HOST buffers, host<->device
            copies inside the timed region.
-`roofline`: the dominant kernel (split-K cross-attention, an HBM streamer) timed alone with CUDA events over all decoder
+`roofline`: the dominant kernel (stream-K cross-attention, a persistent HBM streamer) timed alone with CUDA events over all decoder
            layers' caches (total bytes >> L2), achieved GB/s vs MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the parity oracle (HF transformers Whisper on the host cores, fp32) on a bounded
            sample of the same workload.  The reference's own runtime (mlx_whisper on Apple Metal) cannot run here.
@@ -158,7 +158,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--arch", default="small")
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("WIPA_BENCH_BATCH", "64")), help="clips per GPU per step")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("WIPA_BENCH_BATCH", "256")),
+                    help="clips per GPU per step (the micro-batch of the eval sweep; 16 / 64 / 256 are the named points)")
     ap.add_argument("--dtype", default="bfloat16", choices=["bfloat16", "float32"])
     ap.add_argument("--max-new", type=int, default=220)
     ap.add_argument("--ref-clips", type=int, default=2)
@@ -321,7 +322,7 @@ def main():
     peak, peak_src = measured_peaks()
     steps_per_pass = PROMPT_LEN - 1 + args.max_new
     ca_share = us * 1e-3 * arch.dec_layers * steps_per_pass / (ms_total / K)
-    roofline = {"bound": "hbm", "kernel": "cross_attention_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "cross_attention_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": None, "us_per_launch": us, "bytes_per_launch": bytes_per_launch,
                 "peak_source": peak_src, "share_of_step_est": ca_share}
 

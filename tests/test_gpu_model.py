@@ -113,10 +113,14 @@ def test_eos_handling_matches_oracle(w, tiny_gain_sd, eot_like):
     m.close()
 
 
-@pytest.mark.parametrize("arch,B", [("tiny", 4), ("base", 2)])
-def test_bf16_logits_and_token_agreement(w, arch, B):
+@pytest.mark.parametrize("arch,B,persistent", [("tiny", 4, False), ("base", 2, False), ("tiny", 3, True), ("base", 2, True)])
+def test_bf16_logits_and_token_agreement(w, arch, B, persistent, monkeypatch):
     """bf16 path vs the fp32 oracle: relative L2 error of teacher-forced logits (bf16 operand rounding bounds it at the
-    1e-2 level; the measured value is printed) and greedy-token agreement over 32 steps."""
+    1e-2 level; the measured value is printed) and greedy-token agreement over 32 steps.  `persistent` forces every
+    encoder GEMM through the persistent 128x256 kernel (normally chosen only for >= 2 waves of tiles) so that its
+    fused epilogues (head split, residual add, fast GELU, conv rows) are checked at test sizes too."""
+    if persistent:
+        monkeypatch.setenv("WIPA_PERSISTENT_MIN_TILES", "1")
     from oracle import hf_reference as hf
     from oracle import whisper_oracle as wo
     sd = hf.state_dict_f32(hf.build_hf_model(arch, seed=0))

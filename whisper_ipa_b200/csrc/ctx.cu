@@ -85,6 +85,7 @@ struct wipa_ctx {
     cudaStream_t cap_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy default stream)
     int n_logit_tiles;
     int bn_enc, bn_dec, bn_logits, ca_split;
+    int persistent_min_tiles = 296; // WIPA_PERSISTENT_MIN_TILES: fewer 128x256 tiles than this -> plain 128x128-tile kernel
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
     int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (bf16 path)
     int64_t decode_steps = 0;
@@ -234,7 +235,7 @@ EpiParams epi(int mode, int M, int N) {
 int gemm(wipa_ctx* c, const AOperand& a, const void* W, int M, int N, int K, const EpiParams& ep, int bn, cudaStream_t st) {
     if (c->bf) {
         // bn == 0: the persistent 128 x 256 kernel when there are at least two waves of its tiles, else 128 x 128 tiles
-        if (bn == 0 && (long long)cdiv(M, 128) * cdiv(N, 256) < 2 * 148) bn = 128;
+        if (bn == 0 && (long long)cdiv(M, 128) * cdiv(N, 256) < c->persistent_min_tiles) bn = 128;
         return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, bn, st);
     }
     return launch_gemm_f32(a, (const float*)W, M, N, K, ep, st);
@@ -529,6 +530,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->n_logit_tiles = cdiv(arch->vocab, c->bn_logits);
     c->enc_attn_simt = env_int("WIPA_ENC_ATTN_SIMT", 0);
     c->skip_mask = env_int("WIPA_SKIP_MASK", 0);
+    c->persistent_min_tiles = env_int("WIPA_PERSISTENT_MIN_TILES", 2 * 148);
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;

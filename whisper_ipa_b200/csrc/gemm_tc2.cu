@@ -33,6 +33,26 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g2_encode = nullptr;
 
+// GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the stored value):
+// two MUFU ops (rcp, ex2) + ~12 FMA-pipe instructions instead of erff's ~35.  1 + erf(z) is formed without
+// cancellation on the negative side.  Used only where the result is rounded to bf16 (the fp32 path calls erff).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = x * 0.70710678118654752440f;
+    const float az = fabsf(z);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+    const float c = poly * e;                                  // 1 - erf(|z|)
+    const float one_plus_erf = z < 0.f ? c : 2.0f - c;
+    return 0.5f * x * one_plus_erf;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -156,17 +176,106 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #pragma unroll
                 for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(row + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                 named_bar_sync(bar_id, 128);
+                // each thread owns the 8-column group c8 of rows rr0, rr0 + 16, ..., rr0 + 112 of this 64-column chunk
+                const int c8 = tih & 7, rr0 = tih >> 3;
+                const int nc = n0 + c * 64;                        // first column of the chunk
+                const int ncol = nc + c8 * 8;
+                const bool fast = ep.vec_ok && (nc + 64 <= ep.N) && ep.o_rpb >= G2_BM && ep.T >= G2_BM &&
+                                  (ep.mode == EPI_RESADD || ep.mode == EPI_HEADS || ep.mode == EPI_GELU || ep.mode == EPI_STORE);
+                if (fast) {
+                    float bias8[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) bias8[i] = 0.f;
+                    if (ep.bias != nullptr) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + ncol);
+                        const float4 b1 = *reinterpret_cast<const float4*>(ep.bias + ncol + 4);
+                        bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w;
+                        bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+                    }
+                    const int m_first = batch * a_rpb + t0;        // logical row of the tile's first row
+                    if (ep.mode == EPI_HEADS) {
+                        // one 64-column chunk = one head of one of q|k|v: a single division pair per chunk, and the clip
+                        // index advances at most once inside a 128-row tile (T >= 128)
+                        const int which = nc / ep.d;
+                        const int h = (nc - which * ep.d) >> 6;
+                        const int b0 = m_first / ep.T, tt0 = m_first - b0 * ep.T;
+                        const long long wbase = (long long)which * ep.which_stride + (long long)h * ep.T * WIPA_HEAD_DIM + c8 * 8;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int rr = rr0 + j * 16;
+                            if (t0 + rr < ep.M_rows) {
+                                int tt = tt0 + rr, bb = b0;
+                                if (tt >= ep.T) { tt -= ep.T; ++bb; }
+                                const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
+                                const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                                float w[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
+                                              x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
+                                store_group<8>(ep.out, ep.out_bf16, wbase + ((long long)bb * ep.H * ep.T + tt) * WIPA_HEAD_DIM, w, true);
+                            }
+                        }
+                    } else {
+                        const int ob0 = m_first / ep.o_rpb, ot0 = m_first - ob0 * ep.o_rpb;
+                        long long rowoff[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            int ot = ot0 + rr0 + j * 16, ob = ob0;
+                            if (ot >= ep.o_rpb) { ot -= ep.o_rpb; ++ob; }
+                            rowoff[j] = (long long)ob * ep.o_bstride + (long long)ot * ep.ldo + ncol;
+                        }
+                        if (ep.mode == EPI_RESADD) {
+                            // all residual loads of the chunk are issued before the first use (one HBM round trip per chunk)
+                            float4 r0[8], r1[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                if (t0 + rr0 + j * 16 < ep.M_rows) {
+                                    r0[j] = *reinterpret_cast<const float4*>(ep.resid + rowoff[j]);
+                                    r1[j] = *reinterpret_cast<const float4*>(ep.resid + rowoff[j] + 4);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int rr = rr0 + j * 16;
+                                if (t0 + rr < ep.M_rows) {
+                                    const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
+                                    const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                                    float* o = reinterpret_cast<float*>(ep.out) + rowoff[j];
+                                    *reinterpret_cast<float4*>(o) = make_float4(x0.x + bias8[0] + r0[j].x, x0.y + bias8[1] + r0[j].y,
+                                                                                x0.z + bias8[2] + r0[j].z, x0.w + bias8[3] + r0[j].w);
+                                    *reinterpret_cast<float4*>(o + 4) = make_float4(x1.x + bias8[4] + r1[j].x, x1.y + bias8[5] + r1[j].y,
+                                                                                    x1.z + bias8[6] + r1[j].z, x1.w + bias8[7] + r1[j].w);
+                                }
+                            }
+                        } else {                                    // EPI_STORE / EPI_GELU
+                            const bool gelu = ep.mode == EPI_GELU;
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int rr = rr0 + j * 16;
+                                if (t0 + rr < ep.M_rows) {
+                                    const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
+                                    const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                                    float w[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
+                                                  x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
+                                    if (gelu) {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) w[i] = ep.out_bf16 ? gelu_erf_fast(w[i]) : gelu_erf(w[i]);
+                                    }
+                                    store_group<8>(ep.out, ep.out_bf16, rowoff[j], w, true);
+                                }
+                            }
+                        }
+                    }
+                } else {
 #pragma unroll 2
-                for (int j = 0; j < 8; ++j) {
-                    const int idx = tih + j * 128;
-                    const int rr = idx >> 3, c8 = idx & 7;
-                    const int t = t0 + rr;
-                    if (t < ep.M_rows) {
-                        float w[8];
-                        const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
-                        const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
-                        w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
-                        epi_group<8>(ep, batch * a_rpb + t, n0 + c * 64 + c8 * 8, w);
+                    for (int j = 0; j < 8; ++j) {
+                        const int rr = rr0 + j * 16;
+                        const int t = t0 + rr;
+                        if (t < ep.M_rows) {
+                            float w[8];
+                            const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
+                            const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                            w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
+                            epi_group<8>(ep, batch * a_rpb + t, ncol, w);
+                        }
                     }
                 }
             }
