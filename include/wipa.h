@@ -124,6 +124,11 @@ int wipa_test_enc_attention(const float* q, const float* k, const float* v, floa
                             int use_bf16, void* stream);
 /* Same on bf16 device buffers without conversions (kernel timing): tc = 1 tcgen05 kernel, 0 SIMT kernel. */
 int wipa_test_enc_attention_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int T, int tc, void* stream);
+/* One decode-step self-attention over a caller-built paged KV cache: kpool / vpool [page][H][16][64] (bf16 when is_bf16,
+ * else f32), block_table int32 [B, bt_stride] page ids, *pos_ptr = newest position (length - 1); q f32 [B, H*64];
+ * out [B, H*64] in the pool's element type.  All device pointers. */
+int wipa_test_self_attn(const float* q, const void* kpool, const void* vpool, const int* block_table, int bt_stride,
+                        const int* pos_ptr, void* out, int B, int H, int is_bf16, void* stream);
 /* One decode-step cross-attention sweep over the context's cached encoder K/V (the dominant HBM kernel):
  * q: device f32[B, d] (pre-scaled), out: device f32[B, d]; layer selects which cached K/V. */
 int wipa_test_cross_attn(wipa_ctx*, int B, int layer, const float* q, float* out, void* stream);

@@ -100,6 +100,39 @@ def test_enc_attention(lib, use_bf16, tol, T):
     assert (out - ref).abs().max().item() < tol
 
 
+@pytest.mark.parametrize("is_bf16,tol", [(0, 2e-5), (1, 2e-2)])
+@pytest.mark.parametrize("length", [1, 2, 16, 17, 100, 224, 448])
+def test_self_attention_paged(lib, is_bf16, tol, length):
+    """One decode step of self-attention over a paged KV cache whose pages are deliberately scattered."""
+    B, H, PAGE = 3, 6, 16
+    g = torch.Generator(device="cuda").manual_seed(length)
+    dt = torch.bfloat16 if is_bf16 else torch.float32
+    q = torch.randn(B, H * 64, device="cuda", generator=g) * 0.3
+    k = torch.randn(B, H, length, 64, device="cuda", generator=g).to(dt)
+    v = torch.randn(B, H, length, 64, device="cuda", generator=g).to(dt)
+    pps = (length + PAGE - 1) // PAGE
+    n_pages = B * pps + 5
+    perm = torch.randperm(n_pages, generator=torch.Generator().manual_seed(1))[:B * pps].reshape(B, pps)
+    kpool = torch.full((n_pages, H, PAGE, 64), float("nan"), device="cuda", dtype=dt)
+    vpool = torch.full((n_pages, H, PAGE, 64), float("nan"), device="cuda", dtype=dt)
+    for b in range(B):
+        for pg in range(pps):
+            n = min(PAGE, length - pg * PAGE)
+            kpool[perm[b, pg], :, :n] = k[b, :, pg * PAGE:pg * PAGE + n]
+            vpool[perm[b, pg], :, :n] = v[b, :, pg * PAGE:pg * PAGE + n]
+    bt = torch.zeros(B, 28, dtype=torch.int32)
+    bt[:, :pps] = perm.to(torch.int32)
+    bt = bt.cuda()
+    pos = torch.tensor([length - 1], dtype=torch.int32, device="cuda")
+    out = torch.empty(B, H * 64, device="cuda", dtype=dt)
+    lib.check(lib.lib().wipa_test_self_attn(q.data_ptr(), kpool.data_ptr(), vpool.data_ptr(), bt.data_ptr(), 28, pos.data_ptr(),
+                                            out.data_ptr(), B, H, is_bf16, _st()), "self_attn")
+    qh = q.double().view(B, H, 1, 64)
+    ref = (torch.softmax(qh @ k.double().transpose(-1, -2), -1) @ v.double()).reshape(B, H * 64)
+    err = (out.double() - ref).abs().max().item()
+    assert err < tol, f"max err {err}"
+
+
 @pytest.mark.parametrize("dtype,tol", [("float32", 2e-5), ("bfloat16", 2e-2)])
 def test_cross_attention_streamer(lib, tiny_sd, dtype, tol):
     import whisper_ipa_b200 as w

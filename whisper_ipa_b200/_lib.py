@@ -58,6 +58,7 @@ PROTOTYPES = {
     "wipa_test_gemm_rows": (_i, [_vp, _i, C.c_longlong, _i, C.c_longlong, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_cross_attn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wipa_test_enc_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wipa_test_self_attn": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_enc_attention_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 

@@ -221,115 +221,7 @@ __device__ __forceinline__ float dot64<bf16>(const bf16* kp, const float* qs) {
     return acc;
 }
 
-// One warp per (sequence, head), four independent warps per CTA, no block-level synchronisation:
-//   scores   lane-per-key: lane l owns keys l, l+32, ... (<= 14 of them at 448 positions); it reads the whole 64-element
-//            K row (one full 128 / 256-byte line per lane) and dots it with q held in registers -> no shuffles per key
-//   softmax  one warp max + one warp sum; probabilities parked in shared memory (keeps the code small: the fully
-//            unrolled register version was 125 KB of SASS and thrashed the instruction cache)
-//   P.V      lane-per-dim: lane l owns output dims 2l, 2l+1; p_j is a shared-memory broadcast and the V row is one
-//            coalesced line per key, a whole page (16 keys) of loads in flight at a time
-template <typename T>
-__device__ __forceinline__ float2 ld_v2(const T* p);
-template <> __device__ __forceinline__ float2 ld_v2<float>(const float* p) { return *reinterpret_cast<const float2*>(p); }
-template <> __device__ __forceinline__ float2 ld_v2<bf16>(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
-__device__ __forceinline__ void st_v2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
-__device__ __forceinline__ void st_v2(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
-
-template <typename T>
-__global__ void __launch_bounds__(128)
-self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, const T* __restrict__ vpool,
-                      const int* __restrict__ block_table, int bt_stride, const int* __restrict__ pos_ptr,
-                      T* __restrict__ out, int H, int n_pairs) {
-    __shared__ float sc_all[4][WIPA_MAX_TGT];                      // scores / probabilities of this warp's keys
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int pair = blockIdx.x * 4 + warp;
-    pdl_launch_dependents();
-    pdl_wait();
-    if (pair >= n_pairs) return;
-    float* sc = sc_all[warp];
-    const int b = pair / H, h = pair - b * H;
-    const int d = H * 64;
-    const int len = *pos_ptr + 1;
-    const int* bt = block_table + (size_t)b * bt_stride;
-    float qr[64];
-    {
-        const float4* qp = reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64);
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 t = qp[i];
-            qr[4 * i] = t.x; qr[4 * i + 1] = t.y; qr[4 * i + 2] = t.z; qr[4 * i + 3] = t.w;
-        }
-    }
-    float mx = -INFINITY;
-#pragma unroll 2
-    for (int j = lane; j < len; j += 32) {
-        const int page = bt[j / WIPA_PAGE];
-        const T* kp = kpool + (((size_t)page * H + h) * WIPA_PAGE + (j % WIPA_PAGE)) * 64;
-        const float s = dot64<T>(kp, qr);
-        sc[j] = s;
-        mx = fmaxf(mx, s);
-    }
-    mx = warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < len; j += 32) {
-        const float p = expf(sc[j] - mx);
-        sc[j] = p;
-        sum += p;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    float a0 = 0.f, a1 = 0.f;
-    const size_t hoff = (size_t)h * WIPA_PAGE * 64 + 2 * lane;
-#pragma unroll 1
-    for (int pg = 0; pg * WIPA_PAGE < len; ++pg) {                 // one page (16 keys) per iteration: 16 loads in flight
-        const T* vp = vpool + (size_t)bt[pg] * H * WIPA_PAGE * 64 + hoff;
-        const int n = min(WIPA_PAGE, len - pg * WIPA_PAGE);
-        if (n == WIPA_PAGE) {
-            float2 v2[WIPA_PAGE];
-#pragma unroll
-            for (int jj = 0; jj < WIPA_PAGE; ++jj) v2[jj] = ld_v2<T>(vp + jj * 64);
-#pragma unroll
-            for (int jj = 0; jj < WIPA_PAGE; ++jj) {
-                const float p = sc[pg * WIPA_PAGE + jj];
-                a0 = fmaf(p, v2[jj].x, a0);
-                a1 = fmaf(p, v2[jj].y, a1);
-            }
-        } else {
-            for (int jj = 0; jj < n; ++jj) {
-                const float p = sc[pg * WIPA_PAGE + jj];
-                const float2 v2 = ld_v2<T>(vp + jj * 64);
-                a0 = fmaf(p, v2.x, a0);
-                a1 = fmaf(p, v2.y, a1);
-            }
-        }
-    }
-    const float inv = 1.0f / sum;
-    st_v2(out + (size_t)b * d + h * 64 + 2 * lane, a0 * inv, a1 * inv);
-}
-
-template <typename T>
-int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
-                          const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st) {
-    const int n_pairs = Bs * H;
-    WIPA_CUDA_CHECK(wipa_launch(self_attention_kernel<T>, dim3(cdiv(n_pairs, 4)), dim3(128), (size_t)0, st, q, kpool, vpool,
-                                block_table, bt_stride, pos_ptr, out, H, n_pairs));
-    WIPA_LAUNCHED();
-    return WIPA_OK;
-}
-template int launch_self_attention<float>(const float*, const float*, const float*, const int*, int, const int*, float*, int, int, cudaStream_t);
-template int launch_self_attention<bf16>(const float*, const bf16*, const bf16*, const int*, int, const int*, bf16*, int, int, cudaStream_t);
-
-// ================================================================================================
-// decoder cross-attention, one query per (sequence, head) against 1500 cached encoder keys/values
-// ================================================================================================
-// This kernel moves ~92 % of the decode step's bytes at batch 64 (SURVEY.md §0 fact 5), so it is built as a pure
-// HBM streamer.  K/V of one (utterance, head) are contiguous [1500][64].  The 1500 keys are split into n_split
-// chunks; CTA (chunk, head, seq) issues two cp.async.bulk copies (its K chunk and its V chunk, each one contiguous
-// block) into shared memory behind two mbarriers and only then computes: scores + local softmax from the K
-// buffer while V is still landing, then P.V.  Several CTAs are resident per SM (24-48 KB of loads in flight
-// each), which is what keeps HBM busy; nothing is read twice.  Each CTA emits a flash-decoding partial
-// (max, sum, o[64]); the last CTA to finish a (seq, head) — found with one atomic ticket — merges the partials in
-// chunk order (deterministic) and writes the head's output.
+// ---- helpers shared by the decode-step attention kernels -------------------------------------------------
 #define CA_THREADS 256
 #define CA_WARPS (CA_THREADS / 32)
 #define CA_PART 66                     // floats per partial: m, l, o[64]
@@ -357,6 +249,147 @@ __device__ __forceinline__ void unpack16<bf16>(const uint4& u, float* f) {
 __device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ float2 ld_pair(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
 
+// One CTA of four warps per (sequence, head); warp w takes pages w, w+4, ... of the sequence's block table, so a
+// sequence of 112 positions is 2 pages (one or two memory round trips) per warp instead of 7 for one warp:
+//   per page  all loads are issued up front: the K rows as 16-byte pieces (LPK lanes per key, KPW keys per
+//             instruction, every request a full 128-byte line) and the 16 V rows (lane l owns output dims 2l, 2l+1);
+//             scores by an LPK-lane shuffle reduction, warp-local online softmax (m, l, o) across the warp's pages
+//   merge     the four warp partials are combined through shared memory
+// (an earlier fully unrolled one-warp version was 125 KB of SASS and thrashed the instruction cache)
+template <typename T> struct VRaw;
+template <> struct VRaw<float> { typedef float2 type; };
+template <> struct VRaw<bf16> { typedef __nv_bfloat162 type; };
+__device__ __forceinline__ float2 v_to_f2(float2 v) { return v; }
+__device__ __forceinline__ float2 v_to_f2(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ void st_v2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void st_v2(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+
+template <typename T>
+__global__ void __launch_bounds__(128, sizeof(T) == 2 ? 8 : 4)
+self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, const T* __restrict__ vpool,
+                      const int* __restrict__ block_table, int bt_stride, const int* __restrict__ pos_ptr,
+                      T* __restrict__ out, int H) {
+    using C = CaCfg<T>;
+    constexpr int KPW = 32 / C::LPK;                               // keys per warp instruction
+    constexpr int ITERS = WIPA_PAGE / KPW;
+    typedef typename VRaw<T>::type vraw;
+    __shared__ float part[4][CA_PART];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = blockIdx.x;
+    const int b = pair / H, h = pair - b * H;
+    const int d = H * 64;
+    const int grp = lane / C::LPK, li = lane % C::LPK;
+    pdl_wait();
+    pdl_launch_dependents();                     // only after our own dependency is met: at most two grids overlap
+    const int len = *pos_ptr + 1;
+    const int npages = (len + WIPA_PAGE - 1) / WIPA_PAGE;
+    const int* bt = block_table + (size_t)b * bt_stride;
+    float qv[C::VEC];
+    {
+        const float4* qp = reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64 + li * C::VEC);
+#pragma unroll
+        for (int i = 0; i < C::VEC / 4; ++i) {
+            const float4 t = qp[i];
+            qv[4 * i] = t.x; qv[4 * i + 1] = t.y; qv[4 * i + 2] = t.z; qv[4 * i + 3] = t.w;
+        }
+    }
+    float m_run = -INFINITY, l_run = 0.f, a0 = 0.f, a1 = 0.f;
+    for (int pg = warp; pg < npages; pg += 4) {
+        const int page = bt[pg];
+        const int nkeys = min(WIPA_PAGE, len - pg * WIPA_PAGE);
+        const size_t base = ((size_t)page * H + h) * WIPA_PAGE * 64;
+        uint4 kraw[ITERS];
+        vraw vr[WIPA_PAGE];
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int key = it * KPW + grp;
+            kraw[it] = make_uint4(0u, 0u, 0u, 0u);
+            if (key < nkeys) kraw[it] = *reinterpret_cast<const uint4*>(kpool + base + (size_t)key * 64 + li * C::VEC);
+        }
+#pragma unroll
+        for (int j = 0; j < WIPA_PAGE; ++j) {
+            if (j < nkeys) vr[j] = *reinterpret_cast<const vraw*>(vpool + base + (size_t)j * 64 + 2 * lane);
+        }
+        float sc[ITERS];
+        float mw = -INFINITY;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            float f[C::VEC];
+            unpack16<T>(kraw[it], f);
+            float v = 0.f;
+#pragma unroll
+            for (int i = 0; i < C::VEC; ++i) v = fmaf(f[i], qv[i], v);
+#pragma unroll
+            for (int off = C::LPK / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+            if (it * KPW + grp >= nkeys) v = -INFINITY;
+            sc[it] = v;
+            mw = fmaxf(mw, v);
+        }
+#pragma unroll
+        for (int off = C::LPK; off < 32; off <<= 1) mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, off));
+        const float m_new = fmaxf(m_run, mw);                      // finite: the page holds >= 1 key
+        const float alpha = expf(m_run - m_new);                   // 0 on the warp's first page
+        float lsum = 0.f;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            sc[it] = expf(sc[it] - m_new);
+            lsum += sc[it];
+        }
+#pragma unroll
+        for (int off = C::LPK; off < 32; off <<= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, off);
+        l_run = fmaf(l_run, alpha, lsum);
+        a0 *= alpha; a1 *= alpha;
+        m_run = m_new;
+#pragma unroll
+        for (int j = 0; j < WIPA_PAGE; ++j) {
+            const float p = __shfl_sync(0xffffffffu, sc[j / KPW], (j % KPW) * C::LPK);
+            if (j < nkeys) {
+                const float2 v2 = v_to_f2(vr[j]);
+                a0 = fmaf(p, v2.x, a0);
+                a1 = fmaf(p, v2.y, a1);
+            }
+        }
+    }
+    part[warp][2 + 2 * lane] = a0;
+    part[warp][3 + 2 * lane] = a1;
+    if (lane == 0) { part[warp][0] = m_run; part[warp][1] = l_run; }
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int e = threadIdx.x;
+        const float M = fmaxf(fmaxf(part[0][0], part[1][0]), fmaxf(part[2][0], part[3][0]));   // warp 0 always has page 0
+        float L = 0.f, o = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const float wgt = expf(part[w][0] - M);
+            L = fmaf(part[w][1], wgt, L);
+            o = fmaf(part[w][2 + e], wgt, o);
+        }
+        out[(size_t)b * d + h * 64 + e] = from_f32<T>(o / L);
+    }
+}
+
+template <typename T>
+int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
+                          const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st) {
+    WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T>, dim3(Bs * H), dim3(128), (size_t)0, st, q, kpool, vpool,
+                                block_table, bt_stride, pos_ptr, out, H));
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+template int launch_self_attention<float>(const float*, const float*, const float*, const int*, int, const int*, float*, int, int, cudaStream_t);
+template int launch_self_attention<bf16>(const float*, const bf16*, const bf16*, const int*, int, const int*, bf16*, int, int, cudaStream_t);
+
+// ================================================================================================
+// decoder cross-attention, one query per (sequence, head) against 1500 cached encoder keys/values
+// ================================================================================================
+// This kernel moves ~92 % of the decode step's bytes at batch 64 (SURVEY.md §0 fact 5), so it is built as a pure
+// HBM streamer.  K/V of one (utterance, head) are contiguous [1500][64].  The 1500 keys are split into n_split
+// chunks; CTA (chunk, head, seq) issues two cp.async.bulk copies (its K chunk and its V chunk, each one contiguous
+// block) into shared memory behind two mbarriers and only then computes: scores + local softmax from the K
+// buffer while V is still landing, then P.V.  Several CTAs are resident per SM (24-48 KB of loads in flight
+// each), which is what keeps HBM busy; nothing is read twice.  Each CTA emits a flash-decoding partial
+// (max, sum, o[64]); the last CTA to finish a (seq, head) — found with one atomic ticket — merges the partials in
+// chunk order (deterministic) and writes the head's output.
 template <typename T>
 __global__ void __launch_bounds__(CA_THREADS)
 cross_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc, const T* __restrict__ vc,
@@ -534,7 +567,6 @@ cross_attention_stream_kernel(const float* __restrict__ q, const T* __restrict__
     const int u0 = (int)(n_units * blockIdx.x / gridDim.x);
     const int u1 = (int)(n_units * (blockIdx.x + 1) / gridDim.x);
 
-    pdl_launch_dependents();
     if (tid == 0) {
         for (int s = 0; s < S::STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CS_CONSUMERS); }
         ptx::fence_barrier_init();
@@ -573,6 +605,7 @@ cross_attention_stream_kernel(const float* __restrict__ q, const T* __restrict__
         const int grp = lane / C::LPK;                             // key slot of this lane group within the warp
         const int li = lane % C::LPK;                              // 16-byte piece of the key row
         pdl_wait();                                                // q comes from the previous kernel
+        pdl_launch_dependents();                                   // after the wait: at most two grids overlap
         int s = 0;
         uint32_t ph = 0;
         int parity = 0;
@@ -721,7 +754,7 @@ static int launch_cross_attention_stream(const float* q, const T* k, const T* v,
     }
     const long long n_units = (long long)Bs * H * CS_NCH;
     const int grid = n_units < n_sm ? (int)n_units : n_sm;
-    WIPA_CUDA_CHECK(wipa_launch(cross_attention_stream_kernel<T>, dim3(grid), dim3(CS_THREADS), (size_t)S::SMEM, st, q, k, v,
+    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_stream_kernel<T>, dim3(grid), dim3(CS_THREADS), (size_t)S::SMEM, st, q, k, v,
                                 utt_of_seq, out, part, counters, H, n_units, kv_static));
     WIPA_LAUNCHED();
     return WIPA_OK;

@@ -65,25 +65,35 @@ static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 // cudaLaunchAttributeProgrammaticStreamSerialization, signal `launch_dependents` as soon as they start, prefetch
 // their STATIC operands (weights, cached encoder K/V) and only then `griddepcontrol.wait` for the previous kernel.
 // Launch latency, prologues and the first HBM loads of kernel N+1 therefore overlap the tail of kernel N.
-// RULE: every kernel launched through wipa_launch must execute pdl_wait() before it reads anything a previous
-// kernel wrote and before it writes anything a previous kernel may still read.
+// RULES: (1) every kernel launched through wipa_launch must execute pdl_wait() before it reads anything a previous
+// kernel wrote and before it writes anything a previous kernel may still read; (2) launch_dependents is issued only
+// AFTER the kernel's own pdl_wait() has returned, so at most two consecutive grids are ever in flight.  Triggering
+// at kernel entry lets an unbounded chain of grids pile up behind one another; on B200 (driver 580) a chain of
+// layernorm -> GEMM -> self-attention launched that way read stale q (measured: wrong logits with all three
+// attributes on, exact results when any one of them was off).
 // ------------------------------------------------------------------------------------------------
 extern int g_wipa_pdl;       // 1 (default) or 0 (env WIPA_PDL=0): attach the PDL attribute to launches
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// cls: kernel family bit (1 elementwise, 2 self-attention, 4 cross-attention, 8 tcgen05 GEMM, 16 SIMT GEMM); the
+// attribute is attached when (g_wipa_pdl & cls) != 0  (WIPA_PDL = bitmask, default all families)
 template <typename... KArgs, typename... Args>
-static inline cudaError_t wipa_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                      Args... args) {
+static inline cudaError_t wipa_launch_c(int cls, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = g_wipa_pdl ? 1 : 0;
+    cfg.numAttrs = (g_wipa_pdl & cls) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
+#ifndef WIPA_PDL_CLASS
+#define WIPA_PDL_CLASS 1
+#endif
+#define wipa_launch(...) wipa_launch_c(WIPA_PDL_CLASS, __VA_ARGS__)
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ------------------------------------------------------------------------------------------------

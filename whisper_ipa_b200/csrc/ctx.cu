@@ -834,6 +834,17 @@ extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* 
     return WIPA_OK;
 }
 
+// decoder self-attention step alone over a caller-built paged cache: kpool / vpool [page][H][16][64] (bf16 or f32),
+// block_table int32 [B, bt_stride], *pos_ptr = index of the newest position; q f32 [B, H*64]; out [B, H*64] in the pool type
+extern "C" int wipa_test_self_attn(const float* q, const void* kpool, const void* vpool, const int* block_table, int bt_stride,
+                                   const int* pos_ptr, void* out, int B, int H, int is_bf16, void* stream) {
+    WIPA_CHECK(q && kpool && vpool && block_table && pos_ptr && out && B >= 1 && H >= 1, WIPA_EINVAL, "wipa_test_self_attn: bad argument");
+    if (is_bf16) return launch_self_attention<bf16>(q, (const bf16*)kpool, (const bf16*)vpool, block_table, bt_stride, pos_ptr,
+                                                    (bf16*)out, B, H, (cudaStream_t)stream);
+    return launch_self_attention<float>(q, (const float*)kpool, (const float*)vpool, block_table, bt_stride, pos_ptr, (float*)out,
+                                        B, H, (cudaStream_t)stream);
+}
+
 // encoder self-attention on bf16 device buffers, no conversions (timing): q,k,v bf16 [B,H,T,64] -> out bf16 [B,T,H*64]
 extern "C" int wipa_test_enc_attention_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int T, int tc,
                                             void* stream) {

@@ -12,8 +12,8 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
                  T* __restrict__ out, int M) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();                     // only after our own dependency is met: at most two grids overlap
     if (row >= M) return;
     constexpr int d = NV * 128;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
@@ -105,8 +105,8 @@ template <typename T>
 __global__ void embed_kernel(const T* __restrict__ tok_emb, const float* __restrict__ pos_emb,
                              const int* __restrict__ tok, const int* __restrict__ pos_ptr, float* __restrict__ x, int d) {
     const int b = blockIdx.x;
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();                     // only after our own dependency is met: at most two grids overlap
     const int p = *pos_ptr;
     const T* te = tok_emb + (size_t)tok[b] * d;
     const float* pe = pos_emb + (size_t)p * d;
@@ -178,8 +178,8 @@ row_argmax_kernel(const float* __restrict__ logits, int V, const uint32_t* __res
     __shared__ float smax[8];
     __shared__ int sidx[8];
     const int b = blockIdx.x;
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();                     // only after our own dependency is met: at most two grids overlap
     const float* row = logits + (size_t)b * V;
     const bool begin = (step_ptr != nullptr) && (*step_ptr == 0);
     float best = -INFINITY;
@@ -223,8 +223,8 @@ int launch_row_argmax(const float* logits, int Bs, int V, const uint32_t* mask_a
 __global__ void __launch_bounds__(1024)
 greedy_finalize_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int n_tiles, DecodeState ds, int Bs) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();                     // only after our own dependency is met: at most two grids overlap
     const int pos = *ds.pos;
     const int i = pos - (ds.n_forced - 1);            // index of the token sampled at this step
     for (int b = warp; b < Bs; b += 32) {

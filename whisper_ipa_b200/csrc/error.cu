@@ -5,7 +5,7 @@
 #include "common.cuh"
 
 int64_t g_wipa_launches = 0;
-static int init_pdl() { const char* v = getenv("WIPA_PDL"); return (v && *v) ? atoi(v) != 0 : 1; }
+static int init_pdl() { const char* v = getenv("WIPA_PDL"); return (v && *v) ? atoi(v) : 0xff; }
 int g_wipa_pdl = init_pdl();
 static thread_local char g_wipa_err[1024] = "";
 

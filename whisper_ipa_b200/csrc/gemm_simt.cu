@@ -3,6 +3,7 @@
 // logit margin of a random-init model is ~1e-2, any reduced-precision product flips tokens).
 // 64x64x16 tiles, 256 threads, 4x4 register micro-tile, register-prefetched global loads.
 // Shares the epilogue (bias / GELU / residual / head split / paged-KV scatter) with the tcgen05 kernel.
+#define WIPA_PDL_CLASS 16
 #include "common.cuh"
 
 #define SG_BM 64
@@ -17,8 +18,8 @@ gemm_f32_kernel(AOperand a, const float* __restrict__ W, int M, int N, int K, Ep
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
     const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
-    pdl_launch_dependents();
     pdl_wait();
+    pdl_launch_dependents();                     // only after our own dependency is met: at most two grids overlap
 
     // global->smem mapping: each thread moves one float4 of A and one of W per k-block
     const int lr = tid >> 2;            // 0..63 row within tile

@@ -10,6 +10,7 @@
 // The A operand is described by a 3-D tensor map (K, rows-per-batch, batches) whose row stride may be smaller than
 // K: a k=3 conv1d over a channels-last, zero-row-padded signal is then exactly this GEMM (no im2col buffer),
 // and out-of-range rows / K tails are zero-filled by TMA.
+#define WIPA_PDL_CLASS 8
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -66,7 +67,6 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int batch = blockIdx.y / tiles_per_batch;
     const int t0 = (blockIdx.y - batch * tiles_per_batch) * TC_BM;
 
-    pdl_launch_dependents();                                  // the next kernel may start its own prologue now
     if (threadIdx.x == 0) DBG_STAMP(0);
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
@@ -106,6 +106,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         __syncwarp();
         pdl_wait();
+        pdl_launch_dependents();                                  // the next kernel may start its prologue now (trigger only
+                                                                  // after our own dependency is met: at most two grids overlap)
         if (ptx::elect_one()) {
             DBG_STAMP(2);
             for (int g = 0; g < pre; ++g) {
