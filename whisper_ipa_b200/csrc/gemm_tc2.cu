@@ -180,8 +180,9 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 const int c8 = tih & 7, rr0 = tih >> 3;
                 const int nc = n0 + c * 64;                        // first column of the chunk
                 const int ncol = nc + c8 * 8;
-                const bool fast = ep.vec_ok && (nc + 64 <= ep.N) && ep.o_rpb >= G2_BM && ep.T >= G2_BM &&
-                                  (ep.mode == EPI_RESADD || ep.mode == EPI_HEADS || ep.mode == EPI_GELU || ep.mode == EPI_STORE);
+                const bool fast = ep.vec_ok && (nc + 64 <= ep.N) &&
+                                  ((ep.mode == EPI_HEADS && ep.T >= G2_BM && ep.vt_which < 0) ||
+                                   ((ep.mode == EPI_RESADD || ep.mode == EPI_GELU || ep.mode == EPI_STORE) && ep.o_rpb >= G2_BM));
                 if (fast) {
                     float bias8[8];
 #pragma unroll
@@ -247,6 +248,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                             }
                         } else {                                    // EPI_STORE / EPI_GELU
                             const bool gelu = ep.mode == EPI_GELU;
+                            const bool gelu_fast = gelu && ep.out_bf16;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int rr = rr0 + j * 16;
@@ -255,9 +257,12 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                                     const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
                                     float w[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
                                                   x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
-                                    if (gelu) {
+                                    if (gelu_fast) {                 // bf16 output: two MUFU + ~14 FMA-pipe instructions per value
 #pragma unroll
-                                        for (int i = 0; i < 8; ++i) w[i] = ep.out_bf16 ? gelu_erf_fast(w[i]) : gelu_erf(w[i]);
+                                        for (int i = 0; i < 8; ++i) w[i] = gelu_erf_fast(w[i]);
+                                    } else if (gelu) {
+#pragma unroll
+                                        for (int i = 0; i < 8; ++i) w[i] = gelu_erf(w[i]);
                                     }
                                     store_group<8>(ep.out, ep.out_bf16, rowoff[j], w, true);
                                 }
