@@ -322,8 +322,11 @@ def main():
     peak, peak_src = measured_peaks()
     steps_per_pass = PROMPT_LEN - 1 + args.max_new
     ca_share = us * 1e-3 * arch.dec_layers * steps_per_pass / (ms_total / K)
+    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_cross_attention_stream_ncu_full.txt:
+    # dram__bytes_read.sum 1.180631 GB + dram__bytes_write.sum 4.89 MB at small / bf16 / B=256); other shapes were not captured
+    traffic = 1.180631e9 + 4.891392e6 if (args.arch == "small" and args.dtype == "bfloat16" and B == 256) else None
     roofline = {"bound": "hbm", "kernel": "cross_attention_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "us_per_launch": us, "bytes_per_launch": bytes_per_launch,
+                "frac": achieved / peak, "traffic": traffic, "us_per_launch": us, "bytes_per_launch": bytes_per_launch,
                 "peak_source": peak_src, "share_of_step_est": ca_share}
 
     cpu_baseline = None
