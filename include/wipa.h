@@ -85,7 +85,10 @@ typedef struct wipa_decode_opts {
  * (ref:scripts/evaluate_model.py:200, ref:scripts/transcribe_single.py:55, ref:scripts/train_whisper_ipa.py:356).
  * out_ids: device int32[B, max_new] (EOT-padded), out_len: device int32[B] (tokens before EOT). */
 int wipa_decode_greedy(wipa_ctx*, int B, const wipa_decode_opts*, int32_t* out_ids, int32_t* out_len, void* stream);
-/* Beam search with HF `_beam_search` semantics (early_stopping=False); same outputs (best hypothesis). */
+/* Beam search with HF `_beam_search` semantics (HF:generation/utils.py:3076-3400; early_stopping=False, do_sample=False,
+ * one EOS id); 2 <= beams <= min(8, max_beams of the context).  Beams of an utterance share its cross-attention K/V; the
+ * self-attention cache is never reordered (a per-beam ancestry table says which slot wrote each position).  Same
+ * outputs as the greedy call: the best finished hypothesis per utterance, EOS stripped, EOT-padded. */
 int wipa_decode_beam(wipa_ctx*, int B, int beams, float length_penalty, const wipa_decode_opts*,
                      int32_t* out_ids, int32_t* out_len, void* stream);
 /* Diagnostics for the parity tests: teacher-forced logits.  tokens: host int32[B,T]; logits: device f32[B,T,V]. */

@@ -147,3 +147,55 @@ def test_bf16_logits_and_token_agreement(w, arch, B, persistent, monkeypatch):
     assert enc_rel < 2e-2 and rel < 3e-2
     assert np.isfinite(got_logits.numpy()).all()
     m.close()
+
+
+@pytest.mark.parametrize("beams", [2, 5])
+@pytest.mark.parametrize("gain,eot_like,max_new", [(1.0, None, 24), (3.0, None, 20), (3.0, 40220, 40), (3.0, 2020, 40)])
+def test_beam_search_matches_hf(w, tiny_sd, tiny_gain_sd, beams, gain, eot_like, max_new):
+    """Beam search (HF `_beam_search` semantics: length_penalty 1.0, early_stopping False) on the fp32 path must return
+    HF's own hypotheses: log-softmax + running scores, top-2K continuations, finished-slot bookkeeping with the length
+    penalty, the early-stop heuristic, and beam reordering (done here through the ancestry table, never moving KV)."""
+    from oracle import hf_reference as hf
+    from oracle import whisper_oracle as wo
+    sd = {k: v.clone() for k, v in (tiny_sd if gain == 1.0 else tiny_gain_sd).items()}
+    hf_model = hf.build_hf_model("tiny", seed=0, init_gain=gain)
+    if eot_like is not None:                  # make EOS reachable (see test_eos_handling_matches_oracle)
+        emb = sd["model.decoder.embed_tokens.weight"]
+        emb[wo.EOT] = emb[eot_like] * 1.05
+        sd["proj_out.weight"] = emb
+        with torch.no_grad():
+            hf_model.model.decoder.embed_tokens.weight[wo.EOT] = emb[wo.EOT]
+    B = 3
+    audio = wo.synthetic_audio(B)
+    want = hf.hf_generate(hf_model, hf.hf_log_mel(audio, 80), "tiny", max_new=max_new, num_beams=beams)
+    m = w.WhisperIPA("tiny", dtype="float32", max_batch=B, max_beams=beams)
+    m.load_state_dict(sd)
+    got = m.generate(w.log_mel_features(audio, 80), decoder_input_ids=torch.tensor([wo.PROMPT_PRE_V3] * B),
+                     max_new_tokens=max_new, num_beams=beams, length_penalty=1.0).cpu()
+    m.close()
+    width = max(got.shape[1], want.shape[1])
+    pad = lambda t: torch.nn.functional.pad(t, (0, width - t.shape[1]), value=wo.EOT)
+    assert torch.equal(pad(got), pad(want)), f"beam search differs from HF:\n{got}\n{want}"
+    if eot_like is not None:
+        assert want.shape[1] < max_new, "the crafted weights are meant to finish hypotheses before max_new"
+
+
+def test_beam_search_bf16_runs_and_mostly_agrees(w, tiny_gain_sd):
+    """bf16 path through the same beam bookkeeping: the logits differ from the fp32 oracle at the 1e-2 level, so the
+    hypotheses are compared as token agreement (reported), not exactly."""
+    from oracle import hf_reference as hf
+    from oracle import whisper_oracle as wo
+    B, beams, max_new = 4, 5, 24
+    audio = wo.synthetic_audio(B)
+    hf_model = hf.build_hf_model("tiny", seed=0, init_gain=3.0)
+    want = hf.hf_generate(hf_model, hf.hf_log_mel(audio, 80), "tiny", max_new=max_new, num_beams=beams)
+    m = w.WhisperIPA("tiny", dtype="bfloat16", max_batch=B, max_beams=beams)
+    m.load_state_dict(tiny_gain_sd)
+    got = m.generate(w.log_mel_features(audio, 80), decoder_input_ids=torch.tensor([wo.PROMPT_PRE_V3] * B),
+                     max_new_tokens=max_new, num_beams=beams).cpu()
+    m.close()
+    assert got.shape[0] == B and got.shape[1] <= max_new
+    n = min(got.shape[1], want.shape[1])
+    agree = (got[:, :n] == want[:, :n]).float().mean().item()
+    print(f"\n[bf16 beam {beams}] token agreement with HF fp32 beam search {agree:.3f}")
+    assert agree > 0.8

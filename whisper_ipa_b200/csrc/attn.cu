@@ -268,7 +268,7 @@ template <typename T>
 __global__ void __launch_bounds__(128, sizeof(T) == 2 ? 8 : 4)
 self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, const T* __restrict__ vpool,
                       const int* __restrict__ block_table, int bt_stride, const int* __restrict__ pos_ptr,
-                      T* __restrict__ out, int H) {
+                      T* __restrict__ out, int H, const int* __restrict__ anc_base, const int* __restrict__ flip_ptr, int anc_L) {
     using C = CaCfg<T>;
     constexpr int KPW = 32 / C::LPK;                               // keys per warp instruction
     constexpr int ITERS = WIPA_PAGE / KPW;
@@ -284,6 +284,9 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
     const int len = *pos_ptr + 1;
     const int npages = (len + WIPA_PAGE - 1) / WIPA_PAGE;
     const int* bt = block_table + (size_t)b * bt_stride;
+    // beam search: position p of this sequence lives in the pages of slot anc[p] (p < len - 1); the newest position is
+    // always the sequence's own.  Greedy decoding passes anc_base = nullptr (every position is the sequence's own).
+    const int* anc = anc_base ? anc_base + ((size_t)(*flip_ptr) * gridDim.x / H + b) * anc_L : nullptr;
     float qv[C::VEC];
     {
         const float4* qp = reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64 + li * C::VEC);
@@ -298,17 +301,24 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
         const int page = bt[pg];
         const int nkeys = min(WIPA_PAGE, len - pg * WIPA_PAGE);
         const size_t base = ((size_t)page * H + h) * WIPA_PAGE * 64;
+        auto key_base = [&](int key) -> size_t {                   // element offset of row `key` of this page
+            if (anc == nullptr) return base + (size_t)key * 64;
+            const int p = pg * WIPA_PAGE + key;
+            if (p == len - 1) return base + (size_t)key * 64;
+            const int pg2 = block_table[(size_t)anc[p] * bt_stride + pg];
+            return (((size_t)pg2 * H + h) * WIPA_PAGE + key) * 64;
+        };
         uint4 kraw[ITERS];
         vraw vr[WIPA_PAGE];
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
             const int key = it * KPW + grp;
             kraw[it] = make_uint4(0u, 0u, 0u, 0u);
-            if (key < nkeys) kraw[it] = *reinterpret_cast<const uint4*>(kpool + base + (size_t)key * 64 + li * C::VEC);
+            if (key < nkeys) kraw[it] = *reinterpret_cast<const uint4*>(kpool + key_base(key) + li * C::VEC);
         }
 #pragma unroll
         for (int j = 0; j < WIPA_PAGE; ++j) {
-            if (j < nkeys) vr[j] = *reinterpret_cast<const vraw*>(vpool + base + (size_t)j * 64 + 2 * lane);
+            if (j < nkeys) vr[j] = *reinterpret_cast<const vraw*>(vpool + key_base(j) + 2 * lane);
         }
         float sc[ITERS];
         float mw = -INFINITY;
@@ -370,14 +380,15 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
 
 template <typename T>
 int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
-                          const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st) {
+                          const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st, const int* anc_base, const int* flip_ptr,
+                          int anc_L) {
     WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T>, dim3(Bs * H), dim3(128), (size_t)0, st, q, kpool, vpool,
-                                block_table, bt_stride, pos_ptr, out, H));
+                                block_table, bt_stride, pos_ptr, out, H, anc_base, flip_ptr, anc_L));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
-template int launch_self_attention<float>(const float*, const float*, const float*, const int*, int, const int*, float*, int, int, cudaStream_t);
-template int launch_self_attention<bf16>(const float*, const bf16*, const bf16*, const int*, int, const int*, bf16*, int, int, cudaStream_t);
+template int launch_self_attention<float>(const float*, const float*, const float*, const int*, int, const int*, float*, int, int, cudaStream_t, const int*, const int*, int);
+template int launch_self_attention<bf16>(const float*, const bf16*, const bf16*, const int*, int, const int*, bf16*, int, int, cudaStream_t, const int*, const int*, int);
 
 // ================================================================================================
 // decoder cross-attention, one query per (sequence, head) against 1500 cached encoder keys/values

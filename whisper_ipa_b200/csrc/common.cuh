@@ -351,7 +351,8 @@ int launch_enc_attention(const T* q, const T* k, const T* v, T* out, int B, int 
 int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, int B, int H, int T, cudaStream_t st);   // attn_tc.cu
 template <typename T>
 int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
-                          const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st);
+                          const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st, const int* anc_base = nullptr,
+                          const int* flip_ptr = nullptr, int anc_L = 0);   // anc: beam ancestry [2][Bs][anc_L] (beam search)
 // split-K cross-attention: part = f32 [Bs*H, n_split, 66] scratch, counters = int [Bs*H] (zero, self-resetting)
 template <typename T>
 int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
@@ -383,3 +384,31 @@ struct DecodeState {       // all device pointers, owned by the context
     int eot;
 };
 int launch_greedy_finalize(const float* pmax, const int* pidx, int n_tiles, DecodeState ds, int Bs, cudaStream_t st);
+
+// beam search state (beam.cu); all device pointers owned by the context.  Sequences / ancestry are ping-pong arrays
+// [2][n_utts * beams][L]; *flip selects the current half.
+struct BeamState {
+    int* pos;                // shared with DecodeState: position consumed by the current step
+    int* step;               // index of the token being sampled
+    int* flip;
+    int* cur_tok;            // [n_seqs] token fed to the next step
+    int* run_seq;            // running sequences (prompt included)
+    int* fin_seq;            // finished hypotheses, best first
+    int* anc;                // anc[s][q]: slot whose self-KV pages hold position q of running beam s
+    float* run_score;        // [n_seqs]
+    float* run_score_next;
+    float* fin_score;        // [n_seqs] length-penalised scores of the finished slots (-1e9 = empty)
+    float* fin_score_next;
+    int* fin_done;           // [n_seqs]
+    int* fin_done_next;
+    int* unsat;              // [n_utts] HF's is_early_stop_heuristic_unsatisfied
+    int* n_done;             // utterances that can no longer improve
+    int beams, L, prompt_len, max_length, eot;
+    float length_penalty;
+};
+int launch_beam_row_topk(const float* logits, long long ld, int V, const uint32_t* mask_always, const uint32_t* mask_begin,
+                         const int* step_ptr, const float* run_score, int keep, float* out_val, int* out_idx, int n_rows,
+                         cudaStream_t st);
+int launch_beam_update(const BeamState& bs, const float* cand_val, const int* cand_idx, int V, int n_utts, cudaStream_t st);
+int launch_beam_init(const BeamState& bs, const int* prompt_dev, int n_utts, cudaStream_t st);
+int launch_beam_finish(const BeamState& bs, int n_utts, int max_new, int* out_ids, int* out_len, cudaStream_t st);

@@ -81,10 +81,15 @@ struct wipa_ctx {
     int *block_table, *utt_of_seq, *ca_counters, *pidx;
     int *d_pos, *d_step, *d_cur_tok, *d_done, *d_n_done, *d_forced, *d_out_ids, *d_out_len;
     uint32_t *mask_always, *mask_begin;
+    // beam search state (allocated when max_beams > 1)
+    int *b_flip = nullptr, *b_run_seq = nullptr, *b_fin_seq = nullptr, *b_anc = nullptr, *b_fin_done = nullptr, *b_fin_done_next = nullptr,
+        *b_unsat = nullptr, *b_cand_idx = nullptr, *b_prompt = nullptr;
+    float *b_run_score = nullptr, *b_run_score_next = nullptr, *b_fin_score = nullptr, *b_fin_score_next = nullptr, *b_cand_val = nullptr;
     int* h_pinned = nullptr;       // pinned host scratch (n_done)
     cudaStream_t cap_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy default stream)
     int n_logit_tiles;
     int bn_enc, bn_dec, bn_logits, ca_split;
+    int beam_L = 0;                // row length of the beam-search sequence / ancestry arrays of the current decode
     int persistent_min_tiles = 296; // WIPA_PERSISTENT_MIN_TILES: fewer 128x256 tiles than this -> plain 128x128-tile kernel
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
     int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (bf16 path)
@@ -384,7 +389,8 @@ DecodeState make_state(wipa_ctx* c, int n_forced, int max_new, int eot) {
     return ds;
 }
 
-int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, float* logits_out, long long ldo, cudaStream_t st) {
+int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, float* logits_out, long long ldo, cudaStream_t st,
+                bool beam = false, bool finalize = true) {
     const wipa_arch& a = c->a;
     const int d = a.d_model, H = a.heads, ffn = a.ffn, V = a.vocab;
     const int skip = c->skip_mask;       // ablation bits: 1 LN, 2 self-attn, 4 cross-attn, 8 qkv, 16 d x d GEMMs, 32 fc1, 64 fc2, 128 logits
@@ -401,11 +407,12 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             ep.H = H; ep.d = d; ep.pos_ptr = c->d_pos; ep.block_table = c->block_table; ep.bt_stride = c->pages_per_seq;
             if (!(skip & 8)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.qkv_w, S, 3 * d, d, ep, c->bn_dec, st));
         }
+        const int* anc = beam ? c->b_anc : nullptr;            // beam search reads every position from the slot that wrote it
         if (skip & 2) {}
         else if (c->bf) WIPA_TRY(launch_self_attention<bf16>(c->dq, (const bf16*)kp, (const bf16*)vp, c->block_table, c->pages_per_seq,
-                                                        c->d_pos, (bf16*)c->dattn, S, H, st));
+                                                        c->d_pos, (bf16*)c->dattn, S, H, st, anc, c->b_flip, c->beam_L));
         else WIPA_TRY(launch_self_attention<float>(c->dq, (const float*)kp, (const float*)vp, c->block_table, c->pages_per_seq,
-                                                   c->d_pos, (float*)c->dattn, S, H, st));
+                                                   c->d_pos, (float*)c->dattn, S, H, st, anc, c->b_flip, c->beam_L));
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.o_b; ep.out = c->dx; ep.resid = c->dx;
@@ -465,7 +472,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
                 WIPA_TRY(launch_row_argmax(dst, S, V, c->mask_always, c->mask_begin, c->d_step, c->pmax, c->pidx, st));
         }
     }
-    WIPA_TRY(launch_greedy_finalize(c->pmax, c->pidx, n_tiles, ds, S, st));
+    if (finalize) WIPA_TRY(launch_greedy_finalize(c->pmax, c->pidx, n_tiles, ds, S, st));
     return WIPA_OK;
 }
 
@@ -572,8 +579,25 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     CTX_TRY(ctx_alloc(c, (void**)&c->ca_counters, (size_t)S * H * 4, true));
     CTX_TRY(ctx_alloc(c, (void**)&c->pmax, (size_t)S * c->n_logit_tiles * 4, true));
     CTX_TRY(ctx_alloc(c, (void**)&c->pidx, (size_t)S * c->n_logit_tiles * 4, true));
-    if (!c->bf) CTX_TRY(ctx_alloc(c, (void**)&c->logits, (size_t)S * V * 4, false));
+    if (!c->bf || max_beams > 1) CTX_TRY(ctx_alloc(c, (void**)&c->logits, (size_t)S * V * 4, false));
     else c->logits = nullptr;
+    if (max_beams > 1) {
+        const size_t SL = (size_t)S * WIPA_MAX_TGT;
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_flip, 256, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_run_seq, 2 * SL * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_fin_seq, 2 * SL * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_anc, 2 * SL * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_run_score, (size_t)S * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_run_score_next, (size_t)S * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_fin_score, (size_t)S * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_fin_score_next, (size_t)S * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_fin_done, (size_t)S * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_fin_done_next, (size_t)S * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_unsat, (size_t)S * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_cand_val, (size_t)S * 16 * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_cand_idx, (size_t)S * 16 * 4, true));
+        CTX_TRY(ctx_alloc(c, (void**)&c->b_prompt, (size_t)WIPA_MAX_TGT * 4, true));
+    }
     CTX_TRY(ctx_alloc(c, (void**)&c->block_table, (size_t)S * c->pages_per_seq * 4, true));
     CTX_TRY(ctx_alloc(c, (void**)&c->utt_of_seq, (size_t)S * 4, true));
     CTX_TRY(ctx_alloc(c, (void**)&c->d_pos, 256, true));
@@ -778,9 +802,84 @@ extern "C" int wipa_decode_logits(wipa_ctx* c, int B, const int32_t* tokens, int
 
 extern "C" int wipa_decode_beam(wipa_ctx* c, int B, int beams, float length_penalty, const wipa_decode_opts* o,
                                 int32_t* out_ids, int32_t* out_len, void* stream) {
-    (void)c; (void)B; (void)beams; (void)length_penalty; (void)o; (void)out_ids; (void)out_len; (void)stream;
-    wipa_set_error("wipa_decode_beam: beam search is not built yet");
-    return WIPA_EUNSUPPORTED;
+    WIPA_TRY(check_decode_args(c, B, o, out_ids, out_len));
+    WIPA_TRY(require_weights(c));
+    WIPA_CHECK(beams >= 2 && beams <= 8, WIPA_EINVAL, "wipa_decode_beam: beams=%d outside 2..8 (use wipa_decode_greedy for 1)", beams);
+    WIPA_CHECK(beams <= c->max_beams && B * beams <= c->max_seqs, WIPA_EINVAL,
+               "wipa_decode_beam: B=%d x beams=%d exceeds the context (max_batch %d, max_beams %d)", B, beams, c->max_batch, c->max_beams);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int S = B * beams, P = o->prompt_len, max_new = o->max_new, V = c->a.vocab, keep = 2 * beams;
+    const int L = P + max_new;                                 // HF's max_length
+    WIPA_TRY(upload_mask(c, c->mask_always, o->suppress, o->n_suppress, st));
+    WIPA_TRY(upload_mask(c, c->mask_begin, o->begin_suppress, o->n_begin_suppress, st));
+    std::vector<int32_t> forced((size_t)S * P);
+    for (int b = 0; b < S; ++b) memcpy(&forced[(size_t)b * P], o->prompt, sizeof(int32_t) * P);
+    WIPA_CUDA_CHECK(cudaMemcpyAsync(c->b_prompt, o->prompt, sizeof(int32_t) * P, cudaMemcpyHostToDevice, st));
+    DecodeState ds;
+    WIPA_TRY(decode_setup(c, S, beams, forced, P, max_new, o->eot, &ds, st));   // utt_of_seq[s] = s / beams: beams share the cross-KV
+    c->beam_L = L;
+    BeamState bs;
+    bs.pos = c->d_pos; bs.step = c->d_step; bs.flip = c->b_flip; bs.cur_tok = c->d_cur_tok;
+    bs.run_seq = c->b_run_seq; bs.fin_seq = c->b_fin_seq; bs.anc = c->b_anc;
+    bs.run_score = c->b_run_score; bs.run_score_next = c->b_run_score_next;
+    bs.fin_score = c->b_fin_score; bs.fin_score_next = c->b_fin_score_next;
+    bs.fin_done = c->b_fin_done; bs.fin_done_next = c->b_fin_done_next;
+    bs.unsat = c->b_unsat; bs.n_done = c->d_n_done;
+    bs.beams = beams; bs.L = L; bs.prompt_len = P; bs.max_length = L; bs.eot = o->eot; bs.length_penalty = length_penalty;
+    WIPA_TRY(launch_beam_init(bs, c->b_prompt, B, st));
+
+    auto beam_step = [&](cudaStream_t s2) -> int {
+        // decoder forward for all S running beams with fp32 logits, then the two bookkeeping kernels
+        WIPA_TRY(decode_step(c, S, ds, 2, c->logits, (long long)V, s2, /*beam=*/true, /*finalize=*/false));
+        WIPA_TRY(launch_beam_row_topk(c->logits, (long long)V, V, c->mask_always, c->mask_begin, c->d_step, c->b_run_score, keep,
+                                      c->b_cand_val, c->b_cand_idx, S, s2));
+        WIPA_TRY(launch_beam_update(bs, c->b_cand_val, c->b_cand_idx, V, B, s2));
+        return WIPA_OK;
+    };
+    // the P-1 teacher-forced prompt positions: every beam of an utterance consumes the same tokens
+    for (int s = 0; s < P - 1; ++s) WIPA_TRY(decode_step(c, S, ds, 0, nullptr, 0, st, /*beam=*/true));
+    WIPA_TRY(beam_step(st));                                    // first sampled step eagerly, the rest as graph replays
+    int done_steps = 1;
+    GraphEntry* ge = nullptr;
+    if (env_int("WIPA_NO_GRAPH", 0) == 0 && max_new >= 3) {
+        // everything the captured kernels bake in as parameters: shapes, prompt length, eot, beams, length penalty
+        uint32_t lp_bits;
+        memcpy(&lp_bits, &length_penalty, 4);
+        long long key = 0x4245414dLL;                            // 'BEAM': never equal to a greedy key (those are < 2^62 and even-structured)
+        for (long long v : {(long long)S, (long long)P, (long long)max_new, (long long)o->eot, (long long)beams, (long long)lp_bits})
+            key = key * 1000003LL + v;
+        ge = &c->graphs[key | (1LL << 62)];
+        if (ge->exec == nullptr) {
+            cudaGraph_t g = nullptr;
+            const int64_t before = g_wipa_launches;
+            WIPA_CUDA_CHECK(cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+            const int r = beam_step(c->cap_stream);
+            cudaError_t e = cudaStreamEndCapture(c->cap_stream, &g);
+            if (r != WIPA_OK) { if (g) cudaGraphDestroy(g); return r; }
+            WIPA_CUDA_CHECK(e);
+            ge->nodes = (int)(g_wipa_launches - before);
+            g_wipa_launches = before;
+            WIPA_CUDA_CHECK(cudaGraphInstantiate(&ge->exec, g, 0));
+            cudaGraphDestroy(g);
+        }
+    }
+    int* h_done = c->h_pinned;
+    *h_done = 0;
+    while (done_steps < max_new) {
+        const int burst = max_new - done_steps < 16 ? max_new - done_steps : 16;
+        for (int i = 0; i < burst; ++i) {
+            if (ge) { WIPA_CUDA_CHECK(cudaGraphLaunch(ge->exec, st)); g_wipa_launches += ge->nodes; }
+            else WIPA_TRY(beam_step(st));
+        }
+        done_steps += burst;
+        if (done_steps < max_new) {       // HF stops once no utterance can improve its finished beams any more
+            WIPA_CUDA_CHECK(cudaMemcpyAsync(h_done, c->d_n_done, sizeof(int), cudaMemcpyDeviceToHost, st));
+            WIPA_CUDA_CHECK(cudaStreamSynchronize(st));
+            if (*h_done >= B) break;
+        }
+    }
+    c->decode_steps += P - 1 + done_steps;
+    return launch_beam_finish(bs, B, max_new, out_ids, out_len, st);
 }
 
 extern "C" int wipa_ctx_get_info(wipa_ctx* c, int what, int64_t* out) {
