@@ -199,3 +199,49 @@ def test_beam_search_bf16_runs_and_mostly_agrees(w, tiny_gain_sd):
     agree = (got[:, :n] == want[:, :n]).float().mean().item()
     print(f"\n[bf16 beam {beams}] token agreement with HF fp32 beam search {agree:.3f}")
     assert agree > 0.8
+
+
+@pytest.mark.parametrize("shape", ["large-v3", "medium"])
+def test_wide_architectures_reduced_depth(w, shape):
+    """Shape generality: the large-v3 geometry (d 1280, 20 heads, ffn 5120, 128 mel bins, vocab 51866, +1-shifted prompt
+    ids) and the medium geometry (d 1024, 16 heads), cut to 2+2 layers so the HF oracle stays cheap.  fp32 greedy ids
+    must equal HF's; the bf16 path reports token agreement."""
+    import logging
+    import warnings
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+    from whisper_ipa_b200.archs import ARCHS, WhisperArch
+    from oracle import hf_reference as hf
+    from oracle import whisper_oracle as wo
+    full = ARCHS[shape]
+    arch = WhisperArch(full.name, full.d_model, 2, 2, full.heads, full.ffn, full.n_mels, full.vocab)
+    logging.getLogger("transformers").setLevel(logging.ERROR)
+    cfg = WhisperConfig(**arch.hf_config_kwargs(), decoder_start_token_id=50258, eos_token_id=50257, pad_token_id=50257,
+                        bos_token_id=50257, begin_suppress_tokens=[220, 50257])
+    torch.manual_seed(0)
+    hf_model = WhisperForConditionalGeneration(cfg).eval()
+    with torch.no_grad():
+        for n, p in hf_model.named_parameters():
+            if p.dim() >= 2 and "embed_positions" not in n:
+                p.mul_(2.0)                               # make the ids depend on the audio (see build_hf_model)
+    sd = hf.state_dict_f32(hf_model)
+    B, max_new = 2, 10
+    audio = wo.synthetic_audio(B)
+    prompt = arch.prompt("en", "transcribe", True)
+    feats_hf = hf.hf_log_mel(audio, arch.n_mels)
+    with torch.no_grad(), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        want = hf_model.generate(feats_hf, decoder_input_ids=torch.tensor([prompt] * B), max_new_tokens=max_new, do_sample=False)
+    feats = w.log_mel_features(audio, arch.n_mels)
+    assert (feats.cpu() - feats_hf).abs().max().item() < 1e-3
+    for dtype in ("float32", "bfloat16"):
+        m = w.WhisperIPA(arch, dtype=dtype, max_batch=B)
+        m.load_state_dict(sd)
+        got = m.generate(feats, decoder_input_ids=torch.tensor([prompt] * B), max_new_tokens=max_new).cpu()
+        m.close()
+        n = min(got.shape[1], want.shape[1])
+        agree = (got[:, :n] == want[:, :n]).float().mean().item()
+        print(f"\n[{shape} geometry, 2+2 layers, {dtype}] token agreement with HF {agree:.3f}")
+        if dtype == "float32":
+            assert got.shape == want.shape and torch.equal(got, want)
+        else:
+            assert agree > 0.7
