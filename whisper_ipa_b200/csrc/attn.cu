@@ -264,7 +264,7 @@ __device__ __forceinline__ float2 v_to_f2(__nv_bfloat162 v) { return __bfloat162
 __device__ __forceinline__ void st_v2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void st_v2(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
 
-template <typename T>
+template <typename T, bool ANC>
 __global__ void __launch_bounds__(128, sizeof(T) == 2 ? 8 : 4)
 self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, const T* __restrict__ vpool,
                       const int* __restrict__ block_table, int bt_stride, const int* __restrict__ pos_ptr,
@@ -286,7 +286,7 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
     const int* bt = block_table + (size_t)b * bt_stride;
     // beam search: position p of this sequence lives in the pages of slot anc[p] (p < len - 1); the newest position is
     // always the sequence's own.  Greedy decoding passes anc_base = nullptr (every position is the sequence's own).
-    const int* anc = anc_base ? anc_base + ((size_t)(*flip_ptr) * gridDim.x / H + b) * anc_L : nullptr;
+    const int* anc = ANC ? anc_base + ((size_t)(*flip_ptr) * gridDim.x / H + b) * anc_L : nullptr;
     float qv[C::VEC];
     {
         const float4* qp = reinterpret_cast<const float4*>(q + (size_t)b * d + h * 64 + li * C::VEC);
@@ -302,7 +302,7 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
         const int nkeys = min(WIPA_PAGE, len - pg * WIPA_PAGE);
         const size_t base = ((size_t)page * H + h) * WIPA_PAGE * 64;
         auto key_base = [&](int key) -> size_t {                   // element offset of row `key` of this page
-            if (anc == nullptr) return base + (size_t)key * 64;
+            if (!ANC) return base + (size_t)key * 64;
             const int p = pg * WIPA_PAGE + key;
             if (p == len - 1) return base + (size_t)key * 64;
             const int pg2 = block_table[(size_t)anc[p] * bt_stride + pg];
@@ -382,8 +382,12 @@ template <typename T>
 int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
                           const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st, const int* anc_base, const int* flip_ptr,
                           int anc_L) {
-    WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T>, dim3(Bs * H), dim3(128), (size_t)0, st, q, kpool, vpool,
-                                block_table, bt_stride, pos_ptr, out, H, anc_base, flip_ptr, anc_L));
+    if (anc_base != nullptr)
+        WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T, true>, dim3(Bs * H), dim3(128), (size_t)0, st, q, kpool, vpool,
+                                      block_table, bt_stride, pos_ptr, out, H, anc_base, flip_ptr, anc_L));
+    else
+        WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T, false>, dim3(Bs * H), dim3(128), (size_t)0, st, q, kpool, vpool,
+                                      block_table, bt_stride, pos_ptr, out, H, anc_base, flip_ptr, anc_L));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

@@ -10,6 +10,8 @@
 // The A operand is described by a 3-D tensor map (K, rows-per-batch, batches) whose row stride may be smaller than
 // K: a k=3 conv1d over a channels-last, zero-row-padded signal is then exactly this GEMM (no im2col buffer),
 // and out-of-range rows / K tails are zero-filled by TMA.
+#include <stdlib.h>
+
 #define WIPA_PDL_CLASS 8
 #include "common.cuh"
 #include "ptx.cuh"
@@ -48,7 +50,11 @@ __device__ unsigned long long g_gemm_dbg[4096 * 8];
 #define DBG_STAMP(i) do { } while (0)
 #endif
 
-template <int BN, int BOXM>
+// CL > 1: CL consecutive N tiles of one M tile form a thread-block cluster.  Every CTA fetches 1/CL of the rows of each A
+// k-block and TMA-multicasts it to the whole cluster, so the activations cross L2 -> SM once per cluster instead of
+// once per N tile (the decode GEMMs are A-traffic bound: 24-96 N tiles re-read the same 128 x K rows).  A ring slot may
+// only be refilled when ALL CTAs of the cluster have consumed it: tcgen05.commit multicasts the slot release.
+template <int BN, int BOXM, int CL>
 __global__ void __launch_bounds__(192)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
                     int tiles_per_batch, int a_rpb, EpiParams ep) {
@@ -74,7 +80,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     if (warp == 1) {
         if (lane == 0) {
-            for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+            for (int s = 0; s < Cfg::STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], CL); }
             ptx::mbar_init(tmem_full, 1);
             ptx::fence_barrier_init();
         }
@@ -84,8 +90,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (CL > 1) ptx::cluster_sync_all();                      // every CTA's barriers exist before any peer multicasts into them
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t cta_rank = CL > 1 ? ptx::cluster_ctarank() : 0u;
+    constexpr uint16_t mc_mask = (uint16_t)((1u << CL) - 1u);
+    constexpr int SLICE_ROWS = BOXM / CL;                     // rows of each A k-block this CTA fetches for the cluster
+    constexpr int SLICE_BYTES = SLICE_ROWS * TC_BK * 2;
+    auto load_a = [&](uint8_t* dst, uint64_t* bar, int kcoord) {
+        if (CL > 1) ptx::tma_load_3d_mc(dst + cta_rank * SLICE_BYTES, &tmA, bar, kcoord, t0 + (int)cta_rank * SLICE_ROWS, batch, mc_mask);
+        else ptx::tma_load_3d(dst, &tmA, bar, kcoord, t0, batch);
+    };
 
     // Role warps run warp-uniformly and elect one lane per issue: ptxas then keeps descriptors and barrier addresses
     // in uniform registers and emits bare UTMALDG / UTCHMMA (under `if (lane == 0)` every such instruction is wrapped
@@ -113,7 +128,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int g = 0; g < pre; ++g) {
                 const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
                 for (int i = 0; i < nk; ++i)
-                    ptx::tma_load_3d(sA + g * Cfg::STAGE_A + i * Cfg::A_BYTES, &tmA, &full[g], (g * KPB + i) * TC_BK, t0, batch);
+                    load_a(sA + g * Cfg::STAGE_A + i * Cfg::A_BYTES, &full[g], (g * KPB + i) * TC_BK);
             }
         }
         __syncwarp();
@@ -125,7 +140,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
                 ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)nk * (Cfg::A_BYTES + Cfg::W_BYTES));
                 for (int i = 0; i < nk; ++i) {
-                    ptx::tma_load_3d(sA + s * Cfg::STAGE_A + i * Cfg::A_BYTES, &tmA, &full[s], (g * KPB + i) * TC_BK, t0, batch);
+                    load_a(sA + s * Cfg::STAGE_A + i * Cfg::A_BYTES, &full[s], (g * KPB + i) * TC_BK);
                     ptx::tma_load_2d(sW + s * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[s], (g * KPB + i) * TC_BK, n0);
                 }
             }
@@ -158,7 +173,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                            (g | i | k) != 0 ? 1u : 0u);
                     }
                 }
-                ptx::umma_commit(&empty[s]);                 // frees the ring slot when these MMAs retire
+                if (CL > 1) ptx::umma_commit_mc(&empty[s], mc_mask);   // the slot is free once EVERY CTA of the cluster has consumed it
+                else ptx::umma_commit(&empty[s]);            // frees the ring slot when these MMAs retire
             }
             __syncwarp();
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -270,6 +286,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 64) DBG_STAMP(6);
     ptx::tc_fence_before();
     __syncthreads();
+    if (CL > 1) ptx::cluster_sync_all();                      // no CTA leaves while peers may still signal its barriers
     if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     if (threadIdx.x == 0) DBG_STAMP(7);
 }
@@ -290,19 +307,32 @@ int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dim
     return WIPA_OK;
 }
 
-template <int BN, int BOXM>
+template <int BN, int BOXM, int CL>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int tiles_per_batch, int n_batch, int a_rpb,
               int N, EpiParams ep, cudaStream_t st) {
     using Cfg = TcCfg<BN, BOXM>;
     static bool configured = false;
     if (!configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, BOXM>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+        WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, BOXM, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
     dim3 grid(cdiv(N, BN), tiles_per_batch * n_batch);
     if (ep.mode == EPI_ARGMAX) ep.n_tiles = grid.x;
-    WIPA_CUDA_CHECK(wipa_launch(gemm_bf16_tc_kernel<BN, BOXM>, grid, dim3(192), (size_t)Cfg::SMEM, st, tmA, tmW, num_kb,
-                                tiles_per_batch, a_rpb, ep));
+    if (CL == 1) {
+        WIPA_CUDA_CHECK(wipa_launch(gemm_bf16_tc_kernel<BN, BOXM, CL>, grid, dim3(192), (size_t)Cfg::SMEM, st, tmA, tmW, num_kb,
+                                    tiles_per_batch, a_rpb, ep));
+    } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = (g_wipa_pdl & WIPA_PDL_CLASS) ? 2 : 1;
+        WIPA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, BOXM, CL>, tmA, tmW, num_kb, tiles_per_batch, a_rpb, ep));
+    }
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
@@ -341,12 +371,17 @@ int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, cons
     WIPA_CHECK((reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, WIPA_EINVAL,
                "gemm_bf16: operands must be 16-byte aligned");
     const int box_m = (a.a_rpb <= 64 && block_n == 32) ? 64 : 128;
+    // WIPA_GEMM_MULTICAST=1: clusters of 4 N tiles with A multicast for the narrow (decode) tiles whenever the N tiles
+    // divide evenly.  Parity-tested, but OFF by default: measured on B200 at B=256 the two cluster barriers and the
+    // co-scheduling constraint cost more (3345 us / decode step) than the saved L2->SM traffic (3204 us without).
+    static const int mc_env = [] { const char* e = getenv("WIPA_GEMM_MULTICAST"); return (e && *e) ? atoi(e) : 0; }();
+    const bool mc = mc_env != 0 && block_n <= 64 && (cdiv(N, block_n) % 4 == 0);
     CUtensorMap tmA, tmW;
     {
         cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a.a_rpb, (cuuint64_t)a.n_batch};
         cuuint64_t bstride = a.n_batch > 1 ? (cuuint64_t)a.a_bstride : (cuuint64_t)a.a_rpb * (cuuint64_t)a.lda;
         cuuint64_t strides[2] = {(cuuint64_t)a.lda * 2, bstride * 2};
-        cuuint32_t box[3] = {TC_BK, (cuuint32_t)box_m, 1};
+        cuuint32_t box[3] = {TC_BK, (cuuint32_t)(mc ? box_m / 4 : box_m), 1};
         WIPA_TRY(make_map(&tmA, a.ptr, 3, dims, strides, box));
     }
     {
@@ -361,11 +396,14 @@ int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, cons
     const int tpb = cdiv(a.a_rpb, TC_BM);
     switch (block_n) {
         case 32:
-            if (box_m == 64) return launch_bn<32, 64>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-            return launch_bn<32, 128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-        case 64: return launch_bn<64, 128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-        case 128: return launch_bn<128, 128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-        case 256: return launch_bn<256, 128>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+            if (box_m == 64) return mc ? launch_bn<32, 64, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st)
+                                       : launch_bn<32, 64, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+            return mc ? launch_bn<32, 128, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st)
+                      : launch_bn<32, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 64: return mc ? launch_bn<64, 128, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st)
+                           : launch_bn<64, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 128: return launch_bn<128, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+        case 256: return launch_bn<256, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
         default: break;
     }
     wipa_set_error("gemm_bf16: unsupported block_n %d", block_n);
