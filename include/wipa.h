@@ -102,6 +102,14 @@ int wipa_decode_logits(wipa_ctx*, int B, const int32_t* tokens, int T, float* lo
 int wipa_per_batch(const int32_t* ref, const int32_t* ref_off, const int32_t* hyp, const int32_t* hyp_off,
                    int N, int max_ref_len, int32_t* dist_len, void* stream);
 
+/* Replaces: PFERCalculator.phone_feature_error_rate (mode 0, Hamming / 24; ref:scripts/evaluate_ipa.py:163-213) and
+ * PFERCalculatorCosine.phone_feature_error_rate (mode 1; ref:scripts/evaluate_ipa.py:236-287) for N pairs at once.
+ * Same CSR packing of interned phone ids as wipa_per_batch; feats: device int8[n_phones, 24] (panphon's numeric
+ * features, all-zero rows for unknown phones); dist: device f64[N] = D[len_ref][len_hyp] of the feature-weighted edit
+ * distance, bit-identical to the reference's float64 numpy DP.  The percentage stays on the host. */
+int wipa_pfer_batch(const int32_t* ref, const int32_t* ref_off, const int32_t* hyp, const int32_t* hyp_off,
+                    int N, int max_ref_len, const int8_t* feats, int mode, double* dist, void* stream);
+
 /* ---- introspection -------------------------------------------------------------------------- */
 const char* wipa_strerror(int code);
 const char* wipa_last_error(void);

@@ -89,3 +89,50 @@ def test_per_properties_at_scale(built_lib):
     dele = [np.delete(x, len(x) // 2) for x in a]
     assert (metrics.edit_distance_counts(a, sub).cpu().numpy()[:, 0] == 1).all()
     assert (metrics.edit_distance_counts(a, dele).cpu().numpy()[:, 0] == 1).all()
+
+
+@pytest.mark.parametrize("cosine", [False, True])
+def test_pfer_kernel_bit_exact(cosine):
+    """Feature-weighted edit distance (PFER): the float64 GPU DP equals the numpy restatement of the reference's DP
+    bit for bit, on a synthetic ternary feature table (panphon's table is absent here), incl. empty / long / equal inputs."""
+    import numpy as np
+    import torch
+    from oracle import pfer_oracle as po
+    from whisper_ipa_b200 import metrics
+    rng = np.random.default_rng(7)
+    n_phones = 40
+    feats = rng.integers(-1, 2, size=(n_phones, 24)).astype(np.int8)
+    feats[3] = feats[5]                          # two distinct phones with identical features
+    feats[7] = 0                                 # an "unknown" phone: zero vector (0.001 guard in the cosine variant)
+    feats[8] = 0
+    lens = [(0, 0), (0, 5), (5, 0), (1, 1), (33, 31), (64, 65), (120, 97), (17, 200)] + \
+           [(int(rng.integers(1, 70)), int(rng.integers(1, 70))) for _ in range(40)]
+    refs = [rng.integers(0, n_phones, size=a).tolist() for a, _ in lens]
+    hyps = [rng.integers(0, n_phones, size=b).tolist() for _, b in lens]
+    hyps[4] = list(refs[4][:31])                 # shared prefix
+    refs.append(refs[6]); hyps.append(list(refs[6]))     # identical pair -> 0
+    got = metrics.feature_edit_distances(refs, hyps, feats, cosine=cosine).cpu().numpy()
+    fn = po.pfer_distance_cosine if cosine else po.pfer_distance_hamming
+    lookup = lambda p: feats[p]
+    want = np.array([fn(r, h, lookup) for r, h in zip(refs, hyps)])
+    assert got.dtype == np.float64 and np.array_equal(got, want), f"max diff {np.abs(got - want).max()}"
+    assert got[-1] == 0.0
+
+
+def test_evaluate_batch_with_feature_table():
+    """evaluate_batch fills the PFER keys from the GPU scorer once a feature table is registered."""
+    import numpy as np
+    from oracle import pfer_oracle as po
+    from whisper_ipa_b200 import metrics
+    table = {"a": [1] * 24, "b": [1] * 12 + [-1] * 12, "t": [-1] * 24, "ʃ": [0] * 23 + [1]}
+    metrics.set_feature_table(table)
+    try:
+        refs, hyps = ["abt", "tʃa", "", "ab"], ["abt", "tab", "a", ""]
+        out = metrics.evaluate_batch(refs, hyps)
+        lookup = lambda p: np.asarray(table.get(p, [0] * 24))
+        want = [po.pfer_percent(po.pfer_distance_hamming(metrics.tokenize_ipa(r), metrics.tokenize_ipa(h), lookup),
+                                len(metrics.tokenize_ipa(r)), len(metrics.tokenize_ipa(h))) for r, h in zip(refs, hyps)]
+        assert out["pfer_scores"] == want and out["pfer"] == np.mean(want) and out["pfer_std"] == np.std(want)
+        assert out["pfer_scores"][0] == 0.0 and out["pfer_scores"][2] == 100.0
+    finally:
+        metrics.set_feature_table(None)

@@ -64,3 +64,28 @@ def test_evaluate_batch_semantics():
     out = po.evaluate_batch_per([0.0, 50.0, 100.0])
     assert out["per"] == 50.0 and out["num_samples"] == 3
     assert out["per_std"] == pytest.approx(np.sqrt(5000 / 3))
+
+
+def test_pfer_oracle_properties():
+    """PFER restatement (oracle/pfer_oracle.py): with maximally different features the Hamming variant degenerates to the
+    unit-cost Levenshtein distance; identical sequences cost 0; a one-feature substitution costs 1/24; the cosine variant
+    copies the diagonal for equal vectors and uses the 0.001 guard for zero vectors."""
+    import numpy as np
+    from oracle import per_oracle as per
+    from oracle import pfer_oracle as po
+    rng = np.random.default_rng(3)
+    n = 12
+    feats = {i: np.full(24, 1 if i % 2 else -1) for i in range(n)}      # parity classes: differ in all 24 features or none
+    lookup = lambda p: feats[p]
+    for _ in range(20):
+        r = (rng.integers(0, n // 2, size=int(rng.integers(0, 15))) * 2).tolist()          # even phones
+        h = (rng.integers(0, n // 2, size=int(rng.integers(0, 15))) * 2 + 1).tolist()      # odd phones: never equal, all 24 differ
+        assert po.pfer_distance_hamming(r, h, lookup) == float(per.levenshtein(r, h))
+        assert po.pfer_distance_hamming(r, r, lookup) == 0.0
+    one = {0: np.zeros(24), 1: np.eye(24)[0]}
+    assert po.pfer_distance_hamming([0], [1], lambda p: one[p]) == 1 / 24
+    assert po.pfer_percent(po.pfer_distance_hamming([], [1], lambda p: one[p]), 0, 1) == 100.0
+    # cosine: phones 0 and 2 share a vector -> diagonal copy; zero vector -> denominator guard 0.001 -> penalty 1 - 0/0.001 = 1
+    cos = {0: np.ones(24), 1: np.zeros(24), 2: np.ones(24)}
+    assert po.pfer_distance_cosine([0, 0], [2, 2], lambda p: cos[p]) == 0.0
+    assert po.pfer_distance_cosine([0], [1], lambda p: cos[p]) == 1.0

@@ -49,6 +49,7 @@ PROTOTYPES = {
     "wipa_decode_beam": (_i, [_vp, _i, _i, _f, C.POINTER(DecodeOpts), _vp, _vp, _vp]),
     "wipa_decode_logits": (_i, [_vp, _i, C.POINTER(C.c_int32), _i, _vp, _vp]),
     "wipa_per_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
+    "wipa_pfer_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),
     "wipa_strerror": (C.c_char_p, [_i]),
     "wipa_last_error": (C.c_char_p, []),
     "wipa_launch_count": (_i64, [_i]),

@@ -150,11 +150,101 @@ def summarize(per_scores: Sequence[float]) -> Dict:
             "per_scores": list(per_scores)}
 
 
+# ---- PFER (ref:scripts/evaluate_ipa.py:108-337) ----------------------------------------------------------------------------
+_feature_override: Optional[Dict[str, Sequence[int]]] = None
+
+
+def set_feature_table(table: Optional[Dict[str, Sequence[int]]]) -> None:
+    """Register phone -> 24 numeric features (panphon's `word_to_vector_list(phone, numeric=True)[0]`) for images without
+    panphon; phones missing from the table get the zero vector, as the reference does for unknown phones."""
+    global _feature_override
+    _feature_override = table
+
+
+def _phone_features(phone: str) -> Optional[np.ndarray]:
+    if _feature_override is not None:
+        v = _feature_override.get(phone)
+        return np.zeros(24, dtype=np.int8) if v is None else np.asarray(v, dtype=np.int8)
+    ft = _feature_table()
+    if ft is None:
+        return None
+    try:                                                              # ref:scripts/evaluate_ipa.py:124-134
+        vecs = ft.word_to_vector_list(phone, numeric=True)
+        return np.asarray(vecs[0], dtype=np.int8) if len(vecs) > 0 else np.zeros(24, dtype=np.int8)
+    except Exception:
+        return np.zeros(24, dtype=np.int8)
+
+
+def pfer_available() -> bool:
+    return _feature_override is not None or _feature_table() is not None
+
+
+def feature_edit_distances(ref_ids: Sequence[Sequence[int]], hyp_ids: Sequence[Sequence[int]], feats: np.ndarray,
+                           cosine: bool = False, device: Optional[torch.device] = None) -> torch.Tensor:
+    """Batched feature-weighted edit distance on the GPU (csrc/pfer.cu): float64 D[len_ref][len_hyp] per pair.
+    `feats` is int8 [n_phones, 24] indexed by the interned ids."""
+    assert len(ref_ids) == len(hyp_ids), "Mismatched lengths"
+    n = len(ref_ids)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    out = torch.zeros((n,), dtype=torch.float64, device=dev)
+    if n == 0:
+        return out
+    rf, ro = _pack(ref_ids)
+    hf, ho = _pack(hyp_ids)
+    max_ref = int(np.max(np.diff(ro)))
+    f = np.ascontiguousarray(feats, dtype=np.int8).reshape(-1, 24)
+    if f.shape[0] == 0:
+        f = np.zeros((1, 24), dtype=np.int8)
+    bufs = [torch.from_numpy(a).to(dev) for a in (rf, ro, hf, ho, f)]
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().wipa_pfer_batch(bufs[0].data_ptr(), bufs[1].data_ptr(), bufs[2].data_ptr(), bufs[3].data_ptr(), n,
+                                              max_ref, bufs[4].data_ptr(), 1 if cosine else 0, out.data_ptr(),
+                                              torch.cuda.current_stream().cuda_stream), "wipa_pfer_batch")
+        torch.cuda.current_stream().synchronize()
+    return out
+
+
+def phone_feature_error_rates(references: Sequence[str], hypotheses: Sequence[str], cosine: bool = False) -> List[float]:
+    """ref:scripts/evaluate_ipa.py:301-315 (Hamming) / :329-343 (cosine) for a batch of string pairs."""
+    assert len(references) == len(hypotheses), "Mismatched lengths"
+    if not pfer_available():
+        raise RuntimeError("PFER needs panphon's feature table: install panphon or call metrics.set_feature_table()")
+    rp = [tokenize_ipa(r) for r in references]
+    hp = [tokenize_ipa(h) for h in hypotheses]
+    table: Dict[str, int] = {}
+    def ids(seq):
+        return [table.setdefault(p, len(table)) for p in seq]
+    ri, hi = [ids(s) for s in rp], [ids(s) for s in hp]
+    feats = np.zeros((max(len(table), 1), 24), dtype=np.int8)
+    for phone, i in table.items():
+        feats[i] = _phone_features(phone)
+    d = feature_edit_distances(ri, hi, feats, cosine=cosine).cpu().numpy()
+    out = []
+    for i in range(len(rp)):
+        if len(rp[i]) == 0:                                            # ref:scripts/evaluate_ipa.py:180-181
+            out.append(0.0 if len(hp[i]) == 0 else 100.0)
+        else:
+            out.append((float(d[i]) / len(rp[i])) * 100.0)
+    return out
+
+
+def phone_feature_error_rate(reference: str, hypothesis: str) -> float:
+    return phone_feature_error_rates([reference], [hypothesis])[0]
+
+
+def phone_feature_error_rate_cosine(reference: str, hypothesis: str) -> float:
+    return phone_feature_error_rates([reference], [hypothesis], cosine=True)[0]
+
+
 def evaluate_batch(references: Sequence[str], hypotheses: Sequence[str]) -> Dict:
-    """ref:scripts/evaluate_ipa.py:346-378.  PER is scored here; the PFER keys are present but NaN — the feature-weighted
-    scorer needs panphon's feature table and is the next row of the scope table."""
+    """ref:scripts/evaluate_ipa.py:346-378: PER and (Hamming) PFER per pair, macro mean and population std of both.
+    Without a phone feature table (panphon absent and none registered) the PFER keys are NaN."""
     assert len(references) == len(hypotheses), "Mismatched lengths"
     per = phone_error_rates(references, hypotheses)
     out = summarize(per)
-    out.update({"pfer": float("nan"), "pfer_std": float("nan"), "pfer_scores": [float("nan")] * len(per)})
+    if pfer_available():
+        pfer = phone_feature_error_rates(references, hypotheses)
+        out.update({"pfer": np.mean(pfer), "pfer_std": np.std(pfer), "pfer_scores": list(pfer)})
+    else:
+        out.update({"pfer": float("nan"), "pfer_std": float("nan"), "pfer_scores": [float("nan")] * len(per)})
     return out
