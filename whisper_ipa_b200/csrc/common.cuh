@@ -156,6 +156,11 @@ struct EpiParams {
     const uint32_t* mask_always;   // vocab bitmask, bit set = suppressed (may be nullptr)
     const uint32_t* mask_begin;    // applied when *step_ptr == 0 (may be nullptr)
     const int* step_ptr;
+    // deterministic split-K (decode GEMMs with long K): grid.z CTAs per tile leave raw fp32 partial tiles in `sk_part`
+    // [tile][split][128][BN]; the last one to arrive (ticket in `sk_count[tile]`, self-resetting) sums them in split order
+    float* sk_part;
+    int* sk_count;
+    int gelu_fast;           // EPI_GELU with a bf16 result: A&S-erf GELU (gelu_erf_fast) instead of erff
 };
 
 // A-operand addressing shared by both GEMM kernels: row m of the logical [M, K] matrix lives at
@@ -175,6 +180,26 @@ struct AOperand {
 __device__ __forceinline__ float gelu_erf(float x) {
     // exact-erf GELU (HF activation_function="gelu", HF:models/whisper/configuration_whisper.py:140)
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+
+// GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the stored value):
+// two MUFU ops (rcp, ex2) + ~12 FMA-pipe instructions instead of erff's ~35.  1 + erf(z) is formed without
+// cancellation on the negative side.  Used only where the result is rounded to bf16 (the fp32 path calls erff).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = x * 0.70710678118654752440f;
+    const float az = fabsf(z);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
+    const float c = poly * e;                                  // 1 - erf(|z|)
+    const float one_plus_erf = z < 0.f ? c : 2.0f - c;
+    return 0.5f * x * one_plus_erf;
 }
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
@@ -246,8 +271,13 @@ __device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, fl
     const long long row = (long long)ob * ep.o_bstride + (long long)ot * ep.ldo;
     switch (ep.mode) {
         case EPI_GELU:
+            if (ep.gelu_fast) {
 #pragma unroll
-            for (int i = 0; i < W; ++i) v[i] = gelu_erf(v[i]);
+                for (int i = 0; i < W; ++i) v[i] = gelu_erf_fast(v[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < W; ++i) v[i] = gelu_erf(v[i]);
+            }
             // fallthrough
         case EPI_STORE: {
             if (full) store_group<W>(ep.out, ep.out_bf16, row + n0, v, vec);

@@ -78,6 +78,8 @@ struct wipa_ctx {
     // decoder workspaces
     float *dx, *dq, *ca_part, *pmax, *logits;
     void *dh, *dattn, *dffn;
+    float* sk_part = nullptr;      // split-K scratch of the decode fc2 GEMM
+    int* sk_count = nullptr;
     int *block_table, *utt_of_seq, *ca_counters, *pidx;
     int *d_pos, *d_step, *d_cur_tok, *d_done, *d_n_done, *d_forced, *d_out_ids, *d_out_len;
     uint32_t *mask_always, *mask_begin;
@@ -89,6 +91,7 @@ struct wipa_ctx {
     cudaStream_t cap_stream = nullptr;   // graphs are captured here (the caller's stream may be the legacy default stream)
     int n_logit_tiles;
     int bn_enc, bn_dec, bn_logits, ca_split;
+    int splitk = 1;                // WIPA_SPLITK=0 disables the split-K decode fc2
     int beam_L = 0;                // row length of the beam-search sequence / ancestry arrays of the current decode
     int persistent_min_tiles = 296; // WIPA_PERSISTENT_MIN_TILES: fewer 128x256 tiles than this -> plain 128x128-tile kernel
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
@@ -323,6 +326,7 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
     {   // conv1 (k3, p1) + GELU -> rows 1..3000 of the zero-padded [nb, 3002, d] buffer
         AOperand A; A.ptr = c->mel_rows; A.lda = C; A.a_rpb = T3; A.a_bstride = (long long)(T3 + 2) * C; A.n_batch = nb;
         EpiParams ep = epi(EPI_GELU, nb * T3, d);
+        ep.gelu_fast = c->bf;
         ep.bias = c->conv1_b;
         ep.out = (char*)c->conv1_out + (size_t)d * c->esz; ep.out_bf16 = c->bf;
         ep.ldo = d; ep.o_rpb = T3; ep.o_bstride = (long long)(T3 + 2) * d;
@@ -361,7 +365,7 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
         WIPA_TRY(ln(c, c->ex, L.ln2_w, L.ln2_b, c->eh, M, st));
         {
             EpiParams ep = epi(EPI_GELU, M, ffn);
-            ep.bias = L.fc1_b; ep.out = c->effn; ep.out_bf16 = c->bf;
+            ep.bias = L.fc1_b; ep.out = c->effn; ep.out_bf16 = c->bf; ep.gelu_fast = c->bf;
             WIPA_TRY(gemm(c, plainA(c->eh, M, d), L.fc1_w, M, ffn, d, ep, c->bn_enc, st));
         }
         {
@@ -441,13 +445,14 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln3_w, L.ln3_b, c->dh, S, st));
         {
             EpiParams ep = epi(EPI_GELU, S, ffn);
-            ep.bias = L.fc1_b; ep.out = c->dffn; ep.out_bf16 = c->bf;
+            ep.bias = L.fc1_b; ep.out = c->dffn; ep.out_bf16 = c->bf; ep.gelu_fast = c->bf;
             // N = ffn tiles of 32 columns would not fit one wave once S needs two M tiles: use 64-wide tiles then
             if (!(skip & 32)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.fc1_w, S, ffn, d, ep, (S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec, st));
         }
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.fc2_b; ep.out = c->dx; ep.resid = c->dx;
+            if (c->bf && c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; }    // K = ffn is long: split-K
             if (!(skip & 64)) WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, c->bn_dec, st));
         }
     }
@@ -537,6 +542,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->n_logit_tiles = cdiv(arch->vocab, c->bn_logits);
     c->enc_attn_simt = env_int("WIPA_ENC_ATTN_SIMT", 0);
     c->skip_mask = env_int("WIPA_SKIP_MASK", 0);
+    c->splitk = env_int("WIPA_SPLITK", 1);
     c->persistent_min_tiles = env_int("WIPA_PERSISTENT_MIN_TILES", 2 * 148);
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
@@ -576,6 +582,11 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     CTX_TRY(ctx_alloc(c, &c->dattn, (size_t)S * d * e, false));
     CTX_TRY(ctx_alloc(c, &c->dffn, (size_t)S * ffn * e, false));
     CTX_TRY(ctx_alloc(c, (void**)&c->ca_part, (size_t)S * H * 64 * 66 * 4, false));
+    {
+        const size_t tiles = (size_t)cdiv(d, 32) * cdiv(S, 64);        // N tiles of 32 columns x M tiles (64-row tiles at S <= 64)
+        CTX_TRY(ctx_alloc(c, (void**)&c->sk_part, tiles * 3 * 128 * 64 * 4, false));
+        CTX_TRY(ctx_alloc(c, (void**)&c->sk_count, tiles * 4, true));
+    }
     CTX_TRY(ctx_alloc(c, (void**)&c->ca_counters, (size_t)S * H * 4, true));
     CTX_TRY(ctx_alloc(c, (void**)&c->pmax, (size_t)S * c->n_logit_tiles * 4, true));
     CTX_TRY(ctx_alloc(c, (void**)&c->pidx, (size_t)S * c->n_logit_tiles * 4, true));

@@ -72,6 +72,11 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int n0 = blockIdx.x * BN;
     const int batch = blockIdx.y / tiles_per_batch;
     const int t0 = (blockIdx.y - batch * tiles_per_batch) * TC_BM;
+    // split-K: CTA z of gridDim.z takes k-blocks [kb0, kb0 + num_kb) of the num_kb_total
+    const int num_kb_total = num_kb;
+    const int kb_per = (num_kb_total + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * kb_per;
+    num_kb = min(kb_per, num_kb_total - kb0);
 
     if (threadIdx.x == 0) DBG_STAMP(0);
     if (warp == 0 && lane == 0) {
@@ -115,7 +120,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
                 ptx::mbar_arrive_expect_tx(&full[g], (uint32_t)nk * (Cfg::A_BYTES + Cfg::W_BYTES));
                 for (int i = 0; i < nk; ++i)
-                    ptx::tma_load_2d(sW + g * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[g], (g * KPB + i) * TC_BK, n0);
+                    ptx::tma_load_2d(sW + g * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[g], (kb0 + g * KPB + i) * TC_BK, n0);
             }
             DBG_STAMP(1);
         }
@@ -128,7 +133,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int g = 0; g < pre; ++g) {
                 const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
                 for (int i = 0; i < nk; ++i)
-                    load_a(sA + g * Cfg::STAGE_A + i * Cfg::A_BYTES, &full[g], (g * KPB + i) * TC_BK);
+                    load_a(sA + g * Cfg::STAGE_A + i * Cfg::A_BYTES, &full[g], (kb0 + g * KPB + i) * TC_BK);
             }
         }
         __syncwarp();
@@ -140,8 +145,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
                 ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)nk * (Cfg::A_BYTES + Cfg::W_BYTES));
                 for (int i = 0; i < nk; ++i) {
-                    load_a(sA + s * Cfg::STAGE_A + i * Cfg::A_BYTES, &full[s], (g * KPB + i) * TC_BK);
-                    ptx::tma_load_2d(sW + s * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[s], (g * KPB + i) * TC_BK, n0);
+                    load_a(sA + s * Cfg::STAGE_A + i * Cfg::A_BYTES, &full[s], (kb0 + g * KPB + i) * TC_BK);
+                    ptx::tma_load_2d(sW + s * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[s], (kb0 + g * KPB + i) * TC_BK, n0);
                 }
             }
             __syncwarp();
@@ -193,18 +198,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         pdl_wait();                                          // the epilogue reads / writes activations of earlier kernels
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         if (BN == 32 && ep.mode != EPI_ARGMAX) {
-            // Latency-bound decode tiles: fetch bias and residual for the whole 32-column row segment BEFORE the
+            // Latency-bound decode tiles: fetch bias and residual for the whole BN-column row segment BEFORE the
             // accumulator is ready, so that after the last MMA only tcgen05.ld + adds + stores remain.
+            __shared__ int s_last;
             const bool active = row_ok && !(BOXM == 64 && quarter >= 2);
-            const bool fast = ep.vec_ok && (n0 + 32 <= ep.N);
-            float add[32];
+            const bool fast = ep.vec_ok && (n0 + BN <= ep.N);
+            float add[BN];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) add[i] = 0.f;
+            for (int i = 0; i < BN; ++i) add[i] = 0.f;
             long long row = 0;
             if (active && fast) {
                 if (ep.bias != nullptr) {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
+                    for (int i = 0; i < BN; i += 4) {
                         const float4 b = *reinterpret_cast<const float4*>(ep.bias + n0 + i);
                         add[i] = b.x; add[i + 1] = b.y; add[i + 2] = b.z; add[i + 3] = b.w;
                     }
@@ -213,7 +219,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     const int ob = m / ep.o_rpb;
                     row = (long long)ob * ep.o_bstride + (long long)(m - ob * ep.o_rpb) * ep.ldo + n0;
 #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
+                    for (int i = 0; i < BN; i += 4) {
                         const float4 x = *reinterpret_cast<const float4*>(ep.resid + row + i);
                         add[i] += x.x; add[i + 1] += x.y; add[i + 2] += x.z; add[i + 3] += x.w;
                     }
@@ -222,26 +228,62 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::mbar_wait(tmem_full, 0);
             if (threadIdx.x == 64) DBG_STAMP(5);
             ptx::tc_fence_after();
+            float v[BN];
             if (!(BOXM == 64 && quarter >= 2)) {                 // warp-uniform: tcgen05.ld is a warp-collective
-                float v[32];
-                ptx::tmem_ld32(taddr, v);
+#pragma unroll
+                for (int c0 = 0; c0 < BN; c0 += 32) ptx::tmem_ld32(taddr + c0, v + c0);
                 ptx::tmem_ld_wait();
+            }
+            bool finish = true;
+            if (gridDim.z > 1) {
+                // ---- deterministic split-K: publish the raw partial, take a ticket, the last CTA sums in split order ----
+                const int tile = blockIdx.y * gridDim.x + blockIdx.x;
+                const int trow = quarter * 32 + lane;                       // row of the tile held by this thread
+                float* mine = ep.sk_part + (((size_t)tile * gridDim.z + blockIdx.z) * TC_BM + trow) * BN;
+                if (!(BOXM == 64 && quarter >= 2)) {
+#pragma unroll
+                    for (int i = 0; i < BN; i += 4) *reinterpret_cast<float4*>(mine + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                }
+                __threadfence();
+                asm volatile("bar.sync 1, 128;" ::: "memory");                // the four epilogue warps
+                if (threadIdx.x == 64) {
+                    const int t = atomicAdd(&ep.sk_count[tile], 1);
+                    s_last = (t == (int)gridDim.z - 1);
+                    if (s_last) ep.sk_count[tile] = 0;                        // ready for the next launch
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                finish = s_last != 0;
+                if (finish && !(BOXM == 64 && quarter >= 2)) {
+                    __threadfence();
+#pragma unroll
+                    for (int i = 0; i < BN; ++i) v[i] = 0.f;
+                    for (int z = 0; z < (int)gridDim.z; ++z) {
+                        const float* p = ep.sk_part + (((size_t)tile * gridDim.z + z) * TC_BM + trow) * BN;
+#pragma unroll
+                        for (int i = 0; i < BN; i += 4) {
+                            const float4 x = __ldcg(reinterpret_cast<const float4*>(p + i));
+                            v[i] += x.x; v[i + 1] += x.y; v[i + 2] += x.z; v[i + 3] += x.w;
+                        }
+                    }
+                }
+            }
+            if (finish && !(BOXM == 64 && quarter >= 2)) {
                 if (!active) {
                     // padding row of the M tile: nothing to store
                 } else if (fast) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += add[i];
+                    for (int i = 0; i < BN; ++i) v[i] += add[i];
                     if (ep.mode == EPI_RESADD) {
                         float* o = reinterpret_cast<float*>(ep.out) + row;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        for (int i = 0; i < BN; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 8) epi_group<8, true>(ep, m, n0 + i, v + i);
+                        for (int i = 0; i < BN; i += 8) epi_group<8, true>(ep, m, n0 + i, v + i);
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 32; i += 8) epi_group<8>(ep, m, n0 + i, v + i);
+                    for (int i = 0; i < BN; i += 8) epi_group<8>(ep, m, n0 + i, v + i);
                 }
             }
         } else {
@@ -309,14 +351,14 @@ int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dim
 
 template <int BN, int BOXM, int CL>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int tiles_per_batch, int n_batch, int a_rpb,
-              int N, EpiParams ep, cudaStream_t st) {
+              int N, EpiParams ep, cudaStream_t st, int splits = 1) {
     using Cfg = TcCfg<BN, BOXM>;
     static bool configured = false;
     if (!configured) {
         WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, BOXM, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
         configured = true;
     }
-    dim3 grid(cdiv(N, BN), tiles_per_batch * n_batch);
+    dim3 grid(cdiv(N, BN), tiles_per_batch * n_batch, splits);
     if (ep.mode == EPI_ARGMAX) ep.n_tiles = grid.x;
     if (CL == 1) {
         WIPA_CUDA_CHECK(wipa_launch(gemm_bf16_tc_kernel<BN, BOXM, CL>, grid, dim3(192), (size_t)Cfg::SMEM, st, tmA, tmW, num_kb,
@@ -394,14 +436,18 @@ int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, cons
     ep.M_rows = a.a_rpb;
     const int num_kb = cdiv(K, TC_BK);
     const int tpb = cdiv(a.a_rpb, TC_BM);
+    // split-K (3 ways) when the caller provides scratch and K is long: the narrow tiles are bound by how fast ONE SM can
+    // stream its 128 x K activations + BN x K weights, so a long K wants more CTAs, not wider ones
+    const int splits = (ep.sk_part != nullptr && block_n == 32 && num_kb >= 24) ? 3 : 1;
+    if (splits == 1) { ep.sk_part = nullptr; ep.sk_count = nullptr; }
     switch (block_n) {
         case 32:
-            if (box_m == 64) return mc ? launch_bn<32, 64, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st)
-                                       : launch_bn<32, 64, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-            return mc ? launch_bn<32, 128, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st)
-                      : launch_bn<32, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
-        case 64: return mc ? launch_bn<64, 128, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st)
-                           : launch_bn<64, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
+            if (box_m == 64) return mc ? launch_bn<32, 64, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st, splits)
+                                       : launch_bn<32, 64, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st, splits);
+            return mc ? launch_bn<32, 128, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st, splits)
+                      : launch_bn<32, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st, splits);
+        case 64: return mc ? launch_bn<64, 128, 4>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st, splits)
+                           : launch_bn<64, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st, splits);
         case 128: return launch_bn<128, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
         case 256: return launch_bn<256, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
         default: break;
