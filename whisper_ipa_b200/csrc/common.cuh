@@ -249,12 +249,17 @@ __device__ __forceinline__ void store_group(void* base, int is_bf16, long long i
 
 // Apply the epilogue to W (4 or 8) consecutive accumulator columns n0..n0+W-1 of logical row m.
 // n0 is a multiple of W.  Columns >= ep.N are dropped.
+// bias_tile: optional shared-memory copy of bias[tile_n0 .. tile_n0 + BN) (zero beyond N), indexed by column - tile_n0
 template <int W, bool SKIP_BIAS = false>
-__device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, float* v) {
+__device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, float* v, const float* bias_tile = nullptr,
+                                          int tile_n0 = 0) {
     if (n0 >= ep.N) return;
     const bool full = (n0 + W <= ep.N);
     const bool vec = ep.vec_ok && full;
-    if (!SKIP_BIAS && ep.bias != nullptr) {
+    if (!SKIP_BIAS && bias_tile != nullptr) {
+#pragma unroll
+        for (int i = 0; i < W; ++i) v[i] += bias_tile[n0 - tile_n0 + i];
+    } else if (!SKIP_BIAS && ep.bias != nullptr) {
         if (vec) {
 #pragma unroll
             for (int i = 0; i < W; i += 4) {

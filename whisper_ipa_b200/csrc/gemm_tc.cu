@@ -287,6 +287,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 }
             }
         } else {
+        // the tile's bias goes to shared memory while the main loop runs (weights are static: no dependency), so the
+        // column chunks below never wait on a global load
+        __shared__ float s_bias[BN];
+        const bool have_bias = ep.bias != nullptr && ep.mode != EPI_ARGMAX;
+        if (have_bias) {
+            for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = (n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        const float* bias_tile = have_bias ? s_bias : nullptr;
         ptx::mbar_wait(tmem_full, 0);
         if (threadIdx.x == 64) DBG_STAMP(5);
         ptx::tc_fence_after();
@@ -312,14 +321,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 ep.pidx[(long long)m * ep.n_tiles + blockIdx.x] = best_n;
             }
         } else {
-#pragma unroll 1
+#pragma unroll 2
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 float v[16];
                 ptx::tmem_ld16(taddr + c0, v);
                 ptx::tmem_ld_wait();
                 if (row_ok) {
-                    epi_group<8>(ep, m, n0 + c0, v);
-                    epi_group<8>(ep, m, n0 + c0 + 8, v + 8);
+                    epi_group<8>(ep, m, n0 + c0, v, bias_tile, n0);
+                    epi_group<8>(ep, m, n0 + c0 + 8, v + 8, bias_tile, n0);
                 }
             }
         }
