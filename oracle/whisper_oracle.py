@@ -301,80 +301,82 @@ def greedy_decode(sd, dims: Dims, enc: torch.Tensor, prompt: Sequence[int], max_
 def beam_decode(sd, dims: Dims, enc: torch.Tensor, prompt: Sequence[int], max_new: int, beams: int,
                 length_penalty: float = 1.0, eot: int = EOT,
                 begin_suppress: Sequence[int] = BEGIN_SUPPRESS):
-    """Beam search with HF `_beam_search` semantics (HF:generation/utils.py:3076-3400) for
-    early_stopping=False, num_return_sequences=1: keep 2*beams candidates per step, finished
-    hypotheses scored sum_logprob / (cur_len ** length_penalty) with cur_len counting prompt + generated
-    (including EOS); stop when no running beam can beat the worst finished one.
-    Returns int64[B, max_new] (best hypothesis, EOS stripped, right-padded with eot) and lengths."""
+    """Beam search restating HF's vectorised `_beam_search` (HF:generation/utils.py:3076-3400 and its helpers
+    :2876-3073) for do_sample=False, early_stopping=False, one EOS id, num_return_sequences=1:
+      * log_softmax over the vocabulary, THEN the suppress processor (:3262-3263), plus the running beam scores (:3286)
+      * top 2*beams continuations over beams x vocab (:2945-2997); a candidate "hits the stopping criteria" when its
+        token is EOS or the sequence reaches max_length (:3304-3310)
+      * next running beams = best `beams` of (score - 1e9 * hit) (:2999-3019)
+      * finished slots = best `beams` of [old finished scores, candidate / (generated_len ** length_penalty) - 1e9 *
+        (not among the top `beams` candidates or not hit or the utterance can no longer improve)] (:3021-3073)
+      * early-stop heuristic (:2876-2921) with the already advanced cur_len; the loop ends when no utterance can improve
+        or every candidate hit the stopping criteria (:2923-2943)
+    Returns int64[B, max_new] (best finished hypothesis, prompt and EOS stripped, right-padded with eot) and lengths."""
     B = enc.shape[0]
     P = len(prompt)
+    K, keep = beams, 2 * beams
+    max_length = P + max_new
     xkv1 = cross_kv(sd, dims, enc)
-    xkv = [(k.repeat_interleave(beams, 0), v.repeat_interleave(beams, 0)) for k, v in xkv1]
+    xkv = [(k.repeat_interleave(K, 0), v.repeat_interleave(K, 0)) for k, v in xkv1]
     self_kv = [None] * dims.n_dec
-    toks = torch.tensor([list(prompt)] * (B * beams), dtype=torch.long)
-    logits = decoder_forward(sd, dims, toks, 0, xkv, self_kv)[:, -1].float()
+    running = torch.full((B, K, max_length), eot, dtype=torch.long)
+    running[:, :, :P] = torch.tensor(list(prompt), dtype=torch.long)
+    sequences = running.clone()
+    run_scores = torch.zeros(B, K)
+    run_scores[:, 1:] = -1e9
+    beam_scores = torch.full((B, K), -1e9)
+    finished = torch.zeros(B, K, dtype=torch.bool)
+    unsat = torch.ones(B, 1, dtype=torch.bool)
+    top_mask = torch.cat([torch.ones(K, dtype=torch.bool), torch.zeros(keep - K, dtype=torch.bool)])
+    cur_len = P
+    logits = decoder_forward(sd, dims, running[:, :, :P].reshape(B * K, P), 0, xkv, self_kv)[:, -1].float()
     V = logits.shape[-1]
-    running = toks.view(B, beams, P).clone()
-    run_lp = torch.zeros(B, beams)
-    run_lp[:, 1:] = -1e9
-    fin_seq = [[] for _ in range(B)]         # list of (score, tokens list)
-    fin_done = torch.zeros(B, dtype=torch.bool)
-    pos = P
-    for i in range(max_new):
-        logits = logits.clone()
+    while True:
         lp = torch.log_softmax(logits, dim=-1)
-        if i == 0 and len(begin_suppress):
+        if cur_len == P and len(begin_suppress):
             lp[:, list(begin_suppress)] = float("-inf")
-        lp = lp.view(B, beams, V) + run_lp[:, :, None]
-        top_lp, top_idx = torch.topk(lp.view(B, beams * V), 2 * beams, dim=1)
+        lp = (lp.view(B, K, V) + run_scores[:, :, None]).view(B, K * V)
+        top_lp, top_idx = torch.topk(lp, keep, dim=1)
         src = top_idx // V
         tok = top_idx % V
-        cur_len = P + i + 1
-        new_running = torch.zeros(B, beams, cur_len, dtype=torch.long)
-        new_lp = torch.full((B, beams), -1e9)
-        reorder = torch.zeros(B, beams, dtype=torch.long)
-        for b in range(B):
-            n = 0
-            for c in range(2 * beams):
-                s, t, sc = int(src[b, c]), int(tok[b, c]), float(top_lp[b, c])
-                if t == eot:
-                    # HF only admits an EOS candidate into the finished set if it ranks in the top `beams`
-                    if c < beams and not fin_done[b]:
-                        fin_seq[b].append((sc / (cur_len ** length_penalty),
-                                           running[b, s].tolist() + [t]))
-                    continue
-                if n < beams:
-                    new_running[b, n, :-1] = running[b, s]
-                    new_running[b, n, -1] = t
-                    new_lp[b, n] = sc
-                    reorder[b, n] = b * beams + s
-                    n += 1
-            fin_seq[b] = sorted(fin_seq[b], key=lambda z: -z[0])[:beams]
-            if len(fin_seq[b]) >= beams and not fin_done[b]:
-                # early_stopping=False: best possible running score uses the current length
-                best_running = float(new_lp[b].max()) / (cur_len ** length_penalty) if length_penalty <= 0 \
-                    else float(new_lp[b].max()) / ((P + max_new) ** length_penalty)
-                worst_fin = fin_seq[b][-1][0]
-                if worst_fin >= best_running:
-                    fin_done[b] = True
-        running, run_lp = new_running, new_lp
-        if bool(fin_done.all()) or i == max_new - 1:
+        top_seq = torch.take_along_dim(running, src[:, :, None], dim=1)
+        top_seq[:, :, cur_len] = tok
+        hit = (tok == eot) | (cur_len + 1 >= max_length)
+        # next running beams
+        run_lp = top_lp + hit.to(torch.float32) * -1.0e9
+        nxt = torch.topk(run_lp, K, dim=1)[1]
+        running = torch.take_along_dim(top_seq, nxt[:, :, None], dim=1)
+        run_scores = torch.take_along_dim(run_lp, nxt, dim=1)
+        beam_src = torch.take_along_dim(src, nxt, dim=1)
+        # finished slots
+        did = hit & top_mask[None, :]
+        fin_lp = top_lp / ((cur_len + 1 - P) ** length_penalty)
+        fin_lp = fin_lp + (~unsat).to(torch.float32) * -1.0e9
+        fin_lp = fin_lp + (~did) * -1.0e9
+        m_seq = torch.cat((sequences, top_seq), dim=1)
+        m_sc = torch.cat((beam_scores, fin_lp), dim=1)
+        m_fin = torch.cat((finished, did), dim=1)
+        sel = torch.topk(m_sc, K, dim=1)[1]
+        sequences = torch.take_along_dim(m_seq, sel[:, :, None], dim=1)
+        beam_scores = torch.take_along_dim(m_sc, sel, dim=1)
+        finished = torch.take_along_dim(m_fin, sel, dim=1)
+        cur_len += 1
+        best_possible = run_scores[:, :1] / ((cur_len - P) ** length_penalty)
+        worst = torch.where(finished, beam_scores.min(dim=1, keepdim=True)[0], torch.tensor(-1.0e9))
+        unsat = unsat & (best_possible > worst).any(dim=-1, keepdim=True)
+        if not bool(unsat.any()) or bool(hit.all()):
             break
-        flat = reorder.view(-1)
+        flat = (beam_src + torch.arange(B)[:, None] * K).view(-1)
         self_kv = [(k[flat], v[flat]) for k, v in self_kv]
-        logits = decoder_forward(sd, dims, running[:, :, -1].reshape(-1, 1), pos, xkv, self_kv)[:, -1].float()
-        pos += 1
+        logits = decoder_forward(sd, dims, running[:, :, cur_len - 1].reshape(-1, 1), cur_len - 1, xkv, self_kv)[:, -1].float()
     out = torch.full((B, max_new), eot, dtype=torch.long)
     lens = torch.zeros(B, dtype=torch.long)
     for b in range(B):
-        cur_len = running.shape[-1]
-        cands = list(fin_seq[b])
-        if not fin_done[b]:
-            for k in range(beams):
-                cands.append((float(run_lp[b, k]) / (cur_len ** length_penalty), running[b, k].tolist()))
-        best = max(cands, key=lambda z: z[0])[1][P:]
-        if best and best[-1] == eot:
-            best = best[:-1]
-        out[b, :len(best)] = torch.tensor(best, dtype=torch.long)
-        lens[b] = len(best)
+        best = sequences[b, 0, P:].tolist()
+        n = 0
+        while n < max_new and best[n] != eot:
+            n += 1
+        out[b, :n] = torch.tensor(best[:n], dtype=torch.long)
+        lens[b] = n
     return out, lens
+

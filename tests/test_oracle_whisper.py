@@ -74,3 +74,26 @@ def test_beam_matches_hf_generate_live(tiny):
     enc = wo.encoder_forward(sd, dims, feats)
     ids, lens = wo.beam_decode(sd, dims, enc, wo.PROMPT_PRE_V3, 8, beams=3)
     assert torch.equal(ids[:, :want.shape[1]], want)
+
+
+@pytest.mark.parametrize("beams,eot_like", [(5, None), (2, 40220), (5, 40220), (5, 2020)])
+def test_beam_with_reachable_eos_matches_hf_live(beams, eot_like):
+    """The beam-search restatement against HF's own `generate(num_beams=...)`, including hypotheses that finish early:
+    EOS is made reachable by copying a frequent token's (tied) embedding into the EOT row of an audio-sensitive model."""
+    model = hf.build_hf_model("tiny", seed=0, init_gain=3.0)
+    if eot_like is not None:
+        with torch.no_grad():
+            emb = model.model.decoder.embed_tokens.weight
+            emb[wo.EOT] = emb[eot_like] * 1.05
+    sd = hf.state_dict_f32(model)
+    dims = wo.Dims.from_arch("tiny")
+    max_new = 24 if eot_like is None else 40
+    feats = hf.hf_log_mel(wo.synthetic_audio(2), 80)
+    want = hf.hf_generate(model, feats, "tiny", max_new=max_new, num_beams=beams)
+    enc = wo.encoder_forward(sd, dims, feats)
+    ids, lens = wo.beam_decode(sd, dims, enc, wo.PROMPT_PRE_V3, max_new, beams=beams)
+    width = want.shape[1]
+    assert int(lens.max()) == width or eot_like is None
+    assert torch.equal(ids[:, :width], want) and bool((ids[:, width:] == wo.EOT).all())
+    if eot_like is not None:
+        assert width < max_new, "the crafted weights are meant to finish hypotheses before max_new"
