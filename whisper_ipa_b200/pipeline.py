@@ -42,6 +42,67 @@ class Transcriber:
         hyp_flat, hyp_off = hyps_to_csr(ids, lens)
         return metrics.edit_distance_counts_device(ref_flat, ref_off, hyp_flat, hyp_off, max_ref_len)
 
+    def evaluate_local(self, audio, references: Sequence[Sequence[int]], indices: Optional[Sequence[int]] = None,
+                       micro_batch: Optional[int] = None):
+        """Transcribe + score the utterances `indices` of `audio` (host numpy / torch f32 [N, 480000], ideally pinned; or a
+        device tensor) against `references[i]`.  Micro-batches are double-buffered: while batch k is being transcribed,
+        batch k+1 is gathered into a pinned staging buffer and copied host->device on a side stream.
+        Returns (counts int32 [n, 2] on the device, hypotheses list, hypothesis lengths list), in `indices` order."""
+        idx_all = list(range(len(references))) if indices is None else list(indices)
+        mb = micro_batch or self.model.max_batch
+        dev = self.model.device
+        n = len(idx_all)
+        counts = torch.zeros((n, 2), dtype=torch.int32, device=dev)
+        on_device = isinstance(audio, torch.Tensor) and audio.is_cuda
+        host = None if on_device else (audio if isinstance(audio, torch.Tensor) else torch.from_numpy(np.asarray(audio, dtype=np.float32)))
+        copy_stream = torch.cuda.Stream(device=dev) if not on_device else None
+        staging = [None, None]
+        chunks = [idx_all[s:s + mb] for s in range(0, n, mb)]
+
+        def stage(k):
+            """Start the host->device copy of micro-batch k; returns (device tensor, ready event)."""
+            idx = chunks[k]
+            if on_device:
+                return audio[torch.as_tensor(idx, device=audio.device)], None
+            contiguous = all(idx[j] + 1 == idx[j + 1] for j in range(len(idx) - 1))
+            if contiguous and host.is_pinned():
+                src = host[idx[0]:idx[0] + len(idx)]                      # a view: still pinned, no host copy
+            else:
+                if staging[k & 1] is None or staging[k & 1].shape[0] < len(idx):
+                    staging[k & 1] = torch.empty((mb, host.shape[1]), dtype=torch.float32).pin_memory()
+                src = staging[k & 1][:len(idx)]
+                torch.index_select(host, 0, torch.as_tensor(idx), out=src)
+            with torch.cuda.stream(copy_stream):
+                d = src.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return d, ev
+
+        results = []
+        nxt = stage(0) if chunks else None
+        for k, idx in enumerate(chunks):
+            chunk, ev = nxt
+            nxt = stage(k + 1) if k + 1 < len(chunks) else None           # overlaps with the transcription below
+            if ev is not None:
+                torch.cuda.current_stream(dev).wait_event(ev)
+            ids, lens = self.transcribe_device(chunk)
+            if ev is not None:
+                chunk.record_stream(torch.cuda.current_stream(dev))
+            rf, ro = metrics._pack([references[i] for i in idx])
+            rf_d = torch.from_numpy(rf).to(dev, non_blocking=True)
+            ro_d = torch.from_numpy(ro).to(dev, non_blocking=True)
+            s0 = k * mb
+            counts[s0:s0 + len(idx)] = self.score_device(ids, lens, rf_d, ro_d, int(np.max(np.diff(ro))) if len(idx) else 0)
+            results.append((ids, lens))
+        hyps: List[List[int]] = []
+        hyp_lens: List[int] = []
+        for ids, lens in results:                                         # one read-back pass after everything is queued
+            ids_h, lens_h = ids.cpu().numpy(), lens.cpu().numpy()
+            for j in range(ids_h.shape[0]):
+                hyps.append(ids_h[j, :lens_h[j]].tolist())
+                hyp_lens.append(int(lens_h[j]))
+        return counts, hyps, hyp_lens
+
     def evaluate_ids(self, audio, references: Sequence[Sequence[int]], micro_batch: Optional[int] = None) -> Dict:
         """audio: host (numpy / pinned torch) or device f32 [N, 480000]; references: N id sequences.
         Every rank passes the FULL inputs and works on its strided shard; returns the evaluate_batch-style PER dict
@@ -49,27 +110,10 @@ class Transcriber:
         n_total = len(references)
         rank, ws = parallel.world()
         mine = parallel.shard_indices(n_total, rank, ws)
-        mb = micro_batch or self.model.max_batch
         dev = self.model.device
-        counts_local = torch.zeros((len(mine), 2), dtype=torch.int32, device=dev)
-        hyps_local: List[List[int]] = []
+        counts_local, hyps_local, lens_local = self.evaluate_local(audio, references, mine, micro_batch)
         hyp_lens = np.zeros(n_total, dtype=np.int64)
-        for s in range(0, len(mine), mb):
-            idx = mine[s:s + mb]
-            chunk = audio[idx] if not isinstance(audio, torch.Tensor) else audio[torch.as_tensor(idx)]
-            if isinstance(chunk, np.ndarray):
-                chunk = torch.from_numpy(np.ascontiguousarray(chunk, dtype=np.float32)).pin_memory()
-            chunk = chunk.to(dev, non_blocking=True)
-            ids, lens = self.transcribe_device(chunk)
-            refs = [references[i] for i in idx]
-            rf, ro = metrics._pack(refs)
-            rf_d = torch.from_numpy(rf).to(dev)
-            ro_d = torch.from_numpy(ro).to(dev)
-            counts_local[s:s + len(idx)] = self.score_device(ids, lens, rf_d, ro_d, int(np.max(np.diff(ro))) if len(idx) else 0)
-            ids_h, lens_h = ids.cpu().numpy(), lens.cpu().numpy()
-            for j, i in enumerate(idx):
-                hyps_local.append(ids_h[j, :lens_h[j]].tolist())
-                hyp_lens[i] = lens_h[j]
+        hyp_lens[mine] = lens_local
         table = parallel.gather_counts(counts_local, n_total)
         if ws > 1:
             import torch.distributed as dist
