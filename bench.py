@@ -4,8 +4,9 @@
 One "step" = one pass of the whole hot path over one batch of synthetic clips per GPU:
 log-mel -> encoder (+ cross-K/V projection) -> 220 greedy decode steps (4-token prompt, 224 positions) -> PER counts.
 `value`  : device-timed (CUDA events, max over ranks), audio already resident in HBM.
-`e2e`    : the same pass through the public API (pipeline.Transcriber.evaluate_ids) from pinned HOST buffers, host<->device
-           copies inside the timed region.
+`e2e`    : the same passes through the public API (pipeline.Transcriber.evaluate_local, what evaluate_ids runs per rank) from
+           pinned HOST buffers: host->device copies (double-buffered), reference upload, PER gather and result read-back
+           inside the timed region.
 `roofline`: the dominant kernel (stream-K cross-attention, a persistent HBM streamer) timed alone with CUDA events over all decoder
            layers' caches (total bytes >> L2), achieved GB/s vs MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the parity oracle (HF transformers Whisper on the host cores, fp32) on a bounded

@@ -2,9 +2,12 @@
 //   enc_attention_kernel   : encoder self-attention (non-causal, 1500 x 1500 x 64 per head), flash-style
 //                            online softmax, fp32 math on CUDA cores.  This is the fp32-path kernel
 //                            (HF:models/whisper/modeling_whisper.py:284-357 with scaling folded into q).
-//   self_attention_kernel  : one decode step of decoder self-attention over the paged KV cache (warp per (seq, head)).
-//   cross_attention_kernel : one decode step of cross-attention against the cached encoder K/V —
-//                            the dominant HBM stream of the whole decode.
+//                            The bf16 path uses the tcgen05 flash kernel in attn_tc.cu.
+//   self_attention_kernel  : one decode step of decoder self-attention over the paged KV cache (one CTA of four warps
+//                            per (seq, head); optional beam-ancestry indirection).
+//   cross_attention_stream_kernel : one decode step of cross-attention against the cached encoder K/V — the dominant HBM
+//                            stream of the whole decode: persistent stream-K streamer (default).
+//   cross_attention_kernel : the earlier one-CTA-per-chunk version, kept for A/B runs (WIPA_CA_LEGACY=1).
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -776,7 +779,7 @@ static int launch_cross_attention_stream(const float* q, const T* k, const T* v,
 }
 
 int cross_attention_default_split(int elem_bytes, int Bs, int H) {
-    // chunk sized for ~48 KB of K+V per CTA (4 CTAs / SM resident): 188 keys in bf16, 94 in fp32
+    // legacy kernel only: chunk sized for ~48 KB of K+V per CTA (4 CTAs / SM resident): 188 keys in bf16, 94 in fp32
     (void)Bs; (void)H;
     return elem_bytes == 2 ? 8 : 16;
 }
