@@ -252,12 +252,13 @@ __device__ __forceinline__ void unpack16<bf16>(const uint4& u, float* f) {
 __device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
 __device__ __forceinline__ float2 ld_pair(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
 
-// One CTA of four warps per (sequence, head); warp w takes pages w, w+4, ... of the sequence's block table, so a
-// sequence of 112 positions is 2 pages (one or two memory round trips) per warp instead of 7 for one warp:
+// One CTA of SA_WARPS (4) warps per (sequence, head); warp w takes pages w, w+4, ... of the sequence's block table, so a
+// sequence of 112 positions is 2 pages (one or two memory round trips) per warp instead of 7 for one warp (8 warps per
+// CTA measured slower: 264 vs 226 us per decode step at B=256):
 //   per page  all loads are issued up front: the K rows as 16-byte pieces (LPK lanes per key, KPW keys per
 //             instruction, every request a full 128-byte line) and the 16 V rows (lane l owns output dims 2l, 2l+1);
 //             scores by an LPK-lane shuffle reduction, warp-local online softmax (m, l, o) across the warp's pages
-//   merge     the four warp partials are combined through shared memory
+//   merge     the warp partials are combined through shared memory
 // (an earlier fully unrolled one-warp version was 125 KB of SASS and thrashed the instruction cache)
 template <typename T> struct VRaw;
 template <> struct VRaw<float> { typedef float2 type; };
@@ -267,8 +268,9 @@ __device__ __forceinline__ float2 v_to_f2(__nv_bfloat162 v) { return __bfloat162
 __device__ __forceinline__ void st_v2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
 __device__ __forceinline__ void st_v2(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
 
+#define SA_WARPS 4
 template <typename T, bool ANC>
-__global__ void __launch_bounds__(128, sizeof(T) == 2 ? 8 : 4)
+__global__ void __launch_bounds__(SA_WARPS * 32, sizeof(T) == 2 ? 8 : 4)
 self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, const T* __restrict__ vpool,
                       const int* __restrict__ block_table, int bt_stride, const int* __restrict__ pos_ptr,
                       T* __restrict__ out, int H, const int* __restrict__ anc_base, const int* __restrict__ flip_ptr, int anc_L) {
@@ -276,7 +278,7 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
     constexpr int KPW = 32 / C::LPK;                               // keys per warp instruction
     constexpr int ITERS = WIPA_PAGE / KPW;
     typedef typename VRaw<T>::type vraw;
-    __shared__ float part[4][CA_PART];
+    __shared__ float part[SA_WARPS][CA_PART];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int pair = blockIdx.x;
     const int b = pair / H, h = pair - b * H;
@@ -300,7 +302,7 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
         }
     }
     float m_run = -INFINITY, l_run = 0.f, a0 = 0.f, a1 = 0.f;
-    for (int pg = warp; pg < npages; pg += 4) {
+    for (int pg = warp; pg < npages; pg += SA_WARPS) {
         const int page = bt[pg];
         const int nkeys = min(WIPA_PAGE, len - pg * WIPA_PAGE);
         const size_t base = ((size_t)page * H + h) * WIPA_PAGE * 64;
@@ -369,10 +371,12 @@ self_attention_kernel(const float* __restrict__ q, const T* __restrict__ kpool, 
     __syncthreads();
     if (threadIdx.x < 64) {
         const int e = threadIdx.x;
-        const float M = fmaxf(fmaxf(part[0][0], part[1][0]), fmaxf(part[2][0], part[3][0]));   // warp 0 always has page 0
+        float M = part[0][0];                                      // warp 0 always has page 0: finite
+#pragma unroll
+        for (int w = 1; w < SA_WARPS; ++w) M = fmaxf(M, part[w][0]);
         float L = 0.f, o = 0.f;
 #pragma unroll
-        for (int w = 0; w < 4; ++w) {
+        for (int w = 0; w < SA_WARPS; ++w) {
             const float wgt = expf(part[w][0] - M);
             L = fmaf(part[w][1], wgt, L);
             o = fmaf(part[w][2 + e], wgt, o);
@@ -386,10 +390,10 @@ int launch_self_attention(const float* q, const T* kpool, const T* vpool, const 
                           const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st, const int* anc_base, const int* flip_ptr,
                           int anc_L) {
     if (anc_base != nullptr)
-        WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T, true>, dim3(Bs * H), dim3(128), (size_t)0, st, q, kpool, vpool,
+        WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T, true>, dim3(Bs * H), dim3(SA_WARPS * 32), (size_t)0, st, q, kpool, vpool,
                                       block_table, bt_stride, pos_ptr, out, H, anc_base, flip_ptr, anc_L));
     else
-        WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T, false>, dim3(Bs * H), dim3(128), (size_t)0, st, q, kpool, vpool,
+        WIPA_CUDA_CHECK(wipa_launch_c(2, self_attention_kernel<T, false>, dim3(Bs * H), dim3(SA_WARPS * 32), (size_t)0, st, q, kpool, vpool,
                                       block_table, bt_stride, pos_ptr, out, H, anc_base, flip_ptr, anc_L));
     WIPA_LAUNCHED();
     return WIPA_OK;
