@@ -245,3 +245,52 @@ def test_wide_architectures_reduced_depth(w, shape):
             assert got.shape == want.shape and torch.equal(got, want)
         else:
             assert agree > 0.7
+
+
+def test_fp32_maximum_target_length(w, tiny_gain_sd):
+    """Decode to the architectural limit (4 prompt + 444 new = 448 positions = all 28 pages of the self-KV block
+    table): ids must still equal the oracle's, position by position."""
+    from oracle import whisper_oracle as wo
+    dims = wo.Dims.from_arch("tiny")
+    audio = wo.synthetic_audio(1)
+    mel = wo.log_mel_spectrogram(torch.from_numpy(audio), 80)
+    enc = wo.encoder_forward(tiny_gain_sd, dims, mel)
+    max_new = 448 - len(wo.PROMPT_PRE_V3)
+    want, _ = wo.greedy_decode(tiny_gain_sd, dims, enc, wo.PROMPT_PRE_V3, max_new)
+    m = w.WhisperIPA("tiny", dtype="float32", max_batch=1)
+    m.load_state_dict(tiny_gain_sd)
+    m.set_audio_features(enc)
+    ids, lens = m.decode_tokens(wo.PROMPT_PRE_V3, max_new)
+    m.close()
+    assert ids.shape == (1, max_new) and torch.equal(ids.cpu().long(), want)
+    with pytest.raises(Exception):
+        m2 = w.WhisperIPA("tiny", dtype="float32", max_batch=1)
+        try:
+            m2.load_state_dict(tiny_gain_sd)
+            m2.set_audio_features(enc)
+            m2.decode_tokens(wo.PROMPT_PRE_V3, max_new + 1)          # 449 positions: refused, not truncated
+        finally:
+            m2.close()
+
+
+def test_bf16_decode_is_deterministic_and_batch_stable(w, tiny_gain_sd):
+    """Two runs over the same 37 clips give identical ids (the stream-K cross-attention merges partials in a fixed
+    order), and the ids of a clip do not depend on which other clips share its batch (a ragged last micro-batch)."""
+    from oracle import whisper_oracle as wo
+    B = 37
+    audio = wo.synthetic_audio(B)
+    feats = w.log_mel_features(audio, 80)
+    m = w.WhisperIPA("tiny", dtype="bfloat16", max_batch=B)
+    m.load_state_dict(tiny_gain_sd)
+    prompt = torch.tensor([wo.PROMPT_PRE_V3] * B)
+    a = m.generate(feats, decoder_input_ids=prompt, max_new_tokens=24).cpu()
+    b = m.generate(feats, decoder_input_ids=prompt, max_new_tokens=24).cpu()
+    assert torch.equal(a, b)
+    m.close()
+    m = w.WhisperIPA("tiny", dtype="bfloat16", max_batch=16)                  # micro-batches of 16, 16, 5
+    m.load_state_dict(tiny_gain_sd)
+    c = m.generate(feats, decoder_input_ids=prompt, max_new_tokens=24).cpu()
+    m.close()
+    agree = (a == c).float().mean().item()
+    print(f"\n[bf16 batch stability] token agreement between batch 37 and micro-batches of 16: {agree:.4f}")
+    assert agree > 0.98
