@@ -221,7 +221,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             m = m_new;
             // ---- pass 2: p = exp(s - m), bf16 P tile into swizzled shared memory ---------------------------------------
             float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
-            uint8_t* prow = myP + (j & 1) * FA_P_BYTES + p_row;
+            const uint32_t prow_s = ptx::smem_u32(myP + (j & 1) * FA_P_BYTES + p_row);
 #pragma unroll
             for (int hf = 1; hf >= 0; --hf) {                      // second half first: it is already in registers
                 if (hf == 0) {
@@ -242,7 +242,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                     uint4 u;
                     u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
                     u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
-                    *reinterpret_cast<uint4*>(prow + hf * FA_TILE_BYTES + (((uint32_t)c8 ^ sw) << 4)) = u;
+                    ptx::sts128(prow_s + hf * FA_TILE_BYTES + (((uint32_t)c8 ^ sw) << 4), u);
                 }
             }
             l = fmaf(l, alpha, (sum0 + sum1) + (sum2 + sum3));

@@ -129,6 +129,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         const int r = quarter * 32 + lane;                     // row of the tile held by this thread after tcgen05.ld
         const int tih = (ew & 3) * 32 + lane;                  // thread index within the half-group (0..127)
         float* st = stage_f + half * G2_STAGE_F;
+        const uint32_t st_s = ptx::smem_u32(st);                // shared-space address of this half-group's staging tile
         const int bar_id = 1 + half;
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -152,9 +153,9 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
                 }
                 named_bar_sync(bar_id, 128);                   // previous chunk's readers are done with the staging tile
-                float* row = st + r * G2_LDS;
+                const uint32_t row_s = st_s + (uint32_t)(r * G2_LDS) * 4u;
 #pragma unroll
-                for (int i = 0; i < 64; i += 4) *reinterpret_cast<float4*>(row + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                for (int i = 0; i < 64; i += 4) ptx::sts128(row_s + i * 4, v[i], v[i + 1], v[i + 2], v[i + 3]);
                 named_bar_sync(bar_id, 128);
                 // each thread owns the 8-column group c8 of rows rr0, rr0 + 16, ..., rr0 + 112 of this 64-column chunk
                 const int c8 = tih & 7, rr0 = tih >> 3;
@@ -187,8 +188,8 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                             if (t0 + rr < ep.M_rows) {
                                 int tt = tt0 + rr, bb = b0;
                                 if (tt >= ep.T) { tt -= ep.T; ++bb; }
-                                const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
-                                const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                                const float4 x0 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8) * 4u);
+                                const float4 x1 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8 + 4) * 4u);
                                 float w[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
                                               x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
                                 store_group<8>(ep.out, ep.out_bf16, wbase + ((long long)bb * ep.H * ep.T + tt) * WIPA_HEAD_DIM, w, true);
@@ -217,8 +218,8 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                             for (int j = 0; j < 8; ++j) {
                                 const int rr = rr0 + j * 16;
                                 if (t0 + rr < ep.M_rows) {
-                                    const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
-                                    const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                                    const float4 x0 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8) * 4u);
+                                    const float4 x1 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8 + 4) * 4u);
                                     float* o = reinterpret_cast<float*>(ep.out) + rowoff[j];
                                     *reinterpret_cast<float4*>(o) = make_float4(x0.x + bias8[0] + r0[j].x, x0.y + bias8[1] + r0[j].y,
                                                                                 x0.z + bias8[2] + r0[j].z, x0.w + bias8[3] + r0[j].w);
@@ -233,8 +234,8 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                             for (int j = 0; j < 8; ++j) {
                                 const int rr = rr0 + j * 16;
                                 if (t0 + rr < ep.M_rows) {
-                                    const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
-                                    const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                                    const float4 x0 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8) * 4u);
+                                    const float4 x1 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8 + 4) * 4u);
                                     float w[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
                                                   x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
                                     if (gelu_fast) {                 // bf16 output: two MUFU + ~14 FMA-pipe instructions per value
@@ -256,8 +257,8 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                         const int t = t0 + rr;
                         if (t < ep.M_rows) {
                             float w[8];
-                            const float4 x0 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8);
-                            const float4 x1 = *reinterpret_cast<const float4*>(st + rr * G2_LDS + c8 * 8 + 4);
+                            const float4 x0 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8) * 4u);
+                            const float4 x1 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8 + 4) * 4u);
                             w[0] = x0.x; w[1] = x0.y; w[2] = x0.z; w[3] = x0.w; w[4] = x1.x; w[5] = x1.y; w[6] = x1.z; w[7] = x1.w;
                             epi_group<8>(ep, batch * a_rpb + t, ncol, w);
                         }
