@@ -178,11 +178,8 @@ enc_attention_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* 
 template <typename T>
 int launch_enc_attention(const T* q, const T* k, const T* v, T* out, int B, int H, int Tq, cudaStream_t st) {
     const size_t smem = sizeof(float) * 4 * 64 * EA_LD;
-    static bool configured = false;
-    if (!configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemAttr attr;
+    WIPA_TRY(wipa_ensure_smem(enc_attention_kernel<T>, smem, attr));
     dim3 grid(cdiv(Tq, EA_BQ), B * H);
     enc_attention_kernel<T><<<grid, 256, smem, st>>>(q, k, v, out, H, Tq);
     WIPA_LAUNCHED();
@@ -765,14 +762,13 @@ template <typename T>
 static int launch_cross_attention_stream(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
                                          int* counters, int Bs, int H, int kv_static, cudaStream_t st) {
     using S = CsCfg<T>;
-    static bool configured = false;
-    static int n_sm = 148;
-    if (!configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(cross_attention_stream_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::SMEM));
+    static SmemAttr attr;
+    WIPA_TRY(wipa_ensure_smem(cross_attention_stream_kernel<T>, (size_t)S::SMEM, attr));
+    static int n_sm = 0;
+    if (n_sm == 0) {
         int dev = 0;
         WIPA_CUDA_CHECK(cudaGetDevice(&dev));
         WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
     }
     const long long n_units = (long long)Bs * H * CS_NCH;
     const int grid = n_units < n_sm ? (int)n_units : n_sm;
@@ -798,12 +794,8 @@ int launch_cross_attention(const float* q, const T* k, const T* v, const int* ut
     chunk = (chunk + 3) & ~3;                                       // keeps every chunk's byte count a multiple of 16
     WIPA_CHECK((n_split - 1) * chunk < WIPA_T_ENC, WIPA_EINVAL, "cross_attention: n_split %d leaves an empty chunk", n_split);
     const size_t smem = (size_t)chunk * 64 * sizeof(T) * 2 + (size_t)chunk * sizeof(float);
-    static size_t configured[2] = {0, 0};
-    size_t& cfg = configured[sizeof(T) == 2];
-    if (smem + 4096 > 48 * 1024 && smem > cfg) {      // + static shared memory of the kernel
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(cross_attention_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cfg = smem;
-    }
+    static SmemAttr attr;                              // one per template instantiation
+    WIPA_TRY(wipa_ensure_smem(cross_attention_kernel<T>, smem, attr));
     dim3 grid(n_split, H, Bs);
     cross_attention_kernel<T><<<grid, CA_THREADS, smem, st>>>(q, k, v, utt_of_seq, out, part, counters, H, chunk);
     WIPA_LAUNCHED();

@@ -303,11 +303,8 @@ int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* v, bf16* o
     WIPA_TRY(make_map_3d(&tmQ, q, T, B * H));
     WIPA_TRY(make_map_3d(&tmK, k, T, B * H));
     WIPA_TRY(make_map_3d(&tmV, v, T, B * H));
-    static bool configured = false;
-    if (!configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(enc_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
-        configured = true;
-    }
+    static SmemAttr attr;
+    WIPA_TRY(wipa_ensure_smem(enc_attention_tc_kernel, (size_t)FA_SMEM, attr));
     dim3 grid(cdiv(T, FA_BQ), B * H);
     enc_attention_tc_kernel<<<grid, FA_THREADS, FA_SMEM, st>>>(tmQ, tmK, tmV, out, H, T);
     WIPA_LAUNCHED();

@@ -60,6 +60,19 @@ extern int64_t g_wipa_launches;
 
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel into > 48 KB of dynamic shared memory.  The attribute is per device, so the cache is per device too
+// (a process normally drives one GPU, but nothing here assumes it).
+struct SmemAttr { size_t done[32] = {0}; };
+template <typename K>
+static inline int wipa_ensure_smem(K kernel, size_t bytes, SmemAttr& a) {
+    int dev = 0;
+    WIPA_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 32 && a.done[dev] >= bytes) return WIPA_OK;
+    WIPA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    if (dev >= 0 && dev < 32) a.done[dev] = bytes;
+    return WIPA_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // programmatic dependent launch (PDL): kernels of the decode step are launched with
 // cudaLaunchAttributeProgrammaticStreamSerialization, signal `launch_dependents` as soon as they start, prefetch

@@ -362,11 +362,8 @@ template <int BN, int BOXM, int CL>
 int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int tiles_per_batch, int n_batch, int a_rpb,
               int N, EpiParams ep, cudaStream_t st, int splits = 1) {
     using Cfg = TcCfg<BN, BOXM>;
-    static bool configured = false;
-    if (!configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<BN, BOXM, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-        configured = true;
-    }
+    static SmemAttr attr;
+    WIPA_TRY(wipa_ensure_smem(gemm_bf16_tc_kernel<BN, BOXM, CL>, (size_t)Cfg::SMEM, attr));
     dim3 grid(cdiv(N, BN), tiles_per_batch * n_batch, splits);
     if (ep.mode == EPI_ARGMAX) ep.n_tiles = grid.x;
     if (CL == 1) {

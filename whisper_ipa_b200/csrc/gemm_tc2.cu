@@ -315,14 +315,13 @@ int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, 
     }
     EpiParams ep = ep_in;
     ep.M_rows = a.a_rpb;
-    static bool configured = false;
-    static int n_sm = 148;
-    if (!configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(gemm_bf16_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM));
+    static SmemAttr attr;
+    WIPA_TRY(wipa_ensure_smem(gemm_bf16_persistent_kernel, (size_t)G2_SMEM, attr));
+    static int n_sm = 0;
+    if (n_sm == 0) {
         int dev = 0;
         WIPA_CUDA_CHECK(cudaGetDevice(&dev));
         WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-        configured = true;
     }
     const int tpb = cdiv(a.a_rpb, G2_BM);
     const int n_mtiles = tpb * a.n_batch, n_ntiles = cdiv(N, G2_BN);

@@ -211,11 +211,8 @@ __global__ void logmel_finish_kernel(float* __restrict__ mel, const float* __res
 int launch_logmel(const LogmelTables& t, const float* audio, int B, float* mel, float* clipmax_scratch,
                   cudaStream_t st) {
     const size_t smem = sizeof(float) * (size_t)(WIPA_N_FREQ * LM_PW_STRIDE > LM_SEG ? WIPA_N_FREQ * LM_PW_STRIDE : LM_SEG);
-    static bool configured = false;
-    if (!configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(logmel_stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    static SmemAttr attr;
+    WIPA_TRY(wipa_ensure_smem(logmel_stft_mel_kernel, smem, attr));
     logmel_init_max_kernel<<<cdiv(B, 256), 256, 0, st>>>(clipmax_scratch, B);
     WIPA_LAUNCHED();
     dim3 grid(cdiv(WIPA_N_FRAMES, LM_TILE_F), B);

@@ -81,12 +81,8 @@ extern "C" int wipa_per_batch(const int32_t* ref, const int32_t* ref_off, const 
     int warps = (int)((96 * 1024) / per_warp);
     warps = warps < 1 ? 1 : (warps > 8 ? 8 : warps);
     const size_t smem = per_warp * warps;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(per_levenshtein_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem));
-        configured = smem;
-    }
+    static SmemAttr attr;
+    if (smem > 48 * 1024) WIPA_TRY(wipa_ensure_smem(per_levenshtein_kernel, smem, attr));
     const int grid = cdiv(N, warps);
     per_levenshtein_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(ref, ref_off, hyp, hyp_off, N, words,
                                                                               dist_len);

@@ -112,11 +112,8 @@ extern "C" int wipa_pfer_batch(const int32_t* ref, const int32_t* ref_off, const
     int warps = (int)((96 * 1024) / per_warp);
     warps = warps < 1 ? 1 : (warps > 4 ? 4 : warps);
     const size_t smem = per_warp * warps;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        WIPA_CUDA_CHECK(cudaFuncSetAttribute(pfer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    static SmemAttr attr;
+    if (smem > 48 * 1024) WIPA_TRY(wipa_ensure_smem(pfer_kernel, smem, attr));
     pfer_kernel<<<cdiv(N, warps), warps * 32, smem, (cudaStream_t)stream>>>(ref, ref_off, hyp, hyp_off, N, feats, mode,
                                                                             (int)per_warp, dist);
     WIPA_LAUNCHED();
