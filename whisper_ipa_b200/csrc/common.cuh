@@ -199,20 +199,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // two MUFU ops (rcp, ex2) + ~12 FMA-pipe instructions instead of erff's ~35.  1 + erf(z) is formed without
 // cancellation on the negative side.  Used only where the result is rounded to bf16 (the fp32 path calls erff).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float z = x * 0.70710678118654752440f;
-    const float az = fabsf(z);
+    // gelu(x) = x * Phi(x); with h = 0.5 * (1 - erf(|x| / sqrt 2)) = 0.5 * poly(t) * exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt 2):
+    // Phi(x) = h for x < 0 and 1 - h otherwise.  The 0.5, the 1/sqrt 2 and log2(e) are folded into the constants.
+    const float ax = fabsf(x);
     float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, az, 1.0f)));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, ax, 1.0f)));          // p / sqrt 2 = 0.3275911 * 0.70710678
+    float poly = fmaf(0.5307027145f, t, -0.7265760135f);                                      // a5 / 2, a4 / 2
+    poly = fmaf(poly, t, 0.7107068705f);
+    poly = fmaf(poly, t, -0.142248368f);
+    poly = fmaf(poly, t, 0.127414796f);
     poly *= t;
     float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(az * az * -1.4426950408889634f));
-    const float c = poly * e;                                  // 1 - erf(|z|)
-    const float one_plus_erf = z < 0.f ? c : 2.0f - c;
-    return 0.5f * x * one_plus_erf;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((x * -0.72134752f) * x));               // exp(-x^2 / 2)
+    const float xh = x * (poly * e);                                                          // x * h
+    return x < 0.f ? xh : x - xh;
 }
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
