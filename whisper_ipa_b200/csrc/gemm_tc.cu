@@ -178,8 +178,10 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                                            (g | i | k) != 0 ? 1u : 0u);
                     }
                 }
-                if (CL > 1) ptx::umma_commit_mc(&empty[s], mc_mask);   // the slot is free once EVERY CTA of the cluster has consumed it
-                else ptx::umma_commit(&empty[s]);            // frees the ring slot when these MMAs retire
+                // a slot is free once EVERY CTA of the cluster has consumed it; when the whole K range fits the ring nobody
+                // ever waits for a slot, the release is not sent and the closing cluster barrier is not needed either
+                if (CL > 1 && num_g > Cfg::STAGES) ptx::umma_commit_mc(&empty[s], mc_mask);
+                else if (CL == 1) ptx::umma_commit(&empty[s]);      // frees the ring slot when these MMAs retire
             }
             __syncwarp();
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -337,7 +339,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (threadIdx.x == 64) DBG_STAMP(6);
     ptx::tc_fence_before();
     __syncthreads();
-    if (CL > 1) ptx::cluster_sync_all();                      // no CTA leaves while peers may still signal its barriers
+    if (CL > 1 && (num_kb + Cfg::KPB - 1) / Cfg::KPB > Cfg::STAGES) ptx::cluster_sync_all();   // no CTA leaves while peers may still signal its barriers
     if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     if (threadIdx.x == 0) DBG_STAMP(7);
 }
