@@ -126,6 +126,13 @@ int wipa_ctx_get_info(wipa_ctx*, int what, int64_t* out);
 int wipa_test_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, float* C,
                         int M, int N, int K, int block_n, void* stream);
 int wipa_test_gemm_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, void* stream);
+/* Epilogue variants of the bf16 GEMMs on encoder-shaped problems (M = rows_per_batch * n_batch rows, tiles never straddle
+ * a batch; block_n = 0 selects the persistent kernel and its specialised epilogues).  mode: 0 bias, 1 bias + GELU,
+ * 2 bias + fp32 residual, 3 bias + q|k|v head split into [3][n_batch][H][rows_per_batch][64] with N = 3*H*64
+ * (HF:models/whisper/modeling_whisper.py WhisperEncoderLayer: the projections, fc1 + activation_fn, the two residual adds).
+ * `out` holds bf16 when out_bf16 != 0, fp32 otherwise. */
+int wipa_test_gemm_epilogue(const void* A, const void* W, const float* bias, const float* resid, void* out,
+                            int rows_per_batch, int n_batch, int N, int K, int mode, int out_bf16, int block_n, void* stream);
 /* conv1d-as-GEMM addressing: logical row (batch, t) of A starts at A + batch*bstride + t*lda and spans K >= lda
  * elements (rows overlap); A/W are bf16 (tcgen05 kernel) when is_bf16 else fp32 (SIMT kernel); C fp32 [M, N]. */
 int wipa_test_gemm_rows(const void* A, int is_bf16, long long lda, int rows_per_batch, long long bstride, int n_batch,

@@ -61,6 +61,48 @@ def test_gemm_bf16_persistent(lib, M, N, K):
     assert err < 5e-4 * max(1.0, ref.abs().max().item()), f"max err {err}"
 
 
+def _gelu(x):
+    return torch.nn.functional.gelu(x)          # exact erf form (HF activation_function="gelu")
+
+
+@pytest.mark.parametrize("bn", [0, 128])
+@pytest.mark.parametrize("rpb,nb,N,K", [(1500, 2, 768, 128), (1500, 2, 1152, 64), (200, 3, 384, 192), (128, 1, 192, 64)])
+@pytest.mark.parametrize("mode,out_bf16", [(0, 1), (0, 0), (1, 1), (1, 0), (2, 0), (3, 1), (3, 0)])
+def test_gemm_epilogue_variants(lib, bn, rpb, nb, N, K, mode, out_bf16):
+    """Every epilogue of the encoder GEMMs (bias / GELU / residual / q|k|v head split) on encoder-shaped problems: ragged
+    last row tile per batch (1500 = 11 * 128 + 92), a tile that crosses a batch boundary in the output (200 rows), a last
+    n-tile that is half empty (1152 = 4 * 256 + 128, 384, 192).  bn = 0 runs the persistent kernel's specialised epilogues."""
+    M = rpb * nb
+    g = torch.Generator(device="cuda").manual_seed(rpb + N + K + mode)
+    A = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    W = (torch.randn(N, K, device="cuda", generator=g) * 0.2).to(torch.bfloat16)
+    b = torch.randn(N, device="cuda", generator=g)
+    resid = torch.randn(M, N, device="cuda", generator=g)
+    odt = torch.bfloat16 if out_bf16 else torch.float32
+    if mode == 3:
+        H = N // 192
+        out = torch.full((3, nb, H, rpb, 64), float("nan"), device="cuda", dtype=odt)
+    else:
+        out = torch.full((M, N), float("nan"), device="cuda", dtype=odt)
+    if mode == 2:
+        out.copy_(resid)                                    # in place, as the encoder's residual stream is updated
+    lib.check(lib.lib().wipa_test_gemm_epilogue(A.data_ptr(), W.data_ptr(), b.data_ptr(), out.data_ptr() if mode == 2 else 0,
+                                                out.data_ptr(), rpb, nb, N, K, mode, out_bf16, bn, _st()), "gemm_epilogue")
+    ref = A.double() @ W.double().T + b.double()
+    if mode == 1:
+        ref = _gelu(ref)
+    elif mode == 2:
+        ref = ref + resid.double()
+    elif mode == 3:
+        ref = ref.reshape(nb, rpb, 3, N // 192, 64).permute(2, 0, 3, 1, 4)
+    assert not torch.isnan(out.float()).any(), "unwritten output elements"
+    scale = max(1.0, ref.abs().max().item())
+    err = (out.double() - ref).abs().max().item()
+    # fp32 results: accumulation order only; bf16 results: one rounding of the stored value (2^-9 relative) on top
+    tol = (6e-3 if out_bf16 else 2e-5) * scale
+    assert err < tol, f"max err {err} (tol {tol})"
+
+
 @pytest.mark.parametrize("is_bf16,bn", [(0, 128), (1, 128), (1, 0)])
 @pytest.mark.parametrize("C_in,stride,T_out", [(80, 1, 3000), (128, 1, 3000), (384, 2, 1500)])
 def test_gemm_conv_rows(lib, is_bf16, bn, C_in, stride, T_out):

@@ -56,6 +56,7 @@ PROTOTYPES = {
     "wipa_ctx_get_info": (_i, [_vp, _i, C.POINTER(_i64)]),
     "wipa_test_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wipa_test_gemm_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "wipa_test_gemm_epilogue": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "wipa_test_gemm_rows": (_i, [_vp, _i, C.c_longlong, _i, C.c_longlong, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_cross_attn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wipa_test_enc_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -919,6 +919,33 @@ extern "C" int wipa_test_gemm_f32(const float* A, const float* W, const float* b
     return launch_gemm_f32(plainA(A, M, K), W, M, N, K, ep, (cudaStream_t)stream);
 }
 
+// Epilogue variants of the bf16 GEMMs on encoder-shaped problems: M = rows_per_batch * n_batch rows, processed as the
+// encoder does (tiles never straddle a batch).  mode: 0 bias, 1 bias + GELU, 2 bias + residual (fp32 in place of `out`),
+// 3 bias + q|k|v head split into [3][n_batch][H][rows_per_batch][64] (N = 3 * H * 64).  `out` is bf16 when out_bf16 != 0.
+extern "C" int wipa_test_gemm_epilogue(const void* A, const void* W, const float* bias, const float* resid, void* out,
+                                       int rows_per_batch, int n_batch, int N, int K, int mode, int out_bf16, int block_n,
+                                       void* stream) {
+    WIPA_CHECK(A && W && out && rows_per_batch > 0 && n_batch > 0, WIPA_EINVAL, "wipa_test_gemm_epilogue: bad argument");
+    WIPA_CHECK(mode >= 0 && mode <= 3, WIPA_EINVAL, "wipa_test_gemm_epilogue: mode must be 0..3");
+    const int M = rows_per_batch * n_batch;
+    static const int modes[4] = {EPI_STORE, EPI_GELU, EPI_RESADD, EPI_HEADS};
+    EpiParams ep = epi(modes[mode], M, N);
+    ep.bias = bias; ep.out = out; ep.out_bf16 = out_bf16 ? 1 : 0;
+    ep.o_rpb = rows_per_batch; ep.o_bstride = (long long)rows_per_batch * N;
+    if (mode == 1) ep.gelu_fast = ep.out_bf16;
+    if (mode == 2) {
+        WIPA_CHECK(resid != nullptr && !out_bf16, WIPA_EINVAL, "wipa_test_gemm_epilogue: residual mode is fp32 and needs resid");
+        ep.resid = resid;
+    }
+    if (mode == 3) {
+        WIPA_CHECK(N % (3 * WIPA_HEAD_DIM) == 0, WIPA_EINVAL, "wipa_test_gemm_epilogue: N must be 3 * H * 64");
+        ep.d = N / 3; ep.H = ep.d / WIPA_HEAD_DIM; ep.T = rows_per_batch;
+        ep.which_stride = (long long)n_batch * ep.H * rows_per_batch * WIPA_HEAD_DIM;
+    }
+    AOperand a; a.ptr = A; a.lda = K; a.a_rpb = rows_per_batch; a.a_bstride = (long long)rows_per_batch * K; a.n_batch = n_batch;
+    return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
+}
+
 // conv-as-GEMM addressing check: row m = (batch, t) of A starts at A + batch*bstride + t*lda and spans K >= lda elements
 extern "C" int wipa_test_gemm_rows(const void* A, int is_bf16, long long lda, int rows_per_batch, long long bstride, int n_batch,
                                    const void* W, float* C, int N, int K, int block_n, void* stream) {

@@ -25,7 +25,8 @@ constexpr int G2_A_BYTES = G2_BM * G2_BK * 2;                 // 16 KB
 constexpr int G2_W_BYTES = G2_BN * G2_BK * 2;                 // 32 KB
 constexpr int G2_LDS = 68;                                    // staging row pitch in floats (64 + 4: conflict-free float4 rows)
 constexpr int G2_STAGE_F = G2_BM * G2_LDS;                    // floats per staging tile (128 rows x 64 columns)
-constexpr int G2_SMEM = G2_STAGES * (G2_A_BYTES + G2_W_BYTES) + 2 * G2_STAGE_F * 4 + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int G2_SMEM = G2_STAGES * (G2_A_BYTES + G2_W_BYTES) + 2 * G2_STAGE_F * 4 + 1024 /*align*/ + 256 /*barriers*/ +
+                        1024 /*bias tile*/;
 constexpr int G2_THREADS = 64 + 256;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -37,6 +38,48 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Epilogue variants.  The encoder's four shapes get their own instantiation so that each carries only the code it runs
+// (the generic kernel's SASS is ~64 KB and the eight epilogue warps sit at different places in it: 6 % of its samples
+// were instruction-fetch stalls); anything else takes G2_EP_GENERIC, which decides per chunk at run time.
+enum { G2_EP_GENERIC = 0, G2_EP_HEADS_BF16 = 1, G2_EP_RESADD_F32 = 2, G2_EP_GELU_BF16 = 3, G2_EP_STORE_BF16 = 4 };
+
+// Two GELUs at a time on the packed fp32 pipe (fma/mul.f32x2): 9 issue slots per value instead of 15.  Same A&S 7.1.26
+// erf as gelu_erf_fast; the sign select is folded into gelu(x) = max(x, 0) - |x| * h(|x|).
+__device__ __forceinline__ uint64_t f2_pack(float a, float b) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t r, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(r)); }
+__device__ __forceinline__ uint64_t f2_fma(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_mul(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t f2_dup(float a) { return f2_pack(a, a); }
+__device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
+    float t0, t1, e0, e1, a0, a1, h0, h1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(0.23164189f, fabsf(x0), 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(0.23164189f, fabsf(x1), 1.0f)));
+    const uint64_t t = f2_pack(t0, t1), x = f2_pack(x0, x1);
+    uint64_t p = f2_fma(f2_dup(0.5307027145f), t, f2_dup(-0.7265760135f));
+    p = f2_fma(p, t, f2_dup(0.7107068705f));
+    p = f2_fma(p, t, f2_dup(-0.142248368f));
+    p = f2_fma(p, t, f2_dup(0.127414796f));
+    f2_unpack(f2_mul(f2_mul(x, f2_dup(-0.72134752f)), x), a0, a1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    f2_unpack(f2_mul(p, f2_mul(t, f2_pack(e0, e1))), h0, h1);
+    x0 = fmaf(-fabsf(x0), h0, fmaxf(x0, 0.f));
+    x1 = fmaf(-fabsf(x1), h1, fmaxf(x1, 0.f));
+}
+
+template <int EP>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
                             int tiles_per_batch, int n_mtiles, int n_ntiles, int a_rpb, EpiParams ep) {
@@ -50,6 +93,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     uint64_t* tmem_full = empty + G2_STAGES;                  // [2]
     uint64_t* tmem_empty = tmem_full + 2;                     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    float* s_bias = reinterpret_cast<float*>(full) + 64;          // [2 halves][128], after the 256 bytes of barriers
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = n_mtiles * n_ntiles;
@@ -138,8 +182,13 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             const int t0 = (mt - batch * tiles_per_batch) * G2_BM;
             const int n0 = nt * G2_BN + half * 128;
             const int buf = it & 1;
+            constexpr bool kBf16Staged = EP == G2_EP_HEADS_BF16 || EP == G2_EP_GELU_BF16 || EP == G2_EP_STORE_BF16;
+            float bias_mine = 0.f;                              // column n0 + tih of the bias, fetched ahead of the accumulator
+            if (kBf16Staged && ep.bias != nullptr && n0 + tih < ep.N) bias_mine = __ldg(ep.bias + n0 + tih);
             ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
             ptx::tc_fence_after();
+            if (kBf16Staged) s_bias[half * 128 + tih] = bias_mine;   // read after the next named barrier; the previous tile's
+                                                                   // readers are behind its last one
             const uint32_t taddr = tmem_base + (uint32_t)buf * G2_BN + (uint32_t)half * 128u + ((uint32_t)(quarter * 32) << 16);
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {                      // 64 columns at a time
@@ -152,6 +201,72 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
                 }
+                // ---- bf16 results: bias / GELU by the row-owning thread, then a bf16 staging tile ------------------------------
+                // (The epilogue is issue-bound, not bandwidth-bound: ~24 % of each epilogue warp's samples are `selected`.
+                // Staging the finished bf16 values halves the shared-memory instructions; unstaged row-per-thread stores
+                // were tried and are slower: 32 partial lines per store instruction.)
+                const int nc0 = n0 + c * 64;
+                if (EP != G2_EP_GENERIC && nc0 >= ep.N) continue;   // N % 64 == 0: a chunk of the last n-tile is all in or all out
+                                                                    // (uniform over the half-group, so its barriers stay matched)
+                if constexpr (kBf16Staged) {
+                    constexpr uint32_t PITCH = 144;                // bytes per staged row: 64 bf16 + 16 (conflict-free 16-byte rows)
+                    named_bar_sync(bar_id, 128);               // previous chunk's readers are done with the staging tile; bias tile visible
+                    if (ep.bias != nullptr) {
+                        const uint32_t sb = ptx::smem_u32(s_bias + half * 128 + c * 64);
+#pragma unroll
+                        for (int i = 0; i < 64; i += 4) {
+                            const float4 b4 = ptx::lds128(sb + i * 4);
+                            v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
+                        }
+                    }
+                    if constexpr (EP == G2_EP_GELU_BF16) {
+#pragma unroll
+                        for (int i = 0; i < 64; i += 2) gelu_erf_fast2(v[i], v[i + 1]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 64; i += 8) {
+                        uint4 u;
+                        u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                        u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + (uint32_t)r * PITCH + (uint32_t)i * 2u),
+                                     "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+                    }
+                    named_bar_sync(bar_id, 128);
+                    // readers: thread -> 16-byte piece p8 of rows rr0, rr0 + 16, ...: 8 lanes cover one 128-byte output line
+                    const int p8 = tih & 7, rr0 = tih >> 3;
+                    const int m_first = batch * a_rpb + t0;
+                    long long base_off, wrap_off, row_pitch;
+                    int row0, period;                              // row of tile row 0 within its clip / output batch, and the period
+                    if constexpr (EP == G2_EP_HEADS_BF16) {
+                        const int which = nc0 / ep.d;
+                        const int h = (nc0 - which * ep.d) >> 6;
+                        const int b0 = m_first / ep.T;
+                        row0 = m_first - b0 * ep.T; period = ep.T;
+                        base_off = (long long)which * ep.which_stride + ((long long)(b0 * ep.H + h) * ep.T) * WIPA_HEAD_DIM + p8 * 8;
+                        wrap_off = (long long)(ep.H - 1) * ep.T * WIPA_HEAD_DIM;      // next clip: + H*T rows, - T rows
+                        row_pitch = WIPA_HEAD_DIM;
+                    } else {
+                        const int ob0 = m_first / ep.o_rpb;
+                        row0 = m_first - ob0 * ep.o_rpb; period = ep.o_rpb;
+                        base_off = (long long)ob0 * ep.o_bstride + nc0 + p8 * 8;
+                        wrap_off = ep.o_bstride - (long long)ep.o_rpb * ep.ldo;
+                        row_pitch = ep.ldo;
+                    }
+                    bf16* const out_b = reinterpret_cast<bf16*>(ep.out) + base_off;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int rr = rr0 + j * 16;
+                        if (t0 + rr < ep.M_rows) {
+                            uint4 u;
+                            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+                                         : "r"(st_s + (uint32_t)rr * PITCH + (uint32_t)p8 * 16u) : "memory");
+                            const int tt = row0 + rr;
+                            const long long off = (long long)tt * row_pitch + (tt >= period ? wrap_off : 0ll);
+                            *reinterpret_cast<uint4*>(out_b + off) = u;
+                        }
+                    }
+                    continue;
+                }
                 named_bar_sync(bar_id, 128);                   // previous chunk's readers are done with the staging tile
                 const uint32_t row_s = st_s + (uint32_t)(r * G2_LDS) * 4u;
 #pragma unroll
@@ -161,9 +276,10 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 const int c8 = tih & 7, rr0 = tih >> 3;
                 const int nc = n0 + c * 64;                        // first column of the chunk
                 const int ncol = nc + c8 * 8;
-                const bool fast = ep.vec_ok && (nc + 64 <= ep.N) &&
-                                  ((ep.mode == EPI_HEADS && ep.T >= G2_BM && ep.vt_which < 0) ||
-                                   ((ep.mode == EPI_RESADD || ep.mode == EPI_GELU || ep.mode == EPI_STORE) && ep.o_rpb >= G2_BM));
+                const bool fast = EP == G2_EP_RESADD_F32 ||
+                                  (ep.vec_ok && (nc + 64 <= ep.N) &&
+                                   ((ep.mode == EPI_HEADS && ep.T >= G2_BM && ep.vt_which < 0) ||
+                                    ((ep.mode == EPI_RESADD || ep.mode == EPI_GELU || ep.mode == EPI_STORE) && ep.o_rpb >= G2_BM)));
                 if (fast) {
                     float bias8[8];
 #pragma unroll
@@ -175,7 +291,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                         bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
                     }
                     const int m_first = batch * a_rpb + t0;        // logical row of the tile's first row
-                    if (ep.mode == EPI_HEADS) {
+                    if (EP != G2_EP_RESADD_F32 && ep.mode == EPI_HEADS) {
                         // one 64-column chunk = one head of one of q|k|v: a single division pair per chunk, and the clip
                         // index advances at most once inside a 128-row tile (T >= 128)
                         const int which = nc / ep.d;
@@ -204,7 +320,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                             if (ot >= ep.o_rpb) { ot -= ep.o_rpb; ++ob; }
                             rowoff[j] = (long long)ob * ep.o_bstride + (long long)ot * ep.ldo + ncol;
                         }
-                        if (ep.mode == EPI_RESADD) {
+                        if (EP == G2_EP_RESADD_F32 || ep.mode == EPI_RESADD) {
                             // all residual loads of the chunk are issued before the first use (one HBM round trip per chunk)
                             float4 r0[8], r1[8];
 #pragma unroll
@@ -315,8 +431,6 @@ int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, 
     }
     EpiParams ep = ep_in;
     ep.M_rows = a.a_rpb;
-    static SmemAttr attr;
-    WIPA_TRY(wipa_ensure_smem(gemm_bf16_persistent_kernel, (size_t)G2_SMEM, attr));
     static int n_sm = 0;
     if (n_sm == 0) {
         int dev = 0;
@@ -327,7 +441,31 @@ int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, 
     const int n_mtiles = tpb * a.n_batch, n_ntiles = cdiv(N, G2_BN);
     const int n_tiles = n_mtiles * n_ntiles;
     const int grid = n_tiles < n_sm ? n_tiles : n_sm;
-    gemm_bf16_persistent_kernel<<<grid, G2_THREADS, G2_SMEM, st>>>(tmA, tmW, cdiv(K, G2_BK), tpb, n_mtiles, n_ntiles, a.a_rpb, ep);
+    // specialised epilogues: every 64-column chunk is full and a 128-row tile crosses at most one clip / batch boundary
+    int variant = G2_EP_GENERIC;
+    if (ep.vec_ok && N % 64 == 0) {
+        if (ep.mode == EPI_HEADS && ep.out_bf16 && ep.T >= G2_BM && ep.vt_which < 0 && ep.d % 64 == 0) variant = G2_EP_HEADS_BF16;
+        else if (ep.mode == EPI_RESADD && !ep.out_bf16 && ep.o_rpb >= G2_BM) variant = G2_EP_RESADD_F32;
+        else if (ep.mode == EPI_GELU && ep.out_bf16 && ep.o_rpb >= G2_BM) variant = G2_EP_GELU_BF16;
+        else if (ep.mode == EPI_STORE && ep.out_bf16 && ep.o_rpb >= G2_BM) variant = G2_EP_STORE_BF16;
+    }
+    static const char* force = getenv("WIPA_G2_GENERIC");      // experiment / test switch: always the run-time epilogue
+    if (force != nullptr && force[0] == '1') variant = G2_EP_GENERIC;
+#define G2_LAUNCH(EPV)                                                                                                        \
+    {                                                                                                                         \
+        static SmemAttr attr;                                                                                                 \
+        WIPA_TRY(wipa_ensure_smem(gemm_bf16_persistent_kernel<EPV>, (size_t)G2_SMEM, attr));                                  \
+        gemm_bf16_persistent_kernel<EPV><<<grid, G2_THREADS, G2_SMEM, st>>>(tmA, tmW, cdiv(K, G2_BK), tpb, n_mtiles, n_ntiles, \
+                                                                            a.a_rpb, ep);                                      \
+    }
+    switch (variant) {
+        case G2_EP_HEADS_BF16: G2_LAUNCH(G2_EP_HEADS_BF16) break;
+        case G2_EP_RESADD_F32: G2_LAUNCH(G2_EP_RESADD_F32) break;
+        case G2_EP_GELU_BF16: G2_LAUNCH(G2_EP_GELU_BF16) break;
+        case G2_EP_STORE_BF16: G2_LAUNCH(G2_EP_STORE_BF16) break;
+        default: G2_LAUNCH(G2_EP_GENERIC) break;
+    }
+#undef G2_LAUNCH
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
