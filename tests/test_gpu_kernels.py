@@ -203,3 +203,26 @@ def test_cross_attention_streamer(lib, tiny_sd, dtype, tol):
         err = (out - ref).abs().max().item()
         assert err < tol, f"layer {layer}: max err {err}"
     m.close()
+
+
+@pytest.mark.parametrize("H,T,S,U", [(12, 1500, 5, 3), (12, 100, 200, 4), (6, 1500, 3, 3), (16, 333, 4, 2), (8, 48, 2, 1)])
+def test_cross_attention_latent(lib, H, T, S, U):
+    """Latent cross-attention kernel (mma.sync over TMA-swizzled tiles of the encoder output): C = softmax(Q' E^T) E per
+    sequence, sequences mapped to utterances (beams share E), more sequences than SMs, ragged last key chunk, both key
+    chunk sizes (48 keys up to 12 heads, 32 above)."""
+    d = 64 * H
+    g = torch.Generator(device="cuda").manual_seed(H * 1000 + T + S)
+    E = torch.randn(U, T, d, device="cuda", generator=g).to(torch.bfloat16)
+    Qp = (torch.randn(S, H, d, device="cuda", generator=g) * (1.5 / d ** 0.5)).to(torch.bfloat16)
+    utt = (torch.arange(S, device="cuda", dtype=torch.int32) * U // S).to(torch.int32).contiguous()
+    C = torch.full((S, H, d), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lib.check(lib.lib().wipa_test_cross_attn_latent(Qp.data_ptr(), E.data_ptr(), U, utt.data_ptr(), C.data_ptr(), S, H, T, _st()),
+              "cross_attn_latent")
+    Eu = E.float()[utt.long()]                                          # [S, T, d]
+    scores = torch.einsum("shd,std->sht", Qp.float(), Eu)
+    P = torch.softmax(scores, dim=-1)
+    ref = torch.einsum("sht,std->shd", P, Eu)
+    assert not torch.isnan(C.float()).any()
+    err = (C.float() - ref).abs().max().item()
+    # bf16 probabilities (2^-9 relative each, averaged over the keys) + one bf16 rounding of the result
+    assert err < 1.5e-2 * max(1.0, ref.abs().max().item()), f"max err {err}"

@@ -113,14 +113,17 @@ def test_eos_handling_matches_oracle(w, tiny_gain_sd, eot_like):
     m.close()
 
 
-@pytest.mark.parametrize("arch,B,persistent", [("tiny", 4, False), ("base", 2, False), ("tiny", 3, True), ("base", 2, True)])
-def test_bf16_logits_and_token_agreement(w, arch, B, persistent, monkeypatch):
+@pytest.mark.parametrize("arch,B,persistent,latent", [("tiny", 4, False, False), ("base", 2, False, False), ("tiny", 3, True, False),
+                                                        ("base", 2, True, False), ("tiny", 4, False, True), ("base", 3, False, True)])
+def test_bf16_logits_and_token_agreement(w, arch, B, persistent, latent, monkeypatch):
     """bf16 path vs the fp32 oracle: relative L2 error of teacher-forced logits (bf16 operand rounding bounds it at the
     1e-2 level; the measured value is printed) and greedy-token agreement over 32 steps.  `persistent` forces every
     encoder GEMM through the persistent 128x256 kernel (normally chosen only for >= 2 waves of tiles) so that its
     fused epilogues (head split, residual add, fast GELU, conv rows) are checked at test sizes too."""
     if persistent:
         monkeypatch.setenv("WIPA_PERSISTENT_MIN_TILES", "1")
+    if latent:                      # cross-attention over the encoder output itself, k / v projections folded (attn_lat.cu)
+        monkeypatch.setenv("WIPA_XATTN_LATENT", "1")
     from oracle import hf_reference as hf
     from oracle import whisper_oracle as wo
     sd = hf.state_dict_f32(hf.build_hf_model(arch, seed=0))
@@ -142,7 +145,7 @@ def test_bf16_logits_and_token_agreement(w, arch, B, persistent, monkeypatch):
     agree = (ids.cpu().long() == ref_ids).float().mean().item()
     prefix = np.mean([int((row != ref).nonzero()[0]) if (row != ref).any() else 32
                       for row, ref in zip(ids.cpu().long(), ref_ids)])
-    print(f"\n[bf16 {arch}] encoder rel-L2 {enc_rel:.2e}, logits rel-L2 {rel:.2e}, token agreement {agree:.3f}, "
+    print(f"\n[bf16 {arch}{' latent' if latent else ''}] encoder rel-L2 {enc_rel:.2e}, logits rel-L2 {rel:.2e}, token agreement {agree:.3f}, "
           f"mean agreeing prefix {prefix:.1f}/32")
     assert enc_rel < 2e-2 and rel < 3e-2
     assert np.isfinite(got_logits.numpy()).all()

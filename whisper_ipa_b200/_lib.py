@@ -57,6 +57,7 @@ PROTOTYPES = {
     "wipa_test_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wipa_test_gemm_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_gemm_epilogue": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "wipa_test_cross_attn_latent": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_gemm_rows": (_i, [_vp, _i, C.c_longlong, _i, C.c_longlong, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_cross_attn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wipa_test_enc_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -1,0 +1,295 @@
+// Decoder cross-attention over the encoder output itself ("latent" cross-attention), bf16 path.
+//
+// HF computes, per decoder layer l and utterance u (HF:models/whisper/modeling_whisper.py:241-357),
+//     K_l = E_u Wk_l^T,   V_l = E_u Wv_l^T + bv_l,   ctx_h = softmax_t(q_h . K_l[t, h]) V_l[:, h]
+// with E_u = the encoder output [1500, d], the SAME matrix for every layer.  Streaming K_l and V_l of all layers costs
+// L * 2 * 1500 * d elements per sequence per decode step (55 MB for whisper-small) and is what bounds the decode step.
+// Because K and V are linear images of E, the projections can be moved to the query / output side:
+//     q_h . K_l[t, h] = (Wk_l[h]^T q_h) . E_u[t]           = q'_h . E_u[t],      q'_h in R^d
+//     ctx_h           = Wv_l[h] (sum_t p_h[t] E_u[t]) + bv_l[h] = Wv_l[h] c_h + bv_l[h]     (sum_t p_h[t] = 1)
+// so one pass over E_u (1500 * d elements) serves all heads and both the "key" and the "value" role: half the bytes per
+// layer, no per-layer cross-KV cache (14.2 GB -> 0.59 GB at 256 clips), no cross-K/V projection in the encoder.  The
+// price is H times more arithmetic (every head works in R^d instead of R^64), which the legacy tensor pipe absorbs:
+// S = Q' E^T and C = P E are [16 x keys x d] mma.sync products with M = 16 >= the number of heads.
+//
+//   q' = x (Wq_h^T Wk_h) + bq_h Wk_h      one [S, d] x [d, H*d] GEMM with weights folded at load time (ctx.cu)
+//   this kernel: Q' [S, H, d] bf16, E [U, 1500, d] bf16  ->  C [S, H, d] bf16 (normalised sum_t p_h[t] E[t])
+//   out-projection: x += C (Wo_h Wv_h)^T + (bo + Wo bv)   one [S, H*d] x [H*d, d] GEMM, weights folded at load time
+//
+// Kernel: one CTA per SM walks sequences s = blockIdx.x, += gridDim.x.  Warp H is the TMA producer: chunks of KEYS keys
+// x d columns as H 128B-swizzled tiles [KEYS][64] into a 2-stage ring.  Consumer warp w (0..H-1) owns columns
+// [64w, 64w + 64) of d for BOTH products:
+//   1. partial scores  Sp[w][16 x KEYS] = Q'[:, cols] E[keys, cols]^T    (A fragments of Q' live in registers per sequence)
+//   2. named barrier; warp w sums row w (= head w) over the H partials, does the online-softmax bookkeeping for that
+//      head and writes p (bf16) and the rescale factor alpha[w]; named barrier
+//   3. C[:, cols] = alpha * C[:, cols] + P E[keys, cols]                 (accumulators [16 x 64] per warp, fp32)
+// Rows >= H of the 16-row MMA tile are padding.  Keys beyond 1500 in the last chunk are zero-filled by TMA (3-D map,
+// out-of-bounds rows) and masked to -inf before the softmax.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode_xl = nullptr;
+
+constexpr int XL_STAGES = 2;
+constexpr float XL_LOG2E = 1.4426950408889634f;
+
+template <int KEYS>
+struct XlCfg {
+    static constexpr int PITCH = KEYS + 8;                      // floats per partial-score row / bf16 per P row
+    static size_t smem(int H) {
+        return (size_t)XL_STAGES * KEYS * H * 128 + (size_t)H * H * PITCH * 4 + 16 * PITCH * 2 + 32 * 4 + 64 + 1024;
+    }
+};
+
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+// D[16 x 8] += A[16 x 16] B[16 x 8], bf16 operands, fp32 accumulators
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void xl_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+template <int KEYS>
+__global__ void __launch_bounds__(17 * 32, 1)
+cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf16* __restrict__ Qp,
+                              const int* __restrict__ utt_of_seq, bf16* __restrict__ Cout, int S, int H, int T) {
+    using Cfg = XlCfg<KEYS>;
+    constexpr int PITCH = Cfg::PITCH;
+    extern __shared__ uint8_t xl_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xl_smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int d = H * 64;
+    const uint32_t stage_bytes = (uint32_t)KEYS * (uint32_t)H * 128u;
+    uint8_t* sE = smem;                                                      // [stage][H tiles][KEYS][128 B], 128B-swizzled
+    float* Sp = reinterpret_cast<float*>(sE + XL_STAGES * stage_bytes);      // [warp][head][PITCH]
+    bf16* Pm = reinterpret_cast<bf16*>(Sp + H * H * PITCH);                  // [16][PITCH]
+    float* alpha = reinterpret_cast<float*>(Pm + 16 * PITCH);                // [16] rescale of C, [16] final 1 / l
+    uint64_t* full = reinterpret_cast<uint64_t*>(alpha + 32);
+    uint64_t* empty = full + XL_STAGES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = (T + KEYS - 1) / KEYS;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmE);
+        for (int s = 0; s < XL_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], (uint32_t)H); }
+        ptx::fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 16 * PITCH; i += blockDim.x) Pm[i] = __float2bfloat16(0.f);
+    if (threadIdx.x < 32) alpha[threadIdx.x] = 1.f;
+    __syncthreads();
+
+    if (warp == H) {
+        // ---- producer: E is written by the encoder, long before this decode step: no dependency on the previous kernel
+        int st = 0;
+        uint32_t ph = 0;
+        for (int s = blockIdx.x; s < S; s += gridDim.x) {
+            const int u = utt_of_seq[s];
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                ptx::mbar_wait(&empty[st], ph ^ 1);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+                    uint8_t* dst = sE + st * stage_bytes;
+                    for (int h = 0; h < H; ++h)
+                        ptx::tma_load_3d(dst + h * (KEYS * 128), &tmE, &full[st], h * 64, ch * KEYS, u);
+                }
+                __syncwarp();
+                if (++st == XL_STAGES) { st = 0; ph ^= 1; }
+            }
+        }
+        return;
+    }
+
+    // ---- consumers -----------------------------------------------------------------------------------------------------
+    const int w = warp;
+    const int g = lane >> 2, t = lane & 3;
+    const int nthr = H * 32;
+    const bool row_lo = g < H, row_hi = g + 8 < H;
+    pdl_wait();                                   // Q' comes from the GEMM in front of this kernel
+    pdl_launch_dependents();
+    const uint32_t sE_s = ptx::smem_u32(sE), Pm_s = ptx::smem_u32(Pm);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        // A fragments of Q': rows g / g + 8 (heads), this warp's 64 columns = 4 k-steps of 16
+        uint32_t qa[4][4];
+        {
+            const uint32_t* q_lo = reinterpret_cast<const uint32_t*>(Qp + ((size_t)s * H + g) * d + w * 64 + 2 * t);
+            const uint32_t* q_hi = reinterpret_cast<const uint32_t*>(Qp + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                qa[ks][0] = row_lo ? q_lo[ks * 8] : 0u;           // 16 bf16 = 8 words per k-step
+                qa[ks][1] = row_hi ? q_hi[ks * 8] : 0u;
+                qa[ks][2] = row_lo ? q_lo[ks * 8 + 4] : 0u;       // columns + 8
+                qa[ks][3] = row_hi ? q_hi[ks * 8 + 4] : 0u;
+            }
+        }
+        float acc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+        float m_run = -INFINITY, l_run = 0.f;       // online softmax of head w (replicated over the lanes of warp w)
+
+        for (int ch = 0; ch < n_chunks; ++ch) {
+            ptx::mbar_wait(&full[st], ph);
+            const uint32_t tile = sE_s + (uint32_t)st * stage_bytes + (uint32_t)w * (KEYS * 128);
+            // 1. partial scores over this warp's columns
+#pragma unroll
+            for (int nt = 0; nt < KEYS / 8; ++nt) {
+                float sc[4] = {0.f, 0.f, 0.f, 0.f};
+                const int key = nt * 8 + (lane & 7);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int c16 = half * 4 + (lane >> 3);
+                    uint32_t b0, b1, b2, b3;
+                    ldmatrix_x4(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), b0, b1, b2, b3);
+                    mma_bf16(sc, qa[half * 2], b0, b1);
+                    mma_bf16(sc, qa[half * 2 + 1], b2, b3);
+                }
+                if (row_lo) *reinterpret_cast<float2*>(Sp + (w * H + g) * PITCH + nt * 8 + 2 * t) = make_float2(sc[0], sc[1]);
+                if (row_hi) *reinterpret_cast<float2*>(Sp + (w * H + g + 8) * PITCH + nt * 8 + 2 * t) = make_float2(sc[2], sc[3]);
+            }
+            xl_bar(nthr);
+            // 2. head w: sum the partials, online softmax
+            {
+                float v0 = 0.f, v1 = 0.f;
+                const bool has1 = KEYS > 32 && lane < KEYS - 32;
+                for (int ww = 0; ww < H; ++ww) {
+                    const float* row = Sp + (ww * H + w) * PITCH;
+                    v0 += row[lane];
+                    if (has1) v1 += row[32 + lane];
+                }
+                const int key0 = ch * KEYS + lane;
+                if (key0 >= T) v0 = -INFINITY;
+                if (!has1 || key0 + 32 >= T) v1 = -INFINITY;
+                float mx = fmaxf(v0, v1);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                const float m_new = fmaxf(m_run, mx);             // finite: every chunk holds at least one valid key
+                const float p0 = exp2f((v0 - m_new) * XL_LOG2E), p1 = exp2f((v1 - m_new) * XL_LOG2E);
+                // the weights that multiply E are the bf16-rounded ones: normalise by their sum
+                const bf16 p0b = __float2bfloat16(p0), p1b = __float2bfloat16(p1);
+                float sum = __bfloat162float(p0b) + __bfloat162float(p1b);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                const float a = exp2f((m_run - m_new) * XL_LOG2E);
+                l_run = l_run * a + sum;
+                m_run = m_new;
+                Pm[w * PITCH + lane] = p0b;
+                if (has1) Pm[w * PITCH + 32 + lane] = p1b;
+                if (lane == 0) alpha[w] = a;
+            }
+            xl_bar(nthr);
+            // 3. C = alpha * C + P E over this warp's columns
+            {
+                const float a_lo = alpha[g], a_hi = alpha[g + 8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { acc[j][0] *= a_lo; acc[j][1] *= a_lo; acc[j][2] *= a_hi; acc[j][3] *= a_hi; }
+#pragma unroll
+                for (int ks = 0; ks < KEYS / 16; ++ks) {
+                    uint32_t pa[4];
+                    const uint32_t p_lo = Pm_s + (uint32_t)(g * PITCH + ks * 16 + 2 * t) * 2u;
+                    const uint32_t p_hi = p_lo + 8u * PITCH * 2u;
+                    pa[0] = lds32(p_lo); pa[1] = lds32(p_hi); pa[2] = lds32(p_lo + 16u); pa[3] = lds32(p_hi + 16u);
+                    const int key = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+                    for (int jp = 0; jp < 4; ++jp) {
+                        const int c16 = jp * 2 + (lane >> 4);
+                        uint32_t b0, b1, b2, b3;
+                        ldmatrix_x4_trans(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), b0, b1, b2, b3);
+                        mma_bf16(acc[2 * jp], pa, b0, b1);
+                        mma_bf16(acc[2 * jp + 1], pa, b2, b3);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[st]);
+            if (++st == XL_STAGES) { st = 0; ph ^= 1; }
+        }
+        // normalise and store
+        if (lane == 0) alpha[16 + w] = 1.f / l_run;
+        xl_bar(nthr);
+        {
+            const float il_lo = alpha[16 + g], il_hi = alpha[16 + ((g + 8) & 15)];
+            bf16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
+            bf16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_bf16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
+                if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_bf16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
+            }
+        }
+    }
+}
+
+int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) {
+    cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)T, (cuuint64_t)U};
+    cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)T * d * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)keys, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_xl(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(E), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        wipa_set_error("cross_attention_latent: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return WIPA_ECUDA;
+    }
+    return WIPA_OK;
+}
+
+template <int KEYS>
+int xl_launch(const CUtensorMap& tm, const bf16* Qp, const int* utt_of_seq, bf16* C, int S, int H, int T, int n_sm, cudaStream_t st) {
+    const size_t smem = XlCfg<KEYS>::smem(H);
+    static SmemAttr attr;
+    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS>, XlCfg<KEYS>::smem(KEYS == 48 ? 12 : 16), attr));
+    const int grid = S < n_sm ? S : n_sm;
+    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Qp,
+                                  utt_of_seq, C, S, H, T));
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
+}  // namespace
+
+int cross_attention_latent_supported(int H) { return H >= 1 && H <= 16; }
+
+// Qp: bf16 [S, H, d] absorbed queries; E: bf16 [U, T, d] encoder output (d = 64 H); utt_of_seq: int [S]; C: bf16 [S, H, d]
+int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const int* utt_of_seq, bf16* C, int S, int H, int T,
+                                  cudaStream_t st) {
+    WIPA_CHECK(cross_attention_latent_supported(H), WIPA_EUNSUPPORTED, "cross_attention_latent: %d heads (1..16)", H);
+    WIPA_CHECK(S >= 1 && U >= 1 && T >= 1, WIPA_EINVAL, "cross_attention_latent: bad shape");
+    if (g_encode_xl == nullptr) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        WIPA_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        WIPA_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, WIPA_ECUDA, "cuTensorMapEncodeTiled not available");
+        g_encode_xl = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    static int n_sm = 0;
+    if (n_sm == 0) {
+        int dev = 0;
+        WIPA_CUDA_CHECK(cudaGetDevice(&dev));
+        WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const int keys = H <= 12 ? 48 : 32;             // two stages of keys x d x 2 bytes + H x H partial rows must fit 227 KB
+    CUtensorMap tm;
+    WIPA_TRY(xl_make_map(&tm, E, U, T, H * 64, keys));
+    if (keys == 48) return xl_launch<48>(tm, Qp, utt_of_seq, C, S, H, T, n_sm, st);
+    return xl_launch<32>(tm, Qp, utt_of_seq, C, S, H, T, n_sm, st);
+}

@@ -406,6 +406,10 @@ template <typename T>
 int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
                            int* counters, int Bs, int H, int n_split, int kv_static, cudaStream_t st);
 int cross_attention_default_split(int elem_bytes, int Bs, int H);
+// attn_lat.cu: cross-attention over the encoder output itself (absorbed k / v projections), bf16 only
+int cross_attention_latent_supported(int H);
+int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const int* utt_of_seq, bf16* C, int S, int H, int T,
+                                  cudaStream_t st);
 
 // elementwise.cu
 template <typename T>

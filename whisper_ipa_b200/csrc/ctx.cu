@@ -96,6 +96,13 @@ struct wipa_ctx {
     int persistent_min_tiles = 296; // WIPA_PERSISTENT_MIN_TILES: fewer 128x256 tiles than this -> plain 128x128-tile kernel
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
     int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (bf16 path)
+    // latent cross-attention (attn_lat.cu): the decoder attends over the encoder output itself, k / v projections folded
+    // into the query and output projections.  WIPA_XATTN_LATENT=1, bf16 path, <= 16 heads.
+    int xlat = 0;
+    bool xlat_ready = false;       // folded weights match the loaded weights
+    void *enc_lat = nullptr, *dqlat = nullptr, *dclat = nullptr;     // E [max_batch, 1500, d]; Q' and C [S, H*d]
+    std::vector<void*> xlq_w, xlo_w;                                  // per layer [H*d, d] and [d, H*d]
+    std::vector<float*> xlq_b, xlo_b;
     int64_t decode_steps = 0;
     size_t workspace_bytes = 0, xkv_bytes = 0;
     LogmelTables mel_tables;
@@ -303,6 +310,66 @@ int require_weights(wipa_ctx* c) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// latent cross-attention: fold Wk into the query projection and Wv into the output projection (once per weight load)
+//   Wq'[(h, n), k] = sum_j Wk[64h + j, n] Wq[64h + j, k]      bq'[(h, n)] = sum_j Wk[64h + j, n] bq[64h + j]
+//   Wo'[m, (h, n)] = sum_j Wo[m, 64h + j] Wv[64h + j, n]      bo'[m]      = bo[m] + sum_i Wo[m, i] bv[i]
+// (Wq / bq already carry the 1/8 scaling; k_proj has no bias.)  fp32 sums of the stored bf16 weights, rounded once.
+// ------------------------------------------------------------------------------------------------
+__global__ void xlat_fold_q_kernel(const bf16* __restrict__ Wq, const float* __restrict__ bq, const bf16* __restrict__ Wk,
+                                   bf16* __restrict__ Wq2, float* __restrict__ bq2, int d) {
+    const int h = blockIdx.z, n = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float wk[64];
+    if (threadIdx.x < 64) wk[threadIdx.x] = __bfloat162float(Wk[(size_t)(h * 64 + threadIdx.x) * d + n]);
+    __syncthreads();
+    if (k < d) {
+        float acc = 0.f;
+        for (int j = 0; j < 64; ++j) acc = fmaf(wk[j], __bfloat162float(Wq[(size_t)(h * 64 + j) * d + k]), acc);
+        Wq2[((size_t)h * d + n) * d + k] = __float2bfloat16(acc);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        float acc = 0.f;
+        for (int j = 0; j < 64; ++j) acc = fmaf(wk[j], bq[h * 64 + j], acc);
+        bq2[h * d + n] = acc;
+    }
+}
+
+__global__ void xlat_fold_o_kernel(const bf16* __restrict__ Wo, const float* __restrict__ bo, const bf16* __restrict__ Wv,
+                                   const float* __restrict__ bv, bf16* __restrict__ Wo2, float* __restrict__ bo2, int d, int H) {
+    const int h = blockIdx.z, m = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ float wo[64];
+    if (threadIdx.x < 64) wo[threadIdx.x] = __bfloat162float(Wo[(size_t)m * d + h * 64 + threadIdx.x]);
+    __syncthreads();
+    if (n < d) {
+        float acc = 0.f;
+        for (int j = 0; j < 64; ++j) acc = fmaf(wo[j], __bfloat162float(Wv[(size_t)(h * 64 + j) * d + n]), acc);
+        Wo2[(size_t)m * ((size_t)H * d) + (size_t)h * d + n] = __float2bfloat16(acc);
+    }
+    if (h == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+        float acc = bo[m];
+        for (int i = 0; i < d; ++i) acc = fmaf(__bfloat162float(Wo[(size_t)m * d + i]), bv[i], acc);
+        bo2[m] = acc;
+    }
+}
+
+int xlat_prepare(wipa_ctx* c, cudaStream_t st) {
+    if (!c->xlat || c->xlat_ready) return WIPA_OK;
+    const int d = c->a.d_model, H = c->a.heads;
+    const dim3 grid(cdiv(d, 256), d, H);
+    for (int l = 0; l < c->a.dec_layers; ++l) {
+        const DecLayer& L = c->dec[l];
+        const bf16* Wk = (const bf16*)c->xkv_w + (size_t)(2 * l) * d * d;
+        const bf16* Wv = (const bf16*)c->xkv_w + (size_t)(2 * l + 1) * d * d;
+        const float* bv = c->xkv_b + (size_t)(2 * l + 1) * d;
+        xlat_fold_q_kernel<<<grid, 256, 0, st>>>((const bf16*)L.cq_w, L.cq_b, Wk, (bf16*)c->xlq_w[l], c->xlq_b[l], d);
+        WIPA_LAUNCHED();
+        xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const bf16*)L.co_w, L.co_b, Wv, bv, (bf16*)c->xlo_w[l], c->xlo_b[l], d, H);
+        WIPA_LAUNCHED();
+    }
+    c->xlat_ready = true;
+    return WIPA_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // encoder over clips [u0, u0 + nb) of the current batch; fills enc_T rows and the cross-KV of those utterances
 // ------------------------------------------------------------------------------------------------
 int cross_kv_project(wipa_ctx* c, int u0, int nb, cudaStream_t st) {
@@ -374,8 +441,11 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
             WIPA_TRY(gemm(c, plainA(c->effn, M, ffn), L.fc2_w, M, d, ffn, ep, c->bn_enc, st));
         }
     }
-    WIPA_TRY(ln(c, c->ex, c->enc_ln_w, c->enc_ln_b, c->enc_T, M, st));
+    // latent cross-attention keeps the encoder output itself (bf16) for the whole batch instead of per-layer K / V
+    void* enc_dst = c->xlat ? (void*)((bf16*)c->enc_lat + (size_t)u0 * T * d) : c->enc_T;
+    WIPA_TRY(ln(c, c->ex, c->enc_ln_w, c->enc_ln_b, enc_dst, M, st));
     if (enc_out != nullptr) WIPA_TRY(launch_layernorm<float>(c->ex, c->enc_ln_w, c->enc_ln_b, enc_out, M, d, st));
+    if (c->xlat) return WIPA_OK;
     return cross_kv_project(c, u0, nb, st);
 }
 
@@ -423,6 +493,22 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.o_w, S, d, d, ep, c->bn_dec, st));
         }
         if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
+        if (c->xlat) {
+            const int Hd = H * d;
+            {   // q' = LN(x) Wq'^T + bq'  -> bf16 [S, H, d]
+                EpiParams ep = epi(EPI_STORE, S, Hd);
+                ep.bias = c->xlq_b[l]; ep.out = c->dqlat; ep.out_bf16 = 1;
+                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, (S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec, st));
+            }
+            if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const bf16*)c->dqlat, (const bf16*)c->enc_lat, c->max_batch, c->utt_of_seq,
+                                                                   (bf16*)c->dclat, S, H, WIPA_T_ENC, st));
+            {   // x += C Wo'^T + bo'   (K = H * d is long: split-K)
+                EpiParams ep = epi(EPI_RESADD, S, d);
+                ep.bias = c->xlo_b[l]; ep.out = c->dx; ep.resid = c->dx;
+                if (c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; }
+                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dclat, S, Hd), c->xlo_w[l], S, d, Hd, ep, c->bn_dec, st));
+            }
+        } else {
         {
             EpiParams ep = epi(EPI_STORE, S, d);
             ep.bias = L.cq_b; ep.out = c->dq; ep.out_bf16 = 0;
@@ -441,6 +527,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.co_b; ep.out = c->dx; ep.resid = c->dx;
             if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.co_w, S, d, d, ep, c->bn_dec, st));
+        }
         }
         if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln3_w, L.ln3_b, c->dh, S, st));
         {
@@ -544,6 +631,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->skip_mask = env_int("WIPA_SKIP_MASK", 0);
     c->splitk = env_int("WIPA_SPLITK", 1);
     c->persistent_min_tiles = env_int("WIPA_PERSISTENT_MIN_TILES", 2 * 148);
+    c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", 0) != 0 && cross_attention_latent_supported(arch->heads)) ? 1 : 0;
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
@@ -571,8 +659,25 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     CTX_TRY(ctx_alloc(c, &c->effn, (size_t)mb * T * ffn * e, false));
     CTX_TRY(ctx_alloc(c, &c->enc_T, (size_t)mb * T * d * e, false));
     c->xkv_which_stride = (size_t)max_batch * H * T * 64;
-    c->xkv_bytes = (size_t)arch->dec_layers * 2 * c->xkv_which_stride * e;
-    CTX_TRY(ctx_alloc(c, &c->xkv, c->xkv_bytes, false));
+    if (c->xlat) {
+        // no per-layer cross-KV: the encoder output itself, plus the folded projections and the [S, H*d] rows around the kernel
+        c->xkv = nullptr;
+        c->xkv_bytes = (size_t)max_batch * T * d * e;
+        CTX_TRY(ctx_alloc(c, &c->enc_lat, c->xkv_bytes, false));
+        CTX_TRY(ctx_alloc(c, &c->dqlat, (size_t)S * H * d * e, false));
+        CTX_TRY(ctx_alloc(c, &c->dclat, (size_t)S * H * d * e, false));
+        c->xlq_w.resize(arch->dec_layers); c->xlo_w.resize(arch->dec_layers);
+        c->xlq_b.resize(arch->dec_layers); c->xlo_b.resize(arch->dec_layers);
+        for (int l = 0; l < arch->dec_layers; ++l) {
+            CTX_TRY(ctx_alloc(c, &c->xlq_w[l], (size_t)H * d * d * e, false));
+            CTX_TRY(ctx_alloc(c, &c->xlo_w[l], (size_t)H * d * d * e, false));
+            CTX_TRY(ctx_alloc(c, (void**)&c->xlq_b[l], (size_t)H * d * 4, false));
+            CTX_TRY(ctx_alloc(c, (void**)&c->xlo_b[l], (size_t)d * 4, false));
+        }
+    } else {
+        c->xkv_bytes = (size_t)arch->dec_layers * 2 * c->xkv_which_stride * e;
+        CTX_TRY(ctx_alloc(c, &c->xkv, c->xkv_bytes, false));
+    }
     c->pool_layer_stride = (size_t)S * c->pages_per_seq * H * WIPA_PAGE * 64;
     CTX_TRY(ctx_alloc(c, &c->kpool, (size_t)arch->dec_layers * c->pool_layer_stride * e, false));
     CTX_TRY(ctx_alloc(c, &c->vpool, (size_t)arch->dec_layers * c->pool_layer_stride * e, false));
@@ -658,8 +763,9 @@ extern "C" int wipa_ctx_load_weights(wipa_ctx* c, const wipa_tensor_desc* tensor
         else WIPA_TRY(launch_convert(t.data, s.dst, s.numel, s.scale, s.kind == SLOT_T ? (int)c->bf : 0, st));
         c->loaded.insert(s.canon);
     }
-    // the weights changed: graphs stay valid (same buffers), cached cross-KV does not
+    // the weights changed: graphs stay valid (same buffers), cached cross-KV and folded projections do not
     c->n_utts = 0;
+    c->xlat_ready = false;
     return WIPA_OK;
 }
 
@@ -691,6 +797,7 @@ extern "C" int wipa_encode(wipa_ctx* c, const float* mel, int B, float* enc_out,
     WIPA_CHECK(B >= 1 && B <= c->max_batch, WIPA_EINVAL, "wipa_encode: B=%d outside 1..%d", B, c->max_batch);
     WIPA_TRY(require_weights(c));
     cudaStream_t st = (cudaStream_t)stream;
+    WIPA_TRY(xlat_prepare(c, st));
     const size_t mel_clip = (size_t)c->a.n_mels * WIPA_N_FRAMES, enc_clip = (size_t)WIPA_T_ENC * c->a.d_model;
     for (int u0 = 0; u0 < B; u0 += c->enc_mb) {
         const int nb = (B - u0) < c->enc_mb ? (B - u0) : c->enc_mb;
@@ -706,7 +813,9 @@ extern "C" int wipa_set_audio_features(wipa_ctx* c, const float* enc_out, int B,
     WIPA_TRY(require_weights(c));
     cudaStream_t st = (cudaStream_t)stream;
     const size_t enc_clip = (size_t)WIPA_T_ENC * c->a.d_model;
-    for (int u0 = 0; u0 < B; u0 += c->enc_mb) {
+    WIPA_TRY(xlat_prepare(c, st));
+    if (c->xlat) WIPA_TRY(launch_convert(enc_out, c->enc_lat, (long long)B * enc_clip, 1.0f, 1, st));
+    else for (int u0 = 0; u0 < B; u0 += c->enc_mb) {
         const int nb = (B - u0) < c->enc_mb ? (B - u0) : c->enc_mb;
         WIPA_TRY(launch_convert(enc_out + u0 * enc_clip, c->enc_T, (long long)nb * enc_clip, 1.0f, c->bf, st));
         WIPA_TRY(cross_kv_project(c, u0, nb, st));
@@ -960,6 +1069,7 @@ extern "C" int wipa_test_gemm_rows(const void* A, int is_bf16, long long lda, in
 extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* q, float* out, void* stream) {
     WIPA_CHECK(c && q, WIPA_EINVAL, "wipa_test_cross_attn: null argument");
     WIPA_CHECK(B >= 1 && B <= c->max_seqs && layer >= 0 && layer < c->a.dec_layers, WIPA_EINVAL, "wipa_test_cross_attn: bad B / layer");
+    WIPA_CHECK(!c->xlat, WIPA_ESTATE, "wipa_test_cross_attn: this context keeps no cross-KV (latent cross-attention)");
     cudaStream_t st = (cudaStream_t)stream;
     const char* xk = (const char*)c->xkv + (size_t)(2 * layer) * c->xkv_which_stride * c->esz;
     const char* xv = (const char*)c->xkv + (size_t)(2 * layer + 1) * c->xkv_which_stride * c->esz;
@@ -969,6 +1079,14 @@ extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* 
                                                 c->ca_counters, B, c->a.heads, c->ca_split, 0, st));
     if (out) WIPA_TRY(launch_to_f32(c->dattn, c->bf, out, (long long)B * c->a.d_model, st));
     return WIPA_OK;
+}
+
+// latent cross-attention kernel alone: Qp bf16 [S, H, 64H] absorbed queries, E bf16 [U, T, 64H], utt_of_seq int32 [S]
+// -> C bf16 [S, H, 64H] = softmax_t(Qp[s, h] . E[u, t]) E[u].  All device pointers.
+extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
+                                           void* stream) {
+    WIPA_CHECK(Qp && E && utt_of_seq && C, WIPA_EINVAL, "wipa_test_cross_attn_latent: null argument");
+    return launch_cross_attention_latent((const bf16*)Qp, (const bf16*)E, U, utt_of_seq, (bf16*)C, S, H, T, (cudaStream_t)stream);
 }
 
 // decoder self-attention step alone over a caller-built paged cache: kpool / vpool [page][H][16][64] (bf16 or f32),
