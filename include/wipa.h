@@ -145,7 +145,7 @@ int wipa_test_enc_attention_bf16(const void* q, const void* k, const void* v, vo
 /* Latent cross-attention kernel alone (the decoder attends over the encoder output itself; k / v projections are folded
  * into the query / output projections, HF:models/whisper/modeling_whisper.py:241-357 WhisperAttention as cross-attention):
  * Qp bf16 [S, H, 64*H] absorbed queries, E bf16 [U, T, 64*H] encoder output, utt_of_seq int32 [S] -> C bf16 [S, H, 64*H]
- * = softmax_t(Qp[s,h] . E[u,t]) E[u].  H <= 16.  All device pointers. */
+ * = softmax_t(Qp[s,h] . E[u,t]) E[u].  H = 6, 8, 12 or 16 (Whisper tiny .. medium).  All device pointers. */
 int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
                                 void* stream);
 /* One decode-step self-attention over a caller-built paged KV cache: kpool / vpool [page][H][16][64] (bf16 when is_bf16,

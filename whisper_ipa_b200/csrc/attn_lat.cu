@@ -67,16 +67,22 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
-template <int KEYS>
-__global__ void __launch_bounds__(17 * 32, 1)
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int KEYS, int H>
+__global__ void __launch_bounds__((H + 1) * 32, 1)
 cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf16* __restrict__ Qp,
-                              const int* __restrict__ utt_of_seq, bf16* __restrict__ Cout, int S, int H, int T) {
+                              const int* __restrict__ utt_of_seq, bf16* __restrict__ Cout, int S, int T) {
     using Cfg = XlCfg<KEYS>;
     constexpr int PITCH = Cfg::PITCH;
     extern __shared__ uint8_t xl_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xl_smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int d = H * 64;
-    const uint32_t stage_bytes = (uint32_t)KEYS * (uint32_t)H * 128u;
+    constexpr int d = H * 64;
+    constexpr uint32_t stage_bytes = (uint32_t)KEYS * (uint32_t)H * 128u;
     uint8_t* sE = smem;                                                      // [stage][H tiles][KEYS][128 B], 128B-swizzled
     float* Sp = reinterpret_cast<float*>(sE + XL_STAGES * stage_bytes);      // [warp][head][PITCH]
     bf16* Pm = reinterpret_cast<bf16*>(Sp + H * H * PITCH);                  // [16][PITCH]
@@ -120,7 +126,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
     // ---- consumers -----------------------------------------------------------------------------------------------------
     const int w = warp;
     const int g = lane >> 2, t = lane & 3;
-    const int nthr = H * 32;
+    constexpr int nthr = H * 32;
     const bool row_lo = g < H, row_hi = g + 8 < H;
     pdl_wait();                                   // Q' comes from the GEMM in front of this kernel
     pdl_launch_dependents();
@@ -149,31 +155,58 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
         for (int ch = 0; ch < n_chunks; ++ch) {
             ptx::mbar_wait(&full[st], ph);
             const uint32_t tile = sE_s + (uint32_t)st * stage_bytes + (uint32_t)w * (KEYS * 128);
-            // 1. partial scores over this warp's columns
+            // 1. partial scores over this warp's columns: every fragment load first, then k-step-major MMAs so that
+            //    consecutive instructions hit different accumulators
+            {
+                uint32_t bfr[KEYS / 8][2][4];
 #pragma unroll
-            for (int nt = 0; nt < KEYS / 8; ++nt) {
-                float sc[4] = {0.f, 0.f, 0.f, 0.f};
-                const int key = nt * 8 + (lane & 7);
+                for (int nt = 0; nt < KEYS / 8; ++nt) {
+                    const int key = nt * 8 + (lane & 7);
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int c16 = half * 4 + (lane >> 3);
-                    uint32_t b0, b1, b2, b3;
-                    ldmatrix_x4(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), b0, b1, b2, b3);
-                    mma_bf16(sc, qa[half * 2], b0, b1);
-                    mma_bf16(sc, qa[half * 2 + 1], b2, b3);
+                    for (int half = 0; half < 2; ++half) {
+                        const int c16 = half * 4 + (lane >> 3);
+                        ldmatrix_x4(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), bfr[nt][half][0], bfr[nt][half][1],
+                                    bfr[nt][half][2], bfr[nt][half][3]);
+                    }
                 }
-                if (row_lo) *reinterpret_cast<float2*>(Sp + (w * H + g) * PITCH + nt * 8 + 2 * t) = make_float2(sc[0], sc[1]);
-                if (row_hi) *reinterpret_cast<float2*>(Sp + (w * H + g + 8) * PITCH + nt * 8 + 2 * t) = make_float2(sc[2], sc[3]);
+                float sc[KEYS / 8][4];
+#pragma unroll
+                for (int nt = 0; nt < KEYS / 8; ++nt) { sc[nt][0] = 0.f; sc[nt][1] = 0.f; sc[nt][2] = 0.f; sc[nt][3] = 0.f; }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                    for (int nt = 0; nt < KEYS / 8; ++nt)
+                        mma_bf16(sc[nt], qa[ks], bfr[nt][ks >> 1][(ks & 1) * 2], bfr[nt][ks >> 1][(ks & 1) * 2 + 1]);
+                }
+#pragma unroll
+                for (int nt = 0; nt < KEYS / 8; ++nt) {
+                    if (row_lo) *reinterpret_cast<float2*>(Sp + (w * H + g) * PITCH + nt * 8 + 2 * t) = make_float2(sc[nt][0], sc[nt][1]);
+                    if (row_hi) *reinterpret_cast<float2*>(Sp + (w * H + g + 8) * PITCH + nt * 8 + 2 * t) = make_float2(sc[nt][2], sc[nt][3]);
+                }
             }
             xl_bar(nthr);
+            // fragments of E for step 3 do not depend on the softmax: fetch them now, behind the reduction
+            uint32_t vfr[KEYS / 16][4][4];
+#pragma unroll
+            for (int ks = 0; ks < KEYS / 16; ++ks) {
+                const int key = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    const int c16 = jp * 2 + (lane >> 4);
+                    ldmatrix_x4_trans(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), vfr[ks][jp][0], vfr[ks][jp][1],
+                                      vfr[ks][jp][2], vfr[ks][jp][3]);
+                }
+            }
             // 2. head w: sum the partials, online softmax
             {
                 float v0 = 0.f, v1 = 0.f;
-                const bool has1 = KEYS > 32 && lane < KEYS - 32;
+                constexpr bool kTwo = KEYS > 32;
+                const bool has1 = kTwo && lane < KEYS - 32;
+                const float* row = Sp + w * PITCH + lane;
+#pragma unroll
                 for (int ww = 0; ww < H; ++ww) {
-                    const float* row = Sp + (ww * H + w) * PITCH;
-                    v0 += row[lane];
-                    if (has1) v1 += row[32 + lane];
+                    v0 += row[ww * H * PITCH];
+                    if (kTwo) v1 += row[ww * H * PITCH + (has1 ? 32 : 0)];
                 }
                 const int key0 = ch * KEYS + lane;
                 if (key0 >= T) v0 = -INFINITY;
@@ -182,13 +215,14 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
                 const float m_new = fmaxf(m_run, mx);             // finite: every chunk holds at least one valid key
-                const float p0 = exp2f((v0 - m_new) * XL_LOG2E), p1 = exp2f((v1 - m_new) * XL_LOG2E);
+                const float mb = m_new * XL_LOG2E;
+                const float p0 = ex2_ftz(fmaf(v0, XL_LOG2E, -mb)), p1 = ex2_ftz(fmaf(v1, XL_LOG2E, -mb));
                 // the weights that multiply E are the bf16-rounded ones: normalise by their sum
                 const bf16 p0b = __float2bfloat16(p0), p1b = __float2bfloat16(p1);
                 float sum = __bfloat162float(p0b) + __bfloat162float(p1b);
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                const float a = exp2f((m_run - m_new) * XL_LOG2E);
+                const float a = ex2_ftz(fmaf(m_run, XL_LOG2E, -mb));
                 l_run = l_run * a + sum;
                 m_run = m_new;
                 Pm[w * PITCH + lane] = p0b;
@@ -201,20 +235,19 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                 const float a_lo = alpha[g], a_hi = alpha[g + 8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { acc[j][0] *= a_lo; acc[j][1] *= a_lo; acc[j][2] *= a_hi; acc[j][3] *= a_hi; }
+                uint32_t pa[KEYS / 16][4];
 #pragma unroll
                 for (int ks = 0; ks < KEYS / 16; ++ks) {
-                    uint32_t pa[4];
                     const uint32_t p_lo = Pm_s + (uint32_t)(g * PITCH + ks * 16 + 2 * t) * 2u;
                     const uint32_t p_hi = p_lo + 8u * PITCH * 2u;
-                    pa[0] = lds32(p_lo); pa[1] = lds32(p_hi); pa[2] = lds32(p_lo + 16u); pa[3] = lds32(p_hi + 16u);
-                    const int key = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+                    pa[ks][0] = lds32(p_lo); pa[ks][1] = lds32(p_hi); pa[ks][2] = lds32(p_lo + 16u); pa[ks][3] = lds32(p_hi + 16u);
+                }
+#pragma unroll
+                for (int ks = 0; ks < KEYS / 16; ++ks) {
 #pragma unroll
                     for (int jp = 0; jp < 4; ++jp) {
-                        const int c16 = jp * 2 + (lane >> 4);
-                        uint32_t b0, b1, b2, b3;
-                        ldmatrix_x4_trans(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), b0, b1, b2, b3);
-                        mma_bf16(acc[2 * jp], pa, b0, b1);
-                        mma_bf16(acc[2 * jp + 1], pa, b2, b3);
+                        mma_bf16(acc[2 * jp], pa[ks], vfr[ks][jp][0], vfr[ks][jp][1]);
+                        mma_bf16(acc[2 * jp + 1], pa[ks], vfr[ks][jp][2], vfr[ks][jp][3]);
                     }
                 }
             }
@@ -253,26 +286,27 @@ int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) 
     return WIPA_OK;
 }
 
-template <int KEYS>
-int xl_launch(const CUtensorMap& tm, const bf16* Qp, const int* utt_of_seq, bf16* C, int S, int H, int T, int n_sm, cudaStream_t st) {
+template <int KEYS, int H>
+int xl_launch(const CUtensorMap& tm, const bf16* Qp, const int* utt_of_seq, bf16* C, int S, int T, int n_sm, cudaStream_t st) {
     const size_t smem = XlCfg<KEYS>::smem(H);
     static SmemAttr attr;
-    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS>, XlCfg<KEYS>::smem(KEYS == 48 ? 12 : 16), attr));
+    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H>, smem, attr));
     const int grid = S < n_sm ? S : n_sm;
-    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Qp,
-                                  utt_of_seq, C, S, H, T));
+    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Qp,
+                                  utt_of_seq, C, S, T));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
 
 }  // namespace
 
-int cross_attention_latent_supported(int H) { return H >= 1 && H <= 16; }
+// one instantiation per Whisper width below large (heads = d / 64): tiny 6, base 8, small 12, medium 16
+int cross_attention_latent_supported(int H) { return H == 6 || H == 8 || H == 12 || H == 16; }
 
 // Qp: bf16 [S, H, d] absorbed queries; E: bf16 [U, T, d] encoder output (d = 64 H); utt_of_seq: int [S]; C: bf16 [S, H, d]
 int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const int* utt_of_seq, bf16* C, int S, int H, int T,
                                   cudaStream_t st) {
-    WIPA_CHECK(cross_attention_latent_supported(H), WIPA_EUNSUPPORTED, "cross_attention_latent: %d heads (1..16)", H);
+    WIPA_CHECK(cross_attention_latent_supported(H), WIPA_EUNSUPPORTED, "cross_attention_latent: %d heads (6, 8, 12 or 16)", H);
     WIPA_CHECK(S >= 1 && U >= 1 && T >= 1, WIPA_EINVAL, "cross_attention_latent: bad shape");
     if (g_encode_xl == nullptr) {
         void* fn = nullptr;
@@ -290,6 +324,10 @@ int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const in
     const int keys = H <= 12 ? 48 : 32;             // two stages of keys x d x 2 bytes + H x H partial rows must fit 227 KB
     CUtensorMap tm;
     WIPA_TRY(xl_make_map(&tm, E, U, T, H * 64, keys));
-    if (keys == 48) return xl_launch<48>(tm, Qp, utt_of_seq, C, S, H, T, n_sm, st);
-    return xl_launch<32>(tm, Qp, utt_of_seq, C, S, H, T, n_sm, st);
+    switch (H) {
+        case 6: return xl_launch<48, 6>(tm, Qp, utt_of_seq, C, S, T, n_sm, st);
+        case 8: return xl_launch<48, 8>(tm, Qp, utt_of_seq, C, S, T, n_sm, st);
+        case 12: return xl_launch<48, 12>(tm, Qp, utt_of_seq, C, S, T, n_sm, st);
+        default: return xl_launch<32, 16>(tm, Qp, utt_of_seq, C, S, T, n_sm, st);
+    }
 }
