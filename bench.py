@@ -2,13 +2,14 @@
 """Headline benchmark: whisper-small greedy IPA decode + PER, audio-seconds transcribed per second (RTFx).
 
 One "step" = one pass of the whole hot path over one batch of synthetic clips per GPU:
-log-mel -> encoder (+ cross-K/V projection) -> 220 greedy decode steps (4-token prompt, 224 positions) -> PER counts.
+log-mel -> encoder -> 220 greedy decode steps (4-token prompt, 224 positions) -> PER counts.
 `value`  : device-timed (CUDA events, max over ranks), audio already resident in HBM.
 `e2e`    : the same passes through the public API (pipeline.Transcriber.evaluate_local, what evaluate_ids runs per rank) from
            pinned HOST buffers: host->device copies (double-buffered), reference upload, PER gather and result read-back
            inside the timed region (K steps per pass; the faster of two passes).
-`roofline`: the dominant kernel (stream-K cross-attention, a persistent HBM streamer) timed alone with CUDA events over all decoder
-           layers' caches (total bytes >> L2), achieved GB/s vs MEASURED_PEAKS.json.
+`roofline`: the dominant kernel (decoder cross-attention, a persistent HBM streamer: by default the latent kernel that reads the
+           encoder output once per layer; with WIPA_XATTN_LATENT=0 the stream-K kernel over per-layer K/V caches) timed alone
+           with CUDA events on the decode shapes (bytes per launch >> L2), achieved GB/s vs MEASURED_PEAKS.json.
 `cpu_baseline` / `--impl reference`: the parity oracle (HF transformers Whisper on the host cores, fp32) on a bounded
            sample of the same workload.  The reference's own runtime (mlx_whisper on Apple Metal) cannot run here.
 """
@@ -305,34 +306,62 @@ def main():
               "decode_us_per_step": 1000.0 * t_dec / (PROMPT_LEN - 1 + args.max_new)}
     del mel_dev
 
-    # ---- roofline of the dominant kernel: cross-attention streamer timed alone -------------------------------------
-    import ctypes as C
+    # ---- roofline of the dominant kernel: the cross-attention streamer timed alone ---------------------------------
     esz = 2 if args.dtype == "bfloat16" else 4
-    q = torch.randn(B, arch.d_model, device=dev)
     st = torch.cuda.current_stream().cuda_stream
     lib = _lib.lib()
     reps = 5
-    for l in range(arch.dec_layers):
-        _lib.check(lib.wipa_test_cross_attn(model._ctx, B, l, q.data_ptr(), None, st), "cross_attn")
-    torch.cuda.synchronize()
+    latent = bool(model.info().get("xattn_latent", 0))
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    r0.record()
-    for _ in range(reps):
-        for l in range(arch.dec_layers):     # 12 distinct K/V caches: the working set cycles through >> L2 bytes
-            lib.wipa_test_cross_attn(model._ctx, B, l, q.data_ptr(), None, st)
-    r1.record()
-    torch.cuda.synchronize()
-    n_launch = reps * arch.dec_layers
+    if latent:
+        # latent cross-attention (attn_lat.cu): one pass over the encoder output E [B, 1500, d] per layer serves every head and
+        # both the key and the value role.  Timed on its own buffers of the decode shapes; E (0.59 GB at 256 clips) is far
+        # larger than L2, so every launch re-streams it from HBM.
+        H, dm = arch.heads, arch.d_model
+        E = torch.randn(B, 1500, dm, device=dev).to(torch.bfloat16)
+        Qp = (torch.randn(B, H, dm, device=dev) * (1.5 / dm ** 0.5)).to(torch.bfloat16)
+        Cl = torch.empty(B, H, dm, device=dev, dtype=torch.bfloat16)
+        utt = torch.arange(B, device=dev, dtype=torch.int32)
+        n_launch = reps * arch.dec_layers
+
+        def launch():
+            return lib.wipa_test_cross_attn_latent(Qp.data_ptr(), E.data_ptr(), B, utt.data_ptr(), Cl.data_ptr(), B, H, 1500, st)
+        _lib.check(launch(), "cross_attn_latent")
+        torch.cuda.synchronize()
+        r0.record()
+        for _ in range(n_launch):
+            launch()
+        r1.record()
+        torch.cuda.synchronize()
+        kernel_name = "cross_attention_latent_kernel"
+        bytes_per_launch = B * 1500 * dm * 2 + 2 * B * H * dm * 2       # E once + absorbed queries in + context rows out
+        # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_cross_attention_latent_ncu_full.txt:
+        # dram__bytes_read.sum 594.78 MB + dram__bytes_write.sum 8.63 MB at small / B=256); other shapes were not captured
+        traffic = 594.775808e6 + 8.630784e6 if (args.arch == "small" and B == 256) else None
+        del E
+    else:
+        q = torch.randn(B, arch.d_model, device=dev)
+        for l in range(arch.dec_layers):
+            _lib.check(lib.wipa_test_cross_attn(model._ctx, B, l, q.data_ptr(), None, st), "cross_attn")
+        torch.cuda.synchronize()
+        r0.record()
+        for _ in range(reps):
+            for l in range(arch.dec_layers):     # 12 distinct K/V caches: the working set cycles through >> L2 bytes
+                lib.wipa_test_cross_attn(model._ctx, B, l, q.data_ptr(), None, st)
+        r1.record()
+        torch.cuda.synchronize()
+        n_launch = reps * arch.dec_layers
+        kernel_name = "cross_attention_stream_kernel"
+        bytes_per_launch = B * 2 * 1500 * arch.d_model * esz              # K + V of B utterances, one layer
+        # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_cross_attention_stream_ncu_full.txt:
+        # dram__bytes_read.sum 1.180631 GB + dram__bytes_write.sum 4.89 MB at small / bf16 / B=256); other shapes were not captured
+        traffic = 1.180631e9 + 4.891392e6 if (args.arch == "small" and args.dtype == "bfloat16" and B == 256) else None
     us = 1000.0 * r0.elapsed_time(r1) / n_launch
-    bytes_per_launch = B * 2 * 1500 * arch.d_model * esz              # K + V of B utterances, one layer
     achieved = bytes_per_launch / (us * 1e-6) / 1e9
     peak, peak_src = measured_peaks()
     steps_per_pass = PROMPT_LEN - 1 + args.max_new
     ca_share = us * 1e-3 * arch.dec_layers * steps_per_pass / (ms_total / K)
-    # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_cross_attention_stream_ncu_full.txt:
-    # dram__bytes_read.sum 1.180631 GB + dram__bytes_write.sum 4.89 MB at small / bf16 / B=256); other shapes were not captured
-    traffic = 1.180631e9 + 4.891392e6 if (args.arch == "small" and args.dtype == "bfloat16" and B == 256) else None
-    roofline = {"bound": "hbm", "kernel": "cross_attention_stream_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "us_per_launch": us, "bytes_per_launch": bytes_per_launch,
                 "peak_source": peak_src, "share_of_step_est": ca_share}
 
@@ -357,7 +386,10 @@ def main():
         "config": {"workload": f"whisper-{args.arch} greedy IPA decode + PER, {B} synthetic 30 s clips per GPU per step, "
                                f"{args.max_new} new tokens, random-init weights (BASELINE configs[2])",
                    "clips_per_gpu": B, "max_new_tokens": args.max_new, "parallelism": f"dp{world}",
-                   "l2_policy": f"inputs larger than L2: cross-KV {B * 24 * 1500 * d * esz / 1e9:.2f} GB + weights are re-streamed every decode step"},
+                   "l2_policy": (f"inputs larger than L2: encoder output {B * 1500 * d * 2 / 1e9:.2f} GB is re-streamed by every decoder layer of "
+                                 f"every step, weights every step" if latent else
+                                 f"inputs larger than L2: cross-KV {B * 24 * 1500 * d * esz / 1e9:.2f} GB + weights are re-streamed every decode step"),
+                   "cross_attention": "latent (encoder output, folded k/v projections)" if latent else "per-layer cross-KV"},
         "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches.item()),
         "clocks": clocks,

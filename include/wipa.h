@@ -120,6 +120,7 @@ int wipa_ctx_get_info(wipa_ctx*, int what, int64_t* out);
 #define WIPA_INFO_WORKSPACE_BYTES 0
 #define WIPA_INFO_CROSSKV_BYTES 1
 #define WIPA_INFO_DECODE_STEPS 2
+#define WIPA_INFO_XATTN_LATENT 3   /* 1: cross-attention runs over the encoder output itself (no per-layer cross-KV) */
 
 /* Standalone kernel entry points used by tests/ and bench.py's roofline section. */
 /* C[M,N] = A[M,K] * W[N,K]^T (+bias) in bf16 on tcgen05, fp32 accumulate, fp32 out. All device pointers. */

@@ -176,8 +176,10 @@ def test_self_attention_paged(lib, is_bf16, tol, length):
 
 
 @pytest.mark.parametrize("dtype,tol", [("float32", 2e-5), ("bfloat16", 2e-2)])
-def test_cross_attention_streamer(lib, tiny_sd, dtype, tol):
+def test_cross_attention_streamer(lib, tiny_sd, dtype, tol, monkeypatch):
+    """Stream-K cross-attention over the per-layer cross-KV cache (the fp32 path, and the bf16 path with WIPA_XATTN_LATENT=0)."""
     import whisper_ipa_b200 as w
+    monkeypatch.setenv("WIPA_XATTN_LATENT", "0")
     B = 5
     m = w.WhisperIPA("tiny", dtype=dtype, max_batch=B)
     m.load_state_dict(tiny_sd)

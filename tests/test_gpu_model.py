@@ -122,8 +122,9 @@ def test_bf16_logits_and_token_agreement(w, arch, B, persistent, latent, monkeyp
     fused epilogues (head split, residual add, fast GELU, conv rows) are checked at test sizes too."""
     if persistent:
         monkeypatch.setenv("WIPA_PERSISTENT_MIN_TILES", "1")
-    if latent:                      # cross-attention over the encoder output itself, k / v projections folded (attn_lat.cu)
-        monkeypatch.setenv("WIPA_XATTN_LATENT", "1")
+    # latent: cross-attention over the encoder output itself with the k / v projections folded (attn_lat.cu, the default);
+    # otherwise the per-layer cross-KV cache and its stream-K kernel
+    monkeypatch.setenv("WIPA_XATTN_LATENT", "1" if latent else "0")
     from oracle import hf_reference as hf
     from oracle import whisper_oracle as wo
     sd = hf.state_dict_f32(hf.build_hf_model(arch, seed=0))

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwipa.so")
 
 DTYPE_F32, DTYPE_BF16 = 0, 1
-INFO_WORKSPACE_BYTES, INFO_CROSSKV_BYTES, INFO_DECODE_STEPS = 0, 1, 2
+INFO_WORKSPACE_BYTES, INFO_CROSSKV_BYTES, INFO_DECODE_STEPS, INFO_XATTN_LATENT = 0, 1, 2, 3
 
 
 class WipaError(RuntimeError):

@@ -97,8 +97,9 @@ struct wipa_ctx {
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
     int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (bf16 path)
     // latent cross-attention (attn_lat.cu): the decoder attends over the encoder output itself, k / v projections folded
-    // into the query and output projections.  WIPA_XATTN_LATENT=1, bf16 path, <= 16 heads.
+    // into the query and output projections.  Default on the bf16 path up to 16 heads (WIPA_XATTN_LATENT=0: per-layer cross-KV).
     int xlat = 0;
+    int bn_xlq = 0;                // WIPA_BN_XLQ: tile width of the absorbed-query GEMM (0: as fc1)
     bool xlat_ready = false;       // folded weights match the loaded weights
     void *enc_lat = nullptr, *dqlat = nullptr, *dclat = nullptr;     // E [max_batch, 1500, d]; Q' and C [S, H*d]
     std::vector<void*> xlq_w, xlo_w;                                  // per layer [H*d, d] and [d, H*d]
@@ -498,7 +499,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             {   // q' = LN(x) Wq'^T + bq'  -> bf16 [S, H, d]
                 EpiParams ep = epi(EPI_STORE, S, Hd);
                 ep.bias = c->xlq_b[l]; ep.out = c->dqlat; ep.out_bf16 = 1;
-                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, (S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec, st));
+                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, c->bn_xlq ? c->bn_xlq : ((S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec), st));
             }
             if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const bf16*)c->dqlat, (const bf16*)c->enc_lat, c->max_batch, c->utt_of_seq,
                                                                    (bf16*)c->dclat, S, H, WIPA_T_ENC, st));
@@ -631,7 +632,8 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->skip_mask = env_int("WIPA_SKIP_MASK", 0);
     c->splitk = env_int("WIPA_SPLITK", 1);
     c->persistent_min_tiles = env_int("WIPA_PERSISTENT_MIN_TILES", 2 * 148);
-    c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", 0) != 0 && cross_attention_latent_supported(arch->heads)) ? 1 : 0;
+    c->bn_xlq = env_int("WIPA_BN_XLQ", 0);
+    c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", 1) != 0 && cross_attention_latent_supported(arch->heads)) ? 1 : 0;
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
@@ -1008,6 +1010,7 @@ extern "C" int wipa_ctx_get_info(wipa_ctx* c, int what, int64_t* out) {
         case WIPA_INFO_WORKSPACE_BYTES: *out = (int64_t)c->workspace_bytes; return WIPA_OK;
         case WIPA_INFO_CROSSKV_BYTES: *out = (int64_t)c->xkv_bytes; return WIPA_OK;
         case WIPA_INFO_DECODE_STEPS: *out = c->decode_steps; return WIPA_OK;
+        case WIPA_INFO_XATTN_LATENT: *out = c->xlat; return WIPA_OK;
         default: break;
     }
     wipa_set_error("wipa_ctx_get_info: unknown selector %d", what);

@@ -237,7 +237,7 @@ class WhisperIPA:
         out = {}
         v = C.c_int64()
         for key, sel in (("workspace_bytes", _lib.INFO_WORKSPACE_BYTES), ("crosskv_bytes", _lib.INFO_CROSSKV_BYTES),
-                         ("decode_steps", _lib.INFO_DECODE_STEPS)):
+                         ("decode_steps", _lib.INFO_DECODE_STEPS), ("xattn_latent", _lib.INFO_XATTN_LATENT)):
             _lib.check(_lib.lib().wipa_ctx_get_info(self._ctx, sel, C.byref(v)), "wipa_ctx_get_info")
             out[key] = int(v.value)
         return out
