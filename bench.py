@@ -336,8 +336,8 @@ def main():
         kernel_name = "cross_attention_latent_kernel"
         bytes_per_launch = B * 1500 * dm * 2 + 2 * B * H * dm * 2       # E once + absorbed queries in + context rows out
         # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_cross_attention_latent_ncu_full.txt:
-        # dram__bytes_read.sum 594.78 MB + dram__bytes_write.sum 8.63 MB at small / B=256); other shapes were not captured
-        traffic = 594.775808e6 + 8.630784e6 if (args.arch == "small" and B == 256) else None
+        # dram__bytes_read.sum 594.70 MB + dram__bytes_write.sum 7.64 MB at small / B=256); other shapes were not captured
+        traffic = 594.702336e6 + 7.644672e6 if (args.arch == "small" and B == 256) else None
         del E
     else:
         q = torch.randn(B, arch.d_model, device=dev)

@@ -97,7 +97,7 @@ struct wipa_ctx {
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
     int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (bf16 path)
     // latent cross-attention (attn_lat.cu): the decoder attends over the encoder output itself, k / v projections folded
-    // into the query and output projections.  Default on the bf16 path up to 16 heads (WIPA_XATTN_LATENT=0: per-layer cross-KV).
+    // into the query and output projections.  Default on the bf16 path for contexts of >= 128 sequences and <= 16 heads.
     int xlat = 0;
     int bn_xlq = 0;                // WIPA_BN_XLQ: tile width of the absorbed-query GEMM (0: as fc1)
     bool xlat_ready = false;       // folded weights match the loaded weights
@@ -633,7 +633,10 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->splitk = env_int("WIPA_SPLITK", 1);
     c->persistent_min_tiles = env_int("WIPA_PERSISTENT_MIN_TILES", 2 * 148);
     c->bn_xlq = env_int("WIPA_BN_XLQ", 0);
-    c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", 1) != 0 && cross_attention_latent_supported(arch->heads)) ? 1 : 0;
+    // latent cross-attention gives every SM whole sequences, so it wants about a wave of them; below that the stream-K
+    // kernel over per-layer K / V (exactly balanced at any size) is faster.  WIPA_XATTN_LATENT = 1 / 0 forces either.
+    c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", max_batch * max_beams >= 128 ? 1 : 0) != 0 &&
+               cross_attention_latent_supported(arch->heads)) ? 1 : 0;
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
