@@ -16,7 +16,10 @@
 //   this kernel: Q' [S, H, d] bf16, E [U, 1500, d] bf16  ->  C [S, H, d] bf16 (normalised sum_t p_h[t] E[t])
 //   out-projection: x += C (Wo_h Wv_h)^T + (bo + Wo bv)   one [S, H*d] x [H*d, d] GEMM, weights folded at load time
 //
-// Kernel: one CTA per SM walks sequences s = blockIdx.x, += gridDim.x.  Warp H is the TMA producer: chunks of KEYS keys
+// Kernel: one CTA per SM.  The (sequence, chunk) units of the launch form one list that is cut into equal contiguous
+// ranges, one per CTA (stream-K: exact balance at any number of sequences).  A sequence that lies inside one range is
+// finished in registers; one that is cut leaves a partial (m, l, unnormalised C) per piece in global scratch, and the
+// CTA that completes the sequence's chunk count merges the pieces in order.  Warp H is the TMA producer: chunks of KEYS keys
 // x d columns as H 128B-swizzled tiles [KEYS][64] into a 2-stage ring.  Consumer warp w (0..H-1) owns columns
 // [64w, 64w + 64) of d for BOTH products:
 //   1. partial scores  Sp[w][16 x KEYS] = Q'[:, cols] E[keys, cols]^T    (A fragments of Q' live in registers per sequence)
@@ -76,7 +79,8 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 template <int KEYS, int H>
 __global__ void __launch_bounds__((H + 1) * 32, 1)
 cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf16* __restrict__ Qp,
-                              const int* __restrict__ utt_of_seq, bf16* __restrict__ Cout, int S, int T) {
+                              const int* __restrict__ utt_of_seq, bf16* __restrict__ Cout, int S, int T,
+                              float* __restrict__ part, int* __restrict__ counters, int slots_per_seq) {
     using Cfg = XlCfg<KEYS>;
     constexpr int PITCH = Cfg::PITCH;
     extern __shared__ uint8_t xl_smem_raw[];
@@ -89,9 +93,13 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
     float* alpha = reinterpret_cast<float*>(Pm + 16 * PITCH);                // [16] rescale of C, [16] final 1 / l
     uint64_t* full = reinterpret_cast<uint64_t*>(alpha + 32);
     uint64_t* empty = full + XL_STAGES;
+    int* last_flag = reinterpret_cast<int*>(empty + XL_STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = (T + KEYS - 1) / KEYS;
+    // stream-K: the (sequence, chunk) units form one list cut into equal contiguous ranges, one per CTA
+    const long long n_units = (long long)S * n_chunks;
+    const long long u_lo = n_units * blockIdx.x / gridDim.x, u_hi = n_units * (blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
         ptx::prefetch_tensormap(&tmE);
@@ -106,9 +114,12 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
         // ---- producer: E is written by the encoder, long before this decode step: no dependency on the previous kernel
         int st = 0;
         uint32_t ph = 0;
-        for (int s = blockIdx.x; s < S; s += gridDim.x) {
+        for (long long unit = u_lo; unit < u_hi;) {
+            const int s = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)s * n_chunks);
+            const int ch1 = (u_hi - unit) < (long long)(n_chunks - ch0) ? ch0 + (int)(u_hi - unit) : n_chunks;
+            unit += ch1 - ch0;
             const int u = utt_of_seq[s];
-            for (int ch = 0; ch < n_chunks; ++ch) {
+            for (int ch = ch0; ch < ch1; ++ch) {
                 ptx::mbar_wait(&empty[st], ph ^ 1);
                 if (ptx::elect_one()) {
                     ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
@@ -133,7 +144,10 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
     const uint32_t sE_s = ptx::smem_u32(sE), Pm_s = ptx::smem_u32(Pm);
     int st = 0;
     uint32_t ph = 0;
-    for (int s = blockIdx.x; s < S; s += gridDim.x) {
+    for (long long unit = u_lo; unit < u_hi;) {
+        const int s = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)s * n_chunks);
+        const int ch1 = (u_hi - unit) < (long long)(n_chunks - ch0) ? ch0 + (int)(u_hi - unit) : n_chunks;
+        unit += ch1 - ch0;
         // A fragments of Q': rows g / g + 8 (heads), this warp's 64 columns = 4 k-steps of 16
         uint32_t qa[4][4];
         {
@@ -152,7 +166,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
         for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
         float m_run = -INFINITY, l_run = 0.f;       // online softmax of head w (replicated over the lanes of warp w)
 
-        for (int ch = 0; ch < n_chunks; ++ch) {
+        for (int ch = ch0; ch < ch1; ++ch) {
             ptx::mbar_wait(&full[st], ph);
             const uint32_t tile = sE_s + (uint32_t)st * stage_bytes + (uint32_t)w * (KEYS * 128);
             // 1. partial scores over this warp's columns: every fragment load first, then k-step-major MMAs so that
@@ -255,11 +269,72 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
             if (lane == 0) ptx::mbar_arrive(&empty[st]);
             if (++st == XL_STAGES) { st = 0; ph ^= 1; }
         }
-        // normalise and store
-        if (lane == 0) alpha[16 + w] = 1.f / l_run;
-        xl_bar(nthr);
-        {
+        if (ch0 == 0 && ch1 == n_chunks) {
+            // the whole sequence was ours: normalise and store
+            if (lane == 0) alpha[16 + w] = 1.f / l_run;
+            xl_bar(nthr);
             const float il_lo = alpha[16 + g], il_hi = alpha[16 + ((g + 8) & 15)];
+            bf16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
+            bf16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_bf16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
+                if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_bf16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
+            }
+            continue;
+        }
+        // a part of the sequence: leave (m, l, unnormalised C) in this CTA's slot of the sequence; whoever brings the
+        // sequence's chunk count to n_chunks merges the slots in order (deterministic) and stores
+        constexpr int SLOT_FLOATS = H * 1024 + 32;                 // [warp][lane][32 accumulators] + m[16] + l[16]
+        const long long first_unit = (long long)s * n_chunks;
+        const int cta_first = (int)(((first_unit + 1) * gridDim.x + n_units - 1) / n_units) - 1;      // CTA holding chunk 0
+        const int cta_last = (int)(((first_unit + n_chunks) * gridDim.x + n_units - 1) / n_units) - 1; // CTA holding the last chunk
+        float* seq_part = part + (size_t)s * slots_per_seq * SLOT_FLOATS;
+        {
+            float* slot = seq_part + (size_t)((int)blockIdx.x - cta_first) * SLOT_FLOATS;
+            float4* dst = reinterpret_cast<float4*>(slot + (w * 32 + lane) * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            if (lane == 0) { slot[H * 1024 + w] = m_run; slot[H * 1024 + 16 + w] = l_run; }
+        }
+        __threadfence();
+        xl_bar(nthr);
+        if (threadIdx.x == 0) {
+            const int mine = ch1 - ch0;
+            const int old = atomicAdd(&counters[s], mine);
+            const bool last = old + mine == n_chunks;
+            if (last) counters[s] = 0;                               // ready for the next launch
+            *last_flag = last ? 1 : 0;                             // next written after at least two more barriers
+        }
+        xl_bar(nthr);
+        if (*last_flag == 0) continue;
+        __threadfence();
+        {
+            const int n_slots = cta_last - cta_first + 1;
+            float M_lo = -INFINITY, M_hi = -INFINITY;
+            for (int i = 0; i < n_slots; ++i) {
+                const float* sl = seq_part + (size_t)i * SLOT_FLOATS + H * 1024;
+                if (row_lo) M_lo = fmaxf(M_lo, __ldcg(sl + g));
+                if (row_hi) M_hi = fmaxf(M_hi, __ldcg(sl + g + 8));
+            }
+            float l_lo = 0.f, l_hi = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+            for (int i = 0; i < n_slots; ++i) {
+                const float* sl = seq_part + (size_t)i * SLOT_FLOATS;
+                const float f_lo = row_lo ? ex2_ftz((__ldcg(sl + H * 1024 + g) - M_lo) * XL_LOG2E) : 0.f;
+                const float f_hi = row_hi ? ex2_ftz((__ldcg(sl + H * 1024 + g + 8) - M_hi) * XL_LOG2E) : 0.f;
+                if (row_lo) l_lo = fmaf(f_lo, __ldcg(sl + H * 1024 + 16 + g), l_lo);
+                if (row_hi) l_hi = fmaf(f_hi, __ldcg(sl + H * 1024 + 16 + g + 8), l_hi);
+                const float4* src = reinterpret_cast<const float4*>(sl + (w * 32 + lane) * 32);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = __ldcg(src + j);
+                    acc[j][0] = fmaf(f_lo, v.x, acc[j][0]); acc[j][1] = fmaf(f_lo, v.y, acc[j][1]);
+                    acc[j][2] = fmaf(f_hi, v.z, acc[j][2]); acc[j][3] = fmaf(f_hi, v.w, acc[j][3]);
+                }
+            }
+            const float il_lo = row_lo ? 1.f / l_lo : 0.f, il_hi = row_hi ? 1.f / l_hi : 0.f;
             bf16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
             bf16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
 #pragma unroll
@@ -287,13 +362,20 @@ int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) 
 }
 
 template <int KEYS, int H>
-int xl_launch(const CUtensorMap& tm, const bf16* Qp, const int* utt_of_seq, bf16* C, int S, int T, int n_sm, cudaStream_t st) {
+int xl_launch(const CUtensorMap& tm, const bf16* Qp, const int* utt_of_seq, bf16* C, int S, int T, int n_sm, float* part,
+              size_t part_floats, int* counters, cudaStream_t st) {
     const size_t smem = XlCfg<KEYS>::smem(H);
     static SmemAttr attr;
     WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H>, smem, attr));
-    const int grid = S < n_sm ? S : n_sm;
+    const int n_chunks = cdiv(T, KEYS);
+    const long long n_units = (long long)S * n_chunks;
+    const int grid = n_units < n_sm ? (int)n_units : n_sm;
+    // a sequence is cut by at most n_chunks / (shortest CTA range) range boundaries
+    const int slots_per_seq = n_chunks / (int)(n_units / grid) + 2;
+    WIPA_CHECK((size_t)S * slots_per_seq * (H * 1024 + 32) <= part_floats, WIPA_EINVAL,
+               "cross_attention_latent: partial scratch too small for %d sequences", S);
     WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Qp,
-                                  utt_of_seq, C, S, T));
+                                  utt_of_seq, C, S, T, part, counters, slots_per_seq));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
@@ -303,11 +385,17 @@ int xl_launch(const CUtensorMap& tm, const bf16* Qp, const int* utt_of_seq, bf16
 // one instantiation per Whisper width below large (heads = d / 64): tiny 6, base 8, small 12, medium 16
 int cross_attention_latent_supported(int H) { return H == 6 || H == 8 || H == 12 || H == 16; }
 
-// Qp: bf16 [S, H, d] absorbed queries; E: bf16 [U, T, d] encoder output (d = 64 H); utt_of_seq: int [S]; C: bf16 [S, H, d]
+// floats of partial scratch that any launch with S <= max_seqs sequences can need on a device with n_sm SMs
+size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm) {
+    return (size_t)(2 * n_sm + 3 * max_seqs + 64) * (size_t)(H * 1024 + 32);
+}
+
+// Qp: bf16 [S, H, d] absorbed queries; E: bf16 [U, T, d] encoder output (d = 64 H); utt_of_seq: int [S]; C: bf16 [S, H, d];
+// part / counters: partial scratch (cross_attention_latent_scratch_floats) and int [S] zeroed once (self-resetting)
 int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const int* utt_of_seq, bf16* C, int S, int H, int T,
-                                  cudaStream_t st) {
+                                  float* part, size_t part_floats, int* counters, cudaStream_t st) {
     WIPA_CHECK(cross_attention_latent_supported(H), WIPA_EUNSUPPORTED, "cross_attention_latent: %d heads (6, 8, 12 or 16)", H);
-    WIPA_CHECK(S >= 1 && U >= 1 && T >= 1, WIPA_EINVAL, "cross_attention_latent: bad shape");
+    WIPA_CHECK(S >= 1 && U >= 1 && T >= 1 && part && counters, WIPA_EINVAL, "cross_attention_latent: bad argument");
     if (g_encode_xl == nullptr) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -325,9 +413,9 @@ int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const in
     CUtensorMap tm;
     WIPA_TRY(xl_make_map(&tm, E, U, T, H * 64, keys));
     switch (H) {
-        case 6: return xl_launch<48, 6>(tm, Qp, utt_of_seq, C, S, T, n_sm, st);
-        case 8: return xl_launch<48, 8>(tm, Qp, utt_of_seq, C, S, T, n_sm, st);
-        case 12: return xl_launch<48, 12>(tm, Qp, utt_of_seq, C, S, T, n_sm, st);
-        default: return xl_launch<32, 16>(tm, Qp, utt_of_seq, C, S, T, n_sm, st);
+        case 6: return xl_launch<48, 6>(tm, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        case 8: return xl_launch<48, 8>(tm, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        case 12: return xl_launch<48, 12>(tm, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        default: return xl_launch<32, 16>(tm, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
     }
 }

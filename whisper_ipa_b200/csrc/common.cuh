@@ -408,8 +408,9 @@ int launch_cross_attention(const float* q, const T* k, const T* v, const int* ut
 int cross_attention_default_split(int elem_bytes, int Bs, int H);
 // attn_lat.cu: cross-attention over the encoder output itself (absorbed k / v projections), bf16 only
 int cross_attention_latent_supported(int H);
+size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm);
 int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const int* utt_of_seq, bf16* C, int S, int H, int T,
-                                  cudaStream_t st);
+                                  float* part, size_t part_floats, int* counters, cudaStream_t st);
 
 // elementwise.cu
 template <typename T>

@@ -102,6 +102,8 @@ struct wipa_ctx {
     int bn_xlq = 0;                // WIPA_BN_XLQ: tile width of the absorbed-query GEMM (0: as fc1)
     bool xlat_ready = false;       // folded weights match the loaded weights
     void *enc_lat = nullptr, *dqlat = nullptr, *dclat = nullptr;     // E [max_batch, 1500, d]; Q' and C [S, H*d]
+    float* xl_part = nullptr;      // partials of sequences cut by the stream-K ranges
+    size_t xl_part_floats = 0;
     std::vector<void*> xlq_w, xlo_w;                                  // per layer [H*d, d] and [d, H*d]
     std::vector<float*> xlq_b, xlo_b;
     int64_t decode_steps = 0;
@@ -502,7 +504,8 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
                 if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, c->bn_xlq ? c->bn_xlq : ((S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec), st));
             }
             if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const bf16*)c->dqlat, (const bf16*)c->enc_lat, c->max_batch, c->utt_of_seq,
-                                                                   (bf16*)c->dclat, S, H, WIPA_T_ENC, st));
+                                                                   (bf16*)c->dclat, S, H, WIPA_T_ENC, c->xl_part, c->xl_part_floats,
+                                                                   c->ca_counters, st));
             {   // x += C Wo'^T + bo'   (K = H * d is long: split-K)
                 EpiParams ep = epi(EPI_RESADD, S, d);
                 ep.bias = c->xlo_b[l]; ep.out = c->dx; ep.resid = c->dx;
@@ -671,6 +674,13 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
         CTX_TRY(ctx_alloc(c, &c->enc_lat, c->xkv_bytes, false));
         CTX_TRY(ctx_alloc(c, &c->dqlat, (size_t)S * H * d * e, false));
         CTX_TRY(ctx_alloc(c, &c->dclat, (size_t)S * H * d * e, false));
+        {
+            int dev = 0, n_sm = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+            c->xl_part_floats = cross_attention_latent_scratch_floats(H, S, n_sm);
+            CTX_TRY(ctx_alloc(c, (void**)&c->xl_part, c->xl_part_floats * 4, false));
+        }
         c->xlq_w.resize(arch->dec_layers); c->xlo_w.resize(arch->dec_layers);
         c->xlq_b.resize(arch->dec_layers); c->xlo_b.resize(arch->dec_layers);
         for (int l = 0; l < arch->dec_layers; ++l) {
@@ -1091,8 +1101,32 @@ extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* 
 // -> C bf16 [S, H, 64H] = softmax_t(Qp[s, h] . E[u, t]) E[u].  All device pointers.
 extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
                                            void* stream) {
-    WIPA_CHECK(Qp && E && utt_of_seq && C, WIPA_EINVAL, "wipa_test_cross_attn_latent: null argument");
-    return launch_cross_attention_latent((const bf16*)Qp, (const bf16*)E, U, utt_of_seq, (bf16*)C, S, H, T, (cudaStream_t)stream);
+    WIPA_CHECK(Qp && E && utt_of_seq && C && S >= 1 && cross_attention_latent_supported(H), WIPA_EINVAL,
+               "wipa_test_cross_attn_latent: bad argument");
+    // scratch of the standalone entry point: grow-only, per process (contexts own theirs)
+    static float* part = nullptr;
+    static int* counters = nullptr;
+    static size_t part_floats = 0;
+    static int counters_cap = 0;
+    int dev = 0, n_sm = 148;
+    WIPA_CUDA_CHECK(cudaGetDevice(&dev));
+    WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    const size_t need = cross_attention_latent_scratch_floats(H, S, n_sm);
+    if (need > part_floats) {
+        WIPA_CUDA_CHECK(cudaDeviceSynchronize());
+        if (part) cudaFree(part);
+        WIPA_CUDA_CHECK(cudaMalloc(&part, need * 4));
+        part_floats = need;
+    }
+    if (S > counters_cap) {
+        WIPA_CUDA_CHECK(cudaDeviceSynchronize());
+        if (counters) cudaFree(counters);
+        WIPA_CUDA_CHECK(cudaMalloc(&counters, (size_t)S * 4));
+        WIPA_CUDA_CHECK(cudaMemset(counters, 0, (size_t)S * 4));
+        counters_cap = S;
+    }
+    return launch_cross_attention_latent((const bf16*)Qp, (const bf16*)E, U, utt_of_seq, (bf16*)C, S, H, T, part, part_floats, counters,
+                                         (cudaStream_t)stream);
 }
 
 // decoder self-attention step alone over a caller-built paged cache: kpool / vpool [page][H][16][64] (bf16 or f32),
