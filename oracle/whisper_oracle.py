@@ -234,6 +234,44 @@ def cross_kv(sd, dims: Dims, enc: torch.Tensor) -> List[Tuple[torch.Tensor, torc
     return out
 
 
+def fold_cross_attention(sd, dims: Dims, layer: int):
+    """Folded cross-attention projections of one decoder layer, the algebra libwipa's latent cross-attention kernel
+    (whisper_ipa_b200/csrc/attn_lat.cu, weights built by ctx.cu:xlat_fold_*_kernel) relies on.  With E the encoder output,
+    HF computes K = E Wk^T (no bias), V = E Wv^T + bv, q = (h Wq^T + bq) * scale, ctx_h = softmax(q_h K_h^T) V_h and
+    out = ctx Wo^T + bo (HF:models/whisper/modeling_whisper.py:241-357).  K and V are linear in E, hence
+        q_h . K_h[t]  = (Wk_h^T q_h) . E[t]                       -> q' = h Wq'^T + bq',   Wq'[(h,n),k] = s * sum_j Wk[64h+j,n] Wq[64h+j,k]
+        ctx_h         = Wv_h (sum_t p_h[t] E[t]) + bv_h           -> out = C Wo'^T + bo',  Wo'[m,(h,n)] = sum_j Wo[m,64h+j] Wv[64h+j,n]
+    with C[h] = sum_t p_h[t] E[t] and bo' = bo + Wo bv (sum_t p = 1).  Returns (Wq' [H*d, d], bq' [H*d], Wo' [d, H*d], bo' [d])."""
+    lp = f"model.decoder.layers.{layer}.encoder_attn."
+    d, H = dims.d, dims.heads
+    hd = d // H
+    scale = hd ** -0.5
+    Wq, bq = sd[lp + "q_proj.weight"], sd[lp + "q_proj.bias"]
+    Wk = sd[lp + "k_proj.weight"]
+    Wv, bv = sd[lp + "v_proj.weight"], sd[lp + "v_proj.bias"]
+    Wo, bo = sd[lp + "out_proj.weight"], sd[lp + "out_proj.bias"]
+    Wq_h, Wk_h, Wv_h = Wq.view(H, hd, d), Wk.view(H, hd, d), Wv.view(H, hd, d)
+    Wq2 = scale * torch.einsum("hjn,hjk->hnk", Wk_h, Wq_h).reshape(H * d, d)
+    bq2 = scale * torch.einsum("hjn,hj->hn", Wk_h, bq.view(H, hd)).reshape(H * d)
+    Wo2 = torch.einsum("mhj,hjn->mhn", Wo.view(d, H, hd), Wv_h).reshape(d, H * d)
+    bo2 = bo + Wo @ bv
+    return Wq2, bq2, Wo2, bo2
+
+
+def cross_attention_latent(sd, dims: Dims, layer: int, h: torch.Tensor, enc: torch.Tensor) -> torch.Tensor:
+    """Cross-attention block output (before the residual add) computed over the encoder output itself:
+    h f32[B,T,d] (the LayerNorm output), enc f32[B,1500,d] -> f32[B,T,d].  Must equal
+    out_proj(_attend(q_proj(h) * scale, k_proj(enc), v_proj(enc))) up to rounding."""
+    Wq2, bq2, Wo2, bo2 = fold_cross_attention(sd, dims, layer)
+    B, T, d = h.shape
+    H = dims.heads
+    qp = F.linear(h, Wq2, bq2).view(B, T, H, d)                       # absorbed queries, one R^d vector per head
+    s = torch.einsum("bthd,bkd->bhtk", qp, enc)
+    p = torch.softmax(s, dim=-1)
+    c = torch.einsum("bhtk,bkd->bthd", p, enc).reshape(B, T, H * d)   # per-head averages of the encoder output
+    return F.linear(c, Wo2, bo2)
+
+
 def decoder_forward(sd, dims: Dims, tokens: torch.Tensor, pos0: int, xkv, self_kv: list) -> torch.Tensor:
     """tokens int64[B,T] at positions pos0.. -> logits f32[B,T,V]; appends to self_kv in place."""
     p = "model.decoder."

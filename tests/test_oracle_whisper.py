@@ -97,3 +97,33 @@ def test_beam_with_reachable_eos_matches_hf_live(beams, eot_like):
     assert torch.equal(ids[:, :width], want) and bool((ids[:, width:] == wo.EOT).all())
     if eot_like is not None:
         assert width < max_new, "the crafted weights are meant to finish hypotheses before max_new"
+
+
+def test_latent_cross_attention_equals_hf_formulation():
+    """The folded projections behind libwipa's latent cross-attention (attn_lat.cu) are exact algebra: attending over the
+    encoder output with q' = Wk^T q and folding Wv into the output projection reproduces HF's K/V cross-attention block
+    (float64: agreement to rounding; also through the live HF module for one layer)."""
+    from oracle import hf_reference as hf
+    from oracle import whisper_oracle as wo
+    model = hf.build_hf_model("tiny", seed=0, init_gain=3.0)
+    sd = {k: v.double() for k, v in hf.state_dict_f32(model).items()}
+    dims = wo.Dims.from_arch("tiny")
+    g = torch.Generator().manual_seed(5)
+    B, T = 2, 3
+    h = torch.randn(B, T, dims.d, generator=g, dtype=torch.float64)
+    enc = torch.randn(B, 1500, dims.d, generator=g, dtype=torch.float64)
+    scale = (dims.d // dims.heads) ** -0.5
+    for layer in (0, dims.n_dec - 1):
+        lp = f"model.decoder.layers.{layer}.encoder_attn."
+        q = wo._heads(wo._lin(h, sd, lp + "q_proj") * scale, dims.heads)
+        k = wo._heads(wo._lin(enc, sd, lp + "k_proj", bias=False), dims.heads)
+        v = wo._heads(wo._lin(enc, sd, lp + "v_proj"), dims.heads)
+        want = wo._lin(wo._attend(q, k, v), sd, lp + "out_proj")
+        got = wo.cross_attention_latent(sd, dims, layer, h, enc)
+        assert (got - want).abs().max().item() < 1e-10 * max(1.0, want.abs().max().item())
+    # the live HF attention module (fp32) on the same inputs
+    attn = model.model.decoder.layers[0].encoder_attn
+    with torch.no_grad():
+        hf_out = attn(h.float(), key_value_states=enc.float())[0]
+    got32 = wo.cross_attention_latent({k: v.float() for k, v in sd.items()}, dims, 0, h.float(), enc.float())
+    assert (got32 - hf_out).abs().max().item() < 2e-4 * max(1.0, hf_out.abs().max().item())

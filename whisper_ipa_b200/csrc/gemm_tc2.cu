@@ -7,9 +7,10 @@
 //   warp 0      TMA producer: A (128 x 64) and W (256 x 64) k-blocks, 128B-swizzled, 3-deep ring across tile boundaries
 //   warp 1      tcgen05 issuer: M128 x N256 x K16 MMAs (128 cycles each, 96 B/cycle of operand reads - under the 128
 //               B/cycle shared-memory limit that caps N = 128 tiles) into one of TWO 256-column TMEM accumulators
-//   warps 2-9   epilogue, overlapped with the next tile's main loop: tcgen05.ld (lane = row) -> fp32 staging tile in
-//               shared memory -> re-read as (row, 8-column) items so that bias / residual loads and the output stores
-//               are coalesced 128..256-byte row segments -> shared epilogue (bias, GELU, residual, head split, ...)
+//   warps 2-9   epilogue, overlapped with the next tile's main loop: tcgen05.ld (lane = row), then per instantiation
+//               (G2_EP_*): bf16 results -> bias + packed-f32x2 GELU by the row owner -> bf16 staging tile -> 16-byte
+//               pieces, 8 lanes per 128-byte output line; fp32 results -> fp32 staging tile -> (row, 8-column) items
+//               with coalesced residual loads; anything else -> the generic run-time epilogue (common.cuh epi_group)
 //
 // The A operand is the same 3-D tensor map as in gemm_tc.cu (rows may overlap: conv1d(k=3) as a GEMM).
 #include "common.cuh"
