@@ -364,6 +364,12 @@ def main():
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "us_per_launch": us, "bytes_per_launch": bytes_per_launch,
                 "peak_source": peak_src, "share_of_step_est": ca_share}
+    if latent:
+        # for orientation only: the K/V formulation SURVEY.md 8(d) counts (2 * 1500 * d * 2 bytes per utterance per layer) would
+        # have to move twice the bytes in the same time; `achieved` / `frac` above use the bytes THIS kernel's algorithm needs
+        kv_bytes = B * 2 * 1500 * arch.d_model * 2
+        roofline["kv_formulation_bytes_per_launch"] = kv_bytes
+        roofline["kv_formulation_equivalent_gbs"] = kv_bytes / (us * 1e-6) / 1e9
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

@@ -184,9 +184,12 @@ def test_beam_search_matches_hf(w, tiny_sd, tiny_gain_sd, beams, gain, eot_like,
         assert want.shape[1] < max_new, "the crafted weights are meant to finish hypotheses before max_new"
 
 
-def test_beam_search_bf16_runs_and_mostly_agrees(w, tiny_gain_sd):
+@pytest.mark.parametrize("latent", [False, True])
+def test_beam_search_bf16_runs_and_mostly_agrees(w, tiny_gain_sd, latent, monkeypatch):
     """bf16 path through the same beam bookkeeping: the logits differ from the fp32 oracle at the 1e-2 level, so the
-    hypotheses are compared as token agreement (reported), not exactly."""
+    hypotheses are compared as token agreement (reported), not exactly.  `latent`: cross-attention over the encoder
+    output (the beams of an utterance share it through utt_of_seq) instead of the per-layer cross-KV."""
+    monkeypatch.setenv("WIPA_XATTN_LATENT", "1" if latent else "0")
     from oracle import hf_reference as hf
     from oracle import whisper_oracle as wo
     B, beams, max_new = 4, 5, 24
@@ -201,7 +204,7 @@ def test_beam_search_bf16_runs_and_mostly_agrees(w, tiny_gain_sd):
     assert got.shape[0] == B and got.shape[1] <= max_new
     n = min(got.shape[1], want.shape[1])
     agree = (got[:, :n] == want[:, :n]).float().mean().item()
-    print(f"\n[bf16 beam {beams}] token agreement with HF fp32 beam search {agree:.3f}")
+    print(f"\n[bf16 beam {beams}{' latent' if latent else ''}] token agreement with HF fp32 beam search {agree:.3f}")
     assert agree > 0.8
 
 
