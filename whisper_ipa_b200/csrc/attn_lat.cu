@@ -24,8 +24,9 @@
 // [64w, 64w + 64) of d for BOTH products:
 //   1. partial scores  Sp[w][16 x KEYS] = Q'[:, cols] E[keys, cols]^T    (A fragments of Q' live in registers per sequence)
 //   2. named barrier; warp w sums row w (= head w) over the H partials, does the online-softmax bookkeeping for that
-//      head and writes p (bf16) and the rescale factor alpha[w]; named barrier
-//   3. C[:, cols] = alpha * C[:, cols] + P E[keys, cols]                 (accumulators [16 x 64] per warp, fp32)
+//      head (maximum by redux.sync) and writes p (bf16) and the rescale factor alpha[w]; named barrier
+//   3. C[:, cols] = alpha * C[:, cols] + P E[keys, cols]                 (accumulators [16 x 64] per warp, fp32);
+//      the softmax denominator l = alpha * l + P x ones rides the same MMAs
 // Rows >= H of the 16-row MMA tile are padding.  Keys beyond 1500 in the last chunk are zero-filled by TMA (3-D map,
 // out-of-bounds rows) and masked to -inf before the softmax.
 #include "common.cuh"
@@ -70,6 +71,26 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32x2(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ void sts_b16(uint32_t addr, bf16 v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&v)) : "memory");
+}
+// warp maximum of floats in one redux.sync: IEEE floats order like sign-magnitude integers, so flip the magnitude bits of
+// the negative ones, take the integer maximum and map back (the map is its own inverse; -inf stays the smallest)
+__device__ __forceinline__ float warp_max_f32(float v) {
+    int k = __float_as_int(v);
+    k = k >= 0 ? k : k ^ 0x7fffffff;
+    k = __reduce_max_sync(0xffffffffu, k);
+    k = k >= 0 ? k : k ^ 0x7fffffff;
+    return __int_as_float(k);
+}
 __device__ __forceinline__ float ex2_ftz(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -141,7 +162,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
     const bool row_lo = g < H, row_hi = g + 8 < H;
     pdl_wait();                                   // Q' comes from the GEMM in front of this kernel
     pdl_launch_dependents();
-    const uint32_t sE_s = ptx::smem_u32(sE), Pm_s = ptx::smem_u32(Pm);
+    const uint32_t sE_s = ptx::smem_u32(sE), Pm_s = ptx::smem_u32(Pm), Sp_s = ptx::smem_u32(Sp);
     int st = 0;
     uint32_t ph = 0;
     for (long long unit = u_lo; unit < u_hi;) {
@@ -164,7 +185,10 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
         float acc[8][4];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
-        float m_run = -INFINITY, l_run = 0.f;       // online softmax of head w (replicated over the lanes of warp w)
+        float m_run = -INFINITY;                    // running maximum of head w (replicated over the lanes of warp w)
+        // l = sum_t p[t] rides the tensor pipe: P x ones accumulates it in every warp with exactly the bf16 weights (and the
+        // rescaling) that C sees - no cross-lane sum, no cross-warp exchange.  accl[0] / accl[2]: rows g / g + 8
+        float accl[4] = {0.f, 0.f, 0.f, 0.f};
 
         for (int ch = ch0; ch < ch1; ++ch) {
             ptx::mbar_wait(&full[st], ph);
@@ -194,8 +218,8 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                 }
 #pragma unroll
                 for (int nt = 0; nt < KEYS / 8; ++nt) {
-                    if (row_lo) *reinterpret_cast<float2*>(Sp + (w * H + g) * PITCH + nt * 8 + 2 * t) = make_float2(sc[nt][0], sc[nt][1]);
-                    if (row_hi) *reinterpret_cast<float2*>(Sp + (w * H + g + 8) * PITCH + nt * 8 + 2 * t) = make_float2(sc[nt][2], sc[nt][3]);
+                    if (row_lo) sts_f32x2(Sp_s + (uint32_t)((w * H + g) * PITCH + nt * 8 + 2 * t) * 4u, sc[nt][0], sc[nt][1]);
+                    if (row_hi) sts_f32x2(Sp_s + (uint32_t)((w * H + g + 8) * PITCH + nt * 8 + 2 * t) * 4u, sc[nt][2], sc[nt][3]);
                 }
             }
             xl_bar(nthr);
@@ -211,36 +235,32 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                                       vfr[ks][jp][2], vfr[ks][jp][3]);
                 }
             }
-            // 2. head w: sum the partials, online softmax
+            // 2. head w: sum the partials (two interleaved chains), maximum by redux.sync, p in bf16, rescale factor
             {
-                float v0 = 0.f, v1 = 0.f;
                 constexpr bool kTwo = KEYS > 32;
                 const bool has1 = kTwo && lane < KEYS - 32;
-                const float* row = Sp + w * PITCH + lane;
+                const uint32_t row = Sp_s + (uint32_t)(w * PITCH + lane) * 4u;
+                float v0a = 0.f, v0b = 0.f, v1a = 0.f, v1b = 0.f;
 #pragma unroll
-                for (int ww = 0; ww < H; ++ww) {
-                    v0 += row[ww * H * PITCH];
-                    if (kTwo) v1 += row[ww * H * PITCH + (has1 ? 32 : 0)];
+                for (int ww = 0; ww < H; ww += 2) {
+                    v0a += lds_f32(row + (uint32_t)(ww * H * PITCH) * 4u);
+                    v0b += lds_f32(row + (uint32_t)((ww + 1) * H * PITCH) * 4u);
+                    if (kTwo) {
+                        v1a += lds_f32(row + (uint32_t)(ww * H * PITCH + (has1 ? 32 : 0)) * 4u);
+                        v1b += lds_f32(row + (uint32_t)((ww + 1) * H * PITCH + (has1 ? 32 : 0)) * 4u);
+                    }
                 }
+                float v0 = v0a + v0b, v1 = v1a + v1b;
                 const int key0 = ch * KEYS + lane;
                 if (key0 >= T) v0 = -INFINITY;
                 if (!has1 || key0 + 32 >= T) v1 = -INFINITY;
-                float mx = fmaxf(v0, v1);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                const float m_new = fmaxf(m_run, mx);             // finite: every chunk holds at least one valid key
+                const float m_new = fmaxf(m_run, warp_max_f32(fmaxf(v0, v1)));      // finite: every chunk holds a valid key
                 const float mb = m_new * XL_LOG2E;
                 const float p0 = ex2_ftz(fmaf(v0, XL_LOG2E, -mb)), p1 = ex2_ftz(fmaf(v1, XL_LOG2E, -mb));
-                // the weights that multiply E are the bf16-rounded ones: normalise by their sum
-                const bf16 p0b = __float2bfloat16(p0), p1b = __float2bfloat16(p1);
-                float sum = __bfloat162float(p0b) + __bfloat162float(p1b);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
                 const float a = ex2_ftz(fmaf(m_run, XL_LOG2E, -mb));
-                l_run = l_run * a + sum;
                 m_run = m_new;
-                Pm[w * PITCH + lane] = p0b;
-                if (has1) Pm[w * PITCH + 32 + lane] = p1b;
+                sts_b16(Pm_s + (uint32_t)(w * PITCH + lane) * 2u, __float2bfloat16(p0));
+                if (has1) sts_b16(Pm_s + (uint32_t)(w * PITCH + 32 + lane) * 2u, __float2bfloat16(p1));
                 if (lane == 0) alpha[w] = a;
             }
             xl_bar(nthr);
@@ -249,6 +269,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                 const float a_lo = alpha[g], a_hi = alpha[g + 8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { acc[j][0] *= a_lo; acc[j][1] *= a_lo; acc[j][2] *= a_hi; acc[j][3] *= a_hi; }
+                accl[0] *= a_lo; accl[1] *= a_lo; accl[2] *= a_hi; accl[3] *= a_hi;
                 uint32_t pa[KEYS / 16][4];
 #pragma unroll
                 for (int ks = 0; ks < KEYS / 16; ++ks) {
@@ -263,6 +284,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                         mma_bf16(acc[2 * jp], pa[ks], vfr[ks][jp][0], vfr[ks][jp][1]);
                         mma_bf16(acc[2 * jp + 1], pa[ks], vfr[ks][jp][2], vfr[ks][jp][3]);
                     }
+                    mma_bf16(accl, pa[ks], 0x3f803f80u, 0x3f803f80u);       // x ones (bf16 1.0 pairs): row sums of P
                 }
             }
             __syncwarp();
@@ -271,9 +293,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
         }
         if (ch0 == 0 && ch1 == n_chunks) {
             // the whole sequence was ours: normalise and store
-            if (lane == 0) alpha[16 + w] = 1.f / l_run;
-            xl_bar(nthr);
-            const float il_lo = alpha[16 + g], il_hi = alpha[16 + ((g + 8) & 15)];
+            const float il_lo = row_lo ? 1.f / accl[0] : 0.f, il_hi = row_hi ? 1.f / accl[2] : 0.f;
             bf16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
             bf16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
 #pragma unroll
@@ -295,7 +315,11 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
             float4* dst = reinterpret_cast<float4*>(slot + (w * 32 + lane) * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-            if (lane == 0) { slot[H * 1024 + w] = m_run; slot[H * 1024 + 16 + w] = l_run; }
+            if (lane == 0) slot[H * 1024 + w] = m_run;
+            if (w == 0 && t == 0) {                                  // every warp holds the same l: warp 0 writes rows g / g + 8
+                if (row_lo) slot[H * 1024 + 16 + g] = accl[0];
+                if (row_hi) slot[H * 1024 + 16 + g + 8] = accl[2];
+            }
         }
         __threadfence();
         xl_bar(nthr);
