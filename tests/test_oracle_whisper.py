@@ -127,3 +127,57 @@ def test_latent_cross_attention_equals_hf_formulation():
         hf_out = attn(h.float(), key_value_states=enc.float())[0]
     got32 = wo.cross_attention_latent({k: v.float() for k, v in sd.items()}, dims, 0, h.float(), enc.float())
     assert (got32 - hf_out).abs().max().item() < 2e-4 * max(1.0, hf_out.abs().max().item())
+
+
+def test_latent_cross_attention_bf16_rounding_is_comparable():
+    """Where the bf16 roundings sit differs between the two formulations (K/V path: Wq, Wk, Wv, Wo, K, V, the context;
+    latent path: the folded Wq', Wo', the absorbed queries q', E, the per-head averages C).  Emulated on the CPU with
+    bf16-rounded operands and fp32 accumulation, the error of the cross-attention block against float64 must be of the
+    same size for both (the GPU tests measure the same thing end to end: logits rel-L2 6.2e-3 vs 6.4e-3)."""
+    from oracle import hf_reference as hf
+    from oracle import whisper_oracle as wo
+
+    def r(x):
+        return x.float().to(torch.bfloat16).float()
+
+    model = hf.build_hf_model("tiny", seed=0, init_gain=3.0)
+    sd64 = {k: v.double() for k, v in hf.state_dict_f32(model).items()}
+    dims = wo.Dims.from_arch("tiny")
+    H, d = dims.heads, dims.d
+    g = torch.Generator().manual_seed(11)
+    B, T = 3, 2
+    h = torch.randn(B, T, d, generator=g)
+    enc = torch.randn(B, 1500, d, generator=g)
+    scale = (d // H) ** -0.5
+    layer = 1
+    lp = f"model.decoder.layers.{layer}.encoder_attn."
+    want = wo.cross_attention_latent(sd64, dims, layer, r(h).double(), r(enc).double())       # exact on the rounded inputs
+
+    # K/V formulation as libwipa's per-layer cross-KV path rounds it
+    Wq, bq = r(sd64[lp + "q_proj.weight"] * scale), (sd64[lp + "q_proj.bias"] * scale).float()
+    Wk, Wv, bv = r(sd64[lp + "k_proj.weight"]), r(sd64[lp + "v_proj.weight"]), sd64[lp + "v_proj.bias"].float()
+    Wo, bo = r(sd64[lp + "out_proj.weight"]), sd64[lp + "out_proj.bias"].float()
+    hb, eb = r(h), r(enc)
+    q = wo._heads(hb @ Wq.T + bq, H)                                                          # fp32 queries
+    K = wo._heads(r(eb @ Wk.T), H)
+    V = wo._heads(r(eb @ Wv.T + bv), H)
+    ctx = r(wo._attend(q, K, V))
+    out_kv = ctx @ Wo.T + bo
+
+    # latent formulation as attn_lat.cu / ctx.cu round it: folds of the ROUNDED weights, rounded once more
+    Wq_h, Wk_h, Wv_h = Wq.view(H, d // H, d), Wk.view(H, d // H, d), Wv.view(H, d // H, d)
+    Wq2 = r(torch.einsum("hjn,hjk->hnk", Wk_h, Wq_h).reshape(H * d, d))
+    bq2 = torch.einsum("hjn,hj->hn", Wk_h, bq.view(H, d // H)).reshape(H * d)
+    Wo2 = r(torch.einsum("mhj,hjn->mhn", Wo.view(d, H, d // H), Wv_h).reshape(d, H * d))
+    bo2 = bo + Wo @ bv
+    qp = r(hb @ Wq2.T + bq2).view(B, T, H, d)
+    p = r(torch.softmax(torch.einsum("bthd,bkd->bhtk", qp, eb), dim=-1))
+    c = torch.einsum("bhtk,bkd->bthd", p, eb) / p.sum(-1).permute(0, 2, 1).unsqueeze(-1)      # normalised by the rounded weights
+    out_lat = r(c).reshape(B, T, H * d) @ Wo2.T + bo2
+
+    ref = want.float()
+    e_kv = ((out_kv - ref).norm() / ref.norm()).item()
+    e_lat = ((out_lat - ref).norm() / ref.norm()).item()
+    print(f"\n[cross-attention block, bf16 emulation] rel-L2 vs float64: K/V {e_kv:.2e}, latent {e_lat:.2e}")
+    assert e_kv < 2e-2 and e_lat < 2e-2
+    assert e_lat < 3.0 * e_kv + 1e-3
