@@ -111,7 +111,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
     uint8_t* sE = smem;                                                      // [stage][H tiles][KEYS][128 B], 128B-swizzled
     float* Sp = reinterpret_cast<float*>(sE + XL_STAGES * stage_bytes);      // [warp][head][PITCH]
     bf16* Pm = reinterpret_cast<bf16*>(Sp + H * H * PITCH);                  // [16][PITCH]
-    float* alpha = reinterpret_cast<float*>(Pm + 16 * PITCH);                // [16] rescale of C, [16] final 1 / l
+    float* alpha = reinterpret_cast<float*>(Pm + 16 * PITCH);                // [16] rescale of C (+ 16 spare floats)
     uint64_t* full = reinterpret_cast<uint64_t*>(alpha + 32);
     uint64_t* empty = full + XL_STAGES;
     int* last_flag = reinterpret_cast<int*>(empty + XL_STAGES);
