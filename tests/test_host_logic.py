@@ -104,3 +104,73 @@ def test_no_gpu_is_loud():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU path"):
         w.WhisperIPA("tiny")
+
+
+def test_language_tokens_match_hf_order():
+    from transformers.models.whisper.tokenization_whisper import LANGUAGES as HF_LANGUAGES
+    from whisper_ipa_b200.archs import FIRST_LANGUAGE_TOKEN, LANGUAGES
+    assert list(LANGUAGES) == list(HF_LANGUAGES.keys())
+    small, v3 = w.ARCHS["small"], w.ARCHS["large-v3"]
+    assert small.language_token("en") == 50259 == FIRST_LANGUAGE_TOKEN and small.language_token("su") == 50357
+    assert small.prompt("de") == [50258, 50261, 50359, 50363]
+    assert v3.language_token("yue") == 50358 and v3.prompt("yue", "translate") == [50258, 50358, 50359, 50364]
+    with pytest.raises(ValueError):
+        small.language_token("yue")                    # not in the pre-v3 vocabulary (50358 is <|translate|> there)
+    with pytest.raises(ValueError):
+        small.language_token("xx")
+    assert small.language_of_token(50261) == "de"
+
+
+class _FakeModel:
+    """Stands in for WhisperIPA on the CPU: records which utterances each decode call saw and with which prompt."""
+
+    def __init__(self, lang_of_utt):
+        self.arch = w.ARCHS["tiny"]
+        self.begin_suppress_tokens = (220, 50257)
+        self._lang_of_utt = list(lang_of_utt)
+        self._cached = list(range(len(lang_of_utt)))
+        self.calls = []
+
+    def encoder(self, mel):
+        self._cached = list(range(mel.shape[0]))
+        return torch.arange(mel.shape[0], dtype=torch.float32).view(-1, 1, 1).expand(-1, 1500, self.arch.d_model).clone()
+
+    def set_audio_features(self, feats):
+        self._cached = [int(f[0, 0]) for f in feats]
+
+    def teacher_forced_logits(self, tokens):
+        assert tokens.shape[1] == 1 and int(tokens[0, 0]) == self.arch.sot
+        out = torch.zeros(tokens.shape[0], 1, self.arch.vocab)
+        out[:, :, 100] = 50.0                              # a non-language token with the largest logit: must be masked out
+        for b, u in enumerate(self._cached):
+            out[b, 0, self.arch.language_token(self._lang_of_utt[u])] = 5.0
+        return out
+
+    def decode_tokens(self, prompt, max_new, num_beams=1, length_penalty=1.0, suppress=None, begin_suppress=None):
+        self.calls.append((list(prompt), list(self._cached)))
+        ids = torch.tensor([[1000 + u, prompt[1], 7] for u in self._cached], dtype=torch.int32)
+        return ids, torch.full((len(self._cached),), 2, dtype=torch.int32)
+
+
+def test_detect_language_and_per_language_decode():
+    from whisper_ipa_b200.decoding import DecodingOptions, decode, detect_language
+    mel = torch.zeros(5, 3000, 80)
+    m = _FakeModel(["en", "de", "en", "ja", "de"])
+    langs, probs = detect_language(m, mel)
+    assert langs == ["en", "de", "en", "ja", "de"]
+    assert abs(sum(probs[1].values()) - 1.0) < 1e-5 and max(probs[1], key=probs[1].get) == "de" and len(probs[1]) == 99
+    res = decode(m, mel, DecodingOptions(language=None))
+    assert [r.language for r in res] == ["en", "de", "en", "ja", "de"]
+    # every utterance was decoded once, in the group of its language, with that language's prompt
+    assert sorted(u for _, rows in m.calls for u in rows) == [0, 1, 2, 3, 4]
+    for prompt, rows in m.calls:
+        assert all(m.arch.language_token(["en", "de", "en", "ja", "de"][u]) == prompt[1] for u in rows)
+    assert [r.tokens for r in res] == [[1000, 50259], [1001, 50261], [1002, 50259], [1003, 50266], [1004, 50261]]
+    # one language for the whole batch: a single decode call on the cached encoder output, no regrouping
+    m2 = _FakeModel(["fr", "fr"])
+    res2 = decode(m2, torch.zeros(2, 3000, 80), DecodingOptions(language=None))
+    assert len(m2.calls) == 1 and m2.calls[0][1] == [0, 1] and [r.language for r in res2] == ["fr", "fr"]
+    # the reference's evaluation call (language="en") never runs the detection step
+    m3 = _FakeModel(["ja"])
+    r3 = decode(m3, torch.zeros(3000, 80), DecodingOptions(language="en", without_timestamps=True))
+    assert r3.language == "en" and m3.calls[0][0] == [50258, 50259, 50359, 50363]

@@ -4,11 +4,11 @@ Importing the package does not need a GPU; every compute entry point goes throug
 library or a B200 is missing — there is no CPU fallback."""
 from .archs import ARCHS, WhisperArch, arch_from_name
 from .audio import FeatureExtractor, load_audio, log_mel_features, log_mel_spectrogram, pad_or_trim
-from .decoding import DecodingOptions, DecodingResult, decode
+from .decoding import DecodingOptions, DecodingResult, decode, detect_language
 from .metrics import (evaluate_batch, normalize_ipa_for_comparison, phone_error_rate, phone_error_rates, tokenize_ipa)
 from .model import WhisperIPA, load_model
 
-__all__ = ["ARCHS", "WhisperArch", "arch_from_name", "FeatureExtractor", "load_audio", "log_mel_features",
+__all__ = ["detect_language", "ARCHS", "WhisperArch", "arch_from_name", "FeatureExtractor", "load_audio", "log_mel_features",
            "log_mel_spectrogram", "pad_or_trim", "DecodingOptions", "DecodingResult", "decode", "evaluate_batch",
            "normalize_ipa_for_comparison", "phone_error_rate", "phone_error_rates", "tokenize_ipa", "WhisperIPA",
            "load_model"]

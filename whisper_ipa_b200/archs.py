@@ -7,6 +7,18 @@ from dataclasses import dataclass
 from typing import Dict, List
 
 
+# Whisper's language codes in token order: <|en|> = 50259, <|zh|> = 50260, ... (99 languages; large-v3 appends "yue").
+# Same order as HF:models/whisper/tokenization_whisper.py LANGUAGES (checked in tests/test_host_logic.py).
+LANGUAGES = (
+    "en", "zh", "de", "es", "ru", "ko", "fr", "ja", "pt", "tr", "pl", "ca", "nl", "ar", "sv", "it", "id", "hi", "fi", "vi",
+    "he", "uk", "el", "ms", "cs", "ro", "da", "hu", "ta", "no", "th", "ur", "hr", "bg", "lt", "la", "mi", "ml", "cy", "sk",
+    "te", "fa", "lv", "bn", "sr", "az", "sl", "kn", "et", "mk", "br", "eu", "is", "hy", "ne", "mn", "bs", "kk", "sq", "sw",
+    "gl", "mr", "pa", "si", "km", "sn", "yo", "so", "af", "oc", "ka", "be", "tg", "sd", "gu", "am", "yi", "lo", "uz", "fo",
+    "ht", "ps", "tk", "nn", "mt", "sa", "lb", "my", "bo", "tl", "mg", "as", "tt", "haw", "ln", "ha", "ba", "jw", "su", "yue",
+)
+FIRST_LANGUAGE_TOKEN = 50259
+
+
 @dataclass(frozen=True)
 class WhisperArch:
     name: str
@@ -31,13 +43,32 @@ class WhisperArch:
     def sot(self) -> int:
         return 50258
 
+    @property
+    def n_languages(self) -> int:
+        return 100 if self.is_v3 else 99
+
+    def language_token(self, language: str) -> int:
+        """<|xx|> id of a language code (50259 + its position in LANGUAGES)."""
+        try:
+            i = LANGUAGES.index(language)
+        except ValueError:
+            raise ValueError(f"unknown language code {language!r}") from None
+        if i >= self.n_languages:
+            raise ValueError(f"language {language!r} is not in this model's vocabulary")
+        return FIRST_LANGUAGE_TOKEN + i
+
+    def language_of_token(self, token: int) -> str:
+        i = int(token) - FIRST_LANGUAGE_TOKEN
+        if not 0 <= i < self.n_languages:
+            raise ValueError(f"token {token} is not a language token")
+        return LANGUAGES[i]
+
     def prompt(self, language: str = "en", task: str = "transcribe", without_timestamps: bool = True) -> List[int]:
-        """<|sot|><|lang|><|task|>[<|notimestamps|>] — the reference always decodes with language="en"."""
-        if language != "en":
-            raise ValueError("only the reference's language='en' prompt is wired (ref:scripts/evaluate_model.py:171)")
+        """<|sot|><|lang|><|task|>[<|notimestamps|>] — the evaluation scripts always decode with language="en"
+        (ref:scripts/evaluate_model.py:171); training-time validation detects the language (ref:scripts/train_whisper_ipa.py:339)."""
         shift = 1 if self.is_v3 else 0
         task_id = {"transcribe": 50359, "translate": 50358}[task] + shift
-        out = [self.sot, 50259, task_id]
+        out = [self.sot, self.language_token(language), task_id]
         if without_timestamps:
             out.append(50363 + shift)
         return out

@@ -4,9 +4,11 @@ ref:scripts/train_whisper_ipa.py:338-362).  Greedy, temperature 0, one 30 s wind
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import Callable, List, Optional, Sequence, Union
+from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
+
+from .archs import FIRST_LANGUAGE_TOKEN, LANGUAGES
 
 MAX_TARGET = 448
 
@@ -47,13 +49,7 @@ def _text(tokens: Sequence[int]) -> str:
     return " ".join(str(t) for t in tokens)          # ids as text: PER over token ids stays well defined
 
 
-def decode(model, mel_or_features, options: Optional[DecodingOptions] = None) -> Union[DecodingResult, List[DecodingResult]]:
-    """mel [B,3000,n_mels] / [3000,n_mels] or encoder output [B,1500,d] -> DecodingResult(s)."""
-    o = options or DecodingOptions()
-    if o.temperature != 0.0:
-        raise NotImplementedError("temperature sampling is outside the reference's evaluation path")
-    if o.language not in (None, "en"):
-        raise NotImplementedError("the reference decodes every language with the <|en|> prompt")
+def _encode(model, mel_or_features):
     x = torch.as_tensor(mel_or_features)
     single = x.dim() == 2
     if single:
@@ -63,17 +59,65 @@ def decode(model, mel_or_features, options: Optional[DecodingOptions] = None) ->
         feats = x
     else:
         feats = model.encoder(x)
-    prompt = model.arch.prompt("en", o.task, o.without_timestamps)
+    return feats, single
+
+
+def _detect_cached(model, n: int) -> Tuple[List[str], List[Dict[str, float]]]:
+    """Language of each of the n utterances whose encoder output the model holds: ONE decoder step on <|sot|>, every
+    logit outside the language tokens masked out, argmax and softmax over the rest (mlx_whisper.decoding.detect_language,
+    HF:models/whisper/generation_whisper.py:1610 detect_language do the same)."""
+    arch = model.arch
+    logits = model.teacher_forced_logits(torch.full((n, 1), arch.sot, dtype=torch.int64))[:, 0].float()
+    lo, hi = FIRST_LANGUAGE_TOKEN, FIRST_LANGUAGE_TOKEN + arch.n_languages
+    lang_logits = logits[:, lo:hi]
+    best = lang_logits.argmax(dim=-1).cpu().tolist()
+    probs = torch.softmax(lang_logits, dim=-1).cpu()
+    langs = [LANGUAGES[i] for i in best]
+    return langs, [{LANGUAGES[j]: float(probs[b, j]) for j in range(arch.n_languages)} for b in range(n)]
+
+
+def detect_language(model, mel_or_features) -> Tuple[Union[str, List[str]], Union[Dict[str, float], List[Dict[str, float]]]]:
+    """mel [B,3000,n_mels] / [3000,n_mels] or encoder output [B,1500,d] -> (language code(s), per-language probabilities).
+    What ``DecodingOptions(language=None)`` runs first (ref:scripts/train_whisper_ipa.py:338-343)."""
+    feats, single = _encode(model, mel_or_features)
+    langs, probs = _detect_cached(model, feats.shape[0])
+    return (langs[0], probs[0]) if single else (langs, probs)
+
+
+def decode(model, mel_or_features, options: Optional[DecodingOptions] = None) -> Union[DecodingResult, List[DecodingResult]]:
+    """mel [B,3000,n_mels] / [3000,n_mels] or encoder output [B,1500,d] -> DecodingResult(s).
+    ``language=None`` detects the language of every utterance first and decodes each with its own <|lang|> prompt
+    (utterances are grouped by language: the C ABI takes one prompt per call)."""
+    o = options or DecodingOptions()
+    if o.temperature != 0.0:
+        raise NotImplementedError("temperature sampling is outside the reference's evaluation path")
+    feats, single = _encode(model, mel_or_features)
+    B = feats.shape[0]
     sample_len = o.sample_len if o.sample_len is not None else MAX_TARGET // 2
-    max_new = sample_len - len(prompt)
     begin = list(model.begin_suppress_tokens) if o.suppress_blank else [model.arch.eot]
-    ids, lens = model.decode_tokens(prompt, max_new, num_beams=o.beam_size or 1,
-                                    length_penalty=1.0 if o.length_penalty is None else o.length_penalty,
-                                    suppress=o.suppress_tokens, begin_suppress=begin)
-    ids_h, lens_h = ids.cpu().tolist(), lens.cpu().tolist()
-    results = []
-    for b in range(len(ids_h)):
-        toks = ids_h[b][:lens_h[b]]
-        results.append(DecodingResult(audio_features=feats[b] if feats is not None else None, language="en",
-                                      tokens=toks, text=_text(toks)))
+
+    def run(language: str):
+        prompt = model.arch.prompt(language, o.task, o.without_timestamps)
+        ids, lens = model.decode_tokens(prompt, sample_len - len(prompt), num_beams=o.beam_size or 1,
+                                        length_penalty=1.0 if o.length_penalty is None else o.length_penalty,
+                                        suppress=o.suppress_tokens, begin_suppress=begin)
+        return ids.cpu().tolist(), lens.cpu().tolist()
+
+    langs = [o.language] * B if o.language is not None else _detect_cached(model, B)[0]
+    tokens: List[List[int]] = [[] for _ in range(B)]
+    groups: Dict[str, List[int]] = {}
+    for b, lang in enumerate(langs):
+        groups.setdefault(lang, []).append(b)
+    if len(groups) == 1:                                   # the usual case: the cached encoder output serves as is
+        ids_h, lens_h = run(langs[0])
+        for b in range(B):
+            tokens[b] = ids_h[b][:lens_h[b]]
+    else:
+        for lang, rows in groups.items():
+            model.set_audio_features(feats[rows])
+            ids_h, lens_h = run(lang)
+            for i, b in enumerate(rows):
+                tokens[b] = ids_h[i][:lens_h[i]]
+    results = [DecodingResult(audio_features=feats[b] if feats is not None else None, language=langs[b], tokens=tokens[b],
+                              text=_text(tokens[b])) for b in range(B)]
     return results[0] if single else results
