@@ -162,7 +162,8 @@ def main():
     ap.add_argument("--arch", default="small")
     ap.add_argument("--batch", type=int, default=int(os.environ.get("WIPA_BENCH_BATCH", "256")),
                     help="clips per GPU per step (the micro-batch of the eval sweep; 16 / 64 / 256 are the named points)")
-    ap.add_argument("--dtype", default="bfloat16", choices=["bfloat16", "float32"])
+    ap.add_argument("--dtype", default="float16", choices=["float16", "bfloat16", "float32"],
+                    help="float16 (default: libwipa.so, logits within 1e-3 of the fp32 oracle), bfloat16 (libwipa_bf16.so) or float32")
     ap.add_argument("--max-new", type=int, default=220)
     ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-baseline-clips", type=int, default=8)
@@ -307,9 +308,11 @@ def main():
     del mel_dev
 
     # ---- roofline of the dominant kernel: the cross-attention streamer timed alone ---------------------------------
-    esz = 2 if args.dtype == "bfloat16" else 4
+    esz = 4 if args.dtype == "float32" else 2
+    h16 = "bf16" if args.dtype == "bfloat16" else "f16"
+    tdt = _lib.torch_h16(h16)
     st = torch.cuda.current_stream().cuda_stream
-    lib = _lib.lib()
+    lib = model._lib
     reps = 5
     latent = bool(model.info().get("xattn_latent", 0))
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -318,9 +321,9 @@ def main():
         # both the key and the value role.  Timed on its own buffers of the decode shapes; E (0.59 GB at 256 clips) is far
         # larger than L2, so every launch re-streams it from HBM.
         H, dm = arch.heads, arch.d_model
-        E = torch.randn(B, 1500, dm, device=dev).to(torch.bfloat16)
-        Qp = (torch.randn(B, H, dm, device=dev) * (1.5 / dm ** 0.5)).to(torch.bfloat16)
-        Cl = torch.empty(B, H, dm, device=dev, dtype=torch.bfloat16)
+        E = torch.randn(B, 1500, dm, device=dev).to(tdt)
+        Qp = (torch.randn(B, H, dm, device=dev) * (1.5 / dm ** 0.5)).to(tdt)
+        Cl = torch.empty(B, H, dm, device=dev, dtype=tdt)
         utt = torch.arange(B, device=dev, dtype=torch.int32)
         n_launch = reps * arch.dec_layers
 
@@ -355,7 +358,7 @@ def main():
         bytes_per_launch = B * 2 * 1500 * arch.d_model * esz              # K + V of B utterances, one layer
         # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_cross_attention_stream_ncu_full.txt:
         # dram__bytes_read.sum 1.180631 GB + dram__bytes_write.sum 4.89 MB at small / bf16 / B=256); other shapes were not captured
-        traffic = 1.180631e9 + 4.891392e6 if (args.arch == "small" and args.dtype == "bfloat16" and B == 256) else None
+        traffic = 1.180631e9 + 4.891392e6 if (args.arch == "small" and esz == 2 and B == 256) else None
     us = 1000.0 * r0.elapsed_time(r1) / n_launch
     achieved = bytes_per_launch / (us * 1e-6) / 1e9
     peak, peak_src = measured_peaks()
@@ -388,7 +391,7 @@ def main():
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.dtype == "bfloat16" else "f32", "data": "synthetic",
+        "dtype": {"float16": "f16", "bfloat16": "bf16", "float32": "f32"}[args.dtype], "data": "synthetic",
         "config": {"workload": f"whisper-{args.arch} greedy IPA decode + PER, {B} synthetic 30 s clips per GPU per step, "
                                f"{args.max_new} new tokens, random-init weights (BASELINE configs[2])",
                    "clips_per_gpu": B, "max_new_tokens": args.max_new, "parallelism": f"dp{world}",

@@ -29,7 +29,12 @@ extern "C" {
 #define WIPA_EUNSUPPORTED (-5)
 
 #define WIPA_DTYPE_F32 0      /* "fp32 path": true fp32 FMA everywhere, greedy ids bit-exact vs the oracle */
-#define WIPA_DTYPE_BF16 1     /* "bf16 path": bf16 weights / GEMM operands / KV, fp32 accumulate + residual */
+/* The half-precision path: 16-bit weights / GEMM operands / KV caches, fp32 accumulation, fp32 residual stream and
+ * softmax.  A build of the library carries ONE 16-bit type ("h16" below): libwipa.so is compiled for IEEE fp16 (logits
+ * within 1e-3 relative L2 of the fp32 oracle), libwipa_bf16.so (the same sources with -DWIPA_H16_BF16) for bfloat16
+ * (6e-3).  wipa_h16_dtype() tells which; wipa_ctx_create refuses the other one with WIPA_EUNSUPPORTED. */
+#define WIPA_DTYPE_BF16 1
+#define WIPA_DTYPE_F16 2
 
 typedef struct wipa_ctx wipa_ctx;
 
@@ -111,6 +116,8 @@ int wipa_pfer_batch(const int32_t* ref, const int32_t* ref_off, const int32_t* h
                     int N, int max_ref_len, const int8_t* feats, int mode, double* dist, void* stream);
 
 /* ---- introspection -------------------------------------------------------------------------- */
+/* WIPA_DTYPE_F16 or WIPA_DTYPE_BF16: the 16-bit element type ("h16") this build of the library computes in. */
+int wipa_h16_dtype(void);
 const char* wipa_strerror(int code);
 const char* wipa_last_error(void);
 /* Number of kernels of this library launched since the last reset (bench.py's "gpu_launches"). */
@@ -123,37 +130,37 @@ int wipa_ctx_get_info(wipa_ctx*, int what, int64_t* out);
 #define WIPA_INFO_XATTN_LATENT 3   /* 1: cross-attention runs over the encoder output itself (no per-layer cross-KV) */
 
 /* Standalone kernel entry points used by tests/ and bench.py's roofline section. */
-/* C[M,N] = A[M,K] * W[N,K]^T (+bias) in bf16 on tcgen05, fp32 accumulate, fp32 out. All device pointers. */
-int wipa_test_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, float* C,
+/* C[M,N] = A[M,K] * W[N,K]^T (+bias) in h16 on tcgen05, fp32 accumulate, fp32 out. All device pointers. */
+int wipa_test_gemm_h16(const void* A_h16, const void* W_h16, const float* bias, float* C,
                         int M, int N, int K, int block_n, void* stream);
 int wipa_test_gemm_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, void* stream);
-/* Epilogue variants of the bf16 GEMMs on encoder-shaped problems (M = rows_per_batch * n_batch rows, tiles never straddle
+/* Epilogue variants of the h16 GEMMs on encoder-shaped problems (M = rows_per_batch * n_batch rows, tiles never straddle
  * a batch; block_n = 0 selects the persistent kernel and its specialised epilogues).  mode: 0 bias, 1 bias + GELU,
  * 2 bias + fp32 residual, 3 bias + q|k|v head split into [3][n_batch][H][rows_per_batch][64] with N = 3*H*64
  * (HF:models/whisper/modeling_whisper.py WhisperEncoderLayer: the projections, fc1 + activation_fn, the two residual adds).
- * `out` holds bf16 when out_bf16 != 0, fp32 otherwise. */
+ * `out` holds h16 when out_h16 != 0, fp32 otherwise. */
 int wipa_test_gemm_epilogue(const void* A, const void* W, const float* bias, const float* resid, void* out,
-                            int rows_per_batch, int n_batch, int N, int K, int mode, int out_bf16, int block_n, void* stream);
+                            int rows_per_batch, int n_batch, int N, int K, int mode, int out_h16, int block_n, void* stream);
 /* conv1d-as-GEMM addressing: logical row (batch, t) of A starts at A + batch*bstride + t*lda and spans K >= lda
- * elements (rows overlap); A/W are bf16 (tcgen05 kernel) when is_bf16 else fp32 (SIMT kernel); C fp32 [M, N]. */
-int wipa_test_gemm_rows(const void* A, int is_bf16, long long lda, int rows_per_batch, long long bstride, int n_batch,
+ * elements (rows overlap); A/W are h16 (tcgen05 kernel) when is_h16 else fp32 (SIMT kernel); C fp32 [M, N]. */
+int wipa_test_gemm_rows(const void* A, int is_h16, long long lda, int rows_per_batch, long long bstride, int n_batch,
                         const void* W, float* C, int N, int K, int block_n, void* stream);
 /* Encoder self-attention alone: q,k,v device f32 [B,H,T,64] (q pre-scaled) -> out device f32 [B,T,H*64]. */
 int wipa_test_enc_attention(const float* q, const float* k, const float* v, float* out, int B, int H, int T,
-                            int use_bf16, void* stream);
-/* Same on bf16 device buffers without conversions (kernel timing): tc = 1 tcgen05 kernel, 0 SIMT kernel. */
-int wipa_test_enc_attention_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int T, int tc, void* stream);
+                            int use_h16, void* stream);
+/* Same on h16 device buffers without conversions (kernel timing): tc = 1 tcgen05 kernel, 0 SIMT kernel. */
+int wipa_test_enc_attention_h16(const void* q, const void* k, const void* v, void* out, int B, int H, int T, int tc, void* stream);
 /* Latent cross-attention kernel alone (the decoder attends over the encoder output itself; k / v projections are folded
  * into the query / output projections, HF:models/whisper/modeling_whisper.py:241-357 WhisperAttention as cross-attention):
- * Qp bf16 [S, H, 64*H] absorbed queries, E bf16 [U, T, 64*H] encoder output, utt_of_seq int32 [S] -> C bf16 [S, H, 64*H]
+ * Qp h16 [S, H, 64*H] absorbed queries, E h16 [U, T, 64*H] encoder output, utt_of_seq int32 [S] -> C h16 [S, H, 64*H]
  * = softmax_t(Qp[s,h] . E[u,t]) E[u].  H = 6, 8, 12 or 16 (Whisper tiny .. medium).  All device pointers. */
 int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
                                 void* stream);
-/* One decode-step self-attention over a caller-built paged KV cache: kpool / vpool [page][H][16][64] (bf16 when is_bf16,
+/* One decode-step self-attention over a caller-built paged KV cache: kpool / vpool [page][H][16][64] (h16 when is_h16,
  * else f32), block_table int32 [B, bt_stride] page ids, *pos_ptr = newest position (length - 1); q f32 [B, H*64];
  * out [B, H*64] in the pool's element type.  All device pointers. */
 int wipa_test_self_attn(const float* q, const void* kpool, const void* vpool, const int* block_table, int bt_stride,
-                        const int* pos_ptr, void* out, int B, int H, int is_bf16, void* stream);
+                        const int* pos_ptr, void* out, int B, int H, int is_h16, void* stream);
 /* One decode-step cross-attention sweep over the context's cached encoder K/V (the dominant HBM kernel):
  * q: device f32[B, d] (pre-scaled), out: device f32[B, d]; layer selects which cached K/V. */
 int wipa_test_cross_attn(wipa_ctx*, int B, int layer, const float* q, float* out, void* stream);

@@ -67,3 +67,38 @@ def hf_generate(model, feats: torch.Tensor, arch: str, max_new: int, num_beams: 
             kw.update(num_beams=num_beams, length_penalty=1.0, early_stopping=False)
         out = model.generate(feats, **kw)
     return out
+
+
+def hf_gpu_fp32_reference(model, audio: np.ndarray, prompt: Sequence[int], max_new: int, logit_steps: int,
+                          device: str = "cuda", logit_rows: int | None = None):
+    """The fp32 oracle on the GPU (HF in fp32 with TF32 disabled): stock feature extractor on the host,
+    then the stock encoder, ``generate`` (greedy) and one teacher-forced decoder pass over the prompt + the first
+    ``logit_steps - 1`` greedy tokens, all in true fp32 (cuBLAS fp32 kernels, no TF32, SDPA math).
+
+    Returns a dict of CPU tensors: ``mel`` [B, n_mels, 3000], ``enc`` [B, 1500, d], ``ids`` int64 [B, <= max_new] (prompt and
+    EOS stripped, EOT-padded as ``generate`` returns them), ``tokens`` int64 [B, P + logit_steps - 1] (the teacher-forced
+    input) and ``logits`` fp32 [rows, P + logit_steps - 1, V] for the first ``logit_rows`` utterances (all when None).
+    """
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        mel = hf_log_mel(audio, model.config.num_mel_bins)
+        B = mel.shape[0]
+        m = model.to(device).float().eval()
+        p = torch.tensor([list(prompt)] * B, dtype=torch.long, device=device)
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            feats = mel.to(device)
+            enc = torch.cat([m.model.encoder(feats[i:i + 32]).last_hidden_state for i in range(0, B, 32)])
+            ids = m.generate(feats, decoder_input_ids=p, max_new_tokens=max_new, do_sample=False)
+            n_extra = max(0, min(logit_steps - 1, ids.shape[1]))
+            toks = torch.cat([p, ids[:, :n_extra]], dim=1)
+            rows = B if logit_rows is None else min(B, logit_rows)
+            logits = torch.cat([m(encoder_outputs=(enc[i:i + 16],), decoder_input_ids=toks[i:i + 16]).logits.float()
+                                for i in range(0, rows, 16)])
+        out = {"mel": mel, "enc": enc.cpu(), "ids": ids.cpu(), "tokens": toks.cpu(), "logits": logits.cpu()}
+    finally:
+        model.to("cpu")
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return out

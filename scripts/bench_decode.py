@@ -25,7 +25,7 @@ def main():
     # random weights with the right names/shapes without building the HF module (fast)
     from bench import random_init_state_dict
     _, sd = random_init_state_dict(args.arch)
-    model = w.WhisperIPA(args.arch, dtype="bfloat16", max_batch=args.batch)
+    model = w.WhisperIPA(args.arch, dtype="float16", max_batch=args.batch)
     model.load_state_dict(sd)
     g = torch.Generator(device="cuda").manual_seed(1)
     audio = torch.randn(args.batch, 480000, device="cuda", generator=g) * 0.1

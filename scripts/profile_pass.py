@@ -20,7 +20,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--max-new", type=int, default=20)
     ap.add_argument("--passes", type=int, default=1)
-    ap.add_argument("--dtype", default="bfloat16")
+    ap.add_argument("--dtype", default="float16")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     _, sd = random_init_state_dict(args.arch)

@@ -23,7 +23,7 @@ def built_lib():
     """Make sure libwipa.so and the C oracle exist (compiles them when absent; nvcc cross-compiles without a GPU)."""
     import __graft_entry__ as g
     from whisper_ipa_b200 import _lib
-    if not os.path.exists(_lib.LIB_PATH):
+    if not (os.path.exists(_lib.LIB_PATH) and os.path.exists(_lib.LIB_PATH_BF16)):
         g.build()
     return _lib.lib()
 

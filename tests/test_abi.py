@@ -17,9 +17,15 @@ def declared_symbols():
 def test_header_symbols_exported(built_lib):
     names = declared_symbols()
     assert len(names) >= 19
-    handle = ctypes.CDLL(_lib.LIB_PATH)
-    for n in names:
-        assert hasattr(handle, n), f"{n} declared in include/wipa.h but not exported by libwipa.so"
+    for path in (_lib.LIB_PATH, _lib.LIB_PATH_BF16):               # both builds: fp16 (default) and bfloat16
+        handle = ctypes.CDLL(path)
+        for n in names:
+            assert hasattr(handle, n), f"{n} declared in include/wipa.h but not exported by {os.path.basename(path)}"
+
+
+def test_each_build_reports_its_16_bit_type(built_lib):
+    assert _lib.lib("f16").wipa_h16_dtype() == _lib.DTYPE_F16
+    assert _lib.lib("bf16").wipa_h16_dtype() == _lib.DTYPE_BF16
 
 
 def test_binding_covers_header(built_lib):
@@ -43,7 +49,7 @@ def test_struct_layouts_match_header():
 def test_missing_library_is_loud(monkeypatch, tmp_path):
     import importlib
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
-    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "_libs", {})
     try:
         _lib.lib()
     except ImportError as e:

@@ -1,6 +1,6 @@
 """GPU parity of the model path against the oracle (HF transformers on CPU + its pinned restatement):
 fp32 path — encoder output, teacher-forced logits, and BIT-EXACT greedy ids (config 1: whisper-tiny, 16 clips, 220 tokens);
-bf16 path — logits within a stated relative error and token agreement reported."""
+half-precision path (fp16 and bf16 builds) — logits within a stated relative error and token agreement reported."""
 import os
 
 import numpy as np
@@ -113,11 +113,18 @@ def test_eos_handling_matches_oracle(w, tiny_gain_sd, eot_like):
     m.close()
 
 
+# relative-L2 limits (encoder output, teacher-forced logits) per 16-bit type.  fp16: north_star's 1e-3; bf16: <= 1.5 x the
+# values measured on a B200 in round 1 (encoder 1.7e-3 - 2.6e-3, logits 6.0e-3 - 6.4e-3).  The measured values are printed.
+HALF_LIMITS = {"float16": (1.0e-3, 1.0e-3), "bfloat16": (4.0e-3, 1.0e-2)}
+
+
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("arch,B,persistent,latent", [("tiny", 4, False, False), ("base", 2, False, False), ("tiny", 3, True, False),
                                                         ("base", 2, True, False), ("tiny", 4, False, True), ("base", 3, False, True)])
-def test_bf16_logits_and_token_agreement(w, arch, B, persistent, latent, monkeypatch):
-    """bf16 path vs the fp32 oracle: relative L2 error of teacher-forced logits (bf16 operand rounding bounds it at the
-    1e-2 level; the measured value is printed) and greedy-token agreement over 32 steps.  `persistent` forces every
+def test_half_logits_and_token_agreement(w, arch, B, persistent, latent, dtype, monkeypatch):
+    """Half-precision path (fp16 = libwipa.so, bf16 = libwipa_bf16.so) vs the fp32 oracle: relative L2 error of the encoder
+    output and of teacher-forced logits (north_star: 1e-3, met by fp16; bf16's 8-bit significand bounds it at the 6e-3
+    level) and greedy-token agreement over 32 steps.  `persistent` forces every
     encoder GEMM through the persistent 128x256 kernel (normally chosen only for >= 2 waves of tiles) so that its
     fused epilogues (head split, residual add, fast GELU, conv rows) are checked at test sizes too."""
     if persistent:
@@ -132,7 +139,7 @@ def test_bf16_logits_and_token_agreement(w, arch, B, persistent, latent, monkeyp
     audio = wo.synthetic_audio(B)
     mel_ref = wo.log_mel_spectrogram(torch.from_numpy(audio), 80)
     enc_ref = wo.encoder_forward(sd, dims, mel_ref)
-    m = w.WhisperIPA(arch, dtype="bfloat16", max_batch=B)
+    m = w.WhisperIPA(arch, dtype=dtype, max_batch=B)
     m.load_state_dict(sd)
     enc = m.encoder(w.log_mel_features(audio, 80)).cpu()
     enc_rel = ((enc - enc_ref).norm() / enc_ref.norm()).item()
@@ -146,9 +153,11 @@ def test_bf16_logits_and_token_agreement(w, arch, B, persistent, latent, monkeyp
     agree = (ids.cpu().long() == ref_ids).float().mean().item()
     prefix = np.mean([int((row != ref).nonzero()[0]) if (row != ref).any() else 32
                       for row, ref in zip(ids.cpu().long(), ref_ids)])
-    print(f"\n[bf16 {arch}{' latent' if latent else ''}] encoder rel-L2 {enc_rel:.2e}, logits rel-L2 {rel:.2e}, token agreement {agree:.3f}, "
+    print(f"\n[{dtype} {arch}{' latent' if latent else ''}{' persistent' if persistent else ''}] encoder rel-L2 {enc_rel:.2e}, logits rel-L2 {rel:.2e}, token agreement {agree:.3f}, "
           f"mean agreeing prefix {prefix:.1f}/32")
-    assert enc_rel < 2e-2 and rel < 3e-2
+    lim_enc, lim_logits = HALF_LIMITS[dtype]
+    assert enc_rel < lim_enc and rel < lim_logits
+    assert agree >= 0.9
     assert np.isfinite(got_logits.numpy()).all()
     m.close()
 
@@ -184,8 +193,9 @@ def test_beam_search_matches_hf(w, tiny_sd, tiny_gain_sd, beams, gain, eot_like,
         assert want.shape[1] < max_new, "the crafted weights are meant to finish hypotheses before max_new"
 
 
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("latent", [False, True])
-def test_beam_search_bf16_runs_and_mostly_agrees(w, tiny_gain_sd, latent, monkeypatch):
+def test_beam_search_half_runs_and_mostly_agrees(w, tiny_gain_sd, latent, dtype, monkeypatch):
     """bf16 path through the same beam bookkeeping: the logits differ from the fp32 oracle at the 1e-2 level, so the
     hypotheses are compared as token agreement (reported), not exactly.  `latent`: cross-attention over the encoder
     output (the beams of an utterance share it through utt_of_seq) instead of the per-layer cross-KV."""
@@ -196,7 +206,7 @@ def test_beam_search_bf16_runs_and_mostly_agrees(w, tiny_gain_sd, latent, monkey
     audio = wo.synthetic_audio(B)
     hf_model = hf.build_hf_model("tiny", seed=0, init_gain=3.0)
     want = hf.hf_generate(hf_model, hf.hf_log_mel(audio, 80), "tiny", max_new=max_new, num_beams=beams)
-    m = w.WhisperIPA("tiny", dtype="bfloat16", max_batch=B, max_beams=beams)
+    m = w.WhisperIPA("tiny", dtype=dtype, max_batch=B, max_beams=beams)
     m.load_state_dict(tiny_gain_sd)
     got = m.generate(w.log_mel_features(audio, 80), decoder_input_ids=torch.tensor([wo.PROMPT_PRE_V3] * B),
                      max_new_tokens=max_new, num_beams=beams).cpu()
@@ -204,7 +214,7 @@ def test_beam_search_bf16_runs_and_mostly_agrees(w, tiny_gain_sd, latent, monkey
     assert got.shape[0] == B and got.shape[1] <= max_new
     n = min(got.shape[1], want.shape[1])
     agree = (got[:, :n] == want[:, :n]).float().mean().item()
-    print(f"\n[bf16 beam {beams}{' latent' if latent else ''}] token agreement with HF fp32 beam search {agree:.3f}")
+    print(f"\n[{dtype} beam {beams}{' latent' if latent else ''}] token agreement with HF fp32 beam search {agree:.3f}")
     assert agree > 0.8
 
 
@@ -240,7 +250,7 @@ def test_wide_architectures_reduced_depth(w, shape):
         want = hf_model.generate(feats_hf, decoder_input_ids=torch.tensor([prompt] * B), max_new_tokens=max_new, do_sample=False)
     feats = w.log_mel_features(audio, arch.n_mels)
     assert (feats.cpu() - feats_hf).abs().max().item() < 1e-3
-    for dtype in ("float32", "bfloat16"):
+    for dtype in ("float32", "float16", "bfloat16"):
         m = w.WhisperIPA(arch, dtype=dtype, max_batch=B)
         m.load_state_dict(sd)
         got = m.generate(feats, decoder_input_ids=torch.tensor([prompt] * B), max_new_tokens=max_new).cpu()
@@ -280,24 +290,25 @@ def test_fp32_maximum_target_length(w, tiny_gain_sd):
             m2.close()
 
 
-def test_bf16_decode_is_deterministic_and_batch_stable(w, tiny_gain_sd):
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+def test_half_decode_is_deterministic_and_batch_stable(w, tiny_gain_sd, dtype):
     """Two runs over the same 37 clips give identical ids (the stream-K cross-attention merges partials in a fixed
     order), and the ids of a clip do not depend on which other clips share its batch (a ragged last micro-batch)."""
     from oracle import whisper_oracle as wo
     B = 37
     audio = wo.synthetic_audio(B)
     feats = w.log_mel_features(audio, 80)
-    m = w.WhisperIPA("tiny", dtype="bfloat16", max_batch=B)
+    m = w.WhisperIPA("tiny", dtype=dtype, max_batch=B)
     m.load_state_dict(tiny_gain_sd)
     prompt = torch.tensor([wo.PROMPT_PRE_V3] * B)
     a = m.generate(feats, decoder_input_ids=prompt, max_new_tokens=24).cpu()
     b = m.generate(feats, decoder_input_ids=prompt, max_new_tokens=24).cpu()
     assert torch.equal(a, b)
     m.close()
-    m = w.WhisperIPA("tiny", dtype="bfloat16", max_batch=16)                  # micro-batches of 16, 16, 5
+    m = w.WhisperIPA("tiny", dtype=dtype, max_batch=16)                  # micro-batches of 16, 16, 5
     m.load_state_dict(tiny_gain_sd)
     c = m.generate(feats, decoder_input_ids=prompt, max_new_tokens=24).cpu()
     m.close()
     agree = (a == c).float().mean().item()
-    print(f"\n[bf16 batch stability] token agreement between batch 37 and micro-batches of 16: {agree:.4f}")
+    print(f"\n[{dtype} batch stability] token agreement between batch 37 and micro-batches of 16: {agree:.4f}")
     assert agree > 0.98

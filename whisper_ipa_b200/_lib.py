@@ -9,9 +9,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwipa.so")
+LIB_PATH = os.path.join(_HERE, "libwipa.so")                 # 16-bit path in IEEE fp16 (and the fp32 path)
+LIB_PATH_BF16 = os.path.join(_HERE, "libwipa_bf16.so")        # the same sources compiled with bfloat16 as the 16-bit type
 
-DTYPE_F32, DTYPE_BF16 = 0, 1
+DTYPE_F32, DTYPE_BF16, DTYPE_F16 = 0, 1, 2
 INFO_WORKSPACE_BYTES, INFO_CROSSKV_BYTES, INFO_DECODE_STEPS, INFO_XATTN_LATENT = 0, 1, 2, 3
 
 
@@ -53,8 +54,9 @@ PROTOTYPES = {
     "wipa_strerror": (C.c_char_p, [_i]),
     "wipa_last_error": (C.c_char_p, []),
     "wipa_launch_count": (_i64, [_i]),
+    "wipa_h16_dtype": (_i, []),
     "wipa_ctx_get_info": (_i, [_vp, _i, C.POINTER(_i64)]),
-    "wipa_test_gemm_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wipa_test_gemm_h16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wipa_test_gemm_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_gemm_epilogue": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "wipa_test_cross_attn_latent": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
@@ -62,32 +64,52 @@ PROTOTYPES = {
     "wipa_test_cross_attn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wipa_test_enc_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wipa_test_self_attn": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
-    "wipa_test_enc_attention_bf16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wipa_test_enc_attention_h16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
 }
 
-_lib = None
+_libs = {}
 
 
-def lib() -> C.CDLL:
-    """Load libwipa.so (built in-tree by __graft_entry__.build()).  Raises if it is absent."""
-    global _lib
-    if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise ImportError(f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+def lib(h16: str = "f16") -> C.CDLL:
+    """Load libwipa.so (h16="f16", the default build) or libwipa_bf16.so (h16="bf16"), both built in-tree by
+    __graft_entry__.build().  Raises if the file is absent: there is no CPU fallback."""
+    if h16 not in ("f16", "bf16"):
+        raise ValueError(f"h16 must be 'f16' or 'bf16', got {h16!r}")
+    handle = _libs.get(h16)
+    if handle is None:
+        path = LIB_PATH if h16 == "f16" else LIB_PATH_BF16
+        if not os.path.exists(path):
+            raise ImportError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)")
-        handle = C.CDLL(LIB_PATH)
+        handle = C.CDLL(path)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        _lib = handle
-    return _lib
+        want = DTYPE_F16 if h16 == "f16" else DTYPE_BF16
+        if handle.wipa_h16_dtype() != want:
+            raise ImportError(f"{path} was built for 16-bit dtype {handle.wipa_h16_dtype()}, expected {want}")
+        _libs[h16] = handle
+    return handle
 
 
-def check(rc: int, what: str) -> None:
+def lib_for_dtype(dtype_code: int) -> C.CDLL:
+    return lib("bf16" if dtype_code == DTYPE_BF16 else "f16")
+
+
+def torch_h16(h16: str = "f16"):
+    """torch dtype of the 16-bit element type the named build computes in (for the standalone kernel entry points)."""
+    import torch
+    return torch.float16 if h16 == "f16" else torch.bfloat16
+
+
+def check(rc: int, what: str, handle: C.CDLL = None) -> None:
     if rc != 0:
-        l = lib()
+        l = handle if handle is not None else lib()
         raise WipaError(rc, what, f"{l.wipa_strerror(rc).decode()}: {l.wipa_last_error().decode()}")
 
 
 def launch_count(reset: bool = False) -> int:
-    return int(lib().wipa_launch_count(1 if reset else 0))
+    """Kernels launched by every loaded build of the library since the last reset."""
+    if not _libs:
+        lib()
+    return sum(int(h.wipa_launch_count(1 if reset else 0)) for h in _libs.values())

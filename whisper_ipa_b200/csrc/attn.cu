@@ -2,7 +2,7 @@
 //   enc_attention_kernel   : encoder self-attention (non-causal, 1500 x 1500 x 64 per head), flash-style
 //                            online softmax, fp32 math on CUDA cores.  This is the fp32-path kernel
 //                            (HF:models/whisper/modeling_whisper.py:284-357 with scaling folded into q).
-//                            The bf16 path uses the tcgen05 flash kernel in attn_tc.cu.
+//                            The h16 path uses the tcgen05 flash kernel in attn_tc.cu.
 //   self_attention_kernel  : one decode step of decoder self-attention over the paged KV cache (one CTA of four warps
 //                            per (seq, head); optional beam-ancestry indirection).
 //   cross_attention_stream_kernel : one decode step of cross-attention against the cached encoder K/V — the dominant HBM
@@ -31,14 +31,14 @@ __device__ __forceinline__ void load16_as_float<float>(const float* p, float* ou
     }
 }
 template <>
-__device__ __forceinline__ void load16_as_float<bf16>(const bf16* p, float* out) {
+__device__ __forceinline__ void load16_as_float<h16>(const h16* p, float* out) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
         uint4 u = *reinterpret_cast<const uint4*>(p + 8 * i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+        const h16x2* h = reinterpret_cast<const h16x2*>(&u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            float2 f = __bfloat1622float2(h[j]);
+            float2 f = h16x2_to_f2(h[j]);
             out[8 * i + 2 * j] = f.x; out[8 * i + 2 * j + 1] = f.y;
         }
     }
@@ -186,7 +186,7 @@ int launch_enc_attention(const T* q, const T* k, const T* v, T* out, int B, int 
     return WIPA_OK;
 }
 template int launch_enc_attention<float>(const float*, const float*, const float*, float*, int, int, int, cudaStream_t);
-template int launch_enc_attention<bf16>(const bf16*, const bf16*, const bf16*, bf16*, int, int, int, cudaStream_t);
+template int launch_enc_attention<h16>(const h16*, const h16*, const h16*, h16*, int, int, int, cudaStream_t);
 
 // ================================================================================================
 // decoder self-attention, one new token per sequence, paged KV
@@ -205,15 +205,15 @@ __device__ __forceinline__ float dot64<float>(const float* kp, const float* qs) 
     return acc;
 }
 template <>
-__device__ __forceinline__ float dot64<bf16>(const bf16* kp, const float* qs) {
+__device__ __forceinline__ float dot64<h16>(const h16* kp, const float* qs) {
     float acc = 0.f;
 #pragma unroll
     for (int i = 0; i < 64; i += 8) {
         const uint4 u = *reinterpret_cast<const uint4*>(kp + i);
-        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+        const h16x2* h = reinterpret_cast<const h16x2*>(&u);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float2 f = __bfloat1622float2(h[j]);
+            const float2 f = h16x2_to_f2(h[j]);
             acc = fmaf(f.x, qs[i + 2 * j], acc);
             acc = fmaf(f.y, qs[i + 2 * j + 1], acc);
         }
@@ -228,7 +228,7 @@ __device__ __forceinline__ float dot64<bf16>(const bf16* kp, const float* qs) {
 
 template <typename T> struct CaCfg;
 template <> struct CaCfg<float> { static constexpr int VEC = 4, LPK = 16; };   // lanes per key row (16 B each)
-template <> struct CaCfg<bf16> { static constexpr int VEC = 8, LPK = 8; };
+template <> struct CaCfg<h16> { static constexpr int VEC = 8, LPK = 8; };
 
 template <typename T>
 __device__ __forceinline__ void unpack16(const uint4& u, float* f);
@@ -237,17 +237,17 @@ __device__ __forceinline__ void unpack16<float>(const uint4& u, float* f) {
     f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
 }
 template <>
-__device__ __forceinline__ void unpack16<bf16>(const uint4& u, float* f) {
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+__device__ __forceinline__ void unpack16<h16>(const uint4& u, float* f) {
+    const h16x2* h = reinterpret_cast<const h16x2*>(&u);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float2 t = __bfloat1622float2(h[j]);
+        const float2 t = h16x2_to_f2(h[j]);
         f[2 * j] = t.x; f[2 * j + 1] = t.y;
     }
 }
 
 __device__ __forceinline__ float2 ld_pair(const float* p) { return *reinterpret_cast<const float2*>(p); }
-__device__ __forceinline__ float2 ld_pair(const bf16* p) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p)); }
+__device__ __forceinline__ float2 ld_pair(const h16* p) { return h16x2_to_f2(*reinterpret_cast<const h16x2*>(p)); }
 
 // One CTA of SA_WARPS (4) warps per (sequence, head); warp w takes pages w, w+4, ... of the sequence's block table, so a
 // sequence of 112 positions is 2 pages (one or two memory round trips) per warp instead of 7 for one warp (8 warps per
@@ -259,11 +259,11 @@ __device__ __forceinline__ float2 ld_pair(const bf16* p) { return __bfloat1622fl
 // (an earlier fully unrolled one-warp version was 125 KB of SASS and thrashed the instruction cache)
 template <typename T> struct VRaw;
 template <> struct VRaw<float> { typedef float2 type; };
-template <> struct VRaw<bf16> { typedef __nv_bfloat162 type; };
+template <> struct VRaw<h16> { typedef h16x2 type; };
 __device__ __forceinline__ float2 v_to_f2(float2 v) { return v; }
-__device__ __forceinline__ float2 v_to_f2(__nv_bfloat162 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ float2 v_to_f2(h16x2 v) { return h16x2_to_f2(v); }
 __device__ __forceinline__ void st_v2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
-__device__ __forceinline__ void st_v2(bf16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ void st_v2(h16* p, float a, float b) { *reinterpret_cast<h16x2*>(p) = f2_to_h16x2(a, b); }
 
 #define SA_WARPS 4
 template <typename T, bool ANC>
@@ -396,7 +396,7 @@ int launch_self_attention(const float* q, const T* kpool, const T* vpool, const 
     return WIPA_OK;
 }
 template int launch_self_attention<float>(const float*, const float*, const float*, const int*, int, const int*, float*, int, int, cudaStream_t, const int*, const int*, int);
-template int launch_self_attention<bf16>(const float*, const bf16*, const bf16*, const int*, int, const int*, bf16*, int, int, cudaStream_t, const int*, const int*, int);
+template int launch_self_attention<h16>(const float*, const h16*, const h16*, const int*, int, const int*, h16*, int, int, cudaStream_t, const int*, const int*, int);
 
 // ================================================================================================
 // decoder cross-attention, one query per (sequence, head) against 1500 cached encoder keys/values
@@ -542,7 +542,7 @@ cross_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc, co
 // slot of its first chunk and adds its chunk count to the pair's counter — whoever completes the count of 12 walks
 // the slots in chunk order (deterministic) and writes the head's output.
 //
-// The producer warp runs ahead over pair boundaries, so the ring (6 x 32 KB in bf16) always holds ~190 KB of loads in
+// The producer warp runs ahead over pair boundaries, so the ring (6 x 32 KB in h16) always holds ~190 KB of loads in
 // flight per SM; K/V are static inside a decode step, so under PDL the first slots are requested BEFORE
 // griddepcontrol.wait and HBM does not idle between the layers' launches.  Every consumer warp owns 1/8 of each
 // chunk's keys and carries a warp-local online softmax (m, l, o) across the chunks of a pair; the 8 warp partials are
@@ -557,7 +557,7 @@ cross_attention_kernel(const float* __restrict__ q, const T* __restrict__ kc, co
 #define CS_PART 68                     // floats per global partial: m, l, next chunk, pad, o[64]
 
 template <typename T> struct CsCfg {
-    static constexpr int CHUNK_BYTES = CS_CK * 64 * (int)sizeof(T);              // 16000 (bf16) / 32000 (fp32)
+    static constexpr int CHUNK_BYTES = CS_CK * 64 * (int)sizeof(T);              // 16000 (h16) / 32000 (fp32)
     static constexpr int SLOT_BYTES = 2 * CHUNK_BYTES;
     static constexpr int STAGES = sizeof(T) == 2 ? 6 : 3;
     static constexpr int KPW = 32 / CaCfg<T>::LPK;                               // keys per warp per iteration
@@ -567,7 +567,7 @@ template <typename T> struct CsCfg {
 
 template <typename T> __device__ __forceinline__ float ca_exp(float x);
 template <> __device__ __forceinline__ float ca_exp<float>(float x) { return expf(x); }
-template <> __device__ __forceinline__ float ca_exp<bf16>(float x) { return __expf(x); }
+template <> __device__ __forceinline__ float ca_exp<h16>(float x) { return __expf(x); }
 
 template <typename T>
 __global__ void __launch_bounds__(CS_THREADS, 1)
@@ -787,7 +787,7 @@ static int launch_cross_attention_stream(const float* q, const T* k, const T* v,
 }
 
 int cross_attention_default_split(int elem_bytes, int Bs, int H) {
-    // legacy kernel only: chunk sized for ~48 KB of K+V per CTA (4 CTAs / SM resident): 188 keys in bf16, 94 in fp32
+    // legacy kernel only: chunk sized for ~48 KB of K+V per CTA (4 CTAs / SM resident): 188 keys in h16, 94 in fp32
     (void)Bs; (void)H;
     return elem_bytes == 2 ? 8 : 16;
 }
@@ -810,4 +810,4 @@ int launch_cross_attention(const float* q, const T* k, const T* v, const int* ut
     return WIPA_OK;
 }
 template int launch_cross_attention<float>(const float*, const float*, const float*, const int*, float*, float*, int*, int, int, int, int, cudaStream_t);
-template int launch_cross_attention<bf16>(const float*, const bf16*, const bf16*, const int*, bf16*, float*, int*, int, int, int, int, cudaStream_t);
+template int launch_cross_attention<h16>(const float*, const h16*, const h16*, const int*, h16*, float*, int*, int, int, int, int, cudaStream_t);

@@ -1,4 +1,4 @@
-// Decoder cross-attention over the encoder output itself ("latent" cross-attention), bf16 path.
+// Decoder cross-attention over the encoder output itself ("latent" cross-attention), h16 path.
 //
 // HF computes, per decoder layer l and utterance u (HF:models/whisper/modeling_whisper.py:241-357),
 //     K_l = E_u Wk_l^T,   V_l = E_u Wv_l^T + bv_l,   ctx_h = softmax_t(q_h . K_l[t, h]) V_l[:, h]
@@ -13,7 +13,7 @@
 // S = Q' E^T and C = P E are [16 x keys x d] mma.sync products with M = 16 >= the number of heads.
 //
 //   q' = x (Wq_h^T Wk_h) + bq_h Wk_h      one [S, d] x [d, H*d] GEMM with weights folded at load time (ctx.cu)
-//   this kernel: Q' [S, H, d] bf16, E [U, 1500, d] bf16  ->  C [S, H, d] bf16 (normalised sum_t p_h[t] E[t])
+//   this kernel: Q' [S, H, d] h16, E [U, 1500, d] h16  ->  C [S, H, d] h16 (normalised sum_t p_h[t] E[t])
 //   out-projection: x += C (Wo_h Wv_h)^T + (bo + Wo bv)   one [S, H*d] x [H*d, d] GEMM, weights folded at load time
 //
 // Kernel: one CTA per SM.  The (sequence, chunk) units of the launch form one list that is cut into equal contiguous
@@ -24,7 +24,7 @@
 // [64w, 64w + 64) of d for BOTH products:
 //   1. partial scores  Sp[w][16 x KEYS] = Q'[:, cols] E[keys, cols]^T    (A fragments of Q' live in registers per sequence)
 //   2. named barrier; warp w sums row w (= head w) over the H partials, does the online-softmax bookkeeping for that
-//      head (maximum by redux.sync) and writes p (bf16) and the rescale factor alpha[w]; named barrier
+//      head (maximum by redux.sync) and writes p (h16) and the rescale factor alpha[w]; named barrier
 //   3. C[:, cols] = alpha * C[:, cols] + P E[keys, cols]                 (accumulators [16 x 64] per warp, fp32);
 //      the softmax denominator l = alpha * l + P x ones rides the same MMAs
 // Rows >= H of the 16-row MMA tile are padding.  Keys beyond 1500 in the last chunk are zero-filled by TMA (3-D map,
@@ -44,7 +44,7 @@ constexpr float XL_LOG2E = 1.4426950408889634f;
 
 template <int KEYS>
 struct XlCfg {
-    static constexpr int PITCH = KEYS + 8;                      // floats per partial-score row / bf16 per P row
+    static constexpr int PITCH = KEYS + 8;                      // floats per partial-score row / h16 per P row
     static size_t smem(int H) {
         return (size_t)XL_STAGES * KEYS * H * 128 + (size_t)H * H * PITCH * 4 + 16 * PITCH * 2 + 32 * 4 + 64 + 1024;
     }
@@ -58,9 +58,9 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t& r0, u
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
                  : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
 }
-// D[16 x 8] += A[16 x 16] B[16 x 8], bf16 operands, fp32 accumulators
-__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+// D[16 x 8] += A[16 x 16] B[16 x 8], h16 operands, fp32 accumulators
+__device__ __forceinline__ void mma_h16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32." WIPA_H16_MMA_SUFFIX ".f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -79,7 +79,7 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
 __device__ __forceinline__ void sts_f32x2(uint32_t addr, float a, float b) {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
 }
-__device__ __forceinline__ void sts_b16(uint32_t addr, bf16 v) {
+__device__ __forceinline__ void sts_b16(uint32_t addr, h16 v) {
     asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(*reinterpret_cast<const unsigned short*>(&v)) : "memory");
 }
 // warp maximum of floats in one redux.sync: IEEE floats order like sign-magnitude integers, so flip the magnitude bits of
@@ -99,8 +99,8 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 
 template <int KEYS, int H>
 __global__ void __launch_bounds__((H + 1) * 32, 1)
-cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf16* __restrict__ Qp,
-                              const int* __restrict__ utt_of_seq, bf16* __restrict__ Cout, int S, int T,
+cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Qp,
+                              const int* __restrict__ utt_of_seq, h16* __restrict__ Cout, int S, int T,
                               float* __restrict__ part, int* __restrict__ counters, int slots_per_seq) {
     using Cfg = XlCfg<KEYS>;
     constexpr int PITCH = Cfg::PITCH;
@@ -110,7 +110,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
     constexpr uint32_t stage_bytes = (uint32_t)KEYS * (uint32_t)H * 128u;
     uint8_t* sE = smem;                                                      // [stage][H tiles][KEYS][128 B], 128B-swizzled
     float* Sp = reinterpret_cast<float*>(sE + XL_STAGES * stage_bytes);      // [warp][head][PITCH]
-    bf16* Pm = reinterpret_cast<bf16*>(Sp + H * H * PITCH);                  // [16][PITCH]
+    h16* Pm = reinterpret_cast<h16*>(Sp + H * H * PITCH);                  // [16][PITCH]
     float* alpha = reinterpret_cast<float*>(Pm + 16 * PITCH);                // [16] rescale of C (+ 16 spare floats)
     uint64_t* full = reinterpret_cast<uint64_t*>(alpha + 32);
     uint64_t* empty = full + XL_STAGES;
@@ -127,7 +127,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
         for (int s = 0; s < XL_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], (uint32_t)H); }
         ptx::fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 16 * PITCH; i += blockDim.x) Pm[i] = __float2bfloat16(0.f);
+    for (int i = threadIdx.x; i < 16 * PITCH; i += blockDim.x) Pm[i] = f32_to_h16(0.f);
     if (threadIdx.x < 32) alpha[threadIdx.x] = 1.f;
     __syncthreads();
 
@@ -176,7 +176,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
             const uint32_t* q_hi = reinterpret_cast<const uint32_t*>(Qp + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-                qa[ks][0] = row_lo ? q_lo[ks * 8] : 0u;           // 16 bf16 = 8 words per k-step
+                qa[ks][0] = row_lo ? q_lo[ks * 8] : 0u;           // 16 h16 = 8 words per k-step
                 qa[ks][1] = row_hi ? q_hi[ks * 8] : 0u;
                 qa[ks][2] = row_lo ? q_lo[ks * 8 + 4] : 0u;       // columns + 8
                 qa[ks][3] = row_hi ? q_hi[ks * 8 + 4] : 0u;
@@ -186,7 +186,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
 #pragma unroll
         for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
         float m_run = -INFINITY;                    // running maximum of head w (replicated over the lanes of warp w)
-        // l = sum_t p[t] rides the tensor pipe: P x ones accumulates it in every warp with exactly the bf16 weights (and the
+        // l = sum_t p[t] rides the tensor pipe: P x ones accumulates it in every warp with exactly the h16 weights (and the
         // rescaling) that C sees - no cross-lane sum, no cross-warp exchange.  accl[0] / accl[2]: rows g / g + 8
         float accl[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -214,7 +214,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                 for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll
                     for (int nt = 0; nt < KEYS / 8; ++nt)
-                        mma_bf16(sc[nt], qa[ks], bfr[nt][ks >> 1][(ks & 1) * 2], bfr[nt][ks >> 1][(ks & 1) * 2 + 1]);
+                        mma_h16(sc[nt], qa[ks], bfr[nt][ks >> 1][(ks & 1) * 2], bfr[nt][ks >> 1][(ks & 1) * 2 + 1]);
                 }
 #pragma unroll
                 for (int nt = 0; nt < KEYS / 8; ++nt) {
@@ -235,7 +235,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                                       vfr[ks][jp][2], vfr[ks][jp][3]);
                 }
             }
-            // 2. head w: sum the partials (two interleaved chains), maximum by redux.sync, p in bf16, rescale factor
+            // 2. head w: sum the partials (two interleaved chains), maximum by redux.sync, p in h16, rescale factor
             {
                 constexpr bool kTwo = KEYS > 32;
                 const bool has1 = kTwo && lane < KEYS - 32;
@@ -259,8 +259,8 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                 const float p0 = ex2_ftz(fmaf(v0, XL_LOG2E, -mb)), p1 = ex2_ftz(fmaf(v1, XL_LOG2E, -mb));
                 const float a = ex2_ftz(fmaf(m_run, XL_LOG2E, -mb));
                 m_run = m_new;
-                sts_b16(Pm_s + (uint32_t)(w * PITCH + lane) * 2u, __float2bfloat16(p0));
-                if (has1) sts_b16(Pm_s + (uint32_t)(w * PITCH + 32 + lane) * 2u, __float2bfloat16(p1));
+                sts_b16(Pm_s + (uint32_t)(w * PITCH + lane) * 2u, f32_to_h16(p0));
+                if (has1) sts_b16(Pm_s + (uint32_t)(w * PITCH + 32 + lane) * 2u, f32_to_h16(p1));
                 if (lane == 0) alpha[w] = a;
             }
             xl_bar(nthr);
@@ -281,10 +281,10 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                 for (int ks = 0; ks < KEYS / 16; ++ks) {
 #pragma unroll
                     for (int jp = 0; jp < 4; ++jp) {
-                        mma_bf16(acc[2 * jp], pa[ks], vfr[ks][jp][0], vfr[ks][jp][1]);
-                        mma_bf16(acc[2 * jp + 1], pa[ks], vfr[ks][jp][2], vfr[ks][jp][3]);
+                        mma_h16(acc[2 * jp], pa[ks], vfr[ks][jp][0], vfr[ks][jp][1]);
+                        mma_h16(acc[2 * jp + 1], pa[ks], vfr[ks][jp][2], vfr[ks][jp][3]);
                     }
-                    mma_bf16(accl, pa[ks], 0x3f803f80u, 0x3f803f80u);       // x ones (bf16 1.0 pairs): row sums of P
+                    mma_h16(accl, pa[ks], WIPA_H16_ONE_X2, WIPA_H16_ONE_X2);       // x ones (h16 1.0 pairs): row sums of P
                 }
             }
             __syncwarp();
@@ -294,12 +294,12 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
         if (ch0 == 0 && ch1 == n_chunks) {
             // the whole sequence was ours: normalise and store
             const float il_lo = row_lo ? 1.f / accl[0] : 0.f, il_hi = row_hi ? 1.f / accl[2] : 0.f;
-            bf16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
-            bf16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
+            h16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
+            h16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_bf16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
-                if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_bf16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
+                if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_h16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
+                if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_h16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
             }
             continue;
         }
@@ -359,12 +359,12 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const bf1
                 }
             }
             const float il_lo = row_lo ? 1.f / l_lo : 0.f, il_hi = row_hi ? 1.f / l_hi : 0.f;
-            bf16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
-            bf16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
+            h16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
+            h16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_bf16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
-                if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_bf16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
+                if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_h16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
+                if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_h16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
             }
         }
     }
@@ -375,7 +375,7 @@ int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) 
     cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)T * d * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)keys, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode_xl(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(E), dims, strides, box, estr,
+    CUresult r = g_encode_xl(map, WIPA_H16_TMA_TYPE, 3, const_cast<void*>(E), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -386,7 +386,7 @@ int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) 
 }
 
 template <int KEYS, int H>
-int xl_launch(const CUtensorMap& tm, const bf16* Qp, const int* utt_of_seq, bf16* C, int S, int T, int n_sm, float* part,
+int xl_launch(const CUtensorMap& tm, const h16* Qp, const int* utt_of_seq, h16* C, int S, int T, int n_sm, float* part,
               size_t part_floats, int* counters, cudaStream_t st) {
     const size_t smem = XlCfg<KEYS>::smem(H);
     static SmemAttr attr;
@@ -414,9 +414,9 @@ size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm) {
     return (size_t)(2 * n_sm + 3 * max_seqs + 64) * (size_t)(H * 1024 + 32);
 }
 
-// Qp: bf16 [S, H, d] absorbed queries; E: bf16 [U, T, d] encoder output (d = 64 H); utt_of_seq: int [S]; C: bf16 [S, H, d];
+// Qp: h16 [S, H, d] absorbed queries; E: h16 [U, T, d] encoder output (d = 64 H); utt_of_seq: int [S]; C: h16 [S, H, d];
 // part / counters: partial scratch (cross_attention_latent_scratch_floats) and int [S] zeroed once (self-resetting)
-int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const int* utt_of_seq, bf16* C, int S, int H, int T,
+int launch_cross_attention_latent(const h16* Qp, const h16* E, int U, const int* utt_of_seq, h16* C, int S, int H, int T,
                                   float* part, size_t part_floats, int* counters, cudaStream_t st) {
     WIPA_CHECK(cross_attention_latent_supported(H), WIPA_EUNSUPPORTED, "cross_attention_latent: %d heads (6, 8, 12 or 16)", H);
     WIPA_CHECK(S >= 1 && U >= 1 && T >= 1 && part && counters, WIPA_EINVAL, "cross_attention_latent: bad argument");

@@ -1,4 +1,4 @@
-// Encoder self-attention on the 5th-generation tensor cores (bf16 path).
+// Encoder self-attention on the 5th-generation tensor cores (h16 path).
 //
 // Non-causal attention over T = 1500 frames, head_dim 64 (HF:models/whisper/modeling_whisper.py:284-357; the 64^-0.5
 // scaling is folded into the q projection).  One CTA owns TWO 128-query tiles of one (clip, head) and walks the keys
@@ -7,12 +7,12 @@
 //   warp 0      TMA producer: both Q tiles once, then K / V blocks ([128 keys][64] each, 128B-swizzled), 2-deep ring
 //   warp 1      tcgen05 issuer, per key block j and tile g:
 //                   S_g   = Q_g K_j^T        (M128 x N128 x K64, fp32 in TMEM, one buffer per tile)
-//                   O_g,j = P_g,j V_j        (M128 x N64 x K128; P is the bf16 tile the softmax warps left in shared
+//                   O_g,j = P_g,j V_j        (M128 x N64 x K128; P is the h16 tile the softmax warps left in shared
 //                                             memory, V_j is consumed as an MN-major B operand straight from its TMA
 //                                             image - no transpose anywhere; double-buffered in TMEM)
 //   warps 2-5   softmax of tile 0, warps 6-9 softmax of tile 1, one query row per thread: a max pass and an exp pass
 //               over S in TMEM (64 columns in registers at a time), running max / sum in fp32 (exp2 with log2e folded
-//               into one FFMA), P -> bf16 -> swizzled shared memory, then fold the PREVIOUS block's O_{j-1} from TMEM
+//               into one FFMA), P -> h16 -> swizzled shared memory, then fold the PREVIOUS block's O_{j-1} from TMEM
 //               into the fp32 register accumulator (o = o * alpha + O_{j-1}).  The tensor pipe therefore never waits
 //               for a rescale: every P V product starts from zero in its own TMEM buffer.
 //
@@ -26,7 +26,7 @@ namespace {
 constexpr int FA_BQ = 256;                                    // two 128-row tiles per CTA
 constexpr int FA_BK = 128;
 constexpr int FA_STAGES = 2;
-constexpr int FA_TILE_BYTES = 128 * 64 * 2;                   // one [128][64] bf16 tile
+constexpr int FA_TILE_BYTES = 128 * 64 * 2;                   // one [128][64] h16 tile
 constexpr int FA_P_BYTES = 2 * FA_TILE_BYTES;                 // [128 q][128 keys] as two K-chunks of 64 keys
 constexpr int FA_SMEM = FA_TILE_BYTES * (2 + 2 * FA_STAGES) + 4 * FA_P_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 constexpr int FA_TMEM_COLS = 512;                             // S: 2 tiles x 128 columns, O: 2 tiles x 2 x 64 columns
@@ -47,14 +47,14 @@ __device__ __forceinline__ float ex2(float x) {
 // V_j is consumed as an MN-major B operand with the 128-byte swizzle: rows are K indices (keys), 128 bytes = 64 N
 // elements per row, 8-row groups 1024 bytes apart (cute/atom/mma_traits_sm100.hpp: ((T,8,m),(8,k)):((1,T,LBO),(8T,SBO)),
 // m = 1 here), i.e. exactly the TMA image of a [128 keys][64] tile; 16 keys per MMA = 2048 bytes per K step.
-__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int b_mn_major) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+__host__ __device__ constexpr uint32_t idesc_h16(int M, int N, int b_mn_major) {
+    return (1u << 4) | (WIPA_H16_IDESC_FMT << 7) | (WIPA_H16_IDESC_FMT << 10) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(FA_THREADS, 1)
 enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                        const __grid_constant__ CUtensorMap tmV, bf16* __restrict__ out, int H, int T) {
+                        const __grid_constant__ CUtensorMap tmV, h16* __restrict__ out, int H, int T) {
     extern __shared__ uint8_t fa_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(fa_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sQ = smem;                                        // [2 tiles]
@@ -119,8 +119,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             __syncwarp();
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc_s = idesc_bf16(128, 128, 0);
-        constexpr uint32_t idesc_o = idesc_bf16(128, 64, 1);
+        constexpr uint32_t idesc_s = idesc_h16(128, 128, 0);
+        constexpr uint32_t idesc_o = idesc_h16(128, 64, 1);
         const uint32_t q_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sQ));
         const uint32_t k_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sK));
         const uint32_t p_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sP));
@@ -143,7 +143,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         const uint32_t k_lo = k_lo0 + (uint32_t)(j & 1) * (FA_TILE_BYTES >> 4);
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            ptx::umma_bf16(tmem_S + (uint32_t)g * 128u, ptx::smem_desc_sw128(q_lo + 2 * k),
+                            ptx::umma_h16(tmem_S + (uint32_t)g * 128u, ptx::smem_desc_sw128(q_lo + 2 * k),
                                            ptx::smem_desc_sw128(k_lo + 2 * k), idesc_s, k != 0 ? 1u : 0u);
                         ptx::umma_commit(&s_full[g]);
                     }
@@ -153,7 +153,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                         const uint32_t v_lo = v_lo0 + (uint32_t)(jp & 1) * (FA_TILE_BYTES >> 4);
 #pragma unroll
                         for (int k = 0; k < 8; ++k)
-                            ptx::umma_bf16(tmem_O + (uint32_t)g * 128u + (uint32_t)(jp & 1) * 64u,
+                            ptx::umma_h16(tmem_O + (uint32_t)g * 128u + (uint32_t)(jp & 1) * 64u,
                                            ptx::smem_desc_sw128(p_lo + (uint32_t)(k >> 2) * (FA_TILE_BYTES >> 4) + (uint32_t)(k & 3) * 2u),
                                            ptx::smem_desc_sw128(v_lo + (uint32_t)k * (2048u >> 4)), idesc_o, k != 0 ? 1u : 0u);
                         ptx::umma_commit(&o_full[g * 2 + (jp & 1)]);
@@ -219,7 +219,7 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
             const float alpha = ex2((m - m_new) * LOG2E);         // 0 on the first block (m = -inf)
             const float nm = -m_new * LOG2E;
             m = m_new;
-            // ---- pass 2: p = exp(s - m), bf16 P tile into swizzled shared memory ---------------------------------------
+            // ---- pass 2: p = exp(s - m), h16 P tile into swizzled shared memory ---------------------------------------
             float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f, sum3 = 0.f;
             const uint32_t prow_s = ptx::smem_u32(myP + (j & 1) * FA_P_BYTES + p_row);
 #pragma unroll
@@ -240,8 +240,8 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
                     for (int i = 0; i < 8; ++i) p[i] = ex2(fmaf(s[c8 * 8 + i], LOG2E, nm));
                     sum0 += p[0] + p[4]; sum1 += p[1] + p[5]; sum2 += p[2] + p[6]; sum3 += p[3] + p[7];
                     uint4 u;
-                    u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
-                    u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+                    u.x = pack_h16x2(p[0], p[1]); u.y = pack_h16x2(p[2], p[3]);
+                    u.z = pack_h16x2(p[4], p[5]); u.w = pack_h16x2(p[6], p[7]);
                     ptx::sts128(prow_s + hf * FA_TILE_BYTES + (((uint32_t)c8 ^ sw) << 4), u);
                 }
             }
@@ -257,12 +257,12 @@ enc_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_co
         if (t < T) {
             const float inv = 1.0f / l;
             const int b = bh / H, h = bh - b * H;
-            bf16* dst = out + ((size_t)b * T + t) * ((size_t)H * 64) + (size_t)h * 64;
+            h16* dst = out + ((size_t)b * T + t) * ((size_t)H * 64) + (size_t)h * 64;
 #pragma unroll
             for (int i = 0; i < 64; i += 8) {
                 uint4 u;
-                u.x = pack_bf16x2(o[i] * inv, o[i + 1] * inv); u.y = pack_bf16x2(o[i + 2] * inv, o[i + 3] * inv);
-                u.z = pack_bf16x2(o[i + 4] * inv, o[i + 5] * inv); u.w = pack_bf16x2(o[i + 6] * inv, o[i + 7] * inv);
+                u.x = pack_h16x2(o[i] * inv, o[i + 1] * inv); u.y = pack_h16x2(o[i + 2] * inv, o[i + 3] * inv);
+                u.z = pack_h16x2(o[i + 4] * inv, o[i + 5] * inv); u.w = pack_h16x2(o[i + 6] * inv, o[i + 7] * inv);
                 *reinterpret_cast<uint4*>(dst + i) = u;
             }
         }
@@ -277,7 +277,7 @@ int make_map_3d(CUtensorMap* map, const void* base, int T, int BH) {
     cuuint64_t strides[2] = {128, (cuuint64_t)T * 128};
     cuuint32_t box[3] = {64, 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode_fa(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = g_encode_fa(map, WIPA_H16_TMA_TYPE, 3, const_cast<void*>(base), dims, strides, box, estr,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -289,8 +289,8 @@ int make_map_3d(CUtensorMap* map, const void* base, int T, int BH) {
 
 }  // namespace
 
-// q, k, v: bf16 [B, H, T, 64] (q pre-scaled); out: bf16 [B, T, H*64]
-int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, int B, int H, int T, cudaStream_t st) {
+// q, k, v: h16 [B, H, T, 64] (q pre-scaled); out: h16 [B, T, H*64]
+int launch_enc_attention_tc(const h16* q, const h16* k, const h16* v, h16* out, int B, int H, int T, cudaStream_t st) {
     if (g_encode_fa == nullptr) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -14,7 +15,37 @@
 #error "libwipa is written for sm_100a only"
 #endif
 
-typedef __nv_bfloat16 bf16;
+// h16: the 16-bit operand / storage type of the half-precision path.  The library is compiled once per type:
+// libwipa.so with IEEE fp16 (11-bit significand: logits within 1e-3 of the fp32 oracle, the default) and libwipa_bf16.so
+// with -DWIPA_H16_BF16 (bfloat16).  Both feed the same tcgen05 kind::f16 / mma.sync pipelines at the same rate; only the
+// conversions, the instruction-descriptor format bits, the TMA element type and the mma.sync type suffix differ.
+#ifdef WIPA_H16_BF16
+typedef __nv_bfloat16 h16;
+typedef __nv_bfloat162 h16x2;
+#define WIPA_H16_DTYPE WIPA_DTYPE_BF16
+#define WIPA_H16_NAME "bf16"
+#define WIPA_H16_MMA_SUFFIX "bf16.bf16"
+#define WIPA_H16_ONE_X2 0x3f803f80u                    /* two 1.0 values */
+#define WIPA_H16_TMA_TYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+#define WIPA_H16_IDESC_FMT 1u                          /* tcgen05 kind::f16 a_format / b_format: 0 = f16, 1 = bf16 */
+__host__ __device__ __forceinline__ float h16_to_f32(h16 v) { return __bfloat162float(v); }
+__host__ __device__ __forceinline__ h16 f32_to_h16(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float2 h16x2_to_f2(h16x2 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ h16x2 f2_to_h16x2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+#else
+typedef __half h16;
+typedef __half2 h16x2;
+#define WIPA_H16_DTYPE WIPA_DTYPE_F16
+#define WIPA_H16_NAME "f16"
+#define WIPA_H16_MMA_SUFFIX "f16.f16"
+#define WIPA_H16_ONE_X2 0x3c003c00u
+#define WIPA_H16_TMA_TYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+#define WIPA_H16_IDESC_FMT 0u
+__host__ __device__ __forceinline__ float h16_to_f32(h16 v) { return __half2float(v); }
+__host__ __device__ __forceinline__ h16 f32_to_h16(float v) { return __float2half_rn(v); }
+__device__ __forceinline__ float2 h16x2_to_f2(h16x2 v) { return __half22float2(v); }
+__device__ __forceinline__ h16x2 f2_to_h16x2(float a, float b) { return __floats2half2_rn(a, b); }
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -124,7 +155,7 @@ static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 #define WIPA_PAGE 16             // tokens per self-KV page
 
 // ------------------------------------------------------------------------------------------------
-// epilogue description shared by the SIMT-fp32 and tcgen05-bf16 GEMM kernels
+// epilogue description shared by the SIMT-fp32 and tcgen05-h16 GEMM kernels
 // ------------------------------------------------------------------------------------------------
 enum EpiMode : int {
     EPI_STORE = 0,      // out[m, n] = acc + bias
@@ -138,7 +169,7 @@ enum EpiMode : int {
 
 struct EpiParams {
     int mode;
-    int out_bf16;            // element type of out/out1/out2 (0 = f32, 1 = bf16)
+    int out_h16;            // element type of out/out1/out2 (0 = f32, 1 = h16)
     int vec_ok;              // 8-wide vector stores legal (alignment + N % 8 == 0)
     int M_rows;              // valid rows per batch (rows beyond are padding of the M tile)
     int N;                   // valid columns
@@ -173,7 +204,7 @@ struct EpiParams {
     // [tile][split][128][BN]; the last one to arrive (ticket in `sk_count[tile]`, self-resetting) sums them in split order
     float* sk_part;
     int* sk_count;
-    int gelu_fast;           // EPI_GELU with a bf16 result: A&S-erf GELU (gelu_erf_fast) instead of erff
+    int gelu_fast;           // EPI_GELU with a h16 result: A&S-erf GELU (gelu_erf_fast) instead of erff
 };
 
 // A-operand addressing shared by both GEMM kernels: row m of the logical [M, K] matrix lives at
@@ -195,9 +226,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 
-// GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the bf16 rounding of the stored value):
+// GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the h16 rounding of the stored value):
 // two MUFU ops (rcp, ex2) + ~12 FMA-pipe instructions instead of erff's ~35.  1 + erf(z) is formed without
-// cancellation on the negative side.  Used only where the result is rounded to bf16 (the fp32 path calls erff).
+// cancellation on the negative side.  Used only where the result is rounded to h16 (the fp32 path calls erff).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
     // gelu(x) = x * Phi(x); with h = 0.5 * (1 - erf(|x| / sqrt 2)) = 0.5 * poly(t) * exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt 2):
     // Phi(x) = h for x < 0 and 1 - h otherwise.  The 0.5, the 1/sqrt 2 and log2(e) are folded into the constants.
@@ -216,36 +247,36 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 }
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
-__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(h16 v) { return h16_to_f32(v); }
 
 template <typename T> __device__ __forceinline__ T from_f32(float v);
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
-template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ h16 from_f32<h16>(float v) { return f32_to_h16(v); }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+__device__ __forceinline__ uint32_t pack_h16x2(float a, float b) {
+    h16x2 t = f2_to_h16x2(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
 }
 
-// store W consecutive values starting at element index `idx` of a f32 or bf16 array
+// store W consecutive values starting at element index `idx` of a f32 or h16 array
 template <int W>
-__device__ __forceinline__ void store_group(void* base, int is_bf16, long long idx, const float* v, bool vec) {
-    if (is_bf16) {
-        bf16* p = reinterpret_cast<bf16*>(base) + idx;
+__device__ __forceinline__ void store_group(void* base, int is_h16, long long idx, const float* v, bool vec) {
+    if (is_h16) {
+        h16* p = reinterpret_cast<h16*>(base) + idx;
         if (vec) {
             if (W == 8) {
                 uint4 u;
-                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-                u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+                u.x = pack_h16x2(v[0], v[1]); u.y = pack_h16x2(v[2], v[3]);
+                u.z = pack_h16x2(v[4], v[5]); u.w = pack_h16x2(v[6], v[7]);
                 *reinterpret_cast<uint4*>(p) = u;
             } else {
                 uint2 u;
-                u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+                u.x = pack_h16x2(v[0], v[1]); u.y = pack_h16x2(v[2], v[3]);
                 *reinterpret_cast<uint2*>(p) = u;
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < W; ++i) p[i] = __float2bfloat16_rn(v[i]);
+            for (int i = 0; i < W; ++i) p[i] = f32_to_h16(v[i]);
         }
     } else {
         float* p = reinterpret_cast<float*>(base) + idx;
@@ -298,9 +329,9 @@ __device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, fl
             }
             // fallthrough
         case EPI_STORE: {
-            if (full) store_group<W>(ep.out, ep.out_bf16, row + n0, v, vec);
+            if (full) store_group<W>(ep.out, ep.out_h16, row + n0, v, vec);
             else {
-                for (int i = 0; i < W && n0 + i < ep.N; ++i) store_group<1>(ep.out, ep.out_bf16, row + n0 + i, v + i, false);
+                for (int i = 0; i < W && n0 + i < ep.N; ++i) store_group<1>(ep.out, ep.out_h16, row + n0 + i, v + i, false);
             }
             break;
         }
@@ -337,10 +368,10 @@ __device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, fl
             if (which == ep.vt_which) {
                 const long long base = wbase + ((long long)(b * ep.H + h) * WIPA_HEAD_DIM + e) * ep.Tpad + t;
 #pragma unroll
-                for (int i = 0; i < W; ++i) store_group<1>(ep.out, ep.out_bf16, base + (long long)i * ep.Tpad, v + i, false);
+                for (int i = 0; i < W; ++i) store_group<1>(ep.out, ep.out_h16, base + (long long)i * ep.Tpad, v + i, false);
             } else {
                 const long long base = wbase + ((long long)(b * ep.H + h) * ep.T + t) * WIPA_HEAD_DIM + e;
-                store_group<W>(ep.out, ep.out_bf16, base, v, true);
+                store_group<W>(ep.out, ep.out_h16, base, v, true);
             }
             break;
         }
@@ -355,7 +386,7 @@ __device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, fl
                 const int p = *ep.pos_ptr;
                 const int page = ep.block_table[(long long)m * ep.bt_stride + p / WIPA_PAGE];
                 const long long base = (((long long)page * ep.H + h) * WIPA_PAGE + (p % WIPA_PAGE)) * WIPA_HEAD_DIM + e;
-                store_group<W>(which == 1 ? ep.out1 : ep.out2, ep.out_bf16, base, v, true);
+                store_group<W>(which == 1 ? ep.out1 : ep.out2, ep.out_h16, base, v, true);
             }
             break;
         }
@@ -387,16 +418,16 @@ __device__ __forceinline__ float warp_max(float v) {
 // kernel launch entry points implemented across the .cu files (host side)
 // ------------------------------------------------------------------------------------------------
 int launch_gemm_f32(const AOperand& a, const float* W, int M, int N, int K, const EpiParams& ep, cudaStream_t st);
-int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep, int block_n,
+int launch_gemm_h16(const AOperand& a, const h16* W, int M, int N, int K, const EpiParams& ep, int block_n,
                      cudaStream_t st);
-int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep, cudaStream_t st);   // gemm_tc2.cu
+int launch_gemm_h16_persistent(const AOperand& a, const h16* W, int M, int N, int K, const EpiParams& ep, cudaStream_t st);   // gemm_tc2.cu
 int wipa_init_tma();   // resolves cuTensorMapEncodeTiled through the runtime; idempotent
 
 template <typename T>
 int launch_layernorm(const float* x, const float* w, const float* b, T* out, int M, int d, cudaStream_t st);
 template <typename T>
 int launch_enc_attention(const T* q, const T* k, const T* v, T* out, int B, int H, int Tq, cudaStream_t st);
-int launch_enc_attention_tc(const bf16* q, const bf16* k, const bf16* v, bf16* out, int B, int H, int T, cudaStream_t st);   // attn_tc.cu
+int launch_enc_attention_tc(const h16* q, const h16* k, const h16* v, h16* out, int B, int H, int T, cudaStream_t st);   // attn_tc.cu
 template <typename T>
 int launch_self_attention(const float* q, const T* kpool, const T* vpool, const int* block_table, int bt_stride,
                           const int* pos_ptr, T* out, int Bs, int H, cudaStream_t st, const int* anc_base = nullptr,
@@ -406,10 +437,10 @@ template <typename T>
 int launch_cross_attention(const float* q, const T* k, const T* v, const int* utt_of_seq, T* out, float* part,
                            int* counters, int Bs, int H, int n_split, int kv_static, cudaStream_t st);
 int cross_attention_default_split(int elem_bytes, int Bs, int H);
-// attn_lat.cu: cross-attention over the encoder output itself (absorbed k / v projections), bf16 only
+// attn_lat.cu: cross-attention over the encoder output itself (absorbed k / v projections), h16 only
 int cross_attention_latent_supported(int H);
 size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm);
-int launch_cross_attention_latent(const bf16* Qp, const bf16* E, int U, const int* utt_of_seq, bf16* C, int S, int H, int T,
+int launch_cross_attention_latent(const h16* Qp, const h16* E, int U, const int* utt_of_seq, h16* C, int S, int H, int T,
                                   float* part, size_t part_floats, int* counters, cudaStream_t st);
 
 // elementwise.cu
@@ -418,8 +449,8 @@ int launch_mel_to_rows(const float* mel, T* rows, int B, int C, cudaStream_t st)
 template <typename T>
 int launch_embed(const T* tok_emb, const float* pos_emb, const int* tok, const int* pos_ptr, float* x, int Bs, int d,
                  cudaStream_t st);
-int launch_convert(const float* src, void* dst, long long n, float scale, int to_bf16, cudaStream_t st);
-int launch_conv_weight(const float* src, void* dst, int N, int C, int to_bf16, cudaStream_t st);   // [N,C,3] -> [N,3*C]
+int launch_convert(const float* src, void* dst, long long n, float scale, int to_h16, cudaStream_t st);
+int launch_conv_weight(const float* src, void* dst, int N, int C, int to_h16, cudaStream_t st);   // [N,C,3] -> [N,3*C]
 int launch_row_argmax(const float* logits, int Bs, int V, const uint32_t* mask_always, const uint32_t* mask_begin,
                       const int* step_ptr, float* pmax, int* pidx, cudaStream_t st);
 

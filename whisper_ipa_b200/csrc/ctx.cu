@@ -1,6 +1,6 @@
 // wipa_ctx: weights, workspaces, cross-/self-KV caches and the encoder / decoder schedules built from the kernels.
 //
-// HBM layout (T = float on the fp32 path, bf16 on the bf16 path; residual stream always fp32):
+// HBM layout (T = float on the fp32 path, h16 on the h16 path; residual stream always fp32):
 //   weights      one arena of T (GEMM operands, [N, K] K-major, q/k/v fused to [3d, d] with q pre-scaled by the
 //                exact power of two 64^-0.5) + one fp32 arena (biases, LayerNorm, position tables)
 //   cross-KV     [dec layer][K|V][utterance][head][1500][64] T — one contiguous 1500x64 block per (utt, head), the
@@ -95,9 +95,9 @@ struct wipa_ctx {
     int beam_L = 0;                // row length of the beam-search sequence / ancestry arrays of the current decode
     int persistent_min_tiles = 296; // WIPA_PERSISTENT_MIN_TILES: fewer 128x256 tiles than this -> plain 128x128-tile kernel
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
-    int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (bf16 path)
+    int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (h16 path)
     // latent cross-attention (attn_lat.cu): the decoder attends over the encoder output itself, k / v projections folded
-    // into the query and output projections.  Default on the bf16 path for contexts of >= 128 sequences and <= 16 heads.
+    // into the query and output projections.  Default on the h16 path for contexts of >= 128 sequences and <= 16 heads.
     int xlat = 0;
     int bn_xlq = 0;                // WIPA_BN_XLQ: tile width of the absorbed-query GEMM (0: as fc1)
     bool xlat_ready = false;       // folded weights match the loaded weights
@@ -254,7 +254,7 @@ int gemm(wipa_ctx* c, const AOperand& a, const void* W, int M, int N, int K, con
     if (c->bf) {
         // bn == 0: the persistent 128 x 256 kernel when there are at least two waves of its tiles, else 128 x 128 tiles
         if (bn == 0 && (long long)cdiv(M, 128) * cdiv(N, 256) < c->persistent_min_tiles) bn = 128;
-        return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, bn, st);
+        return launch_gemm_h16(a, (const h16*)W, M, N, K, ep, bn, st);
     }
     return launch_gemm_f32(a, (const float*)W, M, N, K, ep, st);
 }
@@ -264,20 +264,20 @@ int ln_t(const float* x, const float* w, const float* b, void* out, int M, int d
     return launch_layernorm<T>(x, w, b, (T*)out, M, d, st);
 }
 int ln(wipa_ctx* c, const float* x, const float* w, const float* b, void* out, int M, cudaStream_t st) {
-    return c->bf ? ln_t<bf16>(x, w, b, out, M, c->a.d_model, st) : ln_t<float>(x, w, b, out, M, c->a.d_model, st);
+    return c->bf ? ln_t<h16>(x, w, b, out, M, c->a.d_model, st) : ln_t<float>(x, w, b, out, M, c->a.d_model, st);
 }
 
-__global__ void to_f32_kernel(const void* __restrict__ src, int is_bf16, float* __restrict__ dst, long long n) {
+__global__ void to_f32_kernel(const void* __restrict__ src, int is_h16, float* __restrict__ dst, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride)
-        dst[i] = is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
+        dst[i] = is_h16 ? h16_to_f32(reinterpret_cast<const h16*>(src)[i]) : reinterpret_cast<const float*>(src)[i];
 }
-int launch_to_f32(const void* src, int is_bf16, float* dst, long long n, cudaStream_t st) {
+int launch_to_f32(const void* src, int is_h16, float* dst, long long n, cudaStream_t st) {
     if (n == 0) return WIPA_OK;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    to_f32_kernel<<<(int)blocks, 256, 0, st>>>(src, is_bf16, dst, n);
+    to_f32_kernel<<<(int)blocks, 256, 0, st>>>(src, is_h16, dst, n);
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
@@ -316,18 +316,18 @@ int require_weights(wipa_ctx* c) {
 // latent cross-attention: fold Wk into the query projection and Wv into the output projection (once per weight load)
 //   Wq'[(h, n), k] = sum_j Wk[64h + j, n] Wq[64h + j, k]      bq'[(h, n)] = sum_j Wk[64h + j, n] bq[64h + j]
 //   Wo'[m, (h, n)] = sum_j Wo[m, 64h + j] Wv[64h + j, n]      bo'[m]      = bo[m] + sum_i Wo[m, i] bv[i]
-// (Wq / bq already carry the 1/8 scaling; k_proj has no bias.)  fp32 sums of the stored bf16 weights, rounded once.
+// (Wq / bq already carry the 1/8 scaling; k_proj has no bias.)  fp32 sums of the stored h16 weights, rounded once.
 // ------------------------------------------------------------------------------------------------
-__global__ void xlat_fold_q_kernel(const bf16* __restrict__ Wq, const float* __restrict__ bq, const bf16* __restrict__ Wk,
-                                   bf16* __restrict__ Wq2, float* __restrict__ bq2, int d) {
+__global__ void xlat_fold_q_kernel(const h16* __restrict__ Wq, const float* __restrict__ bq, const h16* __restrict__ Wk,
+                                   h16* __restrict__ Wq2, float* __restrict__ bq2, int d) {
     const int h = blockIdx.z, n = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ float wk[64];
-    if (threadIdx.x < 64) wk[threadIdx.x] = __bfloat162float(Wk[(size_t)(h * 64 + threadIdx.x) * d + n]);
+    if (threadIdx.x < 64) wk[threadIdx.x] = h16_to_f32(Wk[(size_t)(h * 64 + threadIdx.x) * d + n]);
     __syncthreads();
     if (k < d) {
         float acc = 0.f;
-        for (int j = 0; j < 64; ++j) acc = fmaf(wk[j], __bfloat162float(Wq[(size_t)(h * 64 + j) * d + k]), acc);
-        Wq2[((size_t)h * d + n) * d + k] = __float2bfloat16(acc);
+        for (int j = 0; j < 64; ++j) acc = fmaf(wk[j], h16_to_f32(Wq[(size_t)(h * 64 + j) * d + k]), acc);
+        Wq2[((size_t)h * d + n) * d + k] = f32_to_h16(acc);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         float acc = 0.f;
@@ -336,20 +336,20 @@ __global__ void xlat_fold_q_kernel(const bf16* __restrict__ Wq, const float* __r
     }
 }
 
-__global__ void xlat_fold_o_kernel(const bf16* __restrict__ Wo, const float* __restrict__ bo, const bf16* __restrict__ Wv,
-                                   const float* __restrict__ bv, bf16* __restrict__ Wo2, float* __restrict__ bo2, int d, int H) {
+__global__ void xlat_fold_o_kernel(const h16* __restrict__ Wo, const float* __restrict__ bo, const h16* __restrict__ Wv,
+                                   const float* __restrict__ bv, h16* __restrict__ Wo2, float* __restrict__ bo2, int d, int H) {
     const int h = blockIdx.z, m = blockIdx.y, n = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ float wo[64];
-    if (threadIdx.x < 64) wo[threadIdx.x] = __bfloat162float(Wo[(size_t)m * d + h * 64 + threadIdx.x]);
+    if (threadIdx.x < 64) wo[threadIdx.x] = h16_to_f32(Wo[(size_t)m * d + h * 64 + threadIdx.x]);
     __syncthreads();
     if (n < d) {
         float acc = 0.f;
-        for (int j = 0; j < 64; ++j) acc = fmaf(wo[j], __bfloat162float(Wv[(size_t)(h * 64 + j) * d + n]), acc);
-        Wo2[(size_t)m * ((size_t)H * d) + (size_t)h * d + n] = __float2bfloat16(acc);
+        for (int j = 0; j < 64; ++j) acc = fmaf(wo[j], h16_to_f32(Wv[(size_t)(h * 64 + j) * d + n]), acc);
+        Wo2[(size_t)m * ((size_t)H * d) + (size_t)h * d + n] = f32_to_h16(acc);
     }
     if (h == 0 && blockIdx.x == 0 && threadIdx.x == 0) {
         float acc = bo[m];
-        for (int i = 0; i < d; ++i) acc = fmaf(__bfloat162float(Wo[(size_t)m * d + i]), bv[i], acc);
+        for (int i = 0; i < d; ++i) acc = fmaf(h16_to_f32(Wo[(size_t)m * d + i]), bv[i], acc);
         bo2[m] = acc;
     }
 }
@@ -360,12 +360,12 @@ int xlat_prepare(wipa_ctx* c, cudaStream_t st) {
     const dim3 grid(cdiv(d, 256), d, H);
     for (int l = 0; l < c->a.dec_layers; ++l) {
         const DecLayer& L = c->dec[l];
-        const bf16* Wk = (const bf16*)c->xkv_w + (size_t)(2 * l) * d * d;
-        const bf16* Wv = (const bf16*)c->xkv_w + (size_t)(2 * l + 1) * d * d;
+        const h16* Wk = (const h16*)c->xkv_w + (size_t)(2 * l) * d * d;
+        const h16* Wv = (const h16*)c->xkv_w + (size_t)(2 * l + 1) * d * d;
         const float* bv = c->xkv_b + (size_t)(2 * l + 1) * d;
-        xlat_fold_q_kernel<<<grid, 256, 0, st>>>((const bf16*)L.cq_w, L.cq_b, Wk, (bf16*)c->xlq_w[l], c->xlq_b[l], d);
+        xlat_fold_q_kernel<<<grid, 256, 0, st>>>((const h16*)L.cq_w, L.cq_b, Wk, (h16*)c->xlq_w[l], c->xlq_b[l], d);
         WIPA_LAUNCHED();
-        xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const bf16*)L.co_w, L.co_b, Wv, bv, (bf16*)c->xlo_w[l], c->xlo_b[l], d, H);
+        xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const h16*)L.co_w, L.co_b, Wv, bv, (h16*)c->xlo_w[l], c->xlo_b[l], d, H);
         WIPA_LAUNCHED();
     }
     c->xlat_ready = true;
@@ -381,7 +381,7 @@ int cross_kv_project(wipa_ctx* c, int u0, int nb, cudaStream_t st) {
     EpiParams ep = epi(EPI_HEADS, M, N);
     ep.bias = c->xkv_b;
     ep.out = (char*)c->xkv + (size_t)u0 * H * WIPA_T_ENC * 64 * c->esz;
-    ep.out_bf16 = c->bf;
+    ep.out_h16 = c->bf;
     ep.T = WIPA_T_ENC; ep.H = H; ep.d = d;
     ep.which_stride = (long long)c->xkv_which_stride;
     return gemm(c, plainA(c->enc_T, M, d), c->xkv_w, M, N, d, ep, c->bn_enc, st);
@@ -391,14 +391,14 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
     const wipa_arch& a = c->a;
     const int d = a.d_model, H = a.heads, ffn = a.ffn, C = a.n_mels;
     const int T3 = WIPA_N_FRAMES, T = WIPA_T_ENC, M = nb * T;
-    if (c->bf) WIPA_TRY(launch_mel_to_rows<bf16>(mel, (bf16*)c->mel_rows, nb, C, st));
+    if (c->bf) WIPA_TRY(launch_mel_to_rows<h16>(mel, (h16*)c->mel_rows, nb, C, st));
     else WIPA_TRY(launch_mel_to_rows<float>(mel, (float*)c->mel_rows, nb, C, st));
     {   // conv1 (k3, p1) + GELU -> rows 1..3000 of the zero-padded [nb, 3002, d] buffer
         AOperand A; A.ptr = c->mel_rows; A.lda = C; A.a_rpb = T3; A.a_bstride = (long long)(T3 + 2) * C; A.n_batch = nb;
         EpiParams ep = epi(EPI_GELU, nb * T3, d);
         ep.gelu_fast = c->bf;
         ep.bias = c->conv1_b;
-        ep.out = (char*)c->conv1_out + (size_t)d * c->esz; ep.out_bf16 = c->bf;
+        ep.out = (char*)c->conv1_out + (size_t)d * c->esz; ep.out_h16 = c->bf;
         ep.ldo = d; ep.o_rpb = T3; ep.o_bstride = (long long)(T3 + 2) * d;
         WIPA_TRY(gemm(c, A, c->conv1_w, nb * T3, d, 3 * C, ep, c->bn_enc, st));
     }
@@ -415,14 +415,14 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
         WIPA_TRY(ln(c, c->ex, L.ln1_w, L.ln1_b, c->eh, M, st));
         {
             EpiParams ep = epi(EPI_HEADS, M, 3 * d);
-            ep.bias = L.qkv_b; ep.out = c->eqkv; ep.out_bf16 = c->bf;
+            ep.bias = L.qkv_b; ep.out = c->eqkv; ep.out_h16 = c->bf;
             ep.T = T; ep.H = H; ep.d = d; ep.which_stride = (long long)hq;
             WIPA_TRY(gemm(c, plainA(c->eh, M, d), L.qkv_w, M, 3 * d, d, ep, c->bn_enc, st));
         }
         if (c->bf) {
-            const bf16* q = (const bf16*)c->eqkv;
-            if (c->enc_attn_simt) WIPA_TRY(launch_enc_attention<bf16>(q, q + hq, q + 2 * hq, (bf16*)c->eattn, nb, H, T, st));
-            else WIPA_TRY(launch_enc_attention_tc(q, q + hq, q + 2 * hq, (bf16*)c->eattn, nb, H, T, st));
+            const h16* q = (const h16*)c->eqkv;
+            if (c->enc_attn_simt) WIPA_TRY(launch_enc_attention<h16>(q, q + hq, q + 2 * hq, (h16*)c->eattn, nb, H, T, st));
+            else WIPA_TRY(launch_enc_attention_tc(q, q + hq, q + 2 * hq, (h16*)c->eattn, nb, H, T, st));
         } else {
             const float* q = (const float*)c->eqkv;
             WIPA_TRY(launch_enc_attention<float>(q, q + hq, q + 2 * hq, (float*)c->eattn, nb, H, T, st));
@@ -435,7 +435,7 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
         WIPA_TRY(ln(c, c->ex, L.ln2_w, L.ln2_b, c->eh, M, st));
         {
             EpiParams ep = epi(EPI_GELU, M, ffn);
-            ep.bias = L.fc1_b; ep.out = c->effn; ep.out_bf16 = c->bf; ep.gelu_fast = c->bf;
+            ep.bias = L.fc1_b; ep.out = c->effn; ep.out_h16 = c->bf; ep.gelu_fast = c->bf;
             WIPA_TRY(gemm(c, plainA(c->eh, M, d), L.fc1_w, M, ffn, d, ep, c->bn_enc, st));
         }
         {
@@ -444,8 +444,8 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
             WIPA_TRY(gemm(c, plainA(c->effn, M, ffn), L.fc2_w, M, d, ffn, ep, c->bn_enc, st));
         }
     }
-    // latent cross-attention keeps the encoder output itself (bf16) for the whole batch instead of per-layer K / V
-    void* enc_dst = c->xlat ? (void*)((bf16*)c->enc_lat + (size_t)u0 * T * d) : c->enc_T;
+    // latent cross-attention keeps the encoder output itself (h16) for the whole batch instead of per-layer K / V
+    void* enc_dst = c->xlat ? (void*)((h16*)c->enc_lat + (size_t)u0 * T * d) : c->enc_T;
     WIPA_TRY(ln(c, c->ex, c->enc_ln_w, c->enc_ln_b, enc_dst, M, st));
     if (enc_out != nullptr) WIPA_TRY(launch_layernorm<float>(c->ex, c->enc_ln_w, c->enc_ln_b, enc_out, M, d, st));
     if (c->xlat) return WIPA_OK;
@@ -471,7 +471,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
     const wipa_arch& a = c->a;
     const int d = a.d_model, H = a.heads, ffn = a.ffn, V = a.vocab;
     const int skip = c->skip_mask;       // ablation bits: 1 LN, 2 self-attn, 4 cross-attn, 8 qkv, 16 d x d GEMMs, 32 fc1, 64 fc2, 128 logits
-    if (c->bf) WIPA_TRY(launch_embed<bf16>((const bf16*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
+    if (c->bf) WIPA_TRY(launch_embed<h16>((const h16*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
     else WIPA_TRY(launch_embed<float>((const float*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
     for (int l = 0; l < a.dec_layers; ++l) {
         const DecLayer& L = c->dec[l];
@@ -480,14 +480,14 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln1_w, L.ln1_b, c->dh, S, st));
         {
             EpiParams ep = epi(EPI_QKV_DEC, S, 3 * d);
-            ep.bias = L.qkv_b; ep.out = c->dq; ep.out1 = kp; ep.out2 = vp; ep.out_bf16 = c->bf;
+            ep.bias = L.qkv_b; ep.out = c->dq; ep.out1 = kp; ep.out2 = vp; ep.out_h16 = c->bf;
             ep.H = H; ep.d = d; ep.pos_ptr = c->d_pos; ep.block_table = c->block_table; ep.bt_stride = c->pages_per_seq;
             if (!(skip & 8)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.qkv_w, S, 3 * d, d, ep, c->bn_dec, st));
         }
         const int* anc = beam ? c->b_anc : nullptr;            // beam search reads every position from the slot that wrote it
         if (skip & 2) {}
-        else if (c->bf) WIPA_TRY(launch_self_attention<bf16>(c->dq, (const bf16*)kp, (const bf16*)vp, c->block_table, c->pages_per_seq,
-                                                        c->d_pos, (bf16*)c->dattn, S, H, st, anc, c->b_flip, c->beam_L));
+        else if (c->bf) WIPA_TRY(launch_self_attention<h16>(c->dq, (const h16*)kp, (const h16*)vp, c->block_table, c->pages_per_seq,
+                                                        c->d_pos, (h16*)c->dattn, S, H, st, anc, c->b_flip, c->beam_L));
         else WIPA_TRY(launch_self_attention<float>(c->dq, (const float*)kp, (const float*)vp, c->block_table, c->pages_per_seq,
                                                    c->d_pos, (float*)c->dattn, S, H, st, anc, c->b_flip, c->beam_L));
         {
@@ -498,13 +498,13 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
         if (c->xlat) {
             const int Hd = H * d;
-            {   // q' = LN(x) Wq'^T + bq'  -> bf16 [S, H, d]
+            {   // q' = LN(x) Wq'^T + bq'  -> h16 [S, H, d]
                 EpiParams ep = epi(EPI_STORE, S, Hd);
-                ep.bias = c->xlq_b[l]; ep.out = c->dqlat; ep.out_bf16 = 1;
+                ep.bias = c->xlq_b[l]; ep.out = c->dqlat; ep.out_h16 = 1;
                 if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, c->bn_xlq ? c->bn_xlq : ((S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec), st));
             }
-            if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const bf16*)c->dqlat, (const bf16*)c->enc_lat, c->max_batch, c->utt_of_seq,
-                                                                   (bf16*)c->dclat, S, H, WIPA_T_ENC, c->xl_part, c->xl_part_floats,
+            if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const h16*)c->dqlat, (const h16*)c->enc_lat, c->max_batch, c->utt_of_seq,
+                                                                   (h16*)c->dclat, S, H, WIPA_T_ENC, c->xl_part, c->xl_part_floats,
                                                                    c->ca_counters, st));
             {   // x += C Wo'^T + bo'   (K = H * d is long: split-K)
                 EpiParams ep = epi(EPI_RESADD, S, d);
@@ -515,14 +515,14 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         } else {
         {
             EpiParams ep = epi(EPI_STORE, S, d);
-            ep.bias = L.cq_b; ep.out = c->dq; ep.out_bf16 = 0;
+            ep.bias = L.cq_b; ep.out = c->dq; ep.out_h16 = 0;
             if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.cq_w, S, d, d, ep, c->bn_dec, st));
         }
         {
             const char* xk = (const char*)c->xkv + (size_t)(2 * l) * c->xkv_which_stride * c->esz;
             const char* xv = (const char*)c->xkv + (size_t)(2 * l + 1) * c->xkv_which_stride * c->esz;
             if (skip & 4) {}
-            else if (c->bf) WIPA_TRY(launch_cross_attention<bf16>(c->dq, (const bf16*)xk, (const bf16*)xv, c->utt_of_seq, (bf16*)c->dattn,
+            else if (c->bf) WIPA_TRY(launch_cross_attention<h16>(c->dq, (const h16*)xk, (const h16*)xv, c->utt_of_seq, (h16*)c->dattn,
                                                              c->ca_part, c->ca_counters, S, H, c->ca_split, 1, st));
             else WIPA_TRY(launch_cross_attention<float>(c->dq, (const float*)xk, (const float*)xv, c->utt_of_seq, (float*)c->dattn,
                                                         c->ca_part, c->ca_counters, S, H, c->ca_split, 1, st));
@@ -536,7 +536,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln3_w, L.ln3_b, c->dh, S, st));
         {
             EpiParams ep = epi(EPI_GELU, S, ffn);
-            ep.bias = L.fc1_b; ep.out = c->dffn; ep.out_bf16 = c->bf; ep.gelu_fast = c->bf;
+            ep.bias = L.fc1_b; ep.out = c->dffn; ep.out_h16 = c->bf; ep.gelu_fast = c->bf;
             // N = ffn tiles of 32 columns would not fit one wave once S needs two M tiles: use 64-wide tiles then
             if (!(skip & 32)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.fc1_w, S, ffn, d, ep, (S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec, st));
         }
@@ -560,7 +560,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         } else {
             float* dst = logits_mode == 2 ? logits_out : c->logits;
             EpiParams ep = epi(EPI_STORE, S, V);
-            ep.out = dst; ep.out_bf16 = 0; ep.vec_ok = 0;
+            ep.out = dst; ep.out_h16 = 0; ep.vec_ok = 0;
             ep.ldo = logits_mode == 2 ? ldo : V;
             ep.o_rpb = 1; ep.o_bstride = ep.ldo;                 // row m -> m * ldo
             WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits, st));
@@ -611,7 +611,11 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     WIPA_CHECK(arch->heads * WIPA_HEAD_DIM == arch->d_model, WIPA_EUNSUPPORTED, "head_dim must be 64 (d_model %d, heads %d)",
                arch->d_model, arch->heads);
     WIPA_CHECK(arch->ffn % 64 == 0 && arch->n_mels % 16 == 0 && arch->vocab > 0, WIPA_EINVAL, "bad ffn / n_mels / vocab");
-    WIPA_CHECK(arch->dtype == WIPA_DTYPE_F32 || arch->dtype == WIPA_DTYPE_BF16, WIPA_EINVAL, "bad dtype %d", arch->dtype);
+    WIPA_CHECK(arch->dtype == WIPA_DTYPE_F32 || arch->dtype == WIPA_DTYPE_BF16 || arch->dtype == WIPA_DTYPE_F16, WIPA_EINVAL,
+               "bad dtype %d", arch->dtype);
+    WIPA_CHECK(arch->dtype == WIPA_DTYPE_F32 || arch->dtype == WIPA_H16_DTYPE, WIPA_EUNSUPPORTED,
+               "this build of libwipa computes its 16-bit path in " WIPA_H16_NAME " (dtype %d); load %s for dtype %d", WIPA_H16_DTYPE,
+               arch->dtype == WIPA_DTYPE_BF16 ? "libwipa_bf16.so" : "libwipa.so", arch->dtype);
     WIPA_CHECK(max_batch >= 1 && max_beams >= 1 && max_batch * max_beams <= 4096, WIPA_EINVAL, "bad max_batch / max_beams");
     int dev = 0, major = 0;
     WIPA_CUDA_CHECK(cudaGetDevice(&dev));
@@ -621,7 +625,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     wipa_ctx* c = new wipa_ctx();
     c->a = *arch;
     c->max_batch = max_batch; c->max_beams = max_beams; c->max_seqs = max_batch * max_beams;
-    c->bf = arch->dtype == WIPA_DTYPE_BF16;
+    c->bf = arch->dtype != WIPA_DTYPE_F32;
     c->esz = c->bf ? 2 : 4;
     c->enc_mb = env_int("WIPA_ENC_MB", 32);
     if (c->enc_mb > max_batch) c->enc_mb = max_batch;
@@ -1017,6 +1021,8 @@ extern "C" int wipa_decode_beam(wipa_ctx* c, int B, int beams, float length_pena
     return launch_beam_finish(bs, B, max_new, out_ids, out_len, st);
 }
 
+extern "C" int wipa_h16_dtype(void) { return WIPA_H16_DTYPE; }
+
 extern "C" int wipa_ctx_get_info(wipa_ctx* c, int what, int64_t* out) {
     WIPA_CHECK(c && out, WIPA_EINVAL, "wipa_ctx_get_info: null argument");
     switch (what) {
@@ -1031,35 +1037,35 @@ extern "C" int wipa_ctx_get_info(wipa_ctx* c, int what, int64_t* out) {
 }
 
 // ---- standalone kernel entry points (tests / roofline) ----------------------------------------------
-extern "C" int wipa_test_gemm_bf16(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int block_n,
+extern "C" int wipa_test_gemm_h16(const void* A, const void* W, const float* bias, float* C, int M, int N, int K, int block_n,
                                    void* stream) {
     EpiParams ep = epi(EPI_STORE, M, N);
-    ep.bias = bias; ep.out = C; ep.out_bf16 = 0;
-    return launch_gemm_bf16(plainA(A, M, K), (const bf16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
+    ep.bias = bias; ep.out = C; ep.out_h16 = 0;
+    return launch_gemm_h16(plainA(A, M, K), (const h16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
 }
 
 extern "C" int wipa_test_gemm_f32(const float* A, const float* W, const float* bias, float* C, int M, int N, int K, void* stream) {
     EpiParams ep = epi(EPI_STORE, M, N);
-    ep.bias = bias; ep.out = C; ep.out_bf16 = 0;
+    ep.bias = bias; ep.out = C; ep.out_h16 = 0;
     return launch_gemm_f32(plainA(A, M, K), W, M, N, K, ep, (cudaStream_t)stream);
 }
 
-// Epilogue variants of the bf16 GEMMs on encoder-shaped problems: M = rows_per_batch * n_batch rows, processed as the
+// Epilogue variants of the h16 GEMMs on encoder-shaped problems: M = rows_per_batch * n_batch rows, processed as the
 // encoder does (tiles never straddle a batch).  mode: 0 bias, 1 bias + GELU, 2 bias + residual (fp32 in place of `out`),
-// 3 bias + q|k|v head split into [3][n_batch][H][rows_per_batch][64] (N = 3 * H * 64).  `out` is bf16 when out_bf16 != 0.
+// 3 bias + q|k|v head split into [3][n_batch][H][rows_per_batch][64] (N = 3 * H * 64).  `out` is h16 when out_h16 != 0.
 extern "C" int wipa_test_gemm_epilogue(const void* A, const void* W, const float* bias, const float* resid, void* out,
-                                       int rows_per_batch, int n_batch, int N, int K, int mode, int out_bf16, int block_n,
+                                       int rows_per_batch, int n_batch, int N, int K, int mode, int out_h16, int block_n,
                                        void* stream) {
     WIPA_CHECK(A && W && out && rows_per_batch > 0 && n_batch > 0, WIPA_EINVAL, "wipa_test_gemm_epilogue: bad argument");
     WIPA_CHECK(mode >= 0 && mode <= 3, WIPA_EINVAL, "wipa_test_gemm_epilogue: mode must be 0..3");
     const int M = rows_per_batch * n_batch;
     static const int modes[4] = {EPI_STORE, EPI_GELU, EPI_RESADD, EPI_HEADS};
     EpiParams ep = epi(modes[mode], M, N);
-    ep.bias = bias; ep.out = out; ep.out_bf16 = out_bf16 ? 1 : 0;
+    ep.bias = bias; ep.out = out; ep.out_h16 = out_h16 ? 1 : 0;
     ep.o_rpb = rows_per_batch; ep.o_bstride = (long long)rows_per_batch * N;
-    if (mode == 1) ep.gelu_fast = ep.out_bf16;
+    if (mode == 1) ep.gelu_fast = ep.out_h16;
     if (mode == 2) {
-        WIPA_CHECK(resid != nullptr && !out_bf16, WIPA_EINVAL, "wipa_test_gemm_epilogue: residual mode is fp32 and needs resid");
+        WIPA_CHECK(resid != nullptr && !out_h16, WIPA_EINVAL, "wipa_test_gemm_epilogue: residual mode is fp32 and needs resid");
         ep.resid = resid;
     }
     if (mode == 3) {
@@ -1068,17 +1074,17 @@ extern "C" int wipa_test_gemm_epilogue(const void* A, const void* W, const float
         ep.which_stride = (long long)n_batch * ep.H * rows_per_batch * WIPA_HEAD_DIM;
     }
     AOperand a; a.ptr = A; a.lda = K; a.a_rpb = rows_per_batch; a.a_bstride = (long long)rows_per_batch * K; a.n_batch = n_batch;
-    return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
+    return launch_gemm_h16(a, (const h16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
 }
 
 // conv-as-GEMM addressing check: row m = (batch, t) of A starts at A + batch*bstride + t*lda and spans K >= lda elements
-extern "C" int wipa_test_gemm_rows(const void* A, int is_bf16, long long lda, int rows_per_batch, long long bstride, int n_batch,
+extern "C" int wipa_test_gemm_rows(const void* A, int is_h16, long long lda, int rows_per_batch, long long bstride, int n_batch,
                                    const void* W, float* C, int N, int K, int block_n, void* stream) {
     const int M = rows_per_batch * n_batch;
     EpiParams ep = epi(EPI_STORE, M, N);
-    ep.out = C; ep.out_bf16 = 0;
+    ep.out = C; ep.out_h16 = 0;
     AOperand a; a.ptr = A; a.lda = lda; a.a_rpb = rows_per_batch; a.a_bstride = bstride; a.n_batch = n_batch;
-    if (is_bf16) return launch_gemm_bf16(a, (const bf16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
+    if (is_h16) return launch_gemm_h16(a, (const h16*)W, M, N, K, ep, block_n, (cudaStream_t)stream);
     return launch_gemm_f32(a, (const float*)W, M, N, K, ep, (cudaStream_t)stream);
 }
 
@@ -1089,7 +1095,7 @@ extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* 
     cudaStream_t st = (cudaStream_t)stream;
     const char* xk = (const char*)c->xkv + (size_t)(2 * layer) * c->xkv_which_stride * c->esz;
     const char* xv = (const char*)c->xkv + (size_t)(2 * layer + 1) * c->xkv_which_stride * c->esz;
-    if (c->bf) WIPA_TRY(launch_cross_attention<bf16>(q, (const bf16*)xk, (const bf16*)xv, nullptr, (bf16*)c->dattn, c->ca_part,
+    if (c->bf) WIPA_TRY(launch_cross_attention<h16>(q, (const h16*)xk, (const h16*)xv, nullptr, (h16*)c->dattn, c->ca_part,
                                                      c->ca_counters, B, c->a.heads, c->ca_split, 0, st));
     else WIPA_TRY(launch_cross_attention<float>(q, (const float*)xk, (const float*)xv, nullptr, (float*)c->dattn, c->ca_part,
                                                 c->ca_counters, B, c->a.heads, c->ca_split, 0, st));
@@ -1097,8 +1103,8 @@ extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* 
     return WIPA_OK;
 }
 
-// latent cross-attention kernel alone: Qp bf16 [S, H, 64H] absorbed queries, E bf16 [U, T, 64H], utt_of_seq int32 [S]
-// -> C bf16 [S, H, 64H] = softmax_t(Qp[s, h] . E[u, t]) E[u].  All device pointers.
+// latent cross-attention kernel alone: Qp h16 [S, H, 64H] absorbed queries, E h16 [U, T, 64H], utt_of_seq int32 [S]
+// -> C h16 [S, H, 64H] = softmax_t(Qp[s, h] . E[u, t]) E[u].  All device pointers.
 extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
                                            void* stream) {
     WIPA_CHECK(Qp && E && utt_of_seq && C && S >= 1 && cross_attention_latent_supported(H), WIPA_EINVAL,
@@ -1125,41 +1131,41 @@ extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U,
         WIPA_CUDA_CHECK(cudaMemset(counters, 0, (size_t)S * 4));
         counters_cap = S;
     }
-    return launch_cross_attention_latent((const bf16*)Qp, (const bf16*)E, U, utt_of_seq, (bf16*)C, S, H, T, part, part_floats, counters,
+    return launch_cross_attention_latent((const h16*)Qp, (const h16*)E, U, utt_of_seq, (h16*)C, S, H, T, part, part_floats, counters,
                                          (cudaStream_t)stream);
 }
 
-// decoder self-attention step alone over a caller-built paged cache: kpool / vpool [page][H][16][64] (bf16 or f32),
+// decoder self-attention step alone over a caller-built paged cache: kpool / vpool [page][H][16][64] (h16 or f32),
 // block_table int32 [B, bt_stride], *pos_ptr = index of the newest position; q f32 [B, H*64]; out [B, H*64] in the pool type
 extern "C" int wipa_test_self_attn(const float* q, const void* kpool, const void* vpool, const int* block_table, int bt_stride,
-                                   const int* pos_ptr, void* out, int B, int H, int is_bf16, void* stream) {
+                                   const int* pos_ptr, void* out, int B, int H, int is_h16, void* stream) {
     WIPA_CHECK(q && kpool && vpool && block_table && pos_ptr && out && B >= 1 && H >= 1, WIPA_EINVAL, "wipa_test_self_attn: bad argument");
-    if (is_bf16) return launch_self_attention<bf16>(q, (const bf16*)kpool, (const bf16*)vpool, block_table, bt_stride, pos_ptr,
-                                                    (bf16*)out, B, H, (cudaStream_t)stream);
+    if (is_h16) return launch_self_attention<h16>(q, (const h16*)kpool, (const h16*)vpool, block_table, bt_stride, pos_ptr,
+                                                    (h16*)out, B, H, (cudaStream_t)stream);
     return launch_self_attention<float>(q, (const float*)kpool, (const float*)vpool, block_table, bt_stride, pos_ptr, (float*)out,
                                         B, H, (cudaStream_t)stream);
 }
 
-// encoder self-attention on bf16 device buffers, no conversions (timing): q,k,v bf16 [B,H,T,64] -> out bf16 [B,T,H*64]
-extern "C" int wipa_test_enc_attention_bf16(const void* q, const void* k, const void* v, void* out, int B, int H, int T, int tc,
+// encoder self-attention on h16 device buffers, no conversions (timing): q,k,v h16 [B,H,T,64] -> out h16 [B,T,H*64]
+extern "C" int wipa_test_enc_attention_h16(const void* q, const void* k, const void* v, void* out, int B, int H, int T, int tc,
                                             void* stream) {
-    if (tc) return launch_enc_attention_tc((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, B, H, T, (cudaStream_t)stream);
-    return launch_enc_attention<bf16>((const bf16*)q, (const bf16*)k, (const bf16*)v, (bf16*)out, B, H, T, (cudaStream_t)stream);
+    if (tc) return launch_enc_attention_tc((const h16*)q, (const h16*)k, (const h16*)v, (h16*)out, B, H, T, (cudaStream_t)stream);
+    return launch_enc_attention<h16>((const h16*)q, (const h16*)k, (const h16*)v, (h16*)out, B, H, T, (cudaStream_t)stream);
 }
 
-// encoder self-attention alone: q,k,v f32 [B,H,T,64] (q pre-scaled) -> out f32 [B,T,H*64]; use_bf16 selects the kernel family
+// encoder self-attention alone: q,k,v f32 [B,H,T,64] (q pre-scaled) -> out f32 [B,T,H*64]; use_h16 selects the kernel family
 extern "C" int wipa_test_enc_attention(const float* q, const float* k, const float* v, float* out, int B, int H, int T,
-                                       int use_bf16, void* stream) {
+                                       int use_h16, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!use_bf16) return launch_enc_attention<float>(q, k, v, out, B, H, T, st);
+    if (!use_h16) return launch_enc_attention<float>(q, k, v, out, B, H, T, st);
     const long long n = (long long)B * H * T * 64;
-    bf16* buf = nullptr;
-    WIPA_CUDA_CHECK(cudaMalloc(&buf, sizeof(bf16) * (size_t)n * 4));
+    h16* buf = nullptr;
+    WIPA_CUDA_CHECK(cudaMalloc(&buf, sizeof(h16) * (size_t)n * 4));
     int r = launch_convert(q, buf, n, 1.f, 1, st);
     if (r == WIPA_OK) r = launch_convert(k, buf + n, n, 1.f, 1, st);
     if (r == WIPA_OK) r = launch_convert(v, buf + 2 * n, n, 1.f, 1, st);
-    if (r == WIPA_OK) r = use_bf16 == 2 ? launch_enc_attention_tc(buf, buf + n, buf + 2 * n, buf + 3 * n, B, H, T, st)
-                                        : launch_enc_attention<bf16>(buf, buf + n, buf + 2 * n, buf + 3 * n, B, H, T, st);
+    if (r == WIPA_OK) r = use_h16 == 2 ? launch_enc_attention_tc(buf, buf + n, buf + 2 * n, buf + 3 * n, B, H, T, st)
+                                        : launch_enc_attention<h16>(buf, buf + n, buf + 2 * n, buf + 3 * n, B, H, T, st);
     if (r == WIPA_OK) r = launch_to_f32(buf + 3 * n, 1, out, n, st);
     cudaStreamSynchronize(st);
     cudaFree(buf);

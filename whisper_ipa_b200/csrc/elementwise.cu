@@ -57,7 +57,7 @@ int launch_layernorm(const float* x, const float* w, const float* b, T* out, int
     return WIPA_OK;
 }
 template int launch_layernorm<float>(const float*, const float*, const float*, float*, int, int, cudaStream_t);
-template int launch_layernorm<bf16>(const float*, const float*, const float*, bf16*, int, int, cudaStream_t);
+template int launch_layernorm<h16>(const float*, const float*, const float*, h16*, int, int, cudaStream_t);
 
 // ================================================================================================
 // mel [B, C, 3000] f32 (HF layout) -> rows [B, 3002, C] in T, written at rows 1..3000; rows 0 and 3001 are the
@@ -96,7 +96,7 @@ int launch_mel_to_rows(const float* mel, T* rows, int B, int C, cudaStream_t st)
     return WIPA_OK;
 }
 template int launch_mel_to_rows<float>(const float*, float*, int, int, cudaStream_t);
-template int launch_mel_to_rows<bf16>(const float*, bf16*, int, int, cudaStream_t);
+template int launch_mel_to_rows<h16>(const float*, h16*, int, int, cudaStream_t);
 
 // ================================================================================================
 // decoder input: x[b] = embed_tokens[tok[b]] + embed_positions[*pos]   (HF:...modeling_whisper.py:737-760)
@@ -121,32 +121,32 @@ int launch_embed(const T* tok_emb, const float* pos_emb, const int* tok, const i
     return WIPA_OK;
 }
 template int launch_embed<float>(const float*, const float*, const int*, const int*, float*, int, int, cudaStream_t);
-template int launch_embed<bf16>(const bf16*, const float*, const int*, const int*, float*, int, int, cudaStream_t);
+template int launch_embed<h16>(const h16*, const float*, const int*, const int*, float*, int, int, cudaStream_t);
 
 // ================================================================================================
-// weight import: fp32 state_dict tensor -> context storage (fp32 or bf16), optional exact scale (q * 2^-3)
+// weight import: fp32 state_dict tensor -> context storage (fp32 or h16), optional exact scale (q * 2^-3)
 // ================================================================================================
-__global__ void convert_kernel(const float* __restrict__ src, void* __restrict__ dst, long long n, float scale, int to_bf16) {
+__global__ void convert_kernel(const float* __restrict__ src, void* __restrict__ dst, long long n, float scale, int to_h16) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < n; i += stride) {
         const float v = src[i] * scale;
-        if (to_bf16) reinterpret_cast<bf16*>(dst)[i] = __float2bfloat16_rn(v);
+        if (to_h16) reinterpret_cast<h16*>(dst)[i] = f32_to_h16(v);
         else reinterpret_cast<float*>(dst)[i] = v;
     }
 }
 
-int launch_convert(const float* src, void* dst, long long n, float scale, int to_bf16, cudaStream_t st) {
+int launch_convert(const float* src, void* dst, long long n, float scale, int to_h16, cudaStream_t st) {
     if (n == 0) return WIPA_OK;
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    convert_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n, scale, to_bf16);
+    convert_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n, scale, to_h16);
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
 
 // conv1d weight [N, C, 3] -> GEMM weight [N, 3*C] with k = tap * C + c (matches rows of [x[t-1] | x[t] | x[t+1]])
-__global__ void conv_weight_kernel(const float* __restrict__ src, void* __restrict__ dst, int N, int C, int to_bf16) {
+__global__ void conv_weight_kernel(const float* __restrict__ src, void* __restrict__ dst, int N, int C, int to_h16) {
     const long long total = (long long)N * C * 3;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -155,15 +155,15 @@ __global__ void conv_weight_kernel(const float* __restrict__ src, void* __restri
         const int r = (int)(i - (long long)n * 3 * C);
         const int tap = r / C, c = r - tap * C;
         const float v = src[((long long)n * C + c) * 3 + tap];
-        if (to_bf16) reinterpret_cast<bf16*>(dst)[i] = __float2bfloat16_rn(v);
+        if (to_h16) reinterpret_cast<h16*>(dst)[i] = f32_to_h16(v);
         else reinterpret_cast<float*>(dst)[i] = v;
     }
 }
 
-int launch_conv_weight(const float* src, void* dst, int N, int C, int to_bf16, cudaStream_t st) {
+int launch_conv_weight(const float* src, void* dst, int N, int C, int to_h16, cudaStream_t st) {
     long long blocks = ((long long)N * C * 3 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    conv_weight_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, N, C, to_bf16);
+    conv_weight_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, N, C, to_h16);
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

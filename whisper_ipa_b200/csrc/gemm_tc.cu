@@ -1,4 +1,4 @@
-// bf16 path GEMM on the 5th-generation tensor cores:  C[M,N] = A[M,K] * W[N,K]^T, fp32 accumulate in TMEM.
+// h16 path GEMM on the 5th-generation tensor cores:  C[M,N] = A[M,K] * W[N,K]^T, fp32 accumulate in TMEM.
 //
 //   warp 0      TMA producer: cp.async.bulk.tensor tiles of A (128 x 64) and W (BN x 64), 128B-swizzled,
 //               into a STAGES-deep shared-memory ring guarded by full/empty mbarriers (KPB k-blocks per ring slot)
@@ -56,7 +56,7 @@ __device__ unsigned long long g_gemm_dbg[4096 * 8];
 // only be refilled when ALL CTAs of the cluster have consumed it: tcgen05.commit multicasts the slot release.
 template <int BN, int BOXM, int CL>
 __global__ void __launch_bounds__(192)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
+gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
                     int tiles_per_batch, int a_rpb, EpiParams ep) {
     using Cfg = TcCfg<BN, BOXM>;
     extern __shared__ uint8_t tc_smem_raw[];
@@ -153,7 +153,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = ptx::idesc_bf16_f32(TC_BM, BN);
+        constexpr uint32_t idesc = ptx::idesc_h16_f32(TC_BM, BN);
         constexpr int KPB = Cfg::KPB;
         const int num_g = (num_kb + KPB - 1) / KPB;
         const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sA));
@@ -173,7 +173,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     if (i < nk) {
 #pragma unroll
                         for (int k = 0; k < TC_BK / 16; ++k)
-                            ptx::umma_bf16(tmem_base, ptx::smem_desc_sw128(a_lo + (uint32_t)i * (Cfg::A_BYTES >> 4) + 2 * k),
+                            ptx::umma_h16(tmem_base, ptx::smem_desc_sw128(a_lo + (uint32_t)i * (Cfg::A_BYTES >> 4) + 2 * k),
                                            ptx::smem_desc_sw128(w_lo + (uint32_t)i * (Cfg::W_BYTES >> 4) + 2 * k), idesc,
                                            (g | i | k) != 0 ? 1u : 0u);
                     }
@@ -347,7 +347,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
              const cuuint32_t* box) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+    CUresult r = g_encode(map, WIPA_H16_TMA_TYPE, (cuuint32_t)rank, const_cast<void*>(base), dims,
                           strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -365,11 +365,11 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int ti
               int N, EpiParams ep, cudaStream_t st, int splits = 1) {
     using Cfg = TcCfg<BN, BOXM>;
     static SmemAttr attr;
-    WIPA_TRY(wipa_ensure_smem(gemm_bf16_tc_kernel<BN, BOXM, CL>, (size_t)Cfg::SMEM, attr));
+    WIPA_TRY(wipa_ensure_smem(gemm_h16_tc_kernel<BN, BOXM, CL>, (size_t)Cfg::SMEM, attr));
     dim3 grid(cdiv(N, BN), tiles_per_batch * n_batch, splits);
     if (ep.mode == EPI_ARGMAX) ep.n_tiles = grid.x;
     if (CL == 1) {
-        WIPA_CUDA_CHECK(wipa_launch(gemm_bf16_tc_kernel<BN, BOXM, CL>, grid, dim3(192), (size_t)Cfg::SMEM, st, tmA, tmW, num_kb,
+        WIPA_CUDA_CHECK(wipa_launch(gemm_h16_tc_kernel<BN, BOXM, CL>, grid, dim3(192), (size_t)Cfg::SMEM, st, tmA, tmW, num_kb,
                                     tiles_per_batch, a_rpb, ep));
     } else {
         cudaLaunchConfig_t cfg = {};
@@ -381,7 +381,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int ti
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = (g_wipa_pdl & WIPA_PDL_CLASS) ? 2 : 1;
-        WIPA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<BN, BOXM, CL>, tmA, tmW, num_kb, tiles_per_batch, a_rpb, ep));
+        WIPA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_h16_tc_kernel<BN, BOXM, CL>, tmA, tmW, num_kb, tiles_per_batch, a_rpb, ep));
     }
     WIPA_LAUNCHED();
     return WIPA_OK;
@@ -400,7 +400,7 @@ int wipa_init_tma() {
     return WIPA_OK;
 }
 
-int gemm_bf16_num_tiles(int N, int block_n) { return cdiv(N, block_n); }
+int gemm_h16_num_tiles(int N, int block_n) { return cdiv(N, block_n); }
 
 extern "C" int wipa_debug_gemm_stamps(unsigned long long* host_out, int n) {
 #ifdef WIPA_GEMM_DBG
@@ -411,15 +411,15 @@ extern "C" int wipa_debug_gemm_stamps(unsigned long long* host_out, int n) {
 #endif
 }
 
-int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep_in, int block_n,
+int launch_gemm_h16(const AOperand& a, const h16* W, int M, int N, int K, const EpiParams& ep_in, int block_n,
                      cudaStream_t st) {
-    if (block_n == 0) return launch_gemm_bf16_persistent(a, W, M, N, K, ep_in, st);     // 128 x 256 persistent kernel
+    if (block_n == 0) return launch_gemm_h16_persistent(a, W, M, N, K, ep_in, st);     // 128 x 256 persistent kernel
     WIPA_TRY(wipa_init_tma());
     WIPA_CHECK(K % 8 == 0 && a.lda % 8 == 0 && a.a_bstride % 8 == 0, WIPA_EINVAL,
-               "gemm_bf16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");
-    WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_bf16: M != rows_per_batch * batches");
+               "gemm_h16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");
+    WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_h16: M != rows_per_batch * batches");
     WIPA_CHECK((reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, WIPA_EINVAL,
-               "gemm_bf16: operands must be 16-byte aligned");
+               "gemm_h16: operands must be 16-byte aligned");
     const int box_m = (a.a_rpb <= 64 && block_n == 32) ? 64 : 128;
     // WIPA_GEMM_MULTICAST=1: clusters of 4 N tiles with A multicast for the narrow (decode) tiles whenever the N tiles
     // divide evenly.  Parity-tested, but OFF by default: measured on B200 at B=256 the two cluster barriers and the
@@ -460,6 +460,6 @@ int launch_gemm_bf16(const AOperand& a, const bf16* W, int M, int N, int K, cons
         case 256: return launch_bn<256, 128, 1>(tmA, tmW, num_kb, tpb, a.n_batch, a.a_rpb, N, ep, st);
         default: break;
     }
-    wipa_set_error("gemm_bf16: unsupported block_n %d", block_n);
+    wipa_set_error("gemm_h16: unsupported block_n %d", block_n);
     return WIPA_EINVAL;
 }

@@ -1,4 +1,4 @@
-// Encoder-side bf16 GEMM on tcgen05: persistent, warp-specialised, double-buffered accumulators.
+// Encoder-side h16 GEMM on tcgen05: persistent, warp-specialised, double-buffered accumulators.
 //
 //   C[M,N] = A[M,K] * W[N,K]^T with M in the tens of thousands (32 clips x 1500 frames per encoder micro-batch).
 //
@@ -8,7 +8,7 @@
 //   warp 1      tcgen05 issuer: M128 x N256 x K16 MMAs (128 cycles each, 96 B/cycle of operand reads - under the 128
 //               B/cycle shared-memory limit that caps N = 128 tiles) into one of TWO 256-column TMEM accumulators
 //   warps 2-9   epilogue, overlapped with the next tile's main loop: tcgen05.ld (lane = row), then per instantiation
-//               (G2_EP_*): bf16 results -> bias + packed-f32x2 GELU by the row owner -> bf16 staging tile -> 16-byte
+//               (G2_EP_*): h16 results -> bias + packed-f32x2 GELU by the row owner -> h16 staging tile -> 16-byte
 //               pieces, 8 lanes per 128-byte output line; fp32 results -> fp32 staging tile -> (row, 8-column) items
 //               with coalesced residual loads; anything else -> the generic run-time epilogue (common.cuh epi_group)
 //
@@ -42,7 +42,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // Epilogue variants.  The encoder's four shapes get their own instantiation so that each carries only the code it runs
 // (the generic kernel's SASS is ~64 KB and the eight epilogue warps sit at different places in it: 6 % of its samples
 // were instruction-fetch stalls); anything else takes G2_EP_GENERIC, which decides per chunk at run time.
-enum { G2_EP_GENERIC = 0, G2_EP_HEADS_BF16 = 1, G2_EP_RESADD_F32 = 2, G2_EP_GELU_BF16 = 3, G2_EP_STORE_BF16 = 4 };
+enum { G2_EP_GENERIC = 0, G2_EP_HEADS_H16 = 1, G2_EP_RESADD_F32 = 2, G2_EP_GELU_H16 = 3, G2_EP_STORE_H16 = 4 };
 
 // Two GELUs at a time on the packed fp32 pipe (fma/mul.f32x2): 9 issue slots per value instead of 15.  Same A&S 7.1.26
 // erf as gelu_erf_fast; the sign select is folded into gelu(x) = max(x, 0) - |x| * h(|x|).
@@ -82,7 +82,7 @@ __device__ __forceinline__ void gelu_erf_fast2(float& x0, float& x1) {
 
 template <int EP>
 __global__ void __launch_bounds__(G2_THREADS, 1)
-gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
+gemm_h16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
                             int tiles_per_batch, int n_mtiles, int n_ntiles, int a_rpb, EpiParams ep) {
     extern __shared__ uint8_t g2_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(g2_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -138,7 +138,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = ptx::idesc_bf16_f32(G2_BM, G2_BN);
+        constexpr uint32_t idesc = ptx::idesc_h16_f32(G2_BM, G2_BN);
         const uint32_t a_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sA));
         const uint32_t w_lo0 = ptx::smem_desc_lo(ptx::smem_u32(sW));
         int s = 0;
@@ -157,7 +157,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                     const uint32_t w_lo = w_lo0 + (uint32_t)s * (G2_W_BYTES >> 4);
 #pragma unroll
                     for (int k = 0; k < G2_BK / 16; ++k)
-                        ptx::umma_bf16(acc, ptx::smem_desc_sw128(a_lo + 2 * k), ptx::smem_desc_sw128(w_lo + 2 * k), idesc,
+                        ptx::umma_h16(acc, ptx::smem_desc_sw128(a_lo + 2 * k), ptx::smem_desc_sw128(w_lo + 2 * k), idesc,
                                        (kb | k) != 0 ? 1u : 0u);
                     ptx::umma_commit(&empty[s]);
                 }
@@ -183,7 +183,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
             const int t0 = (mt - batch * tiles_per_batch) * G2_BM;
             const int n0 = nt * G2_BN + half * 128;
             const int buf = it & 1;
-            constexpr bool kBf16Staged = EP == G2_EP_HEADS_BF16 || EP == G2_EP_GELU_BF16 || EP == G2_EP_STORE_BF16;
+            constexpr bool kBf16Staged = EP == G2_EP_HEADS_H16 || EP == G2_EP_GELU_H16 || EP == G2_EP_STORE_H16;
             float bias_mine = 0.f;                              // column n0 + tih of the bias, fetched ahead of the accumulator
             if (kBf16Staged && ep.bias != nullptr && n0 + tih < ep.N) bias_mine = __ldg(ep.bias + n0 + tih);
             ptx::mbar_wait(&tmem_full[buf], (it >> 1) & 1);
@@ -202,15 +202,15 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
                 }
-                // ---- bf16 results: bias / GELU by the row-owning thread, then a bf16 staging tile ------------------------------
+                // ---- h16 results: bias / GELU by the row-owning thread, then a h16 staging tile ------------------------------
                 // (The epilogue is issue-bound, not bandwidth-bound: ~24 % of each epilogue warp's samples are `selected`.
-                // Staging the finished bf16 values halves the shared-memory instructions; unstaged row-per-thread stores
+                // Staging the finished h16 values halves the shared-memory instructions; unstaged row-per-thread stores
                 // were tried and are slower: 32 partial lines per store instruction.)
                 const int nc0 = n0 + c * 64;
                 if (EP != G2_EP_GENERIC && nc0 >= ep.N) continue;   // N % 64 == 0: a chunk of the last n-tile is all in or all out
                                                                     // (uniform over the half-group, so its barriers stay matched)
                 if constexpr (kBf16Staged) {
-                    constexpr uint32_t PITCH = 144;                // bytes per staged row: 64 bf16 + 16 (conflict-free 16-byte rows)
+                    constexpr uint32_t PITCH = 144;                // bytes per staged row: 64 h16 + 16 (conflict-free 16-byte rows)
                     named_bar_sync(bar_id, 128);               // previous chunk's readers are done with the staging tile; bias tile visible
                     if (ep.bias != nullptr) {
                         const uint32_t sb = ptx::smem_u32(s_bias + half * 128 + c * 64);
@@ -220,15 +220,15 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                             v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                         }
                     }
-                    if constexpr (EP == G2_EP_GELU_BF16) {
+                    if constexpr (EP == G2_EP_GELU_H16) {
 #pragma unroll
                         for (int i = 0; i < 64; i += 2) gelu_erf_fast2(v[i], v[i + 1]);
                     }
 #pragma unroll
                     for (int i = 0; i < 64; i += 8) {
                         uint4 u;
-                        u.x = pack_bf16x2(v[i], v[i + 1]); u.y = pack_bf16x2(v[i + 2], v[i + 3]);
-                        u.z = pack_bf16x2(v[i + 4], v[i + 5]); u.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                        u.x = pack_h16x2(v[i], v[i + 1]); u.y = pack_h16x2(v[i + 2], v[i + 3]);
+                        u.z = pack_h16x2(v[i + 4], v[i + 5]); u.w = pack_h16x2(v[i + 6], v[i + 7]);
                         asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(st_s + (uint32_t)r * PITCH + (uint32_t)i * 2u),
                                      "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
                     }
@@ -238,7 +238,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                     const int m_first = batch * a_rpb + t0;
                     long long base_off, wrap_off, row_pitch;
                     int row0, period;                              // row of tile row 0 within its clip / output batch, and the period
-                    if constexpr (EP == G2_EP_HEADS_BF16) {
+                    if constexpr (EP == G2_EP_HEADS_H16) {
                         const int which = nc0 / ep.d;
                         const int h = (nc0 - which * ep.d) >> 6;
                         const int b0 = m_first / ep.T;
@@ -253,7 +253,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                         wrap_off = ep.o_bstride - (long long)ep.o_rpb * ep.ldo;
                         row_pitch = ep.ldo;
                     }
-                    bf16* const out_b = reinterpret_cast<bf16*>(ep.out) + base_off;
+                    h16* const out_b = reinterpret_cast<h16*>(ep.out) + base_off;
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int rr = rr0 + j * 16;
@@ -309,7 +309,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                                 const float4 x1 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8 + 4) * 4u);
                                 float w[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
                                               x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
-                                store_group<8>(ep.out, ep.out_bf16, wbase + ((long long)bb * ep.H * ep.T + tt) * WIPA_HEAD_DIM, w, true);
+                                store_group<8>(ep.out, ep.out_h16, wbase + ((long long)bb * ep.H * ep.T + tt) * WIPA_HEAD_DIM, w, true);
                             }
                         }
                     } else {
@@ -346,7 +346,7 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                             }
                         } else {                                    // EPI_STORE / EPI_GELU
                             const bool gelu = ep.mode == EPI_GELU;
-                            const bool gelu_fast = gelu && ep.out_bf16;
+                            const bool gelu_fast = gelu && ep.out_h16;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const int rr = rr0 + j * 16;
@@ -355,14 +355,14 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                                     const float4 x1 = ptx::lds128(st_s + (uint32_t)(rr * G2_LDS + c8 * 8 + 4) * 4u);
                                     float w[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
                                                   x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
-                                    if (gelu_fast) {                 // bf16 output: two MUFU + ~14 FMA-pipe instructions per value
+                                    if (gelu_fast) {                 // h16 output: two MUFU + ~14 FMA-pipe instructions per value
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) w[i] = gelu_erf_fast(w[i]);
                                     } else if (gelu) {
 #pragma unroll
                                         for (int i = 0; i < 8; ++i) w[i] = gelu_erf(w[i]);
                                     }
-                                    store_group<8>(ep.out, ep.out_bf16, rowoff[j], w, true);
+                                    store_group<8>(ep.out, ep.out_h16, rowoff[j], w, true);
                                 }
                             }
                         }
@@ -392,11 +392,11 @@ gemm_bf16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 int g2_make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
                 const cuuint32_t* box) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g2_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+    CUresult r = g2_encode(map, WIPA_H16_TMA_TYPE, (cuuint32_t)rank, const_cast<void*>(base), dims,
                            strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        wipa_set_error("gemm_bf16_persistent: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        wipa_set_error("gemm_h16_persistent: cuTensorMapEncodeTiled failed (%d)", (int)r);
         return WIPA_ECUDA;
     }
     return WIPA_OK;
@@ -404,7 +404,7 @@ int g2_make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* 
 
 }  // namespace
 
-int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, int K, const EpiParams& ep_in, cudaStream_t st) {
+int launch_gemm_h16_persistent(const AOperand& a, const h16* W, int M, int N, int K, const EpiParams& ep_in, cudaStream_t st) {
     if (g2_encode == nullptr) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -413,9 +413,9 @@ int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, 
         g2_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
     WIPA_CHECK(K % 8 == 0 && a.lda % 8 == 0 && a.a_bstride % 8 == 0, WIPA_EINVAL,
-               "gemm_bf16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");
-    WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_bf16: M != rows_per_batch * batches");
-    WIPA_CHECK(ep_in.mode != EPI_ARGMAX && ep_in.mode != EPI_QKV_DEC, WIPA_EINVAL, "gemm_bf16_persistent: decode-only epilogue");
+               "gemm_h16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");
+    WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_h16: M != rows_per_batch * batches");
+    WIPA_CHECK(ep_in.mode != EPI_ARGMAX && ep_in.mode != EPI_QKV_DEC, WIPA_EINVAL, "gemm_h16_persistent: decode-only epilogue");
     CUtensorMap tmA, tmW;
     {
         cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a.a_rpb, (cuuint64_t)a.n_batch};
@@ -445,25 +445,25 @@ int launch_gemm_bf16_persistent(const AOperand& a, const bf16* W, int M, int N, 
     // specialised epilogues: every 64-column chunk is full and a 128-row tile crosses at most one clip / batch boundary
     int variant = G2_EP_GENERIC;
     if (ep.vec_ok && N % 64 == 0) {
-        if (ep.mode == EPI_HEADS && ep.out_bf16 && ep.T >= G2_BM && ep.vt_which < 0 && ep.d % 64 == 0) variant = G2_EP_HEADS_BF16;
-        else if (ep.mode == EPI_RESADD && !ep.out_bf16 && ep.o_rpb >= G2_BM) variant = G2_EP_RESADD_F32;
-        else if (ep.mode == EPI_GELU && ep.out_bf16 && ep.o_rpb >= G2_BM) variant = G2_EP_GELU_BF16;
-        else if (ep.mode == EPI_STORE && ep.out_bf16 && ep.o_rpb >= G2_BM) variant = G2_EP_STORE_BF16;
+        if (ep.mode == EPI_HEADS && ep.out_h16 && ep.T >= G2_BM && ep.vt_which < 0 && ep.d % 64 == 0) variant = G2_EP_HEADS_H16;
+        else if (ep.mode == EPI_RESADD && !ep.out_h16 && ep.o_rpb >= G2_BM) variant = G2_EP_RESADD_F32;
+        else if (ep.mode == EPI_GELU && ep.out_h16 && ep.o_rpb >= G2_BM) variant = G2_EP_GELU_H16;
+        else if (ep.mode == EPI_STORE && ep.out_h16 && ep.o_rpb >= G2_BM) variant = G2_EP_STORE_H16;
     }
     static const char* force = getenv("WIPA_G2_GENERIC");      // experiment / test switch: always the run-time epilogue
     if (force != nullptr && force[0] == '1') variant = G2_EP_GENERIC;
 #define G2_LAUNCH(EPV)                                                                                                        \
     {                                                                                                                         \
         static SmemAttr attr;                                                                                                 \
-        WIPA_TRY(wipa_ensure_smem(gemm_bf16_persistent_kernel<EPV>, (size_t)G2_SMEM, attr));                                  \
-        gemm_bf16_persistent_kernel<EPV><<<grid, G2_THREADS, G2_SMEM, st>>>(tmA, tmW, cdiv(K, G2_BK), tpb, n_mtiles, n_ntiles, \
+        WIPA_TRY(wipa_ensure_smem(gemm_h16_persistent_kernel<EPV>, (size_t)G2_SMEM, attr));                                  \
+        gemm_h16_persistent_kernel<EPV><<<grid, G2_THREADS, G2_SMEM, st>>>(tmA, tmW, cdiv(K, G2_BK), tpb, n_mtiles, n_ntiles, \
                                                                             a.a_rpb, ep);                                      \
     }
     switch (variant) {
-        case G2_EP_HEADS_BF16: G2_LAUNCH(G2_EP_HEADS_BF16) break;
+        case G2_EP_HEADS_H16: G2_LAUNCH(G2_EP_HEADS_H16) break;
         case G2_EP_RESADD_F32: G2_LAUNCH(G2_EP_RESADD_F32) break;
-        case G2_EP_GELU_BF16: G2_LAUNCH(G2_EP_GELU_BF16) break;
-        case G2_EP_STORE_BF16: G2_LAUNCH(G2_EP_STORE_BF16) break;
+        case G2_EP_GELU_H16: G2_LAUNCH(G2_EP_GELU_H16) break;
+        case G2_EP_STORE_H16: G2_LAUNCH(G2_EP_STORE_H16) break;
         default: G2_LAUNCH(G2_EP_GENERIC) break;
     }
 #undef G2_LAUNCH

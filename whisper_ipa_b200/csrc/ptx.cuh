@@ -105,8 +105,8 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate; issued by ONE thread
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// D[tmem] (+)= A[smem desc] * B[smem desc], h16 inputs, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_h16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -174,7 +174,7 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
         : "memory");
 }
 
-// Shared-memory matrix descriptor for a K-major bf16 tile stored as rows of 64 elements (128 bytes) with the
+// Shared-memory matrix descriptor for a K-major h16 tile stored as rows of 64 elements (128 bytes) with the
 // 128-byte swizzle TMA applies: 8-row atoms of 1024 bytes, consecutive atoms 1024 bytes apart (SBO).
 // (field layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor; version = 1 on sm_100, layout_type 2 = SWIZZLE_128B)
 __device__ __forceinline__ uint64_t smem_desc_sw128_kmajor(uint32_t smem_addr) {
@@ -195,9 +195,9 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t lo) {
     return ((uint64_t)hi << 32) | lo;
 }
 
-// Instruction descriptor for kind::f16, A/B = bf16 K-major, D = fp32, M x N tile
-__host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// Instruction descriptor for kind::f16, A/B = h16 K-major, D = fp32, M x N tile
+__host__ __device__ constexpr uint32_t idesc_h16_f32(int M, int N) {
+    return (1u << 4) | (WIPA_H16_IDESC_FMT << 7) | (WIPA_H16_IDESC_FMT << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
 __device__ __forceinline__ bool elect_one() {

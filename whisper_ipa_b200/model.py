@@ -23,7 +23,9 @@ N_FRAMES = 3000
 MAX_TARGET = 448
 
 _DTYPES = {"float32": _lib.DTYPE_F32, "fp32": _lib.DTYPE_F32, torch.float32: _lib.DTYPE_F32,
+           "float16": _lib.DTYPE_F16, "fp16": _lib.DTYPE_F16, "f16": _lib.DTYPE_F16, torch.float16: _lib.DTYPE_F16,
            "bfloat16": _lib.DTYPE_BF16, "bf16": _lib.DTYPE_BF16, torch.bfloat16: _lib.DTYPE_BF16}
+_DTYPE_NAMES = {_lib.DTYPE_F32: "float32", _lib.DTYPE_F16: "float16", _lib.DTYPE_BF16: "bfloat16"}
 
 
 def _stream() -> int:
@@ -42,9 +44,10 @@ class WhisperIPA:
                  device: Optional[Union[int, str, torch.device]] = None):
         self.arch = arch if isinstance(arch, WhisperArch) else (ARCHS[arch] if arch in ARCHS else arch_from_name(arch))
         if dtype not in _DTYPES:
-            raise ValueError(f"dtype must be float32 or bfloat16, got {dtype!r}")
+            raise ValueError(f"dtype must be float32, float16 or bfloat16, got {dtype!r}")
         self.dtype_code = _DTYPES[dtype]
-        self.dtype = "bfloat16" if self.dtype_code == _lib.DTYPE_BF16 else "float32"
+        self.dtype = _DTYPE_NAMES[self.dtype_code]
+        self._lib = _lib.lib_for_dtype(self.dtype_code)      # float16 / float32: libwipa.so; bfloat16: libwipa_bf16.so
         if not torch.cuda.is_available():
             raise RuntimeError("whisper_ipa_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -55,16 +58,19 @@ class WhisperIPA:
         self._arch_c = _lib.Arch(a.d_model, a.enc_layers, a.dec_layers, a.heads, a.ffn, a.n_mels, a.vocab, self.dtype_code)
         self._ctx = C.c_void_p()
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().wipa_ctx_create(C.byref(self._arch_c), self.max_batch, self.max_beams,
+            self._check(self._lib.wipa_ctx_create(C.byref(self._arch_c), self.max_batch, self.max_beams,
                                                   C.byref(self._ctx)), "wipa_ctx_create")
         self._n_encoded = 0
         self.suppress_tokens: List[int] = []
         self.begin_suppress_tokens: List[int] = [220, a.eot]
 
+    def _check(self, rc: int, what: str) -> None:
+        _lib.check(rc, what, self._lib)
+
     # ---- lifetime ---------------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_ctx", None) is not None and self._ctx.value:
-            _lib.lib().wipa_ctx_destroy(self._ctx)
+            self._lib.wipa_ctx_destroy(self._ctx)
             self._ctx = C.c_void_p()
 
     def __del__(self):
@@ -78,7 +84,7 @@ class WhisperIPA:
         """Load HF-named tensors (``WhisperForConditionalGeneration.state_dict()`` naming).  May be called again with a
         subset (the reference overlays only ``decoder.*`` keys, ref:scripts/evaluate_model.py:58-73).
         Returns the names that were not recognised (raises on them if ``strict``)."""
-        lib = _lib.lib()
+        lib = self._lib
         names, tensors, unknown = [], [], []
         for k, v in state_dict.items():
             t = torch.as_tensor(v) if not isinstance(v, torch.Tensor) else v
@@ -91,7 +97,7 @@ class WhisperIPA:
                 if rc == -1 and b"unknown tensor name" in lib.wipa_last_error():
                     unknown.append(k)
                     continue
-                _lib.check(rc, f"wipa_ctx_load_weights({k})")
+                self._check(rc, f"wipa_ctx_load_weights({k})")
             torch.cuda.current_stream().synchronize()          # staging tensors die with this frame
         if strict and unknown:
             raise KeyError(f"unrecognised tensors: {unknown[:5]}{'...' if len(unknown) > 5 else ''}")
@@ -133,7 +139,7 @@ class WhisperIPA:
             raise ValueError(f"batch {B} exceeds max_batch {self.max_batch}")
         out = torch.empty((B, T_ENC, self.arch.d_model), dtype=torch.float32, device=self.device) if return_features else None
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().wipa_encode(self._ctx, feats.data_ptr(), B, out.data_ptr() if out is not None else None,
+            self._check(self._lib.wipa_encode(self._ctx, feats.data_ptr(), B, out.data_ptr() if out is not None else None,
                                               _stream()), "wipa_encode")
         self._n_encoded = B
         return out
@@ -148,7 +154,7 @@ class WhisperIPA:
         if af.shape[1:] != (T_ENC, self.arch.d_model):
             raise ValueError(f"audio_features must be [B,{T_ENC},{self.arch.d_model}], got {tuple(af.shape)}")
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().wipa_set_audio_features(self._ctx, af.data_ptr(), af.shape[0], _stream()),
+            self._check(self._lib.wipa_set_audio_features(self._ctx, af.data_ptr(), af.shape[0], _stream()),
                        "wipa_set_audio_features")
         self._n_encoded = af.shape[0]
 
@@ -172,13 +178,13 @@ class WhisperIPA:
         o, keep = self._opts(prompt, max_new, suppress, begin_suppress)
         ids = torch.empty((B, max_new), dtype=torch.int32, device=self.device)
         lens = torch.empty((B,), dtype=torch.int32, device=self.device)
-        lib = _lib.lib()
+        lib = self._lib
         with torch.cuda.device(self.device):
             if num_beams == 1:
-                _lib.check(lib.wipa_decode_greedy(self._ctx, B, C.byref(o), ids.data_ptr(), lens.data_ptr(), _stream()),
+                self._check(lib.wipa_decode_greedy(self._ctx, B, C.byref(o), ids.data_ptr(), lens.data_ptr(), _stream()),
                            "wipa_decode_greedy")
             else:
-                _lib.check(lib.wipa_decode_beam(self._ctx, B, int(num_beams), float(length_penalty), C.byref(o),
+                self._check(lib.wipa_decode_beam(self._ctx, B, int(num_beams), float(length_penalty), C.byref(o),
                                                 ids.data_ptr(), lens.data_ptr(), _stream()), "wipa_decode_beam")
         del keep
         return ids, lens
@@ -189,7 +195,7 @@ class WhisperIPA:
         B, T = tok.shape
         out = torch.empty((B, T, self.arch.vocab), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().wipa_decode_logits(self._ctx, B, tok.ctypes.data_as(C.POINTER(C.c_int32)), T,
+            self._check(self._lib.wipa_decode_logits(self._ctx, B, tok.ctypes.data_as(C.POINTER(C.c_int32)), T,
                                                      out.data_ptr(), _stream()), "wipa_decode_logits")
         return out
 
@@ -238,7 +244,7 @@ class WhisperIPA:
         v = C.c_int64()
         for key, sel in (("workspace_bytes", _lib.INFO_WORKSPACE_BYTES), ("crosskv_bytes", _lib.INFO_CROSSKV_BYTES),
                          ("decode_steps", _lib.INFO_DECODE_STEPS), ("xattn_latent", _lib.INFO_XATTN_LATENT)):
-            _lib.check(_lib.lib().wipa_ctx_get_info(self._ctx, sel, C.byref(v)), "wipa_ctx_get_info")
+            self._check(self._lib.wipa_ctx_get_info(self._ctx, sel, C.byref(v)), "wipa_ctx_get_info")
             out[key] = int(v.value)
         return out
 
