@@ -103,6 +103,8 @@ int wipa_decode_logits(wipa_ctx*, int B, const int32_t* tokens, int T, float* lo
 /* Replaces: editdistance.eval(ref_phones, hyp_phones) (ref:scripts/evaluate_ipa.py:100) for N pairs at once.
  * CSR packing: pair i = ref[ref_off[i]:ref_off[i+1]] vs hyp[hyp_off[i]:hyp_off[i+1]]; all device int32.
  * dist_len: device int32[N,2] = (edit distance, ref length) — the pair layout the multi-GPU gather moves.
+ * max_ref_len: an upper bound of the reference lengths (sizes the per-warp shared-memory slice); a pair whose reference is
+ * longer than it is flagged with distance -1 instead of being scored (checked on the device, never out of bounds).
  * The percentage (d/len)*100.0 and mean/std stay on the host in float64 (ref:scripts/evaluate_ipa.py:103,370). */
 int wipa_per_batch(const int32_t* ref, const int32_t* ref_off, const int32_t* hyp, const int32_t* hyp_off,
                    int N, int max_ref_len, int32_t* dist_len, void* stream);

@@ -113,9 +113,10 @@ def test_eos_handling_matches_oracle(w, tiny_gain_sd, eot_like):
     m.close()
 
 
-# relative-L2 limits (encoder output, teacher-forced logits) per 16-bit type.  fp16: north_star's 1e-3; bf16: <= 1.5 x the
-# values measured on a B200 in round 1 (encoder 1.7e-3 - 2.6e-3, logits 6.0e-3 - 6.4e-3).  The measured values are printed.
-HALF_LIMITS = {"float16": (1.0e-3, 1.0e-3), "bfloat16": (4.0e-3, 1.0e-2)}
+# relative-L2 limits (encoder output, teacher-forced logits) per 16-bit type, <= 1.5 x the worst value measured on a B200
+# over the six cases (round 2, gpurun_out/r2a_tests.log): fp16 encoder 2.08e-4 (tiny) / 3.17e-4 (base), logits 7.07e-4 - 7.23e-4
+# (held to north_star's 1e-3); bf16 encoder 1.71e-3 / 2.61e-3, logits 5.86e-3 - 6.38e-3.  Token agreement was 1.000 everywhere.
+HALF_LIMITS = {"float16": (4.8e-4, 1.0e-3), "bfloat16": (3.9e-3, 9.6e-3)}
 
 
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
@@ -157,7 +158,7 @@ def test_half_logits_and_token_agreement(w, arch, B, persistent, latent, dtype, 
           f"mean agreeing prefix {prefix:.1f}/32")
     lim_enc, lim_logits = HALF_LIMITS[dtype]
     assert enc_rel < lim_enc and rel < lim_logits
-    assert agree >= 0.9
+    assert agree >= 0.97
     assert np.isfinite(got_logits.numpy()).all()
     m.close()
 

@@ -15,12 +15,17 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-# (arch, clips, dtype) -> (mel max-abs, encoder rel-L2, logits rel-L2, teacher-forced argmax agreement >=)
+# (arch, clips, dtype) -> (mel max-abs, encoder rel-L2, logits rel-L2, teacher-forced argmax agreement >=, free-running
+# token agreement >=).  Measured on a B200 (round 2, gpurun_out/r2a_tests.log):
+#   small B=128 fp16: mel 8.1e-5, encoder 4.98e-4, logits 8.45e-4 (worst row 8.55e-4), agreement 1.0 / 1.0, 128/128 rows identical
+#   small B=128 bf16: encoder 4.10e-3, logits 6.79e-3, agreement 1.0 / 1.0
+#   base  B=64  fp16: encoder 3.17e-4, logits 7.09e-4, agreement 1.0 / 1.0;   bf16: encoder 2.61e-3, logits 5.86e-3
+# Limits are 1.5 x measured, except fp16 logits, which are held to north_star's 1e-3 itself (1.18 x / 1.41 x measured).
 LIMITS = {
-    ("small", 128, "float16"): (1e-3, 1.0e-3, 1.0e-3, 0.97),
-    ("small", 128, "bfloat16"): (1e-3, 6.0e-3, 1.2e-2, 0.90),
-    ("base", 64, "float16"): (1e-3, 1.0e-3, 1.0e-3, 0.97),
-    ("base", 64, "bfloat16"): (1e-3, 6.0e-3, 1.2e-2, 0.90),
+    ("small", 128, "float16"): (1.3e-4, 7.5e-4, 1.0e-3, 0.99, 0.97),
+    ("small", 128, "bfloat16"): (1.3e-4, 6.2e-3, 1.0e-2, 0.99, 0.97),
+    ("base", 64, "float16"): (1.3e-4, 4.8e-4, 1.0e-3, 0.99, 0.97),
+    ("base", 64, "bfloat16"): (1.3e-4, 3.9e-3, 8.8e-3, 0.99, 0.97),
 }
 MAX_NEW = 220
 LOGIT_STEPS = 48
@@ -57,7 +62,7 @@ def test_half_precision_path_on_bench_config(w, arch, n, dtype, monkeypatch):
         monkeypatch.delenv(var, raising=False)
     from oracle import whisper_oracle as wo
     ref = _reference(arch, n)
-    lim_mel, lim_enc, lim_logits, lim_agree = LIMITS[(arch, n, dtype)]
+    lim_mel, lim_enc, lim_logits, lim_agree, lim_free = LIMITS[(arch, n, dtype)]
     prompt = wo.prompt_for(arch)
 
     m = w.WhisperIPA(arch, dtype=dtype, max_batch=n)
@@ -96,4 +101,5 @@ def test_half_precision_path_on_bench_config(w, arch, n, dtype, monkeypatch):
     assert enc_rel < lim_enc
     assert rel < lim_logits
     assert tf_agree >= lim_agree
+    assert agree >= lim_free
     assert lens.cpu().tolist() == [want_ids.shape[1]] * n or want_ids.shape[1] < MAX_NEW

@@ -18,6 +18,18 @@ LANGUAGES = (
 )
 FIRST_LANGUAGE_TOKEN = 50259
 
+# The multilingual tokenizer's "non-speech" symbols (brackets, quotes, musical notes, ...): the BPE ids below <|endoftext|>
+# that Whisper masks at every step when suppress_tokens == "-1" (the default of the reference's
+# DecodingOptions(language="en", without_timestamps=True), ref:scripts/evaluate_model.py:170-173).  Same ids for every
+# multilingual vocabulary (tiny ... large-v3); equal to the entries < 50257 of HF:models/whisper/configuration_whisper.py
+# NON_SPEECH_TOKENS_MULTI (checked in tests/test_host_logic.py).
+NON_SPEECH_TOKENS = (
+    1, 2, 7, 8, 9, 10, 14, 25, 26, 27, 28, 29, 31, 58, 59, 60, 61, 62, 63, 90, 91, 92, 93, 359, 503, 522, 542, 873, 893, 902,
+    918, 922, 931, 1350, 1853, 1982, 2460, 2627, 3246, 3253, 3268, 3536, 3846, 3961, 4183, 4667, 6585, 6647, 7273, 9061, 9383,
+    10428, 10929, 11938, 12033, 12331, 12562, 13793, 14157, 14635, 15265, 15618, 16553, 16604, 18362, 18956, 20075, 21675,
+    22520, 26130, 26161, 26435, 28279, 29464, 31650, 32302, 32470, 36865, 42863, 47425, 49870, 50254,
+)
+
 
 @dataclass(frozen=True)
 class WhisperArch:
@@ -63,14 +75,69 @@ class WhisperArch:
             raise ValueError(f"token {token} is not a language token")
         return LANGUAGES[i]
 
+    # <|translate|>, <|transcribe|>, <|startoflm|>, <|startofprev|>, <|nospeech|>, <|notimestamps|>: large-v3 inserted one more
+    # language token in front of them, so they sit one id higher there
+    @property
+    def _shift(self) -> int:
+        return 1 if self.is_v3 else 0
+
+    @property
+    def translate(self) -> int:
+        return 50358 + self._shift
+
+    @property
+    def transcribe(self) -> int:
+        return 50359 + self._shift
+
+    @property
+    def sot_lm(self) -> int:
+        return 50360 + self._shift
+
+    @property
+    def sot_prev(self) -> int:
+        return 50361 + self._shift
+
+    @property
+    def no_speech(self) -> int:
+        return 50362 + self._shift
+
+    @property
+    def no_timestamps(self) -> int:
+        return 50363 + self._shift
+
+    @property
+    def timestamp_begin(self) -> int:
+        return 50364 + self._shift
+
+    def default_suppress_tokens(self) -> List[int]:
+        """What ``suppress_tokens="-1"`` expands to (mlx_whisper / openai-whisper ``_get_suppress_tokens``): the non-speech
+        symbols plus <|transcribe|>, <|translate|>, <|startoftranscript|>, <|startofprev|>, <|startoflm|> and <|nospeech|>."""
+        return sorted(set(NON_SPEECH_TOKENS) | {self.transcribe, self.translate, self.sot, self.sot_prev, self.sot_lm,
+                                                self.no_speech})
+
+    def resolve_suppress_tokens(self, spec) -> List[int]:
+        """``DecodingOptions.suppress_tokens``: None / "" -> nothing; "-1" or a list containing -1 -> the default set (plus
+        the list's other ids); a comma-separated string or an iterable of ids -> those ids."""
+        if spec is None:
+            return []
+        if isinstance(spec, str):
+            spec = [int(t) for t in spec.split(",") if t.strip()]
+        ids = [int(t) for t in spec]
+        out = set(t for t in ids if t >= 0)
+        if any(t == -1 for t in ids):
+            out |= set(self.default_suppress_tokens())
+        bad = [t for t in out if t >= self.vocab]
+        if bad:
+            raise ValueError(f"suppress_tokens outside the vocabulary: {bad[:5]}")
+        return sorted(out)
+
     def prompt(self, language: str = "en", task: str = "transcribe", without_timestamps: bool = True) -> List[int]:
         """<|sot|><|lang|><|task|>[<|notimestamps|>] — the evaluation scripts always decode with language="en"
         (ref:scripts/evaluate_model.py:171); training-time validation detects the language (ref:scripts/train_whisper_ipa.py:339)."""
-        shift = 1 if self.is_v3 else 0
-        task_id = {"transcribe": 50359, "translate": 50358}[task] + shift
+        task_id = {"transcribe": self.transcribe, "translate": self.translate}[task]
         out = [self.sot, self.language_token(language), task_id]
         if without_timestamps:
-            out.append(50363 + shift)
+            out.append(self.no_timestamps)
         return out
 
     def hf_config_kwargs(self) -> Dict[str, int]:

@@ -7,9 +7,12 @@
 //                unit the cross-attention kernel streams with cp.async.bulk; indexed by utterance, so beams share it
 //   self-KV      per layer a pool of pages [page][head][16][64] T addressed through a block table [seq][28]
 //   activations  encoder micro-batch buffers sized for enc_mb clips; decoder buffers sized for max_batch*max_beams rows
+#include <math.h>
 #include <string.h>
 
 #include <string>
+#include <array>
+#include <map>
 #include <unordered_map>
 #include <unordered_set>
 #include <vector>
@@ -111,7 +114,9 @@ struct wipa_ctx {
     LogmelTables mel_tables;
     float* mel_clipmax;
 
-    std::unordered_map<long long, GraphEntry> graphs;
+    // captured decode steps, keyed by EVERYTHING the captured kernels bake in as parameters:
+    // {kind (0 greedy, 1 beam), sequences, prompt length, max_new, eot, beams, length-penalty bits}
+    std::map<std::array<long long, 7>, GraphEntry> graphs;
 };
 
 namespace {
@@ -751,6 +756,27 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
         wipa_ctx_destroy(c);
         return WIPA_ENOMEM;
     }
+    {
+        // The encoder's position table is not a learned weight: Whisper fixes it to sinusoids (HF:models/whisper/
+        // modeling_whisper.py:55-65), and MLX-format checkpoints do not carry it at all (mlx_whisper keeps it as the private
+        // `_positional_embedding`).  Pre-fill it, so the slot is optional; a state dict that has the tensor overwrites it.
+        const int half = d / 2;
+        std::vector<float> pos((size_t)T * d);
+        const double inc = log(10000.0) / (double)(half - 1);
+        for (size_t t = 0; t < T; ++t)
+            for (int i = 0; i < half; ++i) {
+                const double a = (double)t * exp(-inc * (double)i);
+                pos[t * d + i] = (float)sin(a);
+                pos[t * d + half + i] = (float)cos(a);
+            }
+        if (cudaMemcpy(c->enc_pos, pos.data(), pos.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            wipa_set_error("cudaMemcpy of the encoder position table failed");
+            cudaGetLastError();
+            wipa_ctx_destroy(c);
+            return WIPA_ECUDA;
+        }
+        c->loaded.insert("model.encoder.embed_positions.weight");
+    }
 #undef CTX_TRY
     *out = c;
     return WIPA_OK;
@@ -879,8 +905,7 @@ extern "C" int wipa_decode_greedy(wipa_ctx* c, int B, const wipa_decode_opts* o,
     const bool use_graph = env_int("WIPA_NO_GRAPH", 0) == 0 && total_steps - s >= 2;
     GraphEntry* ge = nullptr;
     if (use_graph) {
-        const long long key = ((long long)S << 40) | ((long long)P << 20) | (long long)max_new | ((long long)(o->eot & 0xffff) << 48);
-        ge = &c->graphs[key];
+        ge = &c->graphs[{0LL, (long long)S, (long long)P, (long long)max_new, (long long)o->eot, 1LL, 0LL}];
         if (ge->exec == nullptr) {
             cudaGraph_t g = nullptr;
             const int64_t before = g_wipa_launches;
@@ -981,13 +1006,9 @@ extern "C" int wipa_decode_beam(wipa_ctx* c, int B, int beams, float length_pena
     int done_steps = 1;
     GraphEntry* ge = nullptr;
     if (env_int("WIPA_NO_GRAPH", 0) == 0 && max_new >= 3) {
-        // everything the captured kernels bake in as parameters: shapes, prompt length, eot, beams, length penalty
         uint32_t lp_bits;
         memcpy(&lp_bits, &length_penalty, 4);
-        long long key = 0x4245414dLL;                            // 'BEAM': never equal to a greedy key (those are < 2^62 and even-structured)
-        for (long long v : {(long long)S, (long long)P, (long long)max_new, (long long)o->eot, (long long)beams, (long long)lp_bits})
-            key = key * 1000003LL + v;
-        ge = &c->graphs[key | (1LL << 62)];
+        ge = &c->graphs[{1LL, (long long)S, (long long)P, (long long)max_new, (long long)o->eot, (long long)beams, (long long)lp_bits}];
         if (ge->exec == nullptr) {
             cudaGraph_t g = nullptr;
             const int64_t before = g_wipa_launches;

@@ -17,7 +17,7 @@
 __global__ void __launch_bounds__(256)
 per_levenshtein_kernel(const int32_t* __restrict__ ref, const int32_t* __restrict__ ref_off,
                        const int32_t* __restrict__ hyp, const int32_t* __restrict__ hyp_off, int n_pairs,
-                       int words_per_warp, int32_t* __restrict__ dist_len) {
+                       int words_per_warp, int max_ref_len, int32_t* __restrict__ dist_len) {
     extern __shared__ int32_t smem_per[];
     const int warps_per_cta = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5;
@@ -31,7 +31,9 @@ per_levenshtein_kernel(const int32_t* __restrict__ ref, const int32_t* __restric
     int32_t* sref = col + (nr + 1);                               // nr reference ids
 
     int result;
-    if (nr == 0 || nh == 0) {
+    if (nr > max_ref_len || nr < 0 || nh < 0) {
+        result = -1;                                              // the caller's bound was wrong: flag the pair, never overrun
+    } else if (nr == 0 || nh == 0) {
         result = nr + nh;
     } else {
         for (int i = lane; i <= nr; i += 32) col[i] = i;          // D[i][0]
@@ -85,7 +87,7 @@ extern "C" int wipa_per_batch(const int32_t* ref, const int32_t* ref_off, const 
     if (smem > 48 * 1024) WIPA_TRY(wipa_ensure_smem(per_levenshtein_kernel, smem, attr));
     const int grid = cdiv(N, warps);
     per_levenshtein_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(ref, ref_off, hyp, hyp_off, N, words,
-                                                                              dist_len);
+                                                                              max_ref_len, dist_len);
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

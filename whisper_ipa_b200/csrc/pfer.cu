@@ -38,7 +38,7 @@ __device__ __forceinline__ double pfer_cost(int mode, int ref_id, int hyp_id, co
 __global__ void __launch_bounds__(128)
 pfer_kernel(const int32_t* __restrict__ ref, const int32_t* __restrict__ ref_off, const int32_t* __restrict__ hyp,
             const int32_t* __restrict__ hyp_off, int n_pairs, const int8_t* __restrict__ feats, int mode,
-            int bytes_per_warp, double* __restrict__ dist) {
+            int bytes_per_warp, int max_ref_len, double* __restrict__ dist) {
     extern __shared__ __align__(8) uint8_t smem_pfer[];
     const int warps_per_cta = blockDim.x >> 5;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -52,7 +52,9 @@ pfer_kernel(const int32_t* __restrict__ ref, const int32_t* __restrict__ ref_off
     int8_t* sfeat = reinterpret_cast<int8_t*>(sref + nr);                   // nr x 24 reference features
 
     double result;
-    if (nr == 0 || nh == 0) {
+    if (nr > max_ref_len || nr < 0 || nh < 0) {
+        result = -1.0;                                  // the caller's bound was wrong: flag the pair, never overrun
+    } else if (nr == 0 || nh == 0) {
         result = (double)(nr + nh);                     // first row / column of the DP table
     } else {
         for (int i = lane; i <= nr; i += 32) col[i] = (double)i;
@@ -115,7 +117,7 @@ extern "C" int wipa_pfer_batch(const int32_t* ref, const int32_t* ref_off, const
     static SmemAttr attr;
     if (smem > 48 * 1024) WIPA_TRY(wipa_ensure_smem(pfer_kernel, smem, attr));
     pfer_kernel<<<cdiv(N, warps), warps * 32, smem, (cudaStream_t)stream>>>(ref, ref_off, hyp, hyp_off, N, feats, mode,
-                                                                            (int)per_warp, dist);
+                                                                            (int)per_warp, max_ref_len, dist);
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

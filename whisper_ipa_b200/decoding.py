@@ -12,13 +12,56 @@ from .archs import FIRST_LANGUAGE_TOKEN, LANGUAGES
 
 MAX_TARGET = 448
 
-# optional id -> text hook; the Whisper BPE vocabulary is not shipped in this image
-_detokenizer: Optional[Callable[[Sequence[int]], str]] = None
+# id -> text.  The Whisper BPE vocabulary is not shipped in this image, so it comes from the
+# checkpoint directory (load_detokenizer) or from the caller (set_detokenizer).  Without one, asking for `.text` RAISES:
+# ids printed as text would turn every string PER into a silent ~100 %.  The id-level pipeline (synthetic configs,
+# bench.py) opts in to ids-as-text explicitly with set_detokenizer("ids").
+_detokenizer: Union[None, str, Callable[[Sequence[int]], str]] = None
 
 
-def set_detokenizer(fn: Optional[Callable[[Sequence[int]], str]]) -> None:
+def set_detokenizer(fn: Union[None, str, Callable[[Sequence[int]], str]]) -> None:
+    """fn(ids) -> str; the string "ids" selects space-joined ids (id-level scoring only); None clears it."""
     global _detokenizer
+    if isinstance(fn, str) and fn != "ids":
+        raise ValueError('set_detokenizer takes a callable, "ids" or None')
     _detokenizer = fn
+
+
+def load_detokenizer(path: str, eot: int = 50257) -> Callable[[Sequence[int]], str]:
+    """Build (and register) the id -> text function from tokenizer files next to a checkpoint:
+      * ``multilingual.tiktoken`` / ``gpt2.tiktoken`` (the asset mlx_whisper / openai-whisper ship: one
+        ``base64(token bytes) rank`` pair per line) - decoded here: bytes of the ids below <|endoftext|> joined, UTF-8 with
+        replacement, exactly what tiktoken's ``decode`` does once the special tokens are filtered out
+        (mlx_whisper.tokenizer.Tokenizer.decode drops ids >= timestamp_begin; the reference reads ``result.text``, which
+        is decoded from the tokens before the first EOT, ref:scripts/evaluate_model.py:201);
+      * an HF tokenizer directory (``tokenizer.json`` or ``vocab.json`` + ``merges.txt``) through
+        ``transformers.WhisperTokenizerFast/WhisperTokenizer`` with ``skip_special_tokens=True``."""
+    import base64
+    import os
+    fn: Optional[Callable[[Sequence[int]], str]] = None
+    files = [path] if os.path.isfile(path) else [os.path.join(path, n) for n in ("multilingual.tiktoken", "gpt2.tiktoken")]
+    for f in files:
+        if os.path.isfile(f) and f.endswith(".tiktoken"):
+            table = {}
+            with open(f, "rb") as fh:
+                for line in fh:
+                    if line.strip():
+                        tok, rank = line.split()
+                        table[int(rank)] = base64.b64decode(tok)
+
+            def fn(ids, _t=table, _eot=eot):
+                return b"".join(_t[int(i)] for i in ids if int(i) < _eot and int(i) in _t).decode("utf-8", errors="replace")
+            break
+    if fn is None and os.path.isdir(path) and any(os.path.exists(os.path.join(path, n)) for n in ("tokenizer.json", "vocab.json")):
+        from transformers import AutoTokenizer
+        tok = AutoTokenizer.from_pretrained(path, local_files_only=True)
+
+        def fn(ids, _tok=tok):
+            return _tok.decode([int(i) for i in ids], skip_special_tokens=True)
+    if fn is None:
+        raise FileNotFoundError(f"no multilingual.tiktoken / tokenizer.json / vocab.json under {path!r}")
+    set_detokenizer(fn)
+    return fn
 
 
 @dataclass(frozen=True)
@@ -26,12 +69,13 @@ class DecodingOptions:
     task: str = "transcribe"
     language: Optional[str] = "en"
     temperature: float = 0.0
-    sample_len: Optional[int] = None          # default n_text_ctx // 2 = 224 tokens including the prompt
+    sample_len: Optional[int] = None          # tokens to sample AFTER the prompt; default n_text_ctx // 2 = 224 (mlx_whisper
+                                              # runs `for i in range(sample_len)`), capped by the 448 target positions
     beam_size: Optional[int] = None
     length_penalty: Optional[float] = None
     without_timestamps: bool = True
     fp16: bool = False
-    suppress_tokens: Optional[Sequence[int]] = None
+    suppress_tokens: Union[None, str, Sequence[int]] = "-1"      # "-1": non-speech symbols + special tokens (mlx_whisper default)
     suppress_blank: bool = True
 
 
@@ -44,9 +88,33 @@ class DecodingResult:
 
 
 def _text(tokens: Sequence[int]) -> str:
-    if _detokenizer is not None:
-        return _detokenizer(tokens)
-    return " ".join(str(t) for t in tokens)          # ids as text: PER over token ids stays well defined
+    if _detokenizer is None:
+        raise RuntimeError("no detokenizer is registered: `.text` needs the Whisper vocabulary (decoding.load_detokenizer(<dir "
+                           "with multilingual.tiktoken or tokenizer.json>) or set_detokenizer(fn)); for id-level scoring "
+                           'opt in with set_detokenizer("ids") or read `.tokens`')
+    if _detokenizer == "ids":
+        return " ".join(str(t) for t in tokens)      # ids as text: PER over token ids stays well defined
+    return _detokenizer(tokens)
+
+
+class _LazyText:
+    """`.text` of a DecodingResult is produced on first access, so callers that only read `.tokens` (the id-level pipeline)
+    never need a vocabulary."""
+
+    def __set_name__(self, owner, name):
+        self._name = "_" + name
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        v = getattr(obj, self._name, None)
+        if v is None:
+            v = _text(obj.tokens)
+            setattr(obj, self._name, v)
+        return v
+
+    def __set__(self, obj, value):
+        setattr(obj, self._name, value)
 
 
 def _encode(model, mel_or_features):
