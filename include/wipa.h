@@ -66,6 +66,17 @@ int wipa_ctx_destroy(wipa_ctx*);
  * audio: device f32[B, 480000];  mel: device f32[B, n_mels, 3000] (HF layout).  Context-free. */
 int wipa_logmel(const float* audio, int B, int n_mels, float* mel, void* stream);
 
+/* Audio ingest for a whole micro-batch: interleaved PCM16 at any source rate -> mono f32 at 16 kHz, zero-padded / cut to
+ * out_len samples.  Replaces: mlx_whisper.audio.load_audio (decode -> s16le -> / 32768 -> mono -> 16 kHz) followed by
+ * pad_or_trim (ref:scripts/evaluate_model.py:187-188, ref:scripts/transcribe_single.py:43-44, ref:scripts/ipa_data_loader.py:48,80).
+ * The rate change is scipy.signal.resample_poly's polyphase FIR (the host path's resampler), see csrc/resample.cu.
+ * pcm: device int16; clip b = n_ch-interleaved frames at elements [clip_off[b], clip_off[b] + clip_frames[b] * n_ch)
+ * (clip_off device int64[B], clip_frames device int32[B]); taps: device f32[n_taps] = up * firwin(20 * max(up, down) + 1,
+ * 1 / max(up, down), kaiser 5.0) ({1.0} with up = down = 1 for 16 kHz sources); c0 = n_pre_remove * down - n_pre_pad of
+ * scipy's upfirdn bookkeeping (whisper_ipa_b200/ingest.py computes both); out: device f32[B, out_len].  Context-free. */
+int wipa_resample_pcm16(const int16_t* pcm, const long long* clip_off, const int* clip_frames, int B, int n_ch, int up, int down,
+                        const float* taps, int n_taps, int c0, float* out, int out_len, void* stream);
+
 /* ---- (b) encoder ---------------------------------------------------------------------------- */
 /* Replaces: model.encoder(mel) (ref:scripts/evaluate_model.py:197, ref:scripts/transcribe_single.py:54).
  * mel: device f32[B, n_mels, 3000]; enc_out: device f32[B,1500,d] or NULL.  Also projects and stores the
@@ -96,6 +107,15 @@ int wipa_decode_greedy(wipa_ctx*, int B, const wipa_decode_opts*, int32_t* out_i
  * outputs as the greedy call: the best finished hypothesis per utterance, EOS stripped, EOT-padded. */
 int wipa_decode_beam(wipa_ctx*, int B, int beams, float length_penalty, const wipa_decode_opts*,
                      int32_t* out_ids, int32_t* out_len, void* stream);
+/* Stepwise decoding with the logits handed back, for everything that filters or samples between steps on the caller's
+ * side: HF `generate(..., logits_processor=...)`, and the long-form branch of the reference (mlx_whisper.transcribe with
+ * timestamp rules, temperature fallback and no-speech detection, ref:scripts/evaluate_model.py:112-119).
+ * wipa_decode_begin resets the self-KV cache, consumes T forced tokens per row (host int32[B,T]: the prompt; rows may differ)
+ * and writes the logits that follow the last one (device f32[B,V]).  wipa_decode_next appends ONE token per row (device
+ * int32[B], e.g. an argmax / multinomial result that never left the GPU) and writes the next logits.  Any other decode
+ * call, or a new wipa_encode / wipa_set_audio_features, closes the stepwise state. */
+int wipa_decode_begin(wipa_ctx*, int B, const int32_t* tokens, int T, float* logits, void* stream);
+int wipa_decode_next(wipa_ctx*, int B, const int32_t* tokens_dev, float* logits, void* stream);
 /* Diagnostics for the parity tests: teacher-forced logits.  tokens: host int32[B,T]; logits: device f32[B,T,V]. */
 int wipa_decode_logits(wipa_ctx*, int B, const int32_t* tokens, int T, float* logits, void* stream);
 

@@ -174,3 +174,179 @@ def test_detect_language_and_per_language_decode():
     m3 = _FakeModel(["ja"])
     r3 = decode(m3, torch.zeros(3000, 80), DecodingOptions(language="en", without_timestamps=True))
     assert r3.language == "en" and m3.calls[0][0] == [50258, 50259, 50359, 50363]
+
+
+# ---- round 2: suppress lists, checkpoints, detokenizer, resampler plan, long-form rules ----------------------------------
+def test_default_suppress_tokens_follow_the_tokenizer_lists():
+    from transformers.models.whisper.configuration_whisper import NON_SPEECH_TOKENS_MULTI
+    from whisper_ipa_b200.archs import NON_SPEECH_TOKENS
+    assert list(NON_SPEECH_TOKENS) == [t for t in NON_SPEECH_TOKENS_MULTI if t < 50257]
+    small, v3 = w.ARCHS["small"], w.ARCHS["large-v3"]
+    # "-1" = non-speech symbols + transcribe, translate, sot, sot_prev, sot_lm, no_speech (openai/whisper-small's
+    # generation_config.suppress_tokens is exactly NON_SPEECH_TOKENS_MULTI + {50358, 50359})
+    assert small.default_suppress_tokens() == sorted(set(NON_SPEECH_TOKENS_MULTI) | {50358, 50359})
+    assert set(v3.default_suppress_tokens()) - set(NON_SPEECH_TOKENS) == {50258, 50359, 50360, 50361, 50362, 50363}
+    assert small.resolve_suppress_tokens(None) == [] and small.resolve_suppress_tokens("") == []
+    assert small.resolve_suppress_tokens("-1") == small.default_suppress_tokens()
+    assert small.resolve_suppress_tokens("5,7") == [5, 7]
+    assert small.resolve_suppress_tokens([-1, 123]) == sorted(set(small.default_suppress_tokens()) | {123})
+    with pytest.raises(ValueError):
+        small.resolve_suppress_tokens([60000])
+    assert (small.no_timestamps, small.timestamp_begin, v3.no_timestamps, v3.timestamp_begin) == (50363, 50364, 50364, 50365)
+
+
+def test_decode_passes_reference_defaults_to_the_engine():
+    """DecodingOptions(language="en", without_timestamps=True): suppress_tokens="-1" expands to the default list, 224 tokens
+    are sampled AFTER the prompt (mlx_whisper's sample_len), blank + EOT are masked at the first step."""
+    from whisper_ipa_b200.decoding import DecodingOptions, decode
+    seen = {}
+
+    class M(_FakeModel):
+        def decode_tokens(self, prompt, max_new, num_beams=1, length_penalty=1.0, suppress=None, begin_suppress=None):
+            seen.update(max_new=max_new, suppress=list(suppress), begin=list(begin_suppress))
+            return super().decode_tokens(prompt, max_new)
+    m = M(["en"])
+    decode(m, torch.zeros(1, 3000, 80), DecodingOptions(language="en", without_timestamps=True))
+    assert seen["max_new"] == 224 and seen["suppress"] == m.arch.default_suppress_tokens() and seen["begin"] == [220, 50257]
+    decode(m, torch.zeros(1, 3000, 80), DecodingOptions(language="en", suppress_tokens=None, sample_len=500, suppress_blank=False))
+    assert seen["max_new"] == 444 and seen["suppress"] == [] and seen["begin"] == [50257]
+
+
+def test_mlx_checkpoint_round_trip_with_non_weight_entries(tiny_sd, tmp_path):
+    """A full MLX-named key set, as the reference saves it (flatten_params(model.parameters()),
+    ref:scripts/train_whisper_ipa.py:420-422: it includes `alignment_heads` and has no encoder position table), maps back to
+    the HF names and values; the `decoder.` prefix filter is applied before any name is mapped."""
+    from safetensors.torch import save_file
+    mlx = checkpoint.hf_to_mlx_state_dict(tiny_sd)
+    assert "encoder.blocks.0.attn.query.weight" in mlx and "decoder.blocks.3.mlp2.bias" in mlx
+    assert tuple(mlx["encoder.conv1.weight"].shape) == (384, 3, 80)            # MLX conv layout [out, k, in]
+    mlx["alignment_heads"] = torch.zeros(6, 2)
+    mlx["encoder.positional_embedding"] = torch.zeros(1500, 384)
+    back = checkpoint.to_hf_state_dict(mlx, w.ARCHS["tiny"])
+    assert set(tiny_sd) - set(back) == {"model.encoder.embed_positions.weight", "proj_out.weight"}
+    assert all(torch.equal(back[k], tiny_sd[k]) for k in back)
+    save_file({k: v.contiguous() for k, v in mlx.items()}, str(tmp_path / "model.safetensors"))
+    dec = checkpoint.load_weights_dir(str(tmp_path), w.ARCHS["tiny"], prefix="decoder.")
+    assert dec and all(k.startswith("model.decoder.") for k in dec)
+    assert len(dec) == sum(1 for k in mlx if k.startswith("decoder."))
+    with pytest.raises(KeyError):
+        checkpoint.to_hf_state_dict({"decoder.blocks.0.nonsense.weight": torch.zeros(1)}, w.ARCHS["tiny"])
+
+
+def test_detokenizer_is_required_for_text(tmp_path):
+    import base64
+    from whisper_ipa_b200 import decoding
+    decoding.set_detokenizer(None)
+    r = decoding.DecodingResult(None, "en", [3, 1, 50257])
+    assert r.tokens == [3, 1, 50257]
+    with pytest.raises(RuntimeError, match="no detokenizer"):
+        r.text
+    with pytest.raises(RuntimeError, match="no detokenizer"):
+        w.transcribe_batched(None, [], 80)                     # refused before any work, never swallowed per sample
+    decoding.set_detokenizer("ids")
+    assert decoding.DecodingResult(None, "en", [3, 1]).text == "3 1"
+    # tiktoken-format vocabulary file, as mlx_whisper ships it: base64(token bytes) + rank per line
+    toks = ["k".encode(), "æ".encode(), "t".encode(), " ".encode(), "ʃ".encode()[:1], "ʃ".encode()[1:]]
+    with open(tmp_path / "multilingual.tiktoken", "wb") as f:
+        for i, t in enumerate(toks):
+            f.write(base64.b64encode(t) + b" " + str(i).encode() + b"\n")
+    fn = decoding.load_detokenizer(str(tmp_path))
+    assert fn([0, 1, 2]) == "kæt" and fn([4, 5, 3, 0, 50257, 50363]) == "ʃ k"      # bytes joined across tokens, specials dropped
+    assert decoding.DecodingResult(None, "en", [0, 1, 2, 50257]).text == "kæt"
+    decoding.set_detokenizer(None)
+    with pytest.raises(FileNotFoundError):
+        decoding.load_detokenizer(str(tmp_path / "nowhere"))
+
+
+def test_resample_plan_matches_scipy():
+    """The filter and the index bookkeeping handed to the GPU resampler reproduce scipy.signal.resample_poly (numpy
+    emulation of the kernel's formula; the kernel itself is compared with scipy in the GPU tests)."""
+    from scipy.signal import firwin, resample_poly
+    from whisper_ipa_b200.ingest import resample_plan
+    rng = np.random.default_rng(0)
+    for rate in (48000, 44100, 8000, 22050, 16000):
+        plan = resample_plan(rate)
+        x = rng.standard_normal(1200).astype(np.float32)
+        ref = resample_poly(x, plan.up, plan.down) if rate != 16000 else x
+        if rate != 16000:
+            m = max(plan.up, plan.down)
+            assert np.abs(plan.taps - (firwin(20 * m + 1, 1.0 / m, window=("kaiser", 5.0)) * plan.up)).max() < 1e-6
+        nt = len(plan.taps)
+        got = np.zeros(len(ref))
+        for n in range(len(ref)):
+            c = n * plan.down + plan.c0
+            lo = max(0, -(-(c - nt + 1) // plan.up))
+            hi = min(len(x) - 1, c // plan.up)
+            i = np.arange(lo, hi + 1)
+            got[n] = np.dot(plan.taps[c - i * plan.up].astype(np.float64), x[i])
+        assert np.abs(got - ref).max() < 2e-6, rate
+        assert plan.frames_needed(len(ref)) >= min(len(x), (len(ref) - 1) * plan.down // plan.up)
+
+
+def test_timestamp_rules_match_hf_processor():
+    """transcribe.apply_timestamp_rules (the long-form branch's logit filter) against HF's WhisperTimeStampLogitsProcessor
+    on random logits and random sampled prefixes (HF:generation/logits_process.py:1995-2043)."""
+    from types import SimpleNamespace
+    from transformers.generation.logits_process import WhisperTimeStampLogitsProcessor
+    from whisper_ipa_b200.transcribe import apply_timestamp_rules
+    arch = w.ARCHS["tiny"]
+    cfg = SimpleNamespace(no_timestamps_token_id=arch.no_timestamps, eos_token_id=arch.eot, bos_token_id=arch.eot,
+                          max_initial_timestamp_index=50, _detect_timestamp_from_logprob=True)
+    g = torch.Generator().manual_seed(0)
+    tb = arch.timestamp_begin
+    for trial in range(40):
+        n = int(torch.randint(0, 6, (1,), generator=g))
+        seq = []
+        for _ in range(n):
+            seq.append(int(torch.randint(tb, tb + 200, (1,), generator=g)) if torch.rand(1, generator=g) < 0.5
+                       else int(torch.randint(0, 50000, (1,), generator=g)))
+        logits = torch.randn(arch.vocab, generator=g) * (1.0 if trial % 2 else 6.0)
+        prompt = [arch.sot, 50259, arch.transcribe]
+        hf_proc = WhisperTimeStampLogitsProcessor(cfg, begin_index=len(prompt))
+        want = hf_proc(torch.tensor([prompt + seq]), logits[None].clone())[0]
+        got = apply_timestamp_rules(logits.clone(), seq, arch, first=(n == 0))
+        assert torch.equal(torch.isinf(got), torch.isinf(want)) and torch.equal(got[~torch.isinf(got)], want[~torch.isinf(want)]), seq
+
+
+def test_panphon_csv_table_loader(tmp_path):
+    from whisper_ipa_b200 import metrics
+    head = "ipa,syl,son,cons,cont,delrel,lat,nas,strid,voi,sg,cg,ant,cor,distr,lab,hi,lo,back,round,velaric,tense,long,hitone,hireg"
+    rows = ["p," + ",".join(["-"] * 24), "a," + ",".join(["+"] * 24), "pʰ," + ",".join(["0"] * 23 + ["+"])]
+    (tmp_path / "ipa_all.csv").write_text("\n".join([head] + rows) + "\n", encoding="utf-8")
+    try:
+        table = metrics.load_feature_table(str(tmp_path / "ipa_all.csv"))
+        assert table["p"] == [-1] * 24 and table["a"] == [1] * 24
+        assert metrics._phone_features("pʰ").tolist() == [0] * 23 + [1]         # longest segment wins
+        assert metrics._phone_features("xa").tolist() == [1] * 24                # first KNOWN segment, as panphon's finditer
+        assert metrics._phone_features("x").tolist() == [0] * 24                 # unknown phone -> zero vector
+        assert metrics.pfer_available()
+    finally:
+        metrics.set_feature_table(None)
+
+
+def test_compare_models_prints_and_returns(capsys):
+    out = w.compare_models({"per": 60.0, "pfer": 40.0}, {"per": 30.0, "pfer": 24.0})
+    text = capsys.readouterr().out
+    assert out == {"per_improvement": 30.0, "pfer_improvement": 16.0}
+    assert "Model Comparison" in text and "+30.00%" in text and "EXCELLENT" in text and "SOTA" not in text
+
+
+def test_cli_flags_match_the_reference():
+    import importlib
+    em = importlib.import_module("whisper_ipa_b200.evaluate_model")     # the package attribute of that name is the function
+    seen = {}
+
+    def fake_eval(model_path, test_data_path, num_samples=None, **kw):
+        seen.setdefault("calls", []).append((model_path, test_data_path, num_samples, kw))
+        return {"per": 1.0, "pfer": 2.0, "per_std": 0.0, "pfer_std": 0.0, "num_samples": 0}
+    old = em.evaluate_model
+    em.evaluate_model = fake_eval
+    try:
+        em.main(["--checkpoint", "ck", "--base-model", "whisper-small", "--test-data", "t.json", "--num-samples", "0", "--n-mels", "80"])
+        assert [c[0] for c in seen["calls"]] == ["whisper-small", "ck"] and seen["calls"][1][2] is None
+        assert seen["calls"][0][3]["is_checkpoint"] is False and seen["calls"][1][3]["is_checkpoint"] is True
+        seen.clear()
+        em.main(["--checkpoint", "ck", "--skip-base"])
+        assert len(seen["calls"]) == 1 and seen["calls"][0][2] == 100 and seen["calls"][0][3]["n_mels"] == 128
+    finally:
+        em.evaluate_model = old

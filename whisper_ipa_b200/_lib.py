@@ -44,10 +44,13 @@ PROTOTYPES = {
     "wipa_ctx_load_weights": (_i, [_vp, C.POINTER(TensorDesc), _i, _vp]),
     "wipa_ctx_destroy": (_i, [_vp]),
     "wipa_logmel": (_i, [_vp, _i, _i, _vp, _vp]),
+    "wipa_resample_pcm16": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _vp]),
     "wipa_encode": (_i, [_vp, _vp, _i, _vp, _vp]),
     "wipa_set_audio_features": (_i, [_vp, _vp, _i, _vp]),
     "wipa_decode_greedy": (_i, [_vp, _i, C.POINTER(DecodeOpts), _vp, _vp, _vp]),
     "wipa_decode_beam": (_i, [_vp, _i, _i, _f, C.POINTER(DecodeOpts), _vp, _vp, _vp]),
+    "wipa_decode_begin": (_i, [_vp, _i, C.POINTER(C.c_int32), _i, _vp, _vp]),
+    "wipa_decode_next": (_i, [_vp, _i, _vp, _vp, _vp]),
     "wipa_decode_logits": (_i, [_vp, _i, C.POINTER(C.c_int32), _i, _vp, _vp]),
     "wipa_per_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "wipa_pfer_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp]),

@@ -110,6 +110,7 @@ struct wipa_ctx {
     std::vector<void*> xlq_w, xlo_w;                                  // per layer [H*d, d] and [d, H*d]
     std::vector<float*> xlq_b, xlo_b;
     int64_t decode_steps = 0;
+    int step_pos = 0;              // target positions consumed by wipa_decode_begin / wipa_decode_next (0: no stepwise decode open)
     size_t workspace_bytes = 0, xkv_bytes = 0;
     LogmelTables mel_tables;
     float* mel_clipmax;
@@ -849,6 +850,7 @@ extern "C" int wipa_encode(wipa_ctx* c, const float* mel, int B, float* enc_out,
         WIPA_TRY(encode_chunk(c, mel + u0 * mel_clip, u0, nb, enc_out ? enc_out + u0 * enc_clip : nullptr, st));
     }
     c->n_utts = B;
+    c->step_pos = 0;
     return WIPA_OK;
 }
 
@@ -866,6 +868,7 @@ extern "C" int wipa_set_audio_features(wipa_ctx* c, const float* enc_out, int B,
         WIPA_TRY(cross_kv_project(c, u0, nb, st));
     }
     c->n_utts = B;
+    c->step_pos = 0;
     return WIPA_OK;
 }
 
@@ -887,6 +890,7 @@ static int check_decode_args(wipa_ctx* c, int B, const wipa_decode_opts* o, int3
 extern "C" int wipa_decode_greedy(wipa_ctx* c, int B, const wipa_decode_opts* o, int32_t* out_ids, int32_t* out_len, void* stream) {
     WIPA_TRY(check_decode_args(c, B, o, out_ids, out_len));
     WIPA_TRY(require_weights(c));
+    c->step_pos = 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int S = B, P = o->prompt_len, max_new = o->max_new;
     WIPA_TRY(upload_mask(c, c->mask_always, o->suppress, o->n_suppress, st));
@@ -946,6 +950,7 @@ extern "C" int wipa_decode_logits(wipa_ctx* c, int B, const int32_t* tokens, int
     WIPA_CHECK(c->n_utts > 0 && B == c->n_utts, WIPA_ESTATE, "wipa_decode_logits: %d utterances encoded, B=%d", c->n_utts, B);
     WIPA_CHECK(T >= 1 && T <= WIPA_MAX_TGT, WIPA_EINVAL, "wipa_decode_logits: T=%d", T);
     WIPA_TRY(require_weights(c));
+    c->step_pos = 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int V = c->a.vocab;
     // T forced tokens + one dummy so that every step stays on the teacher-forced branch of the finalize kernel
@@ -964,6 +969,61 @@ extern "C" int wipa_decode_logits(wipa_ctx* c, int B, const int32_t* tokens, int
     return WIPA_OK;
 }
 
+// ---- stepwise decoding with the logits handed back to the caller (host-side logits processors, sampling, fallback) ----
+__global__ void decode_advance_kernel(int* pos, int* step) {
+    pdl_wait();
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) { *pos += 1; *step += 1; }
+}
+
+__global__ void decode_set_tokens_kernel(const int32_t* __restrict__ tokens, int* __restrict__ cur_tok, int n, int vocab) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { const int t = tokens[i]; cur_tok[i] = (t >= 0 && t < vocab) ? t : 0; }
+}
+
+extern "C" int wipa_decode_begin(wipa_ctx* c, int B, const int32_t* tokens, int T, float* logits, void* stream) {
+    WIPA_CHECK(c && tokens && logits, WIPA_EINVAL, "wipa_decode_begin: null argument");
+    WIPA_CHECK(c->n_utts > 0 && B == c->n_utts, WIPA_ESTATE, "wipa_decode_begin: %d utterances encoded, B=%d", c->n_utts, B);
+    WIPA_CHECK(T >= 1 && T <= WIPA_MAX_TGT, WIPA_EINVAL, "wipa_decode_begin: T=%d", T);
+    WIPA_TRY(require_weights(c));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = c->a.vocab;
+    std::vector<int32_t> forced((size_t)B * (T + 1), 0);        // + one dummy: every position stays on the teacher-forced branch
+    for (int b = 0; b < B; ++b)
+        for (int t = 0; t < T; ++t) {
+            const int32_t id = tokens[(size_t)b * T + t];
+            WIPA_CHECK(id >= 0 && id < V, WIPA_EINVAL, "wipa_decode_begin: token %d outside the vocabulary", id);
+            forced[(size_t)b * (T + 1) + t] = id;
+        }
+    DecodeState ds;
+    WIPA_TRY(decode_setup(c, B, 1, forced, T + 1, 0, 0, &ds, st));
+    for (int t = 0; t < T - 1; ++t) WIPA_TRY(decode_step(c, B, ds, 0, nullptr, 0, st));
+    WIPA_TRY(decode_step(c, B, ds, 2, logits, (long long)V, st, /*beam=*/false, /*finalize=*/false));
+    decode_advance_kernel<<<1, 32, 0, st>>>(c->d_pos, c->d_step);
+    WIPA_LAUNCHED();
+    c->decode_steps += T;
+    c->step_pos = T;
+    return WIPA_OK;
+}
+
+extern "C" int wipa_decode_next(wipa_ctx* c, int B, const int32_t* tokens_dev, float* logits, void* stream) {
+    WIPA_CHECK(c && tokens_dev && logits, WIPA_EINVAL, "wipa_decode_next: null argument");
+    WIPA_CHECK(c->step_pos > 0 && B == c->n_utts, WIPA_ESTATE, "wipa_decode_next before wipa_decode_begin (or B=%d != %d)", B, c->n_utts);
+    WIPA_CHECK(c->step_pos < WIPA_MAX_TGT, WIPA_EINVAL, "wipa_decode_next: all %d target positions are used", WIPA_MAX_TGT);
+    cudaStream_t st = (cudaStream_t)stream;
+    decode_set_tokens_kernel<<<cdiv(B, 256), 256, 0, st>>>(tokens_dev, c->d_cur_tok, B, c->a.vocab);
+    WIPA_LAUNCHED();
+    DecodeState ds = make_state(c, 1, 0, 0);
+    WIPA_TRY(decode_step(c, B, ds, 2, logits, (long long)c->a.vocab, st, /*beam=*/false, /*finalize=*/false));
+    decode_advance_kernel<<<1, 32, 0, st>>>(c->d_pos, c->d_step);
+    WIPA_LAUNCHED();
+    c->decode_steps += 1;
+    c->step_pos += 1;
+    return WIPA_OK;
+}
+
 extern "C" int wipa_decode_beam(wipa_ctx* c, int B, int beams, float length_penalty, const wipa_decode_opts* o,
                                 int32_t* out_ids, int32_t* out_len, void* stream) {
     WIPA_TRY(check_decode_args(c, B, o, out_ids, out_len));
@@ -971,6 +1031,7 @@ extern "C" int wipa_decode_beam(wipa_ctx* c, int B, int beams, float length_pena
     WIPA_CHECK(beams >= 2 && beams <= 8, WIPA_EINVAL, "wipa_decode_beam: beams=%d outside 2..8 (use wipa_decode_greedy for 1)", beams);
     WIPA_CHECK(beams <= c->max_beams && B * beams <= c->max_seqs, WIPA_EINVAL,
                "wipa_decode_beam: B=%d x beams=%d exceeds the context (max_batch %d, max_beams %d)", B, beams, c->max_batch, c->max_beams);
+    c->step_pos = 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int S = B * beams, P = o->prompt_len, max_new = o->max_new, V = c->a.vocab, keep = 2 * beams;
     const int L = P + max_new;                                 // HF's max_length

@@ -3,7 +3,7 @@
 ref:scripts/train_whisper_ipa.py:338-362).  Greedy, temperature 0, one 30 s window."""
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional, Sequence, Tuple, Union
 
 import torch
@@ -79,42 +79,46 @@ class DecodingOptions:
     suppress_blank: bool = True
 
 
-@dataclass
 class DecodingResult:
-    audio_features: Optional[torch.Tensor]
-    language: str
-    tokens: List[int] = field(default_factory=list)
-    text: str = ""
+    """mlx_whisper.decoding.DecodingResult's fields the reference reads (`.text`, ref:scripts/evaluate_model.py:201) plus
+    `.tokens` / `.language` / `.audio_features`.  `.text` is detokenized on first access, so id-level callers never need
+    a vocabulary - and string callers get an exception, not ids, when none is registered."""
+    __slots__ = ("audio_features", "language", "tokens", "_text")
+
+    def __init__(self, audio_features: Optional[torch.Tensor], language: str, tokens: Optional[List[int]] = None,
+                 text: Optional[str] = None):
+        self.audio_features, self.language = audio_features, language
+        self.tokens = list(tokens) if tokens is not None else []
+        self._text = text
+
+    @property
+    def text(self) -> str:
+        if self._text is None:
+            self._text = _text(self.tokens)
+        return self._text
+
+    @text.setter
+    def text(self, value: str) -> None:
+        self._text = value
+
+    def __repr__(self) -> str:
+        return f"DecodingResult(language={self.language!r}, tokens={self.tokens!r})"
 
 
-def _text(tokens: Sequence[int]) -> str:
+def require_detokenizer() -> None:
+    """Raise unless text output is possible.  Called by the string-level entry points BEFORE any work, so the failure is
+    never swallowed by the reference's per-sample ``except`` (which would turn it into empty hypotheses and a PER of 100 %)."""
     if _detokenizer is None:
         raise RuntimeError("no detokenizer is registered: `.text` needs the Whisper vocabulary (decoding.load_detokenizer(<dir "
                            "with multilingual.tiktoken or tokenizer.json>) or set_detokenizer(fn)); for id-level scoring "
                            'opt in with set_detokenizer("ids") or read `.tokens`')
+
+
+def _text(tokens: Sequence[int]) -> str:
+    require_detokenizer()
     if _detokenizer == "ids":
         return " ".join(str(t) for t in tokens)      # ids as text: PER over token ids stays well defined
     return _detokenizer(tokens)
-
-
-class _LazyText:
-    """`.text` of a DecodingResult is produced on first access, so callers that only read `.tokens` (the id-level pipeline)
-    never need a vocabulary."""
-
-    def __set_name__(self, owner, name):
-        self._name = "_" + name
-
-    def __get__(self, obj, objtype=None):
-        if obj is None:
-            return self
-        v = getattr(obj, self._name, None)
-        if v is None:
-            v = _text(obj.tokens)
-            setattr(obj, self._name, v)
-        return v
-
-    def __set__(self, obj, value):
-        setattr(obj, self._name, value)
 
 
 def _encode(model, mel_or_features):
@@ -163,12 +167,15 @@ def decode(model, mel_or_features, options: Optional[DecodingOptions] = None) ->
     B = feats.shape[0]
     sample_len = o.sample_len if o.sample_len is not None else MAX_TARGET // 2
     begin = list(model.begin_suppress_tokens) if o.suppress_blank else [model.arch.eot]
+    suppress = model.arch.resolve_suppress_tokens(o.suppress_tokens)
 
     def run(language: str):
         prompt = model.arch.prompt(language, o.task, o.without_timestamps)
-        ids, lens = model.decode_tokens(prompt, sample_len - len(prompt), num_beams=o.beam_size or 1,
+        # mlx_whisper samples `sample_len` tokens after the prompt (`for i in range(sample_len)`); the 448 target positions cap it
+        max_new = min(sample_len, MAX_TARGET - len(prompt))
+        ids, lens = model.decode_tokens(prompt, max_new, num_beams=o.beam_size or 1,
                                         length_penalty=1.0 if o.length_penalty is None else o.length_penalty,
-                                        suppress=o.suppress_tokens, begin_suppress=begin)
+                                        suppress=suppress, begin_suppress=begin)
         return ids.cpu().tolist(), lens.cpu().tolist()
 
     langs = [o.language] * B if o.language is not None else _detect_cached(model, B)[0]
@@ -186,6 +193,6 @@ def decode(model, mel_or_features, options: Optional[DecodingOptions] = None) ->
             ids_h, lens_h = run(lang)
             for i, b in enumerate(rows):
                 tokens[b] = ids_h[i][:lens_h[i]]
-    results = [DecodingResult(audio_features=feats[b] if feats is not None else None, language=langs[b], tokens=tokens[b],
-                              text=_text(tokens[b])) for b in range(B)]
+    results = [DecodingResult(audio_features=feats[b] if feats is not None else None, language=langs[b], tokens=tokens[b])
+               for b in range(B)]
     return results[0] if single else results

@@ -157,13 +157,44 @@ _feature_override: Optional[Dict[str, Sequence[int]]] = None
 def set_feature_table(table: Optional[Dict[str, Sequence[int]]]) -> None:
     """Register phone -> 24 numeric features (panphon's `word_to_vector_list(phone, numeric=True)[0]`) for images without
     panphon; phones missing from the table get the zero vector, as the reference does for unknown phones."""
-    global _feature_override
+    global _feature_override, _feature_regex
     _feature_override = table
+    _feature_regex = None
+
+
+_feature_regex = None
+
+
+def load_feature_table(csv_path: str) -> Dict[str, Sequence[int]]:
+    """Register panphon's segment table from its ``data/ipa_all.csv`` (columns: ipa, then the 24 features syl ... hireg as
+    '+', '-' or '0'), for images where the panphon package is absent but its data file is at hand.  Lookup then follows
+    panphon's ``word_to_vector_list(phone, numeric=True)[0]`` (ref:scripts/evaluate_ipa.py:124-134): the phone string is
+    scanned with a longest-match regex over the table's segments and the FIRST segment found supplies the vector; no
+    segment -> the zero vector."""
+    import csv
+    import re
+    global _feature_regex
+    num = {"+": 1, "-": -1, "0": 0}
+    table: Dict[str, Sequence[int]] = {}
+    with open(csv_path, newline="", encoding="utf-8") as f:
+        rows = csv.reader(f)
+        header = next(rows)
+        if len(header) != 25 or header[0] != "ipa":
+            raise ValueError(f"{csv_path}: expected panphon's ipa_all.csv header (ipa + 24 features), got {header[:3]}...")
+        for r in rows:
+            if len(r) == 25:
+                table[unicodedata.normalize("NFD", r[0])] = [num[v] for v in r[1:]]
+    set_feature_table(table)
+    _feature_regex = re.compile("|".join(re.escape(k) for k in sorted(table, key=len, reverse=True)))
+    return table
 
 
 def _phone_features(phone: str) -> Optional[np.ndarray]:
     if _feature_override is not None:
         v = _feature_override.get(phone)
+        if v is None and _feature_regex is not None:               # panphon's segmenting lookup (load_feature_table)
+            m = _feature_regex.search(unicodedata.normalize("NFD", phone))
+            v = _feature_override.get(m.group(0)) if m else None
         return np.zeros(24, dtype=np.int8) if v is None else np.asarray(v, dtype=np.int8)
     ft = _feature_table()
     if ft is None:

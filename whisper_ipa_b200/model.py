@@ -199,13 +199,70 @@ class WhisperIPA:
                                                      out.data_ptr(), _stream()), "wipa_decode_logits")
         return out
 
+    def decode_begin(self, tokens: Union[torch.Tensor, np.ndarray, Sequence[Sequence[int]]]) -> torch.Tensor:
+        """Open a stepwise decode over the cached utterances: consume the forced tokens int [B, T] (rows may differ) and
+        return the logits that follow the last one, device f32 [B, V].  Continue with decode_next()."""
+        tok = np.ascontiguousarray(torch.as_tensor(tokens).cpu().numpy(), dtype=np.int32)
+        if tok.ndim == 1:
+            tok = tok[None].repeat(self._n_encoded, axis=0)
+        B, T = tok.shape
+        out = torch.empty((B, self.arch.vocab), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.wipa_decode_begin(self._ctx, B, tok.ctypes.data_as(C.POINTER(C.c_int32)), T, out.data_ptr(),
+                                                    _stream()), "wipa_decode_begin")
+        return out
+
+    def decode_next(self, tokens: torch.Tensor) -> torch.Tensor:
+        """Append one token per row (int [B]; a device tensor stays on the device) and return the next logits f32 [B, V]."""
+        tok = torch.as_tensor(tokens).to(device=self.device, dtype=torch.int32).contiguous()
+        out = torch.empty((tok.numel(), self.arch.vocab), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.wipa_decode_next(self._ctx, tok.numel(), tok.data_ptr(), out.data_ptr(), _stream()),
+                        "wipa_decode_next")
+        return out
+
+    def _generate_with_processors(self, prompt: Sequence[int], max_new: int, processors, suppress, begin_suppress):
+        """Greedy decoding with caller-side logits processors (HF ``LogitsProcessor.__call__(input_ids, scores)``,
+        HF:generation/utils.py:2762-2768): one wipa_decode_next per token, the scores never leave the GPU."""
+        B = self._n_encoded
+        ids = torch.tensor([list(prompt)] * B, dtype=torch.int64, device=self.device)
+        scores = self.decode_begin(ids)
+        done = torch.zeros(B, dtype=torch.bool, device=self.device)
+        lens = torch.full((B,), max_new, dtype=torch.int32, device=self.device)
+        sup = torch.tensor(list(suppress), dtype=torch.int64, device=self.device)
+        bsup = torch.tensor(list(begin_suppress), dtype=torch.int64, device=self.device)
+        out = torch.full((B, max_new), self.arch.eot, dtype=torch.int32, device=self.device)
+        for i in range(max_new):
+            if sup.numel():
+                scores[:, sup] = -float("inf")
+            if i == 0 and bsup.numel():
+                scores[:, bsup] = -float("inf")
+            for proc in processors:
+                scores = proc(ids, scores)
+            tok = scores.argmax(dim=-1)
+            tok = torch.where(done, torch.full_like(tok, self.arch.eot), tok)
+            newly = (~done) & (tok == self.arch.eot)
+            lens = torch.where(newly, torch.full_like(lens, i), lens)
+            done |= newly
+            out[:, i] = tok.to(torch.int32)
+            ids = torch.cat([ids, tok[:, None]], dim=1)
+            if bool(done.all()) or i + 1 == max_new:
+                break
+            scores = self.decode_next(tok)
+        return out, lens
+
     @torch.no_grad()
     def generate(self, input_features, decoder_input_ids=None, max_new_tokens: Optional[int] = None,
                  num_beams: int = 1, length_penalty: float = 1.0, language: Optional[str] = None,
                  task: Optional[str] = None, do_sample: bool = False, early_stopping: bool = False,
-                 return_dict_in_generate: bool = False, **unused):
+                 return_dict_in_generate: bool = False, suppress_tokens: Optional[Sequence[int]] = None,
+                 begin_suppress_tokens: Optional[Sequence[int]] = None, logits_processor=None, **unused):
         """HF-shaped greedy / beam generation for one 30 s window: returns int64 [B, L] with the prompt and the EOS
-        stripped, right-padded with pad_token_id (= EOT), as HF:models/whisper/generation_whisper.py:936-951,1085-1086."""
+        stripped, right-padded with pad_token_id (= EOT), as HF:models/whisper/generation_whisper.py:936-951,1085-1086.
+        ``suppress_tokens`` / ``begin_suppress_tokens`` play the role of the checkpoint's ``generation_config`` lists
+        (HF:generation/logits_process.py:1812-1902); they default to the model attributes of the same names (empty /
+        [220, EOT], what a random-init ``WhisperConfig`` gives HF).  ``max_new_tokens`` defaults to HF's
+        ``max_length`` = 448 target positions minus the prompt."""
         if do_sample:
             raise NotImplementedError("sampling is not part of the reference path (temperature 0)")
         if decoder_input_ids is not None:
@@ -217,12 +274,21 @@ class WhisperIPA:
             prompt = [int(x) for x in p[0]]
         else:
             prompt = self.arch.prompt(language or "en", task or "transcribe", True)
-        max_new = int(max_new_tokens) if max_new_tokens is not None else MAX_TARGET // 2 - len(prompt)
+        max_new = int(max_new_tokens) if max_new_tokens is not None else MAX_TARGET - len(prompt)
         feats = self._features_hf_layout(input_features)
         outs, lens_all = [], []
         for b0 in range(0, feats.shape[0], self.max_batch):
             self.encoder(feats[b0:b0 + self.max_batch], return_features=False)
-            ids, lens = self.decode_tokens(prompt, max_new, num_beams=num_beams, length_penalty=length_penalty)
+            if logits_processor:
+                if num_beams != 1:
+                    raise NotImplementedError("logits_processor is supported with greedy decoding only")
+                ids, lens = self._generate_with_processors(
+                    prompt, max_new, list(logits_processor),
+                    self.suppress_tokens if suppress_tokens is None else suppress_tokens,
+                    self.begin_suppress_tokens if begin_suppress_tokens is None else begin_suppress_tokens)
+            else:
+                ids, lens = self.decode_tokens(prompt, max_new, num_beams=num_beams, length_penalty=length_penalty,
+                                               suppress=suppress_tokens, begin_suppress=begin_suppress_tokens)
             outs.append(ids)
             lens_all.append(lens)
         ids = torch.cat(outs).to(torch.int64)

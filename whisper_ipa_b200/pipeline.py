@@ -29,7 +29,8 @@ class Transcriber:
     def __init__(self, model: WhisperIPA, max_new: Optional[int] = None, prompt: Optional[Sequence[int]] = None):
         self.model = model
         self.prompt = list(prompt) if prompt is not None else model.arch.prompt("en", "transcribe", True)
-        self.max_new = int(max_new) if max_new is not None else 224 - len(self.prompt)
+        # the reference samples sample_len = 224 tokens after the prompt (mlx_whisper: `for i in range(sample_len)`)
+        self.max_new = int(max_new) if max_new is not None else min(224, 448 - len(self.prompt))
 
     def transcribe_device(self, audio_dev: torch.Tensor):
         """audio f32 [B, 480000] already in HBM -> device (ids [B, max_new], lens [B])."""
