@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """Headline benchmark: whisper-small greedy IPA decode + PER, audio-seconds transcribed per second (RTFx).
 
-One "step" = one pass of the whole hot path over one batch of synthetic clips per GPU:
-log-mel -> encoder -> 220 greedy decode steps (4-token prompt, 224 positions) -> PER counts.
-`value`  : device-timed (CUDA events, max over ranks), audio already resident in HBM.
-`e2e`    : the same passes through the public API (pipeline.Transcriber.evaluate_local, what evaluate_ids runs per rank) from
-           pinned HOST buffers: host->device copies (double-buffered), reference upload, PER gather and result read-back
-           inside the timed region (K steps per pass; the faster of two passes).
-`roofline`: the dominant kernel (decoder cross-attention, a persistent HBM streamer: by default the latent kernel that reads the
-           encoder output once per layer; with WIPA_XATTN_LATENT=0 the stream-K kernel over per-layer K/V caches) timed alone
-           with CUDA events on the decode shapes (bytes per launch >> L2), achieved GB/s vs MEASURED_PEAKS.json.
-`cpu_baseline` / `--impl reference`: the parity oracle (HF transformers Whisper on the host cores, fp32) on a bounded
-           sample of the same workload.  The reference's own runtime (mlx_whisper on Apple Metal) cannot run here.
+One "step" = one pass of the whole hot path over one micro-batch of synthetic clips per GPU:
+log-mel -> encoder -> 220 greedy decode steps (4-token prompt, 224 positions) -> PER counts.  A run of K steps is ONE
+evaluation sweep of K * B * N utterances sharded over the N ranks (utterance i -> rank i mod N) through the public API,
+``pipeline.Transcriber.evaluate_ids``: per-rank micro-batches, ONE all-gather of the (edit distance, reference length)
+pairs per sweep, the aggregate PER finished with the reference's numpy expressions.
+
+`value`    : the sweep with this rank's audio already resident in HBM (CUDA events, max over ranks).
+`e2e`      : the same sweep from pinned HOST buffers: host->device copies (double-buffered on a side stream), reference
+             upload, PER gather and the read-back of ids / lengths / counts inside the timed region; mean of the timed passes.
+`roofline` : the dominant kernel (decoder cross-attention: a persistent HBM streamer) timed alone with CUDA events on the
+             decode shapes (bytes per launch >> L2), achieved GB/s of its ALGORITHMIC bytes vs MEASURED_PEAKS.json; `traffic`
+             is read from the committed ncu capture profiles/<kernel>.json and dropped when the kernel source changed since.
+             `roofline.decode_step` / `roofline.logits_argmax`: the whole decode step and its vocabulary node the same way.
+`parity`   : the benchmarked build against HF transformers fp32 on the same GPU (TF32 off): teacher-forced logits and
+             220-step greedy ids for the first clips of this very workload.
+`gpu_baseline`: HF transformers ``generate`` in bf16 / SDPA on the same B200 (the library path a user would otherwise run).
+`cpu_baseline` / ``--impl reference``: the parity oracle (HF transformers Whisper on the host cores, fp32) on a bounded
+             sample of the same workload.  The reference's own runtime (mlx_whisper on Apple Metal) cannot run here.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -31,7 +39,8 @@ sys.path.insert(0, ROOT)
 
 CLIP_SECONDS = 30.0
 N_SAMPLES = 480000
-PROMPT_LEN = 4
+CONFIG_OF_ARCH = {"tiny": "configs[0]", "base": "configs[1]", "small": "configs[2], the headline", "medium": "configs[3]",
+                  "large-v3": "configs[4]"}
 
 
 def synthetic_audio(n, first=0):
@@ -104,18 +113,33 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_oracle_pass(hf_model, n_clips, max_new, first=0):
-    """The oracle (HF transformers, fp32, all host threads) over n_clips: features + generate + PER. Returns seconds."""
+def committed_traffic(kernel, source_rel, shape_key):
+    """dram__bytes_read + dram__bytes_write per launch of `kernel` from profiles/<kernel>.json (written by
+    scripts/ncu_summary.py --json from an `ncu --set full` capture).  Returns (bytes or None, note): a capture taken from a
+    different version of the kernel source, or on another shape, is refused."""
+    p = os.path.join(ROOT, "profiles", f"{kernel}.json")
+    if not os.path.exists(p):
+        return None, f"no capture committed (profiles/{kernel}.json)"
+    d = json.load(open(p))
+    sha = hashlib.sha256(open(os.path.join(ROOT, source_rel), "rb").read()).hexdigest()[:16]
+    if d.get("source_sha16") != sha:
+        return None, f"profiles/{kernel}.json was captured from another version of {source_rel}: stale, not quoted"
+    if d.get("shape") != shape_key:
+        return None, f"profiles/{kernel}.json was captured on shape {d.get('shape')!r}, this run is {shape_key!r}"
+    return float(d["dram_bytes_read"]) + float(d["dram_bytes_write"]), f"profiles/{kernel}.json ({d.get('captured', '?')})"
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle (HF transformers fp32) on the host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_oracle_pass(hf_model, fe, audio, refs, prompt, max_new):
+    """Features + generate + PER over the given clips on the host. Returns (seconds, mean PER)."""
     from oracle import per_oracle as po
-    from transformers import WhisperFeatureExtractor
-    audio = synthetic_audio(n_clips, first)
-    refs = synthetic_references(n_clips)
     t0 = time.perf_counter()
-    fe = WhisperFeatureExtractor(feature_size=hf_model.config.num_mel_bins)
     feats = fe(list(audio), sampling_rate=16000, return_tensors="pt").input_features
-    prompt = torch.tensor([[50258, 50259, 50359, 50363]] * n_clips)
+    p = torch.tensor([prompt] * len(audio))
     with torch.no_grad():
-        ids = hf_model.generate(feats, decoder_input_ids=prompt, max_new_tokens=max_new, do_sample=False)
+        ids = hf_model.generate(feats, decoder_input_ids=p, max_new_tokens=max_new, do_sample=False)
     d = po.levenshtein_batch(refs, [np.asarray(r, np.int32) for r in ids.tolist()])
     per = np.mean([po.per_from_counts(int(x), len(r), ids.shape[1]) for x, r in zip(d, refs)])
     return time.perf_counter() - t0, float(per)
@@ -123,34 +147,114 @@ def cpu_oracle_pass(hf_model, n_clips, max_new, first=0):
 
 def run_reference(args):
     """--impl reference: the reference's CPU arm = the HF oracle on the host cores; rank 0 only."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    if int(os.environ.get("RANK", "0")) != 0:
         return
     import logging
     import warnings
+    from transformers import WhisperFeatureExtractor
+    from whisper_ipa_b200 import ARCHS
     warnings.filterwarnings("ignore")
     logging.getLogger("transformers").setLevel(logging.ERROR)
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    arch = ARCHS[args.arch]
     hf_model, _ = random_init_state_dict(args.arch)
+    fe = WhisperFeatureExtractor(feature_size=arch.n_mels)          # built once, outside the timed region
+    prompt = arch.prompt("en", "transcribe", True)
     n_clips = args.ref_clips
+    refs = synthetic_references(n_clips)
+    clips = [synthetic_audio(n_clips, first=s * n_clips) for s in range(max(args.steps, 1))]    # synthesis is not timed either
     for _ in range(args.warmup):
-        cpu_oracle_pass(hf_model, n_clips, args.max_new)
+        cpu_oracle_pass(hf_model, fe, clips[0], refs, prompt, args.max_new)
     t = 0.0
     for s in range(args.steps):
-        dt, _ = cpu_oracle_pass(hf_model, n_clips, args.max_new, first=s * n_clips)
+        dt, _ = cpu_oracle_pass(hf_model, fe, clips[s], refs, prompt, args.max_new)
         t += dt
     value = n_clips * CLIP_SECONDS * args.steps / t
-    sample = f"{n_clips} clips x {args.max_new} greedy tokens per step, HF transformers fp32 on {cores} host threads"
+    sample = (f"{n_clips} clips x {args.max_new} greedy tokens + PER per step (--ref-clips {n_clips}: a bounded sample of the "
+              f"{args.batch}-clip step), HF transformers fp32 on {cores} host threads")
     print(json.dumps({
         "impl": "reference", "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"whisper-{args.arch} greedy IPA decode + PER (random-init weights, synthetic 30 s clips)",
+        "config": {"workload": f"whisper-{args.arch} greedy IPA decode + PER (random-init weights, synthetic 30 s clips, BASELINE "
+                               f"{CONFIG_OF_ARCH[args.arch]}); reference arm: {n_clips} clips per step on the host cores",
                    "clips_per_step": n_clips, "max_new_tokens": args.max_new},
         "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parity of the benchmarked build and the GPU comparator (rank 0, outside every timed region)
+# ---------------------------------------------------------------------------------------------------------------------
+def parity_vs_hf_fp32(model, hf_model, audio_host, prompt, max_new, hyps_first, n_clips=16, logit_steps=32):
+    """The benchmarked build vs HF fp32 on this GPU (TF32 off), on the first clips of the benchmark's own workload."""
+    from oracle import hf_reference as hf
+    import whisper_ipa_b200 as w
+    n = min(n_clips, audio_host.shape[0])
+    audio = audio_host[:n].numpy()
+    ref = hf.hf_gpu_fp32_reference(hf_model, audio, prompt, max_new, logit_steps)
+    mel = w.log_mel_features(audio, model.arch.n_mels)
+    mel_err = (mel.cpu() - ref["mel"]).abs().max().item()
+    enc = model.encoder(mel).cpu()
+    enc_rel = ((enc - ref["enc"]).norm() / ref["enc"].norm()).item()
+    got = model.teacher_forced_logits(ref["tokens"]).cpu()
+    rel = ((got - ref["logits"]).norm() / ref["logits"].norm()).item()
+    P = len(prompt)
+    tf_agree = (got[:, P - 1:].argmax(-1) == ref["logits"][:, P - 1:].argmax(-1)).float().mean().item()
+    want = ref["ids"]
+    L = want.shape[1]
+    mine = torch.tensor([list(h[:L]) + [50257] * (L - len(h[:L])) for h in hyps_first[:n]])
+    agree = (mine == want).float().mean().item()
+    return {"oracle": "HF transformers fp32 on this GPU, TF32 off", "clips": n, "mel_max_abs": mel_err, "encoder_rel_l2": enc_rel,
+            "logits_rel_l2": rel, "logit_positions": int(got.shape[1]), "teacher_forced_argmax_agreement": tf_agree,
+            "token_agreement": agree, "tokens_compared": int(mine.numel()),
+            "rows_identical": int((mine == want).all(dim=1).sum())}
+
+
+def hf_gpu_baseline(hf_model, audio_host, prompt, max_new, batch, beams=1):
+    """HF transformers generate() in bf16 with SDPA attention on this GPU: features on the GPU-resident model, same prompt,
+    same token budget.  Largest batch that fits, capped at the benchmark's."""
+    import warnings
+    from transformers import WhisperFeatureExtractor
+    dev = torch.device("cuda", torch.cuda.current_device())
+    fe = WhisperFeatureExtractor(feature_size=hf_model.config.num_mel_bins)
+    n = min(batch, audio_host.shape[0])
+    feats = fe(list(audio_host[:n].numpy()), sampling_rate=16000, return_tensors="pt").input_features
+    import copy
+    m = copy.deepcopy(hf_model).to(dev).to(torch.bfloat16).eval()
+    try:
+        m.config._attn_implementation = "sdpa"
+    except Exception:
+        pass
+    p = torch.tensor([prompt] * n, device=dev)
+    kw = dict(decoder_input_ids=p, max_new_tokens=max_new, do_sample=False)
+    if beams > 1:
+        kw.update(num_beams=beams, length_penalty=1.0, early_stopping=False)
+    out = None
+    try:
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            f = feats.to(dev, torch.bfloat16)
+            m.generate(f[:min(n, 8)], **{**kw, "decoder_input_ids": p[:min(n, 8)], "max_new_tokens": 8})      # warm-up
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f = feats.pin_memory().to(dev, torch.bfloat16, non_blocking=True)      # host features in, like the HF pipeline
+            ids = m.generate(f, **kw)
+            ids.cpu()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+        out = {"value": n * CLIP_SECONDS / (ms / 1000.0), "unit": "audio-s/s", "kind": "HF transformers generate, bf16, sdpa, on this GPU",
+               "clips": n, "ms": ms, "note": "log-mel on the host is NOT timed (HF's extractor is numpy); encoder + generate + read-back are"}
+    except Exception as e:                                     # e.g. out of memory at this batch: report, do not fail the bench
+        out = {"value": None, "unit": "audio-s/s", "kind": "HF transformers generate, bf16, sdpa", "error": repr(e)[:200]}
+    finally:
+        del m
+        torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -159,15 +263,18 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--arch", default="small")
+    ap.add_argument("--arch", default="small", choices=list(CONFIG_OF_ARCH))
     ap.add_argument("--batch", type=int, default=int(os.environ.get("WIPA_BENCH_BATCH", "256")),
                     help="clips per GPU per step (the micro-batch of the eval sweep; 16 / 64 / 256 are the named points)")
+    ap.add_argument("--beams", type=int, default=1, help="beam search width (BASELINE configs[3]: medium, 5 beams)")
     ap.add_argument("--dtype", default="float16", choices=["float16", "bfloat16", "float32"],
                     help="float16 (default: libwipa.so, logits within 1e-3 of the fp32 oracle), bfloat16 (libwipa_bf16.so) or float32")
     ap.add_argument("--max-new", type=int, default=220)
     ap.add_argument("--ref-clips", type=int, default=8, help="clips per step of the CPU reference arm (bounded sample)")
     ap.add_argument("--cpu-baseline-clips", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true")
     ap.add_argument("--profiler-range", action="store_true", help="cudaProfilerStart/Stop around the timed region (for ncu --profile-from-start off)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -178,7 +285,7 @@ def main():
 
     import torch.distributed as dist
     import whisper_ipa_b200 as w
-    from whisper_ipa_b200 import _lib, metrics, pipeline
+    from whisper_ipa_b200 import _lib, metrics, parallel, pipeline
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -191,29 +298,22 @@ def main():
     arch = w.ARCHS[args.arch]
 
     hf_model, sd = random_init_state_dict(args.arch)
-    model = w.WhisperIPA(args.arch, dtype=args.dtype, max_batch=B)
+    model = w.WhisperIPA(args.arch, dtype=args.dtype, max_batch=B, max_beams=args.beams)
     model.load_state_dict(sd)
     del sd
-    tr = pipeline.Transcriber(model, max_new=args.max_new)
+    tr = pipeline.Transcriber(model, max_new=args.max_new, num_beams=args.beams)
+    P = len(tr.prompt)
 
-    # this rank's clips: global clip index = step-independent (same audio every step; weights / audio resident)
-    n_total = B * world
-    mine = list(range(rank, n_total, world))
-    audio_host = torch.from_numpy(synthetic_audio(B, first=rank * B)).pin_memory()
+    # The sweep: K * B * world utterances; utterance i belongs to rank i % world and is its (i // world)-th local clip.
+    # Every rank re-uses B distinct synthetic clips K times (weights and audio stay resident; no clip is cached across steps:
+    # the whole path runs for each), references are distinct per utterance.
+    n_total = K * B * world
+    audio_b = torch.from_numpy(synthetic_audio(B, first=rank * B)).pin_memory()          # this rank's B resident clips (pinned)
+    audio_dev = audio_b.to(dev)
+    rows = [j % B for j in range(K * B)]                 # local utterance j -> clip j % B
     refs_all = synthetic_references(n_total)
-    refs = [refs_all[i] for i in mine]
-    rf, ro = metrics._pack(refs)
-    rf_d, ro_d = torch.from_numpy(rf).to(dev), torch.from_numpy(ro).to(dev)
-    max_ref = int(np.max(np.diff(ro)))
-    audio_dev = audio_host.to(dev)
-    gathered = [torch.empty((B, 2), dtype=torch.int32, device=dev) for _ in range(world)] if world > 1 else None
-
-    def device_step():
-        ids, lens = tr.transcribe_device(audio_dev)
-        counts = tr.score_device(ids, lens, rf_d, ro_d, max_ref)
-        if world > 1:
-            dist.all_gather(gathered, counts)        # the one collective of the path: 8 bytes per utterance
-        return ids, lens, counts
+    n_warm = B * world
+    refs_warm = refs_all[:n_warm]
 
     def sync_all():
         torch.cuda.synchronize()
@@ -221,8 +321,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(W):
-        device_step()
+    for _ in range(W):                                   # warm-up steps: one micro-batch per rank each, same code path
+        tr.evaluate_ids(audio_dev, refs_warm, micro_batch=B, local_shard=True)
     sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -233,8 +333,7 @@ def main():
     if args.profiler_range:
         torch.cuda.profiler.start()
     e0.record()
-    for _ in range(K):
-        ids, lens, counts = device_step()
+    res_dev = tr.evaluate_ids(audio_dev, refs_all, micro_batch=B, local_shard=True, local_rows=rows)      # K steps per rank, ONE gather
     e1.record()
     sync_all()
     if args.profiler_range:
@@ -245,40 +344,55 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(launches)
     ms_total = float(ms.item())
-    value = n_total * CLIP_SECONDS * K / (ms_total / 1000.0)
+    value = n_total * CLIP_SECONDS / (ms_total / 1000.0)
 
-    # ---- e2e: host buffers in, host results out, through the public API -----------------------------------------------
-    # Transcriber.evaluate_local over K micro-batches of pinned HOST audio: every step's host->device copy (double-
-    # buffered on a side stream by the pipeline), the references' upload, the PER all-gather and the read-back of ids,
-    # lengths and counts are inside the timed region.
-    audio_all = audio_host.repeat(K, 1).pin_memory() if K > 1 else audio_host
-    refs_k = refs * K
-
-    def e2e_pass():
-        c, hyps, hyp_lens = tr.evaluate_local(audio_all, refs_k, micro_batch=B)
-        if world > 1:
-            for k in range(K):
-                dist.all_gather(gathered, c[k * B:(k + 1) * B].contiguous())
-        return c.cpu(), hyps, hyp_lens
-
-    e2e_pass()                                                  # warm-up: staging buffers, side stream, allocator blocks of K live micro-batches
+    # ---- e2e: pinned host audio in, host results out, through the same public call --------------------------------------
+    tr.evaluate_ids(audio_b, refs_warm, micro_batch=B, local_shard=True)          # warm-up: staging, side stream
     sync_all()
-    best_ms = None
-    for _ in range(2):            # two timed passes of K steps each, the faster one is reported (host-side hiccups are one-off)
-        t0 = torch.cuda.Event(enable_timing=True)
-        t1 = torch.cuda.Event(enable_timing=True)
+    e2e_ms = []
+    for _ in range(2):
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
-        counts_h, hyps_h, lens_h = e2e_pass()
+        res_e2e = tr.evaluate_ids(audio_b, refs_all, micro_batch=B, local_shard=True, local_rows=rows)
         t1.record()
         sync_all()
-        best_ms = t0.elapsed_time(t1) if best_ms is None else min(best_ms, t0.elapsed_time(t1))
-    ms2 = torch.tensor([best_ms], device=dev)
+        e2e_ms.append(t0.elapsed_time(t1))
+    ms2 = torch.tensor([float(np.mean(e2e_ms))], device=dev)             # mean of the timed passes
     if world > 1:
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
-    e2e_value = n_total * CLIP_SECONDS * K / (float(ms2.item()) / 1000.0)
-    h2d = B * N_SAMPLES * 4 + rf.nbytes + ro.nbytes
+    e2e_value = n_total * CLIP_SECONDS / (float(ms2.item()) / 1000.0)
+    mean_ref = float(np.mean([len(r) for r in refs_all]))
+    h2d = B * N_SAMPLES * 4 + int(B * mean_ref * 4) + (B + 1) * 4
     d2h = B * args.max_new * 4 + B * 4 + B * 8
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- the sharded aggregate equals a single-process aggregate over the same utterances ---------------------------------
+    # every rank's hypotheses go to rank 0 (outside the timed regions), which scores all of them with the CPU oracle
+    mine = res_dev["local_indices"]
+    hyp_pad = torch.full((len(mine), args.max_new), -1, dtype=torch.int32)
+    for j, h in enumerate(res_dev["local_hypotheses"]):
+        hyp_pad[j, :len(h)] = torch.tensor(h, dtype=torch.int32)
+    if world > 1:
+        gathered = [torch.empty_like(hyp_pad, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, hyp_pad.to(dev))
+        gathered = [g.cpu() for g in gathered]
+    else:
+        gathered = [hyp_pad]
+    aggregate_check = None
+    if rank == 0:
+        from oracle import per_oracle as po
+        hyps_all = [None] * n_total
+        for r in range(world):
+            for j, i in enumerate(parallel.shard_indices(n_total, r, world)):
+                row = gathered[r][j]
+                hyps_all[i] = row[row >= 0].numpy().astype(np.int32)
+        d = po.levenshtein_batch(refs_all, hyps_all)
+        per_single = [po.per_from_counts(int(x), len(r), len(h)) for x, r, h in zip(d, refs_all, hyps_all)]
+        same = (res_dev["per_scores"] == per_single and res_dev["per"] == np.mean(per_single)
+                and res_dev["per_std"] == np.std(per_single) and res_e2e["per_scores"] == per_single)
+        aggregate_check = {"utterances": n_total, "sharded_equals_single_process": bool(same),
+                           "checker": "CPU oracle (oracle/per_oracle.c) over every rank's hypotheses"}
+        assert same, "the sharded PER aggregate differs from the single-process aggregate over the same utterances"
 
     if rank != 0:
         if world > 1:
@@ -287,6 +401,9 @@ def main():
 
     # ---- where the pass goes: each phase timed on its own (CUDA events, device-resident inputs) --------------------
     from whisper_ipa_b200.audio import log_mel_features
+    rf, ro = metrics._pack(refs_all[:B])
+    rf_d, ro_d = torch.from_numpy(rf).to(dev), torch.from_numpy(ro).to(dev)
+    max_ref = int(np.max(np.diff(ro)))
 
     def timed(fn, reps=2):
         fn()
@@ -301,10 +418,11 @@ def main():
 
     t_mel, mel_dev = timed(lambda: log_mel_features(audio_dev, arch.n_mels))
     t_enc, _ = timed(lambda: model.encoder(mel_dev, return_features=False))
-    t_dec, (ids_d, lens_d) = timed(lambda: model.decode_tokens(tr.prompt, args.max_new))
+    t_dec, (ids_d, lens_d) = timed(lambda: model.decode_tokens(tr.prompt, args.max_new, num_beams=args.beams))
     t_per, _ = timed(lambda: tr.score_device(ids_d, lens_d, rf_d, ro_d, max_ref))
+    steps_per_pass = P - 1 + args.max_new
     phases = {"logmel_ms": t_mel, "encoder_ms": t_enc, "decode_ms": t_dec, "per_ms": t_per,
-              "decode_us_per_step": 1000.0 * t_dec / (PROMPT_LEN - 1 + args.max_new)}
+              "decode_us_per_step": 1000.0 * t_dec / steps_per_pass}
     del mel_dev
 
     # ---- roofline of the dominant kernel: the cross-attention streamer timed alone ---------------------------------
@@ -314,98 +432,142 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     lib = model._lib
     reps = 5
+    S = B * args.beams
+    H, dm, L, ffn, V = arch.heads, arch.d_model, arch.dec_layers, arch.ffn, arch.vocab
     latent = bool(model.info().get("xattn_latent", 0))
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    shape_key = f"{args.arch}/B{B}/beams{args.beams}/{h16 if esz == 2 else 'f32'}"
     if latent:
         # latent cross-attention (attn_lat.cu): one pass over the encoder output E [B, 1500, d] per layer serves every head and
         # both the key and the value role.  Timed on its own buffers of the decode shapes; E (0.59 GB at 256 clips) is far
         # larger than L2, so every launch re-streams it from HBM.
-        H, dm = arch.heads, arch.d_model
         E = torch.randn(B, 1500, dm, device=dev).to(tdt)
-        Qp = (torch.randn(B, H, dm, device=dev) * (1.5 / dm ** 0.5)).to(tdt)
-        Cl = torch.empty(B, H, dm, device=dev, dtype=tdt)
-        utt = torch.arange(B, device=dev, dtype=torch.int32)
-        n_launch = reps * arch.dec_layers
+        Qp = (torch.randn(S, H, dm, device=dev) * (1.5 / dm ** 0.5)).to(tdt)
+        Cl = torch.empty(S, H, dm, device=dev, dtype=tdt)
+        utt = (torch.arange(S, device=dev, dtype=torch.int32) // args.beams).to(torch.int32)
+        n_launch = reps * L
 
         def launch():
-            return lib.wipa_test_cross_attn_latent(Qp.data_ptr(), E.data_ptr(), B, utt.data_ptr(), Cl.data_ptr(), B, H, 1500, st)
-        _lib.check(launch(), "cross_attn_latent")
+            return lib.wipa_test_cross_attn_latent(Qp.data_ptr(), E.data_ptr(), B, utt.data_ptr(), Cl.data_ptr(), S, H, 1500, st)
+        _lib.check(launch(), "cross_attn_latent", lib)
         torch.cuda.synchronize()
         r0.record()
         for _ in range(n_launch):
             launch()
         r1.record()
         torch.cuda.synchronize()
-        kernel_name = "cross_attention_latent_kernel"
-        bytes_per_launch = B * 1500 * dm * 2 + 2 * B * H * dm * 2       # E once + absorbed queries in + context rows out
-        # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_cross_attention_latent_ncu_full.txt:
-        # dram__bytes_read.sum 594.70 MB + dram__bytes_write.sum 7.64 MB at small / B=256); other shapes were not captured
-        traffic = 594.702336e6 + 7.644672e6 if (args.arch == "small" and B == 256) else None
+        kernel_name, source = "cross_attention_latent_kernel", "whisper_ipa_b200/csrc/attn_lat.cu"
+        bytes_per_launch = B * 1500 * dm * 2 + 2 * S * H * dm * 2       # E once + absorbed queries in + context rows out
+        xattn_step_bytes = L * bytes_per_launch
         del E
     else:
-        q = torch.randn(B, arch.d_model, device=dev)
-        for l in range(arch.dec_layers):
-            _lib.check(lib.wipa_test_cross_attn(model._ctx, B, l, q.data_ptr(), None, st), "cross_attn")
+        q = torch.randn(S, dm, device=dev)
+        for l in range(L):
+            _lib.check(lib.wipa_test_cross_attn(model._ctx, S, l, q.data_ptr(), None, st), "cross_attn", lib)
         torch.cuda.synchronize()
         r0.record()
         for _ in range(reps):
-            for l in range(arch.dec_layers):     # 12 distinct K/V caches: the working set cycles through >> L2 bytes
-                lib.wipa_test_cross_attn(model._ctx, B, l, q.data_ptr(), None, st)
+            for l in range(L):     # L distinct K/V caches: the working set cycles through >> L2 bytes
+                lib.wipa_test_cross_attn(model._ctx, S, l, q.data_ptr(), None, st)
         r1.record()
         torch.cuda.synchronize()
-        n_launch = reps * arch.dec_layers
-        kernel_name = "cross_attention_stream_kernel"
-        bytes_per_launch = B * 2 * 1500 * arch.d_model * esz              # K + V of B utterances, one layer
-        # DRAM traffic per launch from the committed `ncu --set full` capture (profiles/r01_cross_attention_stream_ncu_full.txt:
-        # dram__bytes_read.sum 1.180631 GB + dram__bytes_write.sum 4.89 MB at small / bf16 / B=256); other shapes were not captured
-        traffic = 1.180631e9 + 4.891392e6 if (args.arch == "small" and esz == 2 and B == 256) else None
+        n_launch = reps * L
+        kernel_name, source = "cross_attention_stream_kernel", "whisper_ipa_b200/csrc/attn.cu"
+        bytes_per_launch = B * 2 * 1500 * dm * esz                        # K + V of B utterances, one layer
+        xattn_step_bytes = L * bytes_per_launch
     us = 1000.0 * r0.elapsed_time(r1) / n_launch
     achieved = bytes_per_launch / (us * 1e-6) / 1e9
     peak, peak_src = measured_peaks()
-    steps_per_pass = PROMPT_LEN - 1 + args.max_new
-    ca_share = us * 1e-3 * arch.dec_layers * steps_per_pass / (ms_total / K)
+    traffic, traffic_src = committed_traffic(kernel_name, source, shape_key)
+    ca_share = us * 1e-3 * L * steps_per_pass / (ms_total / K)
     roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "us_per_launch": us, "bytes_per_launch": bytes_per_launch,
-                "peak_source": peak_src, "share_of_step_est": ca_share}
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "us_per_launch": us,
+                "bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "share_of_step_est": ca_share}
     if latent:
         # for orientation only: the K/V formulation SURVEY.md 8(d) counts (2 * 1500 * d * 2 bytes per utterance per layer) would
         # have to move twice the bytes in the same time; `achieved` / `frac` above use the bytes THIS kernel's algorithm needs
-        kv_bytes = B * 2 * 1500 * arch.d_model * 2
+        kv_bytes = B * 2 * 1500 * dm * 2
         roofline["kv_formulation_bytes_per_launch"] = kv_bytes
         roofline["kv_formulation_equivalent_gbs"] = kv_bytes / (us * 1e-6) / 1e9
 
+    # the whole decode step against the same peak: algorithmic bytes = cross-attention stream + decoder weights (once per step,
+    # incl. the folded projections in latent mode) + self-KV read at the mean length + new K/V written
+    w_dec = ((L * (6 * dm * dm + 2 * dm * ffn) + V * dm) * esz if not latent
+             else (L * (4 * dm * dm + 2 * H * dm * dm + 2 * dm * ffn) + V * dm) * esz)
+    t_mean = P + (args.max_new - 1) / 2.0
+    self_kv = S * L * 2 * t_mean * dm * esz + S * L * 2 * dm * esz
+    step_bytes = xattn_step_bytes + w_dec + self_kv
+    step_us = phases["decode_us_per_step"]
+    roofline["decode_step"] = {"bytes": step_bytes, "us": step_us, "achieved": step_bytes / (step_us * 1e-6) / 1e9,
+                               "frac": step_bytes / (step_us * 1e-6) / 1e9 / peak, "unit": "GB/s",
+                               "terms": {"cross_attention": xattn_step_bytes, "weights": w_dec, "self_kv": self_kv}}
+    if esz == 2 and args.beams == 1:
+        # the node that ends the step: vocabulary projection fused with the masked argmax (V * d weights streamed once, logits
+        # never stored).  L2 (126 MB) would hold the 80 MB matrix between back-to-back launches, which the real step never
+        # allows: flush it before every timed launch and time each launch on its own.
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+        _lib.check(lib.wipa_test_logits_argmax(model._ctx, S, st), "logits_argmax", lib)
+        ts = []
+        for _ in range(8):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lib.wipa_test_logits_argmax(model._ctx, S, st)
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1000.0)
+        lus = float(np.median(ts))
+        lbytes = V * dm * 2 + S * dm * 2
+        roofline["logits_argmax"] = {"bytes": lbytes, "us": lus, "achieved": lbytes / (lus * 1e-6) / 1e9,
+                                     "frac": lbytes / (lus * 1e-6) / 1e9 / peak, "unit": "GB/s", "l2": "flushed before each launch"}
+        del flush
+
+    parity = None
+    if not args.no_parity and args.beams == 1:
+        parity = parity_vs_hf_fp32(model, hf_model, audio_b, tr.prompt, args.max_new, res_dev["local_hypotheses"])
+    gpu_baseline = None
+    if not args.no_gpu_baseline:
+        gpu_baseline = hf_gpu_baseline(hf_model, audio_b, tr.prompt, args.max_new, B, beams=args.beams)
+
     cpu_baseline = None
     if not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
         import logging
         import warnings
+        from transformers import WhisperFeatureExtractor
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
         warnings.filterwarnings("ignore")
         logging.getLogger("transformers").setLevel(logging.ERROR)
         n = args.cpu_baseline_clips
-        dt, _ = cpu_oracle_pass(hf_model, n, args.max_new)
+        fe = WhisperFeatureExtractor(feature_size=arch.n_mels)
+        dt, _ = cpu_oracle_pass(hf_model, fe, audio_b[:n].numpy(), refs_all[:n], tr.prompt, args.max_new)
         cpu_baseline = {"value": n * CLIP_SECONDS / dt, "unit": "audio-s/s", "cores": cores, "kind": "port",
                         "sample": f"{n} clips x {args.max_new} greedy tokens + PER, HF transformers fp32 (the parity oracle) on {cores} host threads, {dt:.1f} s"}
 
-    d = arch.d_model
     line = {
         "metric": "audio_seconds_per_second", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"float16": "f16", "bfloat16": "bf16", "float32": "f32"}[args.dtype], "data": "synthetic",
-        "config": {"workload": f"whisper-{args.arch} greedy IPA decode + PER, {B} synthetic 30 s clips per GPU per step, "
-                               f"{args.max_new} new tokens, random-init weights (BASELINE configs[2])",
-                   "clips_per_gpu": B, "max_new_tokens": args.max_new, "parallelism": f"dp{world}",
-                   "l2_policy": (f"inputs larger than L2: encoder output {B * 1500 * d * 2 / 1e9:.2f} GB is re-streamed by every decoder layer of "
+        "config": {"workload": f"whisper-{args.arch} {'greedy' if args.beams == 1 else f'beam-{args.beams}'} IPA decode + PER, {B} synthetic "
+                               f"30 s clips per GPU per step, {args.max_new} new tokens, random-init weights (BASELINE "
+                               f"{CONFIG_OF_ARCH[args.arch]}); one evaluate_ids sweep of {n_total} utterances per timed region",
+                   "clips_per_gpu": B, "max_new_tokens": args.max_new, "beams": args.beams, "parallelism": f"dp{world}",
+                   "sweep_utterances": n_total,
+                   "l2_policy": (f"inputs larger than L2: encoder output {B * 1500 * dm * 2 / 1e9:.2f} GB is re-streamed by every decoder layer of "
                                  f"every step, weights every step" if latent else
-                                 f"inputs larger than L2: cross-KV {B * 24 * 1500 * d * esz / 1e9:.2f} GB + weights are re-streamed every decode step"),
+                                 f"inputs larger than L2: cross-KV {B * 2 * L * 1500 * dm * esz / 1e9:.2f} GB + weights are re-streamed every decode step"),
                    "cross_attention": "latent (encoder output, folded k/v projections)" if latent else "per-layer cross-KV"},
-        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "passes_ms": e2e_ms, "reported": "mean of the timed passes"},
         "gpu_launches": int(launches.item()),
         "clocks": clocks,
         "roofline": roofline,
         "phases": phases,
+        "parity": parity,
         "cpu_baseline": cpu_baseline,
-        "per_mean": float(np.mean([metrics.per_from_counts(int(c[0]), int(c[1]), int(l)) for c, l in zip(counts_h.tolist(), lens_h)])),
+        "gpu_baseline": gpu_baseline,
+        "per_mean": float(res_dev["per"]),
+        "aggregate_check": aggregate_check,
     }
     print(json.dumps(line))
     if world > 1:

@@ -183,6 +183,9 @@ int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int*
  * out [B, H*64] in the pool's element type.  All device pointers. */
 int wipa_test_self_attn(const float* q, const void* kpool, const void* vpool, const int* block_table, int bt_stride,
                         const int* pos_ptr, void* out, int B, int H, int is_h16, void* stream);
+/* The node that ends a decode step, alone: fused vocabulary projection + masked argmax over the S rows in the context's
+ * LayerNorm-output buffer (weights V x d streamed once, logits never stored).  16-bit contexts. */
+int wipa_test_logits_argmax(wipa_ctx*, int S, void* stream);
 /* One decode-step cross-attention sweep over the context's cached encoder K/V (the dominant HBM kernel):
  * q: device f32[B, d] (pre-scaled), out: device f32[B, d]; layer selects which cached K/V. */
 int wipa_test_cross_attn(wipa_ctx*, int B, int layer, const float* q, float* out, void* stream);

@@ -1,5 +1,10 @@
 """Summarise an .ncu-rep (read with `ncu -i ... --page raw --csv`) into the handful of counters the roofline uses.
-Usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [> profiles/xxx.txt]"""
+Usage: python scripts/ncu_summary.py gpurun_out/prof.ncu-rep [> profiles/xxx.txt]
+       python scripts/ncu_summary.py gpurun_out/prof.ncu-rep --json profiles/<kernel>.json --kernel <name substring>
+              --source whisper_ipa_b200/csrc/<file>.cu --shape small/B256/beams1/f16 [--captured "r02, command ..."]
+The JSON form is what bench.py's roofline.traffic reads: per-launch DRAM bytes (mean over the captured launches of that
+kernel), duration, pipe utilisation, plus the sha256 of the kernel's source file at capture time - bench.py refuses the
+numbers once that file has changed."""
 import csv
 import io
 import subprocess
@@ -35,5 +40,70 @@ def main(path):
             pass
 
 
+def _num(x):
+    try:
+        return float(x.replace(",", ""))
+    except ValueError:
+        return None
+
+
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3, "second": 1e6}
+
+
+def write_json(path, out_json, kernel, source, shape, captured):
+    import hashlib
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+    sel = [r for r in rows[2:] if kernel in r[col["Kernel Name"]]]
+    if not sel:
+        raise SystemExit(f"no launch of a kernel matching {kernel!r} in {path}")
+
+    def mean(metric, scale_units=True):
+        i = col.get(metric)
+        if i is None:
+            return None
+        vals = [_num(r[i]) for r in sel]
+        vals = [v for v in vals if v is not None]
+        if not vals:
+            return None
+        m = sum(vals) / len(vals)
+        return m * UNIT.get(units[i], 1.0) if scale_units else m
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = {
+        "kernel": sel[0][col["Kernel Name"]], "launches_captured": len(sel), "grid": sel[0][col["Grid Size"]], "block": sel[0][col["Block Size"]],
+        "shape": shape, "captured": captured,
+        "source": source, "source_sha16": hashlib.sha256(open(os.path.join(root, source), "rb").read()).hexdigest()[:16],
+        "duration_us": mean("gpu__time_duration.sum"),
+        "dram_bytes_read": mean("dram__bytes_read.sum"), "dram_bytes_write": mean("dram__bytes_write.sum"),
+        "dram_throughput_pct": mean("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", False),
+        "tensor_pipe_pct": mean("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", False),
+        "sm_throughput_pct": mean("sm__throughput.avg.pct_of_peak_sustained_elapsed", False),
+        "warps_active_pct": mean("sm__warps_active.avg.pct_of_peak_sustained_active", False),
+        "registers_per_thread": mean("launch__registers_per_thread", False),
+        "l2_hit_rate_pct": mean("lts__t_sector_hit_rate.pct", False),
+        "note": "under ncu: cold cache, serialised, replayed ~40x; durations are for shares only, never bench values",
+    }
+    with open(out_json, "w") as f:
+        json.dump(d, f, indent=1)
+        f.write("\n")
+    print(json.dumps(d))
+
+
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if "--json" in sys.argv:
+        import argparse
+        ap = argparse.ArgumentParser()
+        ap.add_argument("rep")
+        ap.add_argument("--json", required=True)
+        ap.add_argument("--kernel", required=True)
+        ap.add_argument("--source", required=True)
+        ap.add_argument("--shape", required=True)
+        ap.add_argument("--captured", default="")
+        a = ap.parse_args()
+        write_json(a.rep, a.json, a.kernel, a.source, a.shape, a.captured)
+    else:
+        main(sys.argv[1])

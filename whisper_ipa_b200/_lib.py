@@ -64,6 +64,7 @@ PROTOTYPES = {
     "wipa_test_gemm_epilogue": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "wipa_test_cross_attn_latent": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_gemm_rows": (_i, [_vp, _i, C.c_longlong, _i, C.c_longlong, _i, _vp, _vp, _i, _i, _i, _vp]),
+    "wipa_test_logits_argmax": (_i, [_vp, _i, _vp]),
     "wipa_test_cross_attn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),
     "wipa_test_enc_attention": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wipa_test_self_attn": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),

@@ -158,8 +158,10 @@ ARCHS: Dict[str, WhisperArch] = {a.name: a for a in (
 
 def arch_from_name(base_model: str) -> WhisperArch:
     """Map a reference-style model id ("mlx-community/whisper-small-mlx", "openai/whisper-large-v3", "small") to an arch."""
-    s = base_model.lower()
-    for key in ("large-v3", "medium", "small", "base", "tiny"):
-        if key in s:
-            return ARCHS[key]
+    import os
+    # the last path component first: a local directory such as /data/base/whisper-small-mlx names "small", not "base"
+    for s in (os.path.basename(base_model.rstrip("/")).lower(), base_model.lower()):
+        for key in ("large-v3", "medium", "small", "base", "tiny"):
+            if key in s:
+                return ARCHS[key]
     raise ValueError(f"cannot infer a Whisper architecture from {base_model!r}")

@@ -464,6 +464,16 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
 //               1: fused / fp32 argmax with the suppress masks
 //               2: store fp32 logits rows at logits_out (row stride ldo)
 // ------------------------------------------------------------------------------------------------
+// fused vocabulary projection + running argmax over the rows in c->dh: the [S, V] logits never reach HBM;
+// leaves (max, argmax) per (row, n-tile) in pmax / pidx for the finalize kernel
+int logits_argmax(wipa_ctx* c, int S, int* n_tiles, cudaStream_t st) {
+    EpiParams ep = epi(EPI_ARGMAX, S, c->a.vocab);
+    ep.pmax = c->pmax; ep.pidx = c->pidx;
+    ep.mask_always = c->mask_always; ep.mask_begin = c->mask_begin; ep.step_ptr = c->d_step;
+    *n_tiles = c->n_logit_tiles;
+    return gemm(c, plainA(c->dh, S, c->a.d_model), c->tok_emb, S, c->a.vocab, c->a.d_model, ep, c->bn_logits, st);
+}
+
 DecodeState make_state(wipa_ctx* c, int n_forced, int max_new, int eot) {
     DecodeState ds;
     ds.pos = c->d_pos; ds.step = c->d_step; ds.cur_tok = c->d_cur_tok; ds.done = c->d_done; ds.n_done = c->d_n_done;
@@ -557,12 +567,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
     if (logits_mode != 0) {
         WIPA_TRY(ln(c, c->dx, c->dec_ln_w, c->dec_ln_b, c->dh, S, st));
         if (logits_mode == 1 && c->bf) {
-            // fused vocabulary projection + running argmax: the [S, V] logits never reach HBM
-            EpiParams ep = epi(EPI_ARGMAX, S, V);
-            ep.pmax = c->pmax; ep.pidx = c->pidx;
-            ep.mask_always = c->mask_always; ep.mask_begin = c->mask_begin; ep.step_ptr = c->d_step;
-            n_tiles = c->n_logit_tiles;
-            if (!(skip & 128)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits, st));
+            if (!(skip & 128)) WIPA_TRY(logits_argmax(c, S, &n_tiles, st));
         } else {
             float* dst = logits_mode == 2 ? logits_out : c->logits;
             EpiParams ep = epi(EPI_STORE, S, V);
@@ -1183,6 +1188,15 @@ extern "C" int wipa_test_cross_attn(wipa_ctx* c, int B, int layer, const float* 
                                                 c->ca_counters, B, c->a.heads, c->ca_split, 0, st));
     if (out) WIPA_TRY(launch_to_f32(c->dattn, c->bf, out, (long long)B * c->a.d_model, st));
     return WIPA_OK;
+}
+
+// the fused vocabulary projection + argmax node of a decode step alone, on the S rows currently in the context's
+// LayerNorm-output buffer (16-bit contexts only): bench.py times it for its achieved HBM GB/s
+extern "C" int wipa_test_logits_argmax(wipa_ctx* c, int S, void* stream) {
+    WIPA_CHECK(c && c->bf && S >= 1 && S <= c->max_seqs, WIPA_EINVAL, "wipa_test_logits_argmax: 16-bit context and 1 <= S <= %d", c ? c->max_seqs : 0);
+    WIPA_TRY(require_weights(c));
+    int n_tiles = 0;
+    return logits_argmax(c, S, &n_tiles, (cudaStream_t)stream);
 }
 
 // latent cross-attention kernel alone: Qp h16 [S, H, 64H] absorbed queries, E h16 [U, T, 64H], utt_of_seq int32 [S]

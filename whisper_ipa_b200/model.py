@@ -37,6 +37,15 @@ def _i32_array(values: Sequence[int]):
     return arr
 
 
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    """Whisper's fixed positional table [length, channels], op for op as HF:models/whisper/modeling_whisper.py:55-65."""
+    import math
+    log_timescale_increment = math.log(max_timescale) / (channels // 2 - 1)
+    inv_timescales = torch.exp(-log_timescale_increment * torch.arange(channels // 2))
+    scaled_time = torch.arange(length).view(-1, 1) * inv_timescales.view(1, -1)
+    return torch.cat([scaled_time.sin(), scaled_time.cos()], dim=1)
+
+
 class WhisperIPA:
     """One Whisper replica on one GPU (weights + workspaces + KV caches live in a ``wipa_ctx``)."""
 
@@ -60,7 +69,13 @@ class WhisperIPA:
         with torch.cuda.device(self.device):
             self._check(self._lib.wipa_ctx_create(C.byref(self._arch_c), self.max_batch, self.max_beams,
                                                   C.byref(self._ctx)), "wipa_ctx_create")
+        # The encoder's position table is a constant, not a learned weight, and MLX-format checkpoints do not carry it.
+        # Load HF's own construction of it (float32 torch ops on the host, bit-identical to what WhisperEncoder.__init__
+        # writes); a state dict that has "model.encoder.embed_positions.weight" simply overwrites it.  (libwipa pre-fills
+        # the slot with double-precision sinusoids for callers of the bare C ABI.)
         self._n_encoded = 0
+        self._features_key = None
+        self.load_state_dict({"model.encoder.embed_positions.weight": sinusoids(T_ENC, a.d_model)})
         self.suppress_tokens: List[int] = []
         self.begin_suppress_tokens: List[int] = [220, a.eot]
 
@@ -102,6 +117,7 @@ class WhisperIPA:
         if strict and unknown:
             raise KeyError(f"unrecognised tensors: {unknown[:5]}{'...' if len(unknown) > 5 else ''}")
         self._n_encoded = 0
+        self._features_key = None
         return unknown
 
     def update(self, params: Mapping[str, Union[torch.Tensor, np.ndarray]]) -> None:
@@ -142,13 +158,18 @@ class WhisperIPA:
             self._check(self._lib.wipa_encode(self._ctx, feats.data_ptr(), B, out.data_ptr() if out is not None else None,
                                               _stream()), "wipa_encode")
         self._n_encoded = B
+        self._features_key = None if out is None else (out.data_ptr(), tuple(out.shape), out._version)
         return out
 
     embed_audio = encoder
     __call_encoder__ = encoder
 
     def set_audio_features(self, audio_features: torch.Tensor) -> None:
-        af = torch.as_tensor(audio_features).to(device=self.device, dtype=torch.float32).contiguous()
+        af = torch.as_tensor(audio_features)
+        if (self._features_key is not None and af.is_cuda and self._n_encoded == (af.shape[0] if af.dim() == 3 else 1)
+                and self._features_key == (af.data_ptr(), tuple(af.shape), af._version)):
+            return          # exactly the tensor encoder() just returned (the reference's `decode(model, model.encoder(mel), ...)`)
+        af = af.to(device=self.device, dtype=torch.float32).contiguous()
         if af.dim() == 2:
             af = af[None]
         if af.shape[1:] != (T_ENC, self.arch.d_model):

@@ -26,8 +26,10 @@ def hyps_to_csr(ids: torch.Tensor, lens: torch.Tensor):
 
 
 class Transcriber:
-    def __init__(self, model: WhisperIPA, max_new: Optional[int] = None, prompt: Optional[Sequence[int]] = None):
+    def __init__(self, model: WhisperIPA, max_new: Optional[int] = None, prompt: Optional[Sequence[int]] = None,
+                 num_beams: int = 1, length_penalty: float = 1.0):
         self.model = model
+        self.num_beams, self.length_penalty = int(num_beams), float(length_penalty)
         self.prompt = list(prompt) if prompt is not None else model.arch.prompt("en", "transcribe", True)
         # the reference samples sample_len = 224 tokens after the prompt (mlx_whisper: `for i in range(sample_len)`)
         self.max_new = int(max_new) if max_new is not None else min(224, 448 - len(self.prompt))
@@ -36,7 +38,7 @@ class Transcriber:
         """audio f32 [B, 480000] already in HBM -> device (ids [B, max_new], lens [B])."""
         mel = log_mel_features(audio_dev, self.model.arch.n_mels)
         self.model.encoder(mel, return_features=False)
-        return self.model.decode_tokens(self.prompt, self.max_new)
+        return self.model.decode_tokens(self.prompt, self.max_new, num_beams=self.num_beams, length_penalty=self.length_penalty)
 
     def score_device(self, ids: torch.Tensor, lens: torch.Tensor, ref_flat: torch.Tensor, ref_off: torch.Tensor,
                      max_ref_len: int) -> torch.Tensor:
@@ -44,12 +46,16 @@ class Transcriber:
         return metrics.edit_distance_counts_device(ref_flat, ref_off, hyp_flat, hyp_off, max_ref_len)
 
     def evaluate_local(self, audio, references: Sequence[Sequence[int]], indices: Optional[Sequence[int]] = None,
-                       micro_batch: Optional[int] = None):
+                       micro_batch: Optional[int] = None, audio_rows: Optional[Sequence[int]] = None):
         """Transcribe + score the utterances `indices` of `audio` (host numpy / torch f32 [N, 480000], ideally pinned; or a
         device tensor) against `references[i]`.  Micro-batches are double-buffered: while batch k is being transcribed,
         batch k+1 is gathered into a pinned staging buffer and copied host->device on a side stream.
+        ``audio_rows[j]`` names the row of `audio` that holds utterance `indices[j]` (default: the index itself).
         Returns (counts int32 [n, 2] on the device, hypotheses list, hypothesis lengths list), in `indices` order."""
         idx_all = list(range(len(references))) if indices is None else list(indices)
+        rows_all = idx_all if audio_rows is None else list(audio_rows)
+        if len(rows_all) != len(idx_all):
+            raise ValueError("audio_rows must name one row per utterance")
         mb = micro_batch or self.model.max_batch
         dev = self.model.device
         n = len(idx_all)
@@ -59,13 +65,14 @@ class Transcriber:
         copy_stream = torch.cuda.Stream(device=dev) if not on_device else None
         staging = [None, None]
         chunks = [idx_all[s:s + mb] for s in range(0, n, mb)]
+        row_chunks = [rows_all[s:s + mb] for s in range(0, n, mb)]
 
         def stage(k):
             """Start the host->device copy of micro-batch k; returns (device tensor, ready event)."""
-            idx = chunks[k]
-            if on_device:
-                return audio[torch.as_tensor(idx, device=audio.device)], None
+            idx = row_chunks[k]
             contiguous = all(idx[j] + 1 == idx[j + 1] for j in range(len(idx) - 1))
+            if on_device:
+                return (audio[idx[0]:idx[0] + len(idx)] if contiguous else audio[torch.as_tensor(idx, device=audio.device)]), None
             if contiguous and host.is_pinned():
                 src = host[idx[0]:idx[0] + len(idx)]                      # a view: still pinned, no host copy
             else:
@@ -104,15 +111,26 @@ class Transcriber:
                 hyp_lens.append(int(lens_h[j]))
         return counts, hyps, hyp_lens
 
-    def evaluate_ids(self, audio, references: Sequence[Sequence[int]], micro_batch: Optional[int] = None) -> Dict:
-        """audio: host (numpy / pinned torch) or device f32 [N, 480000]; references: N id sequences.
-        Every rank passes the FULL inputs and works on its strided shard; returns the evaluate_batch-style PER dict
-        (identical on every rank) plus the hypotheses of the local shard."""
+    def evaluate_ids(self, audio, references: Sequence[Sequence[int]], micro_batch: Optional[int] = None,
+                     local_shard: bool = False, local_rows: Optional[Sequence[int]] = None) -> Dict:
+        """audio: host (numpy / pinned torch) or device f32 [N, 480000]; references: N id sequences (always the full list).
+        Every rank works on its strided shard `i % world == rank` and the per-utterance (distance, reference length) pairs are
+        exchanged ONCE per sweep; returns the evaluate_batch-style PER dict (identical on every rank) plus the hypotheses of
+        the local shard.  ``local_shard``: `audio` holds only this rank's clips, in shard order (row j = utterance
+        rank + j * world) - what a sharded data loader provides - instead of all N; ``local_rows[j]`` then overrides which row
+        of `audio` local utterance j uses (a sweep that re-uses a resident set of clips)."""
         n_total = len(references)
         rank, ws = parallel.world()
         mine = parallel.shard_indices(n_total, rank, ws)
         dev = self.model.device
-        counts_local, hyps_local, lens_local = self.evaluate_local(audio, references, mine, micro_batch)
+        if local_shard:
+            rows = list(range(len(mine))) if local_rows is None else list(local_rows)
+            if len(rows) != len(mine) or (len(rows) and max(rows) >= len(audio)):
+                raise ValueError(f"local_shard: {len(rows)} audio rows (max {max(rows) if rows else -1}) for a shard of {len(mine)} "
+                                 f"utterances and {len(audio)} clips")
+            counts_local, hyps_local, lens_local = self.evaluate_local(audio, references, mine, micro_batch, audio_rows=rows)
+        else:
+            counts_local, hyps_local, lens_local = self.evaluate_local(audio, references, mine, micro_batch)
         hyp_lens = np.zeros(n_total, dtype=np.int64)
         hyp_lens[mine] = lens_local
         table = parallel.gather_counts(counts_local, n_total)

@@ -176,6 +176,7 @@ def transcribe(audio: Union[str, np.ndarray, torch.Tensor], model, *, language: 
     segments: List[Dict] = []
     tb = arch.timestamp_begin
     while seek < content_frames:
+        seek_before = seek
         time_offset = seek * HOP / SAMPLE_RATE
         segment_size = min(N_FRAMES, content_frames - seek)
         segment_duration = segment_size * HOP / SAMPLE_RATE
@@ -225,6 +226,8 @@ def transcribe(audio: Union[str, np.ndarray, torch.Tensor], model, *, language: 
                 duration = (ts[-1] - tb) * TIME_PRECISION
             new_segment(time_offset, time_offset + duration, tokens)
             seek += segment_size
+        if seek <= seek_before:
+            seek = seek_before + segment_size        # a closing timestamp of 0.00 must not stall the loop
         if not condition_on_previous_text or result.temperature > 0.5:
             prompt_reset_since = len(all_tokens)     # do not feed a prompt that is likely wrong
         for seg in current:
