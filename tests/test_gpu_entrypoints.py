@@ -232,8 +232,10 @@ def test_language_none_matches_hf_detect_language_and_per_row_prompts(w, tiny_ga
     assert all(abs(sum(p.values()) - 1.0) < 1e-4 for p in probs)
     res = m.decode(mel, w.DecodingOptions(language=None, without_timestamps=True, fp16=False, sample_len=20))
     assert [r.language for r in res] == want_lang
-    got = torch.tensor([r.tokens + [arch.eot] * (want_ids.shape[1] - len(r.tokens)) for r in res])
-    assert torch.equal(got, want_ids)
+    # HF's generate() is its long-form loop: a row that samples timestamp tokens (nothing suppresses them here) gets a second
+    # segment appended, so only the first window's 20 tokens are comparable
+    got = torch.tensor([r.tokens + [arch.eot] * (20 - len(r.tokens)) for r in res])
+    assert torch.equal(got, want_ids[:, :20])
     print(f"\n[language=None] detected {want_lang}")
     m.close()
 

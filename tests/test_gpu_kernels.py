@@ -219,11 +219,14 @@ def test_cross_attention_streamer(lib, tiny_sd, dtype, tol, monkeypatch):
     m.close()
 
 
-@pytest.mark.parametrize("H,T,S,U", [(12, 1500, 5, 3), (12, 100, 200, 4), (6, 1500, 3, 3), (16, 333, 4, 2), (8, 48, 2, 1)])
-def test_cross_attention_latent(lib, h16, H, T, S, U):
-    """Latent cross-attention kernel (mma.sync over TMA-swizzled tiles of the encoder output): C = softmax(Q' E^T) E per
+@pytest.mark.parametrize("pipe", [0, 1])
+@pytest.mark.parametrize("H,T,S,U", [(12, 1500, 5, 3), (12, 100, 200, 4), (6, 1500, 3, 3), (16, 333, 4, 2), (8, 48, 2, 1), (12, 1500, 300, 150)])
+def test_cross_attention_latent(lib, h16, H, T, S, U, pipe, monkeypatch):
+    """`pipe` selects the pipelined variant (WIPA_XL_PIPE=1: 32-key chunks, 3-stage ring, one barrier per chunk; up to 12 heads).
+    Latent cross-attention kernel (mma.sync over TMA-swizzled tiles of the encoder output): C = softmax(Q' E^T) E per
     sequence, sequences mapped to utterances (beams share E), more sequences than SMs, ragged last key chunk, both key
     chunk sizes (48 keys up to 12 heads, 32 above)."""
+    monkeypatch.setenv("WIPA_XL_PIPE", str(pipe))
     d = 64 * H
     g = torch.Generator(device="cuda").manual_seed(H * 1000 + T + S)
     E = torch.randn(U, T, d, device="cuda", generator=g).to(lib.torch_h16(h16))

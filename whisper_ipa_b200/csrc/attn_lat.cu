@@ -97,6 +97,95 @@ __device__ __forceinline__ float ex2_ftz(float x) {
     return y;
 }
 
+// End of a (sequence, chunk range) segment: a whole sequence is normalised and stored from registers; a part of one
+// leaves (m, l, unnormalised C) in this CTA's slot, and the CTA that completes the sequence's chunk count merges the
+// slots in order.  Called by every consumer thread of the CTA (it contains named barriers).
+template <int H>
+__device__ __forceinline__ void xl_finish_segment(int s, int ch0, int ch1, int n_chunks, long long n_units, float (&acc)[8][4],
+                                                  float (&accl)[4], float m_run, h16* __restrict__ Cout, float* __restrict__ part,
+                                                  int* __restrict__ counters, int slots_per_seq, int* last_flag, int w, int lane) {
+    constexpr int d = H * 64;
+    constexpr int nthr = H * 32;
+    const int g = lane >> 2, t = lane & 3;
+    const bool row_lo = g < H, row_hi = g + 8 < H;
+    if (ch0 == 0 && ch1 == n_chunks) {
+        // the whole sequence was ours: normalise and store
+        const float il_lo = row_lo ? 1.f / accl[0] : 0.f, il_hi = row_hi ? 1.f / accl[2] : 0.f;
+        h16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
+        h16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_h16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
+            if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_h16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
+        }
+        return;
+    }
+    // a part of the sequence: leave (m, l, unnormalised C) in this CTA's slot of the sequence; whoever brings the
+    // sequence's chunk count to n_chunks merges the slots in order (deterministic) and stores
+    constexpr int SLOT_FLOATS = H * 1024 + 32;                 // [warp][lane][32 accumulators] + m[16] + l[16]
+    const long long first_unit = (long long)s * n_chunks;
+    const int cta_first = (int)(((first_unit + 1) * gridDim.x + n_units - 1) / n_units) - 1;      // CTA holding chunk 0
+    const int cta_last = (int)(((first_unit + n_chunks) * gridDim.x + n_units - 1) / n_units) - 1; // CTA holding the last chunk
+    float* seq_part = part + (size_t)s * slots_per_seq * SLOT_FLOATS;
+    {
+        float* slot = seq_part + (size_t)((int)blockIdx.x - cta_first) * SLOT_FLOATS;
+        float4* dst = reinterpret_cast<float4*>(slot + (w * 32 + lane) * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+        if (lane == 0) slot[H * 1024 + w] = m_run;
+        if (w == 0 && t == 0) {                                  // every warp holds the same l: warp 0 writes rows g / g + 8
+            if (row_lo) slot[H * 1024 + 16 + g] = accl[0];
+            if (row_hi) slot[H * 1024 + 16 + g + 8] = accl[2];
+        }
+    }
+    __threadfence();
+    xl_bar(nthr);
+    if (threadIdx.x == 0) {
+        const int mine = ch1 - ch0;
+        const int old = atomicAdd(&counters[s], mine);
+        const bool last = old + mine == n_chunks;
+        if (last) counters[s] = 0;                               // ready for the next launch
+        *last_flag = last ? 1 : 0;                             // next written after at least two more barriers
+    }
+    xl_bar(nthr);
+    if (*last_flag == 0) return;
+    __threadfence();
+    {
+        const int n_slots = cta_last - cta_first + 1;
+        float M_lo = -INFINITY, M_hi = -INFINITY;
+        for (int i = 0; i < n_slots; ++i) {
+            const float* sl = seq_part + (size_t)i * SLOT_FLOATS + H * 1024;
+            if (row_lo) M_lo = fmaxf(M_lo, __ldcg(sl + g));
+            if (row_hi) M_hi = fmaxf(M_hi, __ldcg(sl + g + 8));
+        }
+        float l_lo = 0.f, l_hi = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+        for (int i = 0; i < n_slots; ++i) {
+            const float* sl = seq_part + (size_t)i * SLOT_FLOATS;
+            const float f_lo = row_lo ? ex2_ftz((__ldcg(sl + H * 1024 + g) - M_lo) * XL_LOG2E) : 0.f;
+            const float f_hi = row_hi ? ex2_ftz((__ldcg(sl + H * 1024 + g + 8) - M_hi) * XL_LOG2E) : 0.f;
+            if (row_lo) l_lo = fmaf(f_lo, __ldcg(sl + H * 1024 + 16 + g), l_lo);
+            if (row_hi) l_hi = fmaf(f_hi, __ldcg(sl + H * 1024 + 16 + g + 8), l_hi);
+            const float4* src = reinterpret_cast<const float4*>(sl + (w * 32 + lane) * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 v = __ldcg(src + j);
+                acc[j][0] = fmaf(f_lo, v.x, acc[j][0]); acc[j][1] = fmaf(f_lo, v.y, acc[j][1]);
+                acc[j][2] = fmaf(f_hi, v.z, acc[j][2]); acc[j][3] = fmaf(f_hi, v.w, acc[j][3]);
+            }
+        }
+        const float il_lo = row_lo ? 1.f / l_lo : 0.f, il_hi = row_hi ? 1.f / l_hi : 0.f;
+        h16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
+        h16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_h16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
+            if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_h16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
+        }
+    }
+}
+
 template <int KEYS, int H>
 __global__ void __launch_bounds__((H + 1) * 32, 1)
 cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Qp,
@@ -111,7 +200,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
     uint8_t* sE = smem;                                                      // [stage][H tiles][KEYS][128 B], 128B-swizzled
     float* Sp = reinterpret_cast<float*>(sE + XL_STAGES * stage_bytes);      // [warp][head][PITCH]
     h16* Pm = reinterpret_cast<h16*>(Sp + H * H * PITCH);                  // [16][PITCH]
-    float* alpha = reinterpret_cast<float*>(Pm + 16 * PITCH);                // [16] rescale of C (+ 16 spare floats)
+    float* alpha = reinterpret_cast<float*>(Pm + 16 * PITCH);                // [16] rescale of C, [16] final 1 / l
     uint64_t* full = reinterpret_cast<uint64_t*>(alpha + 32);
     uint64_t* empty = full + XL_STAGES;
     int* last_flag = reinterpret_cast<int*>(empty + XL_STAGES);
@@ -291,82 +380,219 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
             if (lane == 0) ptx::mbar_arrive(&empty[st]);
             if (++st == XL_STAGES) { st = 0; ph ^= 1; }
         }
-        if (ch0 == 0 && ch1 == n_chunks) {
-            // the whole sequence was ours: normalise and store
-            const float il_lo = row_lo ? 1.f / accl[0] : 0.f, il_hi = row_hi ? 1.f / accl[2] : 0.f;
-            h16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
-            h16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_h16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
-                if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_h16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
+        xl_finish_segment<H>(s, ch0, ch1, n_chunks, n_units, acc, accl, m_run, Cout, part, counters, slots_per_seq, last_flag, w, lane);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined variant (UNVALIDATED ON HARDWARE: written after the round's GPU budget was spent; WIPA_XL_PIPE=1 selects it).
+// Same algorithm and scratch protocol; 32-key chunks in a 3-stage ring and ONE named barrier per chunk.  Between two
+// barriers every consumer warp runs, as one instruction stream,
+//     P.E of chunk i-1   (tensor pipe; P[(i-1)&1] and alpha[(i-1)&1] were published before the barrier)
+//     reduction of chunk i (LDS / redux / MUFU latency chain; Sp[i&1] was completed before the barrier)
+//     scores of chunk i+1  (tensor pipe; writes Sp[(i+1)&1])
+// so the reduction's latency hides behind the two MMA phases instead of idling the tensor pipe.
+// ------------------------------------------------------------------------------------------------
+template <int H>
+struct XlPipeCfg {
+    static constexpr int KEYS = 32, STAGES = 3, PITCH = KEYS + 8;
+    static constexpr size_t smem() {
+        return (size_t)STAGES * KEYS * H * 128 + 2 * (size_t)H * H * PITCH * 4 + 2 * 16 * PITCH * 2 + 2 * 16 * 4 + 64 + 1024;
+    }
+};
+
+template <int H>
+__global__ void __launch_bounds__((H + 1) * 32, 1)
+cross_attention_latent_pipe_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Qp,
+                                   const int* __restrict__ utt_of_seq, h16* __restrict__ Cout, int S, int T,
+                                   float* __restrict__ part, int* __restrict__ counters, int slots_per_seq) {
+    using Cfg = XlPipeCfg<H>;
+    constexpr int KEYS = Cfg::KEYS, STAGES = Cfg::STAGES, PITCH = Cfg::PITCH;
+    extern __shared__ uint8_t xl_smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xl_smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int d = H * 64;
+    constexpr uint32_t stage_bytes = (uint32_t)KEYS * (uint32_t)H * 128u;
+    uint8_t* sE = smem;                                                      // [stage][H tiles][KEYS][128 B], 128B-swizzled
+    float* Sp = reinterpret_cast<float*>(sE + STAGES * stage_bytes);         // [2][warp][head][PITCH]
+    h16* Pm = reinterpret_cast<h16*>(Sp + 2 * H * H * PITCH);              // [2][16][PITCH]
+    float* alpha = reinterpret_cast<float*>(Pm + 2 * 16 * PITCH);            // [2][16]
+    uint64_t* full = reinterpret_cast<uint64_t*>(alpha + 32);
+    uint64_t* empty = full + STAGES;
+    int* last_flag = reinterpret_cast<int*>(empty + STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_chunks = (T + KEYS - 1) / KEYS;
+    const long long n_units = (long long)S * n_chunks;
+    const long long u_lo = n_units * blockIdx.x / gridDim.x, u_hi = n_units * (blockIdx.x + 1) / gridDim.x;
+
+    if (threadIdx.x == 0) {
+        ptx::prefetch_tensormap(&tmE);
+        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], (uint32_t)H); }
+        ptx::fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 2 * 16 * PITCH; i += blockDim.x) Pm[i] = f32_to_h16(0.f);
+    if (threadIdx.x < 32) alpha[threadIdx.x] = 1.f;
+    __syncthreads();
+
+    if (warp == H) {
+        int st = 0;
+        uint32_t ph = 0;
+        for (long long unit = u_lo; unit < u_hi;) {
+            const int s = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)s * n_chunks);
+            const int ch1 = (u_hi - unit) < (long long)(n_chunks - ch0) ? ch0 + (int)(u_hi - unit) : n_chunks;
+            unit += ch1 - ch0;
+            const int u = utt_of_seq[s];
+            for (int ch = ch0; ch < ch1; ++ch) {
+                ptx::mbar_wait(&empty[st], ph ^ 1);
+                if (ptx::elect_one()) {
+                    ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+                    uint8_t* dst = sE + st * stage_bytes;
+                    for (int h = 0; h < H; ++h)
+                        ptx::tma_load_3d(dst + h * (KEYS * 128), &tmE, &full[st], h * 64, ch * KEYS, u);
+                }
+                __syncwarp();
+                if (++st == STAGES) { st = 0; ph ^= 1; }
             }
-            continue;
         }
-        // a part of the sequence: leave (m, l, unnormalised C) in this CTA's slot of the sequence; whoever brings the
-        // sequence's chunk count to n_chunks merges the slots in order (deterministic) and stores
-        constexpr int SLOT_FLOATS = H * 1024 + 32;                 // [warp][lane][32 accumulators] + m[16] + l[16]
-        const long long first_unit = (long long)s * n_chunks;
-        const int cta_first = (int)(((first_unit + 1) * gridDim.x + n_units - 1) / n_units) - 1;      // CTA holding chunk 0
-        const int cta_last = (int)(((first_unit + n_chunks) * gridDim.x + n_units - 1) / n_units) - 1; // CTA holding the last chunk
-        float* seq_part = part + (size_t)s * slots_per_seq * SLOT_FLOATS;
+        return;
+    }
+
+    const int w = warp;
+    const int g = lane >> 2, t = lane & 3;
+    constexpr int nthr = H * 32;
+    const bool row_lo = g < H, row_hi = g + 8 < H;
+    pdl_wait();
+    pdl_launch_dependents();
+    const uint32_t sE_s = ptx::smem_u32(sE), Pm_s = ptx::smem_u32(Pm), Sp_s = ptx::smem_u32(Sp);
+    // ring position of the next chunk whose scores start (sc_*) and of the next chunk whose P.E finishes (pv_*): chunks
+    // are consumed in the order the producer loads them
+    int sc_st = 0, pv_st = 0;
+    uint32_t sc_ph = 0;
+
+    for (long long unit = u_lo; unit < u_hi;) {
+        const int s = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)s * n_chunks);
+        const int ch1 = (u_hi - unit) < (long long)(n_chunks - ch0) ? ch0 + (int)(u_hi - unit) : n_chunks;
+        unit += ch1 - ch0;
+        uint32_t qa[4][4];
         {
-            float* slot = seq_part + (size_t)((int)blockIdx.x - cta_first) * SLOT_FLOATS;
-            float4* dst = reinterpret_cast<float4*>(slot + (w * 32 + lane) * 32);
+            const uint32_t* q_lo = reinterpret_cast<const uint32_t*>(Qp + ((size_t)s * H + g) * d + w * 64 + 2 * t);
+            const uint32_t* q_hi = reinterpret_cast<const uint32_t*>(Qp + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
-            if (lane == 0) slot[H * 1024 + w] = m_run;
-            if (w == 0 && t == 0) {                                  // every warp holds the same l: warp 0 writes rows g / g + 8
-                if (row_lo) slot[H * 1024 + 16 + g] = accl[0];
-                if (row_hi) slot[H * 1024 + 16 + g + 8] = accl[2];
+            for (int ks = 0; ks < 4; ++ks) {
+                qa[ks][0] = row_lo ? q_lo[ks * 8] : 0u;
+                qa[ks][1] = row_hi ? q_hi[ks * 8] : 0u;
+                qa[ks][2] = row_lo ? q_lo[ks * 8 + 4] : 0u;
+                qa[ks][3] = row_hi ? q_hi[ks * 8 + 4] : 0u;
             }
         }
-        __threadfence();
-        xl_bar(nthr);
-        if (threadIdx.x == 0) {
-            const int mine = ch1 - ch0;
-            const int old = atomicAdd(&counters[s], mine);
-            const bool last = old + mine == n_chunks;
-            if (last) counters[s] = 0;                               // ready for the next launch
-            *last_flag = last ? 1 : 0;                             // next written after at least two more barriers
-        }
-        xl_bar(nthr);
-        if (*last_flag == 0) continue;
-        __threadfence();
-        {
-            const int n_slots = cta_last - cta_first + 1;
-            float M_lo = -INFINITY, M_hi = -INFINITY;
-            for (int i = 0; i < n_slots; ++i) {
-                const float* sl = seq_part + (size_t)i * SLOT_FLOATS + H * 1024;
-                if (row_lo) M_lo = fmaxf(M_lo, __ldcg(sl + g));
-                if (row_hi) M_hi = fmaxf(M_hi, __ldcg(sl + g + 8));
-            }
-            float l_lo = 0.f, l_hi = 0.f;
+        float acc[8][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
-            for (int i = 0; i < n_slots; ++i) {
-                const float* sl = seq_part + (size_t)i * SLOT_FLOATS;
-                const float f_lo = row_lo ? ex2_ftz((__ldcg(sl + H * 1024 + g) - M_lo) * XL_LOG2E) : 0.f;
-                const float f_hi = row_hi ? ex2_ftz((__ldcg(sl + H * 1024 + g + 8) - M_hi) * XL_LOG2E) : 0.f;
-                if (row_lo) l_lo = fmaf(f_lo, __ldcg(sl + H * 1024 + 16 + g), l_lo);
-                if (row_hi) l_hi = fmaf(f_hi, __ldcg(sl + H * 1024 + 16 + g + 8), l_hi);
-                const float4* src = reinterpret_cast<const float4*>(sl + (w * 32 + lane) * 32);
+        for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+        float accl[4] = {0.f, 0.f, 0.f, 0.f};
+        float m_run = -INFINITY;
+
+        // scores of the next chunk in ring order over this warp's columns -> Sp[buf]
+        auto scores = [&](int buf) {
+            ptx::mbar_wait(&full[sc_st], sc_ph);
+            const uint32_t tile = sE_s + (uint32_t)sc_st * stage_bytes + (uint32_t)w * (KEYS * 128);
+            uint32_t bfr[KEYS / 8][2][4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 v = __ldcg(src + j);
-                    acc[j][0] = fmaf(f_lo, v.x, acc[j][0]); acc[j][1] = fmaf(f_lo, v.y, acc[j][1]);
-                    acc[j][2] = fmaf(f_hi, v.z, acc[j][2]); acc[j][3] = fmaf(f_hi, v.w, acc[j][3]);
+            for (int nt = 0; nt < KEYS / 8; ++nt) {
+                const int key = nt * 8 + (lane & 7);
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int c16 = half * 4 + (lane >> 3);
+                    ldmatrix_x4(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), bfr[nt][half][0], bfr[nt][half][1],
+                                bfr[nt][half][2], bfr[nt][half][3]);
                 }
             }
-            const float il_lo = row_lo ? 1.f / l_lo : 0.f, il_hi = row_hi ? 1.f / l_hi : 0.f;
-            h16* c_lo = Cout + ((size_t)s * H + g) * d + w * 64 + 2 * t;
-            h16* c_hi = Cout + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t;
+            float sc[KEYS / 8][4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (row_lo) *reinterpret_cast<uint32_t*>(c_lo + j * 8) = pack_h16x2(acc[j][0] * il_lo, acc[j][1] * il_lo);
-                if (row_hi) *reinterpret_cast<uint32_t*>(c_hi + j * 8) = pack_h16x2(acc[j][2] * il_hi, acc[j][3] * il_hi);
+            for (int nt = 0; nt < KEYS / 8; ++nt) { sc[nt][0] = 0.f; sc[nt][1] = 0.f; sc[nt][2] = 0.f; sc[nt][3] = 0.f; }
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                for (int nt = 0; nt < KEYS / 8; ++nt)
+                    mma_h16(sc[nt], qa[ks], bfr[nt][ks >> 1][(ks & 1) * 2], bfr[nt][ks >> 1][(ks & 1) * 2 + 1]);
             }
+            const uint32_t base = Sp_s + (uint32_t)(buf * H * H * PITCH) * 4u;
+#pragma unroll
+            for (int nt = 0; nt < KEYS / 8; ++nt) {
+                if (row_lo) sts_f32x2(base + (uint32_t)((w * H + g) * PITCH + nt * 8 + 2 * t) * 4u, sc[nt][0], sc[nt][1]);
+                if (row_hi) sts_f32x2(base + (uint32_t)((w * H + g + 8) * PITCH + nt * 8 + 2 * t) * 4u, sc[nt][2], sc[nt][3]);
+            }
+            if (++sc_st == STAGES) { sc_st = 0; sc_ph ^= 1; }
+        };
+        // head w of chunk ch: sum the partials in Sp[buf], maximum by redux.sync, p -> Pm[buf], rescale factor -> alpha[buf]
+        auto reduce = [&](int ch, int buf) {
+            const uint32_t row = Sp_s + (uint32_t)(buf * H * H * PITCH + w * PITCH + lane) * 4u;
+            float va = 0.f, vb = 0.f;
+#pragma unroll
+            for (int ww = 0; ww < H; ww += 2) {
+                va += lds_f32(row + (uint32_t)(ww * H * PITCH) * 4u);
+                vb += lds_f32(row + (uint32_t)((ww + 1) * H * PITCH) * 4u);
+            }
+            float v = va + vb;
+            if (ch * KEYS + lane >= T) v = -INFINITY;
+            const float m_new = fmaxf(m_run, warp_max_f32(v));       // finite: every chunk holds a valid key
+            const float mb = m_new * XL_LOG2E;
+            const float p = ex2_ftz(fmaf(v, XL_LOG2E, -mb));
+            const float a = ex2_ftz(fmaf(m_run, XL_LOG2E, -mb));
+            m_run = m_new;
+            sts_b16(Pm_s + (uint32_t)(buf * 16 * PITCH + w * PITCH + lane) * 2u, f32_to_h16(p));
+            if (lane == 0) alpha[buf * 16 + w] = a;
+        };
+        // C = alpha * C + P E (and l = alpha * l + P x ones) for the oldest chunk still in the ring, then release its slot
+        auto pv = [&](int buf) {
+            const uint32_t tile = sE_s + (uint32_t)pv_st * stage_bytes + (uint32_t)w * (KEYS * 128);
+            uint32_t vfr[KEYS / 16][4][4];
+#pragma unroll
+            for (int ks = 0; ks < KEYS / 16; ++ks) {
+                const int key = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    const int c16 = jp * 2 + (lane >> 4);
+                    ldmatrix_x4_trans(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), vfr[ks][jp][0], vfr[ks][jp][1],
+                                      vfr[ks][jp][2], vfr[ks][jp][3]);
+                }
+            }
+            const float a_lo = alpha[buf * 16 + g], a_hi = alpha[buf * 16 + g + 8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { acc[j][0] *= a_lo; acc[j][1] *= a_lo; acc[j][2] *= a_hi; acc[j][3] *= a_hi; }
+            accl[0] *= a_lo; accl[1] *= a_lo; accl[2] *= a_hi; accl[3] *= a_hi;
+            uint32_t pa[KEYS / 16][4];
+#pragma unroll
+            for (int ks = 0; ks < KEYS / 16; ++ks) {
+                const uint32_t p_lo = Pm_s + (uint32_t)(buf * 16 * PITCH + g * PITCH + ks * 16 + 2 * t) * 2u;
+                const uint32_t p_hi = p_lo + 8u * PITCH * 2u;
+                pa[ks][0] = lds32(p_lo); pa[ks][1] = lds32(p_hi); pa[ks][2] = lds32(p_lo + 16u); pa[ks][3] = lds32(p_hi + 16u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KEYS / 16; ++ks) {
+#pragma unroll
+                for (int jp = 0; jp < 4; ++jp) {
+                    mma_h16(acc[2 * jp], pa[ks], vfr[ks][jp][0], vfr[ks][jp][1]);
+                    mma_h16(acc[2 * jp + 1], pa[ks], vfr[ks][jp][2], vfr[ks][jp][3]);
+                }
+                mma_h16(accl, pa[ks], WIPA_H16_ONE_X2, WIPA_H16_ONE_X2);
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&empty[pv_st]);           // the fragments are in registers: the slot can be refilled
+            if (++pv_st == STAGES) pv_st = 0;
+        };
+
+        scores(0);
+        xl_bar(nthr);
+        for (int ch = ch0; ch < ch1; ++ch) {
+            const int b = (ch - ch0) & 1;
+            if (ch > ch0) pv(b ^ 1);
+            reduce(ch, b);
+            if (ch + 1 < ch1) scores(b ^ 1);
+            xl_bar(nthr);
         }
+        pv((ch1 - 1 - ch0) & 1);
+
+        xl_finish_segment<H>(s, ch0, ch1, n_chunks, n_units, acc, accl, m_run, Cout, part, counters, slots_per_seq, last_flag, w, lane);
     }
 }
 
@@ -409,6 +635,26 @@ int xl_launch(const CUtensorMap& tm, const h16* Qp, const int* utt_of_seq, h16* 
 // one instantiation per Whisper width below large (heads = d / 64): tiny 6, base 8, small 12, medium 16
 int cross_attention_latent_supported(int H) { return H == 6 || H == 8 || H == 12 || H == 16; }
 
+template <int H>
+int xl_launch_pipe(const h16* E, int U, const h16* Qp, const int* utt_of_seq, h16* C, int S, int T, int n_sm, float* part,
+                   size_t part_floats, int* counters, cudaStream_t st) {
+    using Cfg = XlPipeCfg<H>;
+    CUtensorMap tm;
+    WIPA_TRY(xl_make_map(&tm, E, U, T, H * 64, Cfg::KEYS));
+    static SmemAttr attr;
+    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_pipe_kernel<H>, Cfg::smem(), attr));
+    const int n_chunks = cdiv(T, Cfg::KEYS);
+    const long long n_units = (long long)S * n_chunks;
+    const int grid = n_units < n_sm ? (int)n_units : n_sm;
+    const int slots_per_seq = n_chunks / (int)(n_units / grid) + 2;
+    WIPA_CHECK((size_t)S * slots_per_seq * (H * 1024 + 32) <= part_floats, WIPA_EINVAL,
+               "cross_attention_latent: partial scratch too small for %d sequences", S);
+    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_pipe_kernel<H>, dim3(grid), dim3((H + 1) * 32), Cfg::smem(), st, tm, Qp,
+                                  utt_of_seq, C, S, T, part, counters, slots_per_seq));
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
 // floats of partial scratch that any launch with S <= max_seqs sequences can need on a device with n_sm SMs
 size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm) {
     return (size_t)(2 * n_sm + 3 * max_seqs + 64) * (size_t)(H * 1024 + 32);
@@ -432,6 +678,14 @@ int launch_cross_attention_latent(const h16* Qp, const h16* E, int U, const int*
         int dev = 0;
         WIPA_CUDA_CHECK(cudaGetDevice(&dev));
         WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    const char* pipe_env = getenv("WIPA_XL_PIPE");              // pipelined variant (unvalidated): 32-key chunks, 3 stages
+    if (pipe_env != nullptr && pipe_env[0] == '1' && H <= 12) {
+        switch (H) {
+            case 6: return xl_launch_pipe<6>(E, U, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+            case 8: return xl_launch_pipe<8>(E, U, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+            default: return xl_launch_pipe<12>(E, U, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        }
     }
     const int keys = H <= 12 ? 48 : 32;             // two stages of keys x d x 2 bytes + H x H partial rows must fit 227 KB
     CUtensorMap tm;

@@ -294,7 +294,8 @@ __device__ __forceinline__ void store_group(void* base, int is_h16, long long id
 // Apply the epilogue to W (4 or 8) consecutive accumulator columns n0..n0+W-1 of logical row m.
 // n0 is a multiple of W.  Columns >= ep.N are dropped.
 // bias_tile: optional shared-memory copy of bias[tile_n0 .. tile_n0 + BN) (zero beyond N), indexed by column - tile_n0
-template <int W, bool SKIP_BIAS = false>
+// MODE >= 0 fixes the epilogue at compile time (the kernel instantiation then carries only that branch); -1 reads ep.mode
+template <int W, bool SKIP_BIAS = false, int MODE = -1>
 __device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, float* v, const float* bias_tile = nullptr,
                                           int tile_n0 = 0) {
     if (n0 >= ep.N) return;
@@ -318,7 +319,7 @@ __device__ __forceinline__ void epi_group(const EpiParams& ep, int m, int n0, fl
     const int ob = m / ep.o_rpb;
     const int ot = m - ob * ep.o_rpb;
     const long long row = (long long)ob * ep.o_bstride + (long long)ot * ep.ldo;
-    switch (ep.mode) {
+    switch (MODE >= 0 ? MODE : ep.mode) {
         case EPI_GELU:
             if (ep.gelu_fast) {
 #pragma unroll

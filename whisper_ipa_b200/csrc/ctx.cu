@@ -259,7 +259,8 @@ EpiParams epi(int mode, int M, int N) {
 int gemm(wipa_ctx* c, const AOperand& a, const void* W, int M, int N, int K, const EpiParams& ep, int bn, cudaStream_t st) {
     if (c->bf) {
         // bn == 0: the persistent 128 x 256 kernel when there are at least two waves of its tiles, else 128 x 128 tiles
-        if (bn == 0 && (long long)cdiv(M, 128) * cdiv(N, 256) < c->persistent_min_tiles) bn = 128;
+        // (the vocabulary argmax always takes the persistent kernel: its 128 x 256 tiles stream the embedding matrix once)
+        if (bn == 0 && ep.mode != EPI_ARGMAX && (long long)cdiv(M, 128) * cdiv(N, 256) < c->persistent_min_tiles) bn = 128;
         return launch_gemm_h16(a, (const h16*)W, M, N, K, ep, bn, st);
     }
     return launch_gemm_f32(a, (const float*)W, M, N, K, ep, st);
@@ -470,7 +471,8 @@ int logits_argmax(wipa_ctx* c, int S, int* n_tiles, cudaStream_t st) {
     EpiParams ep = epi(EPI_ARGMAX, S, c->a.vocab);
     ep.pmax = c->pmax; ep.pidx = c->pidx;
     ep.mask_always = c->mask_always; ep.mask_begin = c->mask_begin; ep.step_ptr = c->d_step;
-    *n_tiles = c->n_logit_tiles;
+    // bn_logits 0: persistent 128 x 256 tiles, one (max, argmax) pair per 128-column half; 128: one CTA per 128-column tile
+    *n_tiles = c->bn_logits == 0 ? 2 * cdiv(c->a.vocab, 256) : cdiv(c->a.vocab, c->bn_logits);
     return gemm(c, plainA(c->dh, S, c->a.d_model), c->tok_emb, S, c->a.vocab, c->a.d_model, ep, c->bn_logits, st);
 }
 
@@ -574,7 +576,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             ep.out = dst; ep.out_h16 = 0; ep.vec_ok = 0;
             ep.ldo = logits_mode == 2 ? ldo : V;
             ep.o_rpb = 1; ep.o_bstride = ep.ldo;                 // row m -> m * ldo
-            WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits, st));
+            WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits ? c->bn_logits : 128, st));
             if (logits_mode == 1)
                 WIPA_TRY(launch_row_argmax(dst, S, V, c->mask_always, c->mask_begin, c->d_step, c->pmax, c->pidx, st));
         }
@@ -643,9 +645,9 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->pages_per_seq = WIPA_MAX_TGT / WIPA_PAGE;
     c->bn_enc = env_int("WIPA_BN_ENC", 0);
     c->bn_dec = env_int("WIPA_BN_DEC", 32);
-    c->bn_logits = env_int("WIPA_BN_LOGITS", 128);
+    c->bn_logits = env_int("WIPA_BN_LOGITS", 0);
     c->ca_split = env_int("WIPA_CA_SPLIT", cross_attention_default_split((int)c->esz, max_batch, arch->heads));
-    c->n_logit_tiles = cdiv(arch->vocab, c->bn_logits);
+    c->n_logit_tiles = c->bn_logits == 0 ? 2 * cdiv(arch->vocab, 256) : cdiv(arch->vocab, c->bn_logits);
     c->enc_attn_simt = env_int("WIPA_ENC_ATTN_SIMT", 0);
     c->skip_mask = env_int("WIPA_SKIP_MASK", 0);
     c->splitk = env_int("WIPA_SPLITK", 1);

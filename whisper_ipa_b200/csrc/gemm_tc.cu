@@ -54,11 +54,15 @@ __device__ unsigned long long g_gemm_dbg[4096 * 8];
 // k-block and TMA-multicasts it to the whole cluster, so the activations cross L2 -> SM once per cluster instead of
 // once per N tile (the decode GEMMs are A-traffic bound: 24-96 N tiles re-read the same 128 x K rows).  A ring slot may
 // only be refilled when ALL CTAs of the cluster have consumed it: tcgen05.commit multicasts the slot release.
-template <int BN, int BOXM, int CL>
+// MODE: the epilogue (EpiMode) fixed at compile time, or -1 for the run-time switch.  The decode step's nodes each get their
+// own instantiation, so that an 8 us kernel does not page in the SASS of seven epilogues it never runs (the all-in-one
+// instantiations were 11.6 k instructions; the specialised ones are 1 - 3 k).
+template <int BN, int BOXM, int CL, int MODE>
 __global__ void __launch_bounds__(192)
 gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, int num_kb,
                     int tiles_per_batch, int a_rpb, EpiParams ep) {
     using Cfg = TcCfg<BN, BOXM>;
+    const int mode = MODE >= 0 ? MODE : ep.mode;
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
     uint8_t* sA = smem;
@@ -199,7 +203,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int m = batch * a_rpb + t;
         pdl_wait();                                          // the epilogue reads / writes activations of earlier kernels
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        if (BN == 32 && ep.mode != EPI_ARGMAX) {
+        if (BN == 32 && mode != EPI_ARGMAX) {
             // Latency-bound decode tiles: fetch bias and residual for the whole BN-column row segment BEFORE the
             // accumulator is ready, so that after the last MMA only tcgen05.ld + adds + stores remain.
             __shared__ int s_last;
@@ -217,7 +221,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         add[i] = b.x; add[i + 1] = b.y; add[i + 2] = b.z; add[i + 3] = b.w;
                     }
                 }
-                if (ep.mode == EPI_RESADD) {
+                if (mode == EPI_RESADD) {
                     const int ob = m / ep.o_rpb;
                     row = (long long)ob * ep.o_bstride + (long long)(m - ob * ep.o_rpb) * ep.ldo + n0;
 #pragma unroll
@@ -275,24 +279,24 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 } else if (fast) {
 #pragma unroll
                     for (int i = 0; i < BN; ++i) v[i] += add[i];
-                    if (ep.mode == EPI_RESADD) {
+                    if (mode == EPI_RESADD) {
                         float* o = reinterpret_cast<float*>(ep.out) + row;
 #pragma unroll
                         for (int i = 0; i < BN; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                     } else {
 #pragma unroll
-                        for (int i = 0; i < BN; i += 8) epi_group<8, true>(ep, m, n0 + i, v + i);
+                        for (int i = 0; i < BN; i += 8) epi_group<8, true, MODE>(ep, m, n0 + i, v + i);
                     }
                 } else {
 #pragma unroll
-                    for (int i = 0; i < BN; i += 8) epi_group<8>(ep, m, n0 + i, v + i);
+                    for (int i = 0; i < BN; i += 8) epi_group<8, false, MODE>(ep, m, n0 + i, v + i);
                 }
             }
         } else {
         // the tile's bias goes to shared memory while the main loop runs (weights are static: no dependency), so the
         // column chunks below never wait on a global load
         __shared__ float s_bias[BN];
-        const bool have_bias = ep.bias != nullptr && ep.mode != EPI_ARGMAX;
+        const bool have_bias = ep.bias != nullptr && mode != EPI_ARGMAX;
         if (have_bias) {
             for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = (n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -303,7 +307,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         ptx::tc_fence_after();
         if (BOXM == 64 && quarter >= 2) {
             // lanes 64..127 hold garbage (see TcCfg); nothing to do
-        } else if (ep.mode == EPI_ARGMAX) {
+        } else if (mode == EPI_ARGMAX) {
             const bool begin = (ep.step_ptr != nullptr) && (*ep.step_ptr == 0);
             float best = -INFINITY;
             int best_n = 0x7fffffff;
@@ -329,8 +333,8 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 ptx::tmem_ld16(taddr + c0, v);
                 ptx::tmem_ld_wait();
                 if (row_ok) {
-                    epi_group<8>(ep, m, n0 + c0, v, bias_tile, n0);
-                    epi_group<8>(ep, m, n0 + c0 + 8, v + 8, bias_tile, n0);
+                    epi_group<8, false, MODE>(ep, m, n0 + c0, v, bias_tile, n0);
+                    epi_group<8, false, MODE>(ep, m, n0 + c0 + 8, v + 8, bias_tile, n0);
                 }
             }
         }
@@ -360,16 +364,16 @@ int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dim
     return WIPA_OK;
 }
 
-template <int BN, int BOXM, int CL>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int tiles_per_batch, int n_batch, int a_rpb,
-              int N, EpiParams ep, cudaStream_t st, int splits = 1) {
+template <int BN, int BOXM, int CL, int MODE>
+int launch_bn_mode(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int tiles_per_batch, int n_batch, int a_rpb,
+                   int N, EpiParams ep, cudaStream_t st, int splits) {
     using Cfg = TcCfg<BN, BOXM>;
     static SmemAttr attr;
-    WIPA_TRY(wipa_ensure_smem(gemm_h16_tc_kernel<BN, BOXM, CL>, (size_t)Cfg::SMEM, attr));
+    WIPA_TRY(wipa_ensure_smem(gemm_h16_tc_kernel<BN, BOXM, CL, MODE>, (size_t)Cfg::SMEM, attr));
     dim3 grid(cdiv(N, BN), tiles_per_batch * n_batch, splits);
     if (ep.mode == EPI_ARGMAX) ep.n_tiles = grid.x;
     if (CL == 1) {
-        WIPA_CUDA_CHECK(wipa_launch(gemm_h16_tc_kernel<BN, BOXM, CL>, grid, dim3(192), (size_t)Cfg::SMEM, st, tmA, tmW, num_kb,
+        WIPA_CUDA_CHECK(wipa_launch(gemm_h16_tc_kernel<BN, BOXM, CL, MODE>, grid, dim3(192), (size_t)Cfg::SMEM, st, tmA, tmW, num_kb,
                                     tiles_per_batch, a_rpb, ep));
     } else {
         cudaLaunchConfig_t cfg = {};
@@ -381,10 +385,27 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int ti
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = (g_wipa_pdl & WIPA_PDL_CLASS) ? 2 : 1;
-        WIPA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_h16_tc_kernel<BN, BOXM, CL>, tmA, tmW, num_kb, tiles_per_batch, a_rpb, ep));
+        WIPA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gemm_h16_tc_kernel<BN, BOXM, CL, MODE>, tmA, tmW, num_kb, tiles_per_batch, a_rpb, ep));
     }
     WIPA_LAUNCHED();
     return WIPA_OK;
+}
+
+// The decode step's (tile width, epilogue) pairs get specialised instantiations; everything else (encoder shapes below the
+// persistent kernel's threshold, tests, the multicast experiment) takes the run-time switch.
+template <int BN, int BOXM, int CL>
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int tiles_per_batch, int n_batch, int a_rpb,
+              int N, const EpiParams& ep, cudaStream_t st, int splits = 1) {
+#define WIPA_TC_CASE(M) case M: return launch_bn_mode<BN, BOXM, CL, M>(tmA, tmW, num_kb, tiles_per_batch, n_batch, a_rpb, N, ep, st, splits)
+    if constexpr (CL == 1 && BN == 32) {
+        switch (ep.mode) { WIPA_TC_CASE(EPI_QKV_DEC); WIPA_TC_CASE(EPI_RESADD); WIPA_TC_CASE(EPI_STORE); default: break; }
+    } else if constexpr (CL == 1 && BN == 64) {
+        switch (ep.mode) { WIPA_TC_CASE(EPI_GELU); WIPA_TC_CASE(EPI_STORE); WIPA_TC_CASE(EPI_QKV_DEC); default: break; }
+    } else if constexpr (CL == 1 && BN == 128) {
+        switch (ep.mode) { WIPA_TC_CASE(EPI_ARGMAX); WIPA_TC_CASE(EPI_STORE); default: break; }
+    }
+#undef WIPA_TC_CASE
+    return launch_bn_mode<BN, BOXM, CL, -1>(tmA, tmW, num_kb, tiles_per_batch, n_batch, a_rpb, N, ep, st, splits);
 }
 
 }  // namespace

@@ -13,6 +13,7 @@
 //               with coalesced residual loads; anything else -> the generic run-time epilogue (common.cuh epi_group)
 //
 // The A operand is the same 3-D tensor map as in gemm_tc.cu (rows may overlap: conv1d(k=3) as a GEMM).
+#define WIPA_PDL_CLASS 8
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -42,7 +43,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // Epilogue variants.  The encoder's four shapes get their own instantiation so that each carries only the code it runs
 // (the generic kernel's SASS is ~64 KB and the eight epilogue warps sit at different places in it: 6 % of its samples
 // were instruction-fetch stalls); anything else takes G2_EP_GENERIC, which decides per chunk at run time.
-enum { G2_EP_GENERIC = 0, G2_EP_HEADS_H16 = 1, G2_EP_RESADD_F32 = 2, G2_EP_GELU_H16 = 3, G2_EP_STORE_H16 = 4 };
+enum { G2_EP_GENERIC = 0, G2_EP_HEADS_H16 = 1, G2_EP_RESADD_F32 = 2, G2_EP_GELU_H16 = 3, G2_EP_STORE_H16 = 4, G2_EP_ARGMAX = 5 };
 
 // Two GELUs at a time on the packed fp32 pipe (fma/mul.f32x2): 9 issue slots per value instead of 15.  Same A&S 7.1.26
 // erf as gelu_erf_fast; the sign select is folded into gelu(x) = max(x, 0) - |x| * h(|x|).
@@ -117,6 +118,10 @@ gemm_h16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch (common.cuh): barriers and TMEM are set up; everything below touches activations of
+    // earlier kernels, so wait for them here, and only then let the next kernel begin its own prologue
+    pdl_wait();
+    pdl_launch_dependents();
 
     if (warp == 0) {
         int s = 0;
@@ -191,6 +196,45 @@ gemm_h16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
             if (kBf16Staged) s_bias[half * 128 + tih] = bias_mine;   // read after the next named barrier; the previous tile's
                                                                    // readers are behind its last one
             const uint32_t taddr = tmem_base + (uint32_t)buf * G2_BN + (uint32_t)half * 128u + ((uint32_t)(quarter * 32) << 16);
+            if constexpr (EP == G2_EP_ARGMAX) {
+                // fused vocabulary argmax (decode step): this thread's row, the 128 columns of its half; nothing is stored but
+                // one (max, argmax) pair per (row, 128-column piece).  Suppress masks arrive as two 32-bit words per 64 columns.
+                const bool begin = (ep.step_ptr != nullptr) && (*ep.step_ptr == 0);
+                float best = -INFINITY;
+                int best_n = 0x7fffffff;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    float v[64];
+                    ptx::tmem_ld32(taddr + c * 64, v);
+                    ptx::tmem_ld32(taddr + c * 64 + 32, v + 32);
+                    ptx::tmem_ld_wait();
+                    const int nc0 = n0 + c * 64;
+#pragma unroll
+                    for (int wd = 0; wd < 2; ++wd) {
+                        const int nw = nc0 + wd * 32;              // a multiple of 32: one mask word
+                        uint32_t mk = 0u;
+                        if (nw < ep.N) {
+                            if (ep.mask_always != nullptr) mk = __ldg(ep.mask_always + (nw >> 5));
+                            if (begin && ep.mask_begin != nullptr) mk |= __ldg(ep.mask_begin + (nw >> 5));
+                        }
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            const int n = nw + i;
+                            const float x = v[wd * 32 + i];
+                            if (n < ep.N && !((mk >> i) & 1u) && x > best) { best = x; best_n = n; }
+                        }
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty[buf]);
+                if (t0 + r < ep.M_rows) {
+                    const long long m = (long long)batch * a_rpb + t0 + r;
+                    ep.pmax[m * ep.n_tiles + nt * 2 + half] = best;
+                    ep.pidx[m * ep.n_tiles + nt * 2 + half] = best_n;
+                }
+                continue;
+            } else {
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {                      // 64 columns at a time
                 float v[64];
@@ -382,6 +426,7 @@ gemm_h16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     }
                 }
             }
+            }
         }
     }
     ptx::tc_fence_before();
@@ -415,7 +460,7 @@ int launch_gemm_h16_persistent(const AOperand& a, const h16* W, int M, int N, in
     WIPA_CHECK(K % 8 == 0 && a.lda % 8 == 0 && a.a_bstride % 8 == 0, WIPA_EINVAL,
                "gemm_h16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");
     WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_h16: M != rows_per_batch * batches");
-    WIPA_CHECK(ep_in.mode != EPI_ARGMAX && ep_in.mode != EPI_QKV_DEC, WIPA_EINVAL, "gemm_h16_persistent: decode-only epilogue");
+    WIPA_CHECK(ep_in.mode != EPI_QKV_DEC, WIPA_EINVAL, "gemm_h16_persistent: decode-only epilogue");
     CUtensorMap tmA, tmW;
     {
         cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a.a_rpb, (cuuint64_t)a.n_batch};
@@ -452,18 +497,20 @@ int launch_gemm_h16_persistent(const AOperand& a, const h16* W, int M, int N, in
     }
     static const char* force = getenv("WIPA_G2_GENERIC");      // experiment / test switch: always the run-time epilogue
     if (force != nullptr && force[0] == '1') variant = G2_EP_GENERIC;
+    if (ep.mode == EPI_ARGMAX) { variant = G2_EP_ARGMAX; ep.n_tiles = 2 * n_ntiles; }     // one (max, argmax) per 128-column piece
 #define G2_LAUNCH(EPV)                                                                                                        \
     {                                                                                                                         \
         static SmemAttr attr;                                                                                                 \
         WIPA_TRY(wipa_ensure_smem(gemm_h16_persistent_kernel<EPV>, (size_t)G2_SMEM, attr));                                  \
-        gemm_h16_persistent_kernel<EPV><<<grid, G2_THREADS, G2_SMEM, st>>>(tmA, tmW, cdiv(K, G2_BK), tpb, n_mtiles, n_ntiles, \
-                                                                            a.a_rpb, ep);                                      \
+        WIPA_CUDA_CHECK(wipa_launch(gemm_h16_persistent_kernel<EPV>, dim3(grid), dim3(G2_THREADS), (size_t)G2_SMEM, st, tmA, tmW,  \
+                                    cdiv(K, G2_BK), tpb, n_mtiles, n_ntiles, a.a_rpb, ep));                                   \
     }
     switch (variant) {
         case G2_EP_HEADS_H16: G2_LAUNCH(G2_EP_HEADS_H16) break;
         case G2_EP_RESADD_F32: G2_LAUNCH(G2_EP_RESADD_F32) break;
         case G2_EP_GELU_H16: G2_LAUNCH(G2_EP_GELU_H16) break;
         case G2_EP_STORE_H16: G2_LAUNCH(G2_EP_STORE_H16) break;
+        case G2_EP_ARGMAX: G2_LAUNCH(G2_EP_ARGMAX) break;
         default: G2_LAUNCH(G2_EP_GENERIC) break;
     }
 #undef G2_LAUNCH
