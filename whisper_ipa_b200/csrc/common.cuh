@@ -205,7 +205,50 @@ struct EpiParams {
     float* sk_part;
     int* sk_count;
     int gelu_fast;           // EPI_GELU with a h16 result: A&S-erf GELU (gelu_erf_fast) instead of erff
+    // ---- LayerNorm folded around the decode GEMMs (16-bit decode path; see "folded LayerNorm" below) ----
+    // consumer side: the A operand is the RAW residual stream rounded to h16 and W carries the LayerNorm gain; the epilogue
+    // finishes the normalisation per row:  y = rstd * (acc - mean * ln_c[n]) + bias'[n]
+    const float* ln_stats;   // [M, ln_nt] (mean, M2) of each 32-column piece of the row, or nullptr
+    const float* ln_c;       // [N] row sums of the gain-folded weights
+    int ln_nt;               // pieces per row (d / 32)
+    // producer side (EPI_RESADD of the decode step, 32-column tiles): also leave the new residual rounded to h16 and the
+    // (mean, M2) of this tile's 32 columns for the next consumer
+    void* x16_out;           // h16 [M, N], or nullptr
+    float* ln_stats_out;     // [M, N / 32] (mean, M2)
 };
+
+// ------------------------------------------------------------------------------------------------
+// folded LayerNorm: LN(x) W^T + b = rstd * (x W'^T - mean * c) + b'   with W' = W * gain (per input column),
+// c[n] = sum_k W'[n, k], b'[n] = b[n] + sum_k beta[k] W[n, k].  The kernel that produces the residual stream leaves its
+// row statistics as per-tile (mean, M2) pairs (Welford pieces of 32 columns, merged exactly by Chan's formula), so no
+// LayerNorm kernel sits between two GEMM nodes of a decode step.
+// ------------------------------------------------------------------------------------------------
+#define WIPA_LN_PIECE 32
+// (mean, rstd) of one row from its `nt` pieces of WIPA_LN_PIECE columns each; eps as HF (1e-5), biased variance
+__device__ __forceinline__ float2 ln_row_stats(const float* __restrict__ stats_row, int nt) {
+    const float2* p = reinterpret_cast<const float2*>(stats_row);
+    float ms = 0.f;
+    for (int t = 0; t < nt; ++t) ms += __ldcg(p + t).x;
+    const float mean = ms / (float)nt;
+    float m2 = 0.f;
+    for (int t = 0; t < nt; ++t) {
+        const float2 q = __ldcg(p + t);
+        const float dlt = q.x - mean;
+        m2 += q.y + (float)WIPA_LN_PIECE * dlt * dlt;
+    }
+    return make_float2(mean, rsqrtf(m2 / (float)(nt * WIPA_LN_PIECE) + 1e-5f));
+}
+// (mean, M2) of WIPA_LN_PIECE values held by one thread
+__device__ __forceinline__ float2 ln_piece_stats(const float* v) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < WIPA_LN_PIECE; ++i) s += v[i];
+    const float mean = s * (1.0f / WIPA_LN_PIECE);
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < WIPA_LN_PIECE; ++i) { const float dlt = v[i] - mean; m2 = fmaf(dlt, dlt, m2); }
+    return make_float2(mean, m2);
+}
 
 // A-operand addressing shared by both GEMM kernels: row m of the logical [M, K] matrix lives at
 //   A + (m / a_rpb) * a_bstride + (m % a_rpb) * lda        (elements)
@@ -450,6 +493,8 @@ int launch_mel_to_rows(const float* mel, T* rows, int B, int C, cudaStream_t st)
 template <typename T>
 int launch_embed(const T* tok_emb, const float* pos_emb, const int* tok, const int* pos_ptr, float* x, int Bs, int d,
                  cudaStream_t st);
+int launch_embed_lnf(const h16* tok_emb, const float* pos_emb, const int* tok, const int* pos_ptr, float* x, h16* x16, float* stats,
+                     int Bs, int d, cudaStream_t st);   // folded-LayerNorm decode path: + x in h16 and per-piece (mean, M2)
 int launch_convert(const float* src, void* dst, long long n, float scale, int to_h16, cudaStream_t st);
 int launch_conv_weight(const float* src, void* dst, int N, int C, int to_h16, cudaStream_t st);   // [N,C,3] -> [N,3*C]
 int launch_row_argmax(const float* logits, int Bs, int V, const uint32_t* mask_always, const uint32_t* mask_begin,

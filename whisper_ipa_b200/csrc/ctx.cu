@@ -109,6 +109,15 @@ struct wipa_ctx {
     size_t xl_part_floats = 0;
     std::vector<void*> xlq_w, xlo_w;                                  // per layer [H*d, d] and [d, H*d]
     std::vector<float*> xlq_b, xlo_b;
+    // folded LayerNorm (common.cuh): the decode step of the 16-bit path runs without LayerNorm kernels.  Gain-folded copies of
+    // the weights that consume a LayerNorm output, their column sums c and the beta-folded biases b'; the residual stream
+    // rounded to h16 and its per-piece statistics.  WIPA_LN_FOLD=0 restores the LayerNorm kernels.
+    int lnf = 0;
+    bool lnf_ready = false;
+    void *dx16 = nullptr, *emb_wf = nullptr;
+    float *dstats = nullptr, *emb_c = nullptr, *emb_bf = nullptr;
+    std::vector<void*> qkv_wf, cq_wf, fc1_wf;
+    std::vector<float*> qkv_c, qkv_bf, cq_c, cq_bf, fc1_c, fc1_bf, xlq_c, xlq_beff;
     int64_t decode_steps = 0;
     int step_pos = 0;              // target positions consumed by wipa_decode_begin / wipa_decode_next (0: no stepwise decode open)
     size_t workspace_bytes = 0, xkv_bytes = 0;
@@ -325,8 +334,10 @@ int require_weights(wipa_ctx* c) {
 //   Wo'[m, (h, n)] = sum_j Wo[m, 64h + j] Wv[64h + j, n]      bo'[m]      = bo[m] + sum_i Wo[m, i] bv[i]
 // (Wq / bq already carry the 1/8 scaling; k_proj has no bias.)  fp32 sums of the stored h16 weights, rounded once.
 // ------------------------------------------------------------------------------------------------
+// `gain` (nullable): the LayerNorm gain of the folded-LayerNorm decode path, multiplied onto input column k before the single
+// rounding; `bq` is then the beta-folded bias bq + Wq beta (ln_fold_rows), which carries through the fold unchanged
 __global__ void xlat_fold_q_kernel(const h16* __restrict__ Wq, const float* __restrict__ bq, const h16* __restrict__ Wk,
-                                   h16* __restrict__ Wq2, float* __restrict__ bq2, int d) {
+                                   h16* __restrict__ Wq2, float* __restrict__ bq2, int d, const float* __restrict__ gain) {
     const int h = blockIdx.z, n = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ float wk[64];
     if (threadIdx.x < 64) wk[threadIdx.x] = h16_to_f32(Wk[(size_t)(h * 64 + threadIdx.x) * d + n]);
@@ -334,7 +345,7 @@ __global__ void xlat_fold_q_kernel(const h16* __restrict__ Wq, const float* __re
     if (k < d) {
         float acc = 0.f;
         for (int j = 0; j < 64; ++j) acc = fmaf(wk[j], h16_to_f32(Wq[(size_t)(h * 64 + j) * d + k]), acc);
-        Wq2[((size_t)h * d + n) * d + k] = f32_to_h16(acc);
+        Wq2[((size_t)h * d + n) * d + k] = f32_to_h16(gain != nullptr ? acc * gain[k] : acc);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         float acc = 0.f;
@@ -361,6 +372,38 @@ __global__ void xlat_fold_o_kernel(const h16* __restrict__ Wo, const float* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// folded LayerNorm: W'[n, k] = W[n, k] * gain[k] (one rounding), c[n] = sum_k W'[n, k] (of the ROUNDED values: what the
+// tensor cores will multiply), b'[n] = b[n] + sum_k beta[k] W[n, k].  One warp per output row; any output may be null.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ln_fold_rows_kernel(const h16* __restrict__ W, const float* __restrict__ gain, const float* __restrict__ beta,
+                    const float* __restrict__ bias, h16* __restrict__ Wf, float* __restrict__ csum, float* __restrict__ bf, int N, int K) {
+    const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= N) return;
+    float cs = 0.f, bs = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float w = h16_to_f32(W[(size_t)n * K + k]);
+        const h16 wf = f32_to_h16(gain != nullptr ? w * gain[k] : w);
+        if (Wf != nullptr) Wf[(size_t)n * K + k] = wf;
+        cs += h16_to_f32(wf);
+        if (beta != nullptr) bs = fmaf(beta[k], w, bs);
+    }
+    cs = warp_sum(cs);
+    bs = warp_sum(bs);
+    if (lane == 0) {
+        if (csum != nullptr) csum[n] = cs;
+        if (bf != nullptr) bf[n] = (bias != nullptr ? bias[n] : 0.f) + bs;
+    }
+}
+
+int ln_fold_rows(const void* W, const float* gain, const float* beta, const float* bias, void* Wf, float* csum, float* bf, int N, int K,
+                 cudaStream_t st) {
+    ln_fold_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>((const h16*)W, gain, beta, bias, (h16*)Wf, csum, bf, N, K);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
 int xlat_prepare(wipa_ctx* c, cudaStream_t st) {
     if (!c->xlat || c->xlat_ready) return WIPA_OK;
     const int d = c->a.d_model, H = c->a.heads;
@@ -370,12 +413,35 @@ int xlat_prepare(wipa_ctx* c, cudaStream_t st) {
         const h16* Wk = (const h16*)c->xkv_w + (size_t)(2 * l) * d * d;
         const h16* Wv = (const h16*)c->xkv_w + (size_t)(2 * l + 1) * d * d;
         const float* bv = c->xkv_b + (size_t)(2 * l + 1) * d;
-        xlat_fold_q_kernel<<<grid, 256, 0, st>>>((const h16*)L.cq_w, L.cq_b, Wk, (h16*)c->xlq_w[l], c->xlq_b[l], d);
+        const float* bq = L.cq_b;
+        if (c->lnf) {       // beta of the cross-attention LayerNorm folds into the query bias first: bq + Wq beta
+            WIPA_TRY(ln_fold_rows(L.cq_w, nullptr, L.ln2_b, L.cq_b, nullptr, nullptr, c->xlq_beff[l], d, d, st));
+            bq = c->xlq_beff[l];
+        }
+        xlat_fold_q_kernel<<<grid, 256, 0, st>>>((const h16*)L.cq_w, bq, Wk, (h16*)c->xlq_w[l], c->xlq_b[l], d, c->lnf ? L.ln2_w : nullptr);
         WIPA_LAUNCHED();
+        if (c->lnf) {       // column sums of the finished (gain-folded, rounded) weights; beta is all zero here
+            WIPA_TRY(ln_fold_rows(c->xlq_w[l], nullptr, nullptr, nullptr, nullptr, c->xlq_c[l], nullptr, H * d, d, st));
+        }
         xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const h16*)L.co_w, L.co_b, Wv, bv, (h16*)c->xlo_w[l], c->xlo_b[l], d, H);
         WIPA_LAUNCHED();
     }
     c->xlat_ready = true;
+    return WIPA_OK;
+}
+
+// gain-folded copies of the decoder weights that consume a LayerNorm output (once per weight load)
+int lnf_prepare(wipa_ctx* c, cudaStream_t st) {
+    if (!c->lnf || c->lnf_ready) return WIPA_OK;
+    const int d = c->a.d_model, ffn = c->a.ffn, V = c->a.vocab;
+    for (int l = 0; l < c->a.dec_layers; ++l) {
+        const DecLayer& L = c->dec[l];
+        WIPA_TRY(ln_fold_rows(L.qkv_w, L.ln1_w, L.ln1_b, L.qkv_b, c->qkv_wf[l], c->qkv_c[l], c->qkv_bf[l], 3 * d, d, st));
+        if (!c->xlat) WIPA_TRY(ln_fold_rows(L.cq_w, L.ln2_w, L.ln2_b, L.cq_b, c->cq_wf[l], c->cq_c[l], c->cq_bf[l], d, d, st));
+        WIPA_TRY(ln_fold_rows(L.fc1_w, L.ln3_w, L.ln3_b, L.fc1_b, c->fc1_wf[l], c->fc1_c[l], c->fc1_bf[l], ffn, d, st));
+    }
+    WIPA_TRY(ln_fold_rows(c->tok_emb, c->dec_ln_w, c->dec_ln_b, nullptr, c->emb_wf, c->emb_c, c->emb_bf, V, d, st));
+    c->lnf_ready = true;
     return WIPA_OK;
 }
 
@@ -473,6 +539,10 @@ int logits_argmax(wipa_ctx* c, int S, int* n_tiles, cudaStream_t st) {
     ep.mask_always = c->mask_always; ep.mask_begin = c->mask_begin; ep.step_ptr = c->d_step;
     // bn_logits 0: persistent 128 x 256 tiles, one (max, argmax) pair per 128-column half; 128: one CTA per 128-column tile
     *n_tiles = c->bn_logits == 0 ? 2 * cdiv(c->a.vocab, 256) : cdiv(c->a.vocab, c->bn_logits);
+    if (c->lnf) {       // folded final LayerNorm: raw residual (h16) x gain-folded embedding matrix, finished in the epilogue
+        ep.ln_stats = c->dstats; ep.ln_c = c->emb_c; ep.ln_nt = c->a.d_model / WIPA_LN_PIECE; ep.bias = c->emb_bf;
+        return gemm(c, plainA(c->dx16, S, c->a.d_model), c->emb_wf, S, c->a.vocab, c->a.d_model, ep, c->bn_logits, st);
+    }
     return gemm(c, plainA(c->dh, S, c->a.d_model), c->tok_emb, S, c->a.vocab, c->a.d_model, ep, c->bn_logits, st);
 }
 
@@ -489,18 +559,31 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
     const wipa_arch& a = c->a;
     const int d = a.d_model, H = a.heads, ffn = a.ffn, V = a.vocab;
     const int skip = c->skip_mask;       // ablation bits: 1 LN, 2 self-attn, 4 cross-attn, 8 qkv, 16 d x d GEMMs, 32 fc1, 64 fc2, 128 logits
-    if (c->bf) WIPA_TRY(launch_embed<h16>((const h16*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
+    // folded LayerNorm (common.cuh): no LayerNorm kernels; every consumer of a LayerNorm output reads the raw residual in h16
+    // (dx16) with gain-folded weights and finishes the normalisation in its epilogue from the statistics (dstats) that the
+    // producer of the residual left behind
+    const bool lnf = c->lnf != 0;
+    const int ln_nt = d / WIPA_LN_PIECE;
+    auto consume_ln = [&](EpiParams& ep, const float* csum, const float* bias_f) {
+        ep.ln_stats = c->dstats; ep.ln_c = csum; ep.ln_nt = ln_nt; ep.bias = bias_f;
+    };
+    auto produce_ln = [&](EpiParams& ep) {
+        if (lnf) { ep.x16_out = c->dx16; ep.ln_stats_out = c->dstats; }
+    };
+    if (lnf) WIPA_TRY(launch_embed_lnf((const h16*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, (h16*)c->dx16, c->dstats, S, d, st));
+    else if (c->bf) WIPA_TRY(launch_embed<h16>((const h16*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
     else WIPA_TRY(launch_embed<float>((const float*)c->tok_emb, c->dec_pos, c->d_cur_tok, c->d_pos, c->dx, S, d, st));
     for (int l = 0; l < a.dec_layers; ++l) {
         const DecLayer& L = c->dec[l];
         char* kp = (char*)c->kpool + (size_t)l * c->pool_layer_stride * c->esz;
         char* vp = (char*)c->vpool + (size_t)l * c->pool_layer_stride * c->esz;
-        if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln1_w, L.ln1_b, c->dh, S, st));
+        if (!lnf && !(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln1_w, L.ln1_b, c->dh, S, st));
         {
             EpiParams ep = epi(EPI_QKV_DEC, S, 3 * d);
             ep.bias = L.qkv_b; ep.out = c->dq; ep.out1 = kp; ep.out2 = vp; ep.out_h16 = c->bf;
             ep.H = H; ep.d = d; ep.pos_ptr = c->d_pos; ep.block_table = c->block_table; ep.bt_stride = c->pages_per_seq;
-            if (!(skip & 8)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.qkv_w, S, 3 * d, d, ep, c->bn_dec, st));
+            if (lnf) consume_ln(ep, c->qkv_c[l], c->qkv_bf[l]);
+            if (!(skip & 8)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->qkv_wf[l] : L.qkv_w, S, 3 * d, d, ep, c->bn_dec, st));
         }
         const int* anc = beam ? c->b_anc : nullptr;            // beam search reads every position from the slot that wrote it
         if (skip & 2) {}
@@ -511,15 +594,17 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.o_b; ep.out = c->dx; ep.resid = c->dx;
+            produce_ln(ep);
             if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.o_w, S, d, d, ep, c->bn_dec, st));
         }
-        if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
+        if (!lnf && !(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
         if (c->xlat) {
             const int Hd = H * d;
             {   // q' = LN(x) Wq'^T + bq'  -> h16 [S, H, d]
                 EpiParams ep = epi(EPI_STORE, S, Hd);
                 ep.bias = c->xlq_b[l]; ep.out = c->dqlat; ep.out_h16 = 1;
-                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, c->bn_xlq ? c->bn_xlq : ((S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec), st));
+                if (lnf) consume_ln(ep, c->xlq_c[l], c->xlq_b[l]);          // xlq_w / xlq_b were folded with the gain / beta already
+                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, c->bn_xlq ? c->bn_xlq : ((S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec), st));
             }
             if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const h16*)c->dqlat, (const h16*)c->enc_lat, c->max_batch, c->utt_of_seq,
                                                                    (h16*)c->dclat, S, H, WIPA_T_ENC, c->xl_part, c->xl_part_floats,
@@ -528,13 +613,15 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
                 EpiParams ep = epi(EPI_RESADD, S, d);
                 ep.bias = c->xlo_b[l]; ep.out = c->dx; ep.resid = c->dx;
                 if (c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; }
+                produce_ln(ep);
                 if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dclat, S, Hd), c->xlo_w[l], S, d, Hd, ep, c->bn_dec, st));
             }
         } else {
         {
             EpiParams ep = epi(EPI_STORE, S, d);
             ep.bias = L.cq_b; ep.out = c->dq; ep.out_h16 = 0;
-            if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.cq_w, S, d, d, ep, c->bn_dec, st));
+            if (lnf) consume_ln(ep, c->cq_c[l], c->cq_bf[l]);
+            if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->cq_wf[l] : L.cq_w, S, d, d, ep, c->bn_dec, st));
         }
         {
             const char* xk = (const char*)c->xkv + (size_t)(2 * l) * c->xkv_which_stride * c->esz;
@@ -548,26 +635,29 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.co_b; ep.out = c->dx; ep.resid = c->dx;
+            produce_ln(ep);
             if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.co_w, S, d, d, ep, c->bn_dec, st));
         }
         }
-        if (!(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln3_w, L.ln3_b, c->dh, S, st));
+        if (!lnf && !(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln3_w, L.ln3_b, c->dh, S, st));
         {
             EpiParams ep = epi(EPI_GELU, S, ffn);
             ep.bias = L.fc1_b; ep.out = c->dffn; ep.out_h16 = c->bf; ep.gelu_fast = c->bf;
+            if (lnf) consume_ln(ep, c->fc1_c[l], c->fc1_bf[l]);
             // N = ffn tiles of 32 columns would not fit one wave once S needs two M tiles: use 64-wide tiles then
-            if (!(skip & 32)) WIPA_TRY(gemm(c, plainA(c->dh, S, d), L.fc1_w, S, ffn, d, ep, (S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec, st));
+            if (!(skip & 32)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->fc1_wf[l] : L.fc1_w, S, ffn, d, ep, (S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec, st));
         }
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.fc2_b; ep.out = c->dx; ep.resid = c->dx;
             if (c->bf && c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; }    // K = ffn is long: split-K
+            produce_ln(ep);
             if (!(skip & 64)) WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, c->bn_dec, st));
         }
     }
     int n_tiles = 1;
     if (logits_mode != 0) {
-        WIPA_TRY(ln(c, c->dx, c->dec_ln_w, c->dec_ln_b, c->dh, S, st));
+        if (!lnf) WIPA_TRY(ln(c, c->dx, c->dec_ln_w, c->dec_ln_b, c->dh, S, st));
         if (logits_mode == 1 && c->bf) {
             if (!(skip & 128)) WIPA_TRY(logits_argmax(c, S, &n_tiles, st));
         } else {
@@ -576,7 +666,8 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             ep.out = dst; ep.out_h16 = 0; ep.vec_ok = 0;
             ep.ldo = logits_mode == 2 ? ldo : V;
             ep.o_rpb = 1; ep.o_bstride = ep.ldo;                 // row m -> m * ldo
-            WIPA_TRY(gemm(c, plainA(c->dh, S, d), c->tok_emb, S, V, d, ep, c->bn_logits ? c->bn_logits : 128, st));
+            if (lnf) consume_ln(ep, c->emb_c, c->emb_bf);
+            WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->emb_wf : c->tok_emb, S, V, d, ep, c->bn_logits ? c->bn_logits : 128, st));
             if (logits_mode == 1)
                 WIPA_TRY(launch_row_argmax(dst, S, V, c->mask_always, c->mask_begin, c->d_step, c->pmax, c->pidx, st));
         }
@@ -657,6 +748,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     // kernel over per-layer K / V (exactly balanced at any size) is faster.  WIPA_XATTN_LATENT = 1 / 0 forces either.
     c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", max_batch * max_beams >= 128 ? 1 : 0) != 0 &&
                cross_attention_latent_supported(arch->heads)) ? 1 : 0;
+    c->lnf = (c->bf && env_int("WIPA_LN_FOLD", 1) != 0 && arch->d_model % WIPA_LN_PIECE == 0) ? 1 : 0;
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
@@ -709,6 +801,33 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     } else {
         c->xkv_bytes = (size_t)arch->dec_layers * 2 * c->xkv_which_stride * e;
         CTX_TRY(ctx_alloc(c, &c->xkv, c->xkv_bytes, false));
+    }
+    if (c->lnf) {
+        const int Ld = arch->dec_layers;
+        CTX_TRY(ctx_alloc(c, &c->dx16, (size_t)S * d * e, false));
+        CTX_TRY(ctx_alloc(c, (void**)&c->dstats, (size_t)S * (d / WIPA_LN_PIECE) * 2 * 4, true));
+        CTX_TRY(ctx_alloc(c, &c->emb_wf, (size_t)V * d * e, false));
+        CTX_TRY(ctx_alloc(c, (void**)&c->emb_c, (size_t)V * 4, false));
+        CTX_TRY(ctx_alloc(c, (void**)&c->emb_bf, (size_t)V * 4, false));
+        c->qkv_wf.assign(Ld, nullptr); c->cq_wf.assign(Ld, nullptr); c->fc1_wf.assign(Ld, nullptr);
+        c->qkv_c.assign(Ld, nullptr); c->qkv_bf.assign(Ld, nullptr); c->cq_c.assign(Ld, nullptr); c->cq_bf.assign(Ld, nullptr);
+        c->fc1_c.assign(Ld, nullptr); c->fc1_bf.assign(Ld, nullptr); c->xlq_c.assign(Ld, nullptr); c->xlq_beff.assign(Ld, nullptr);
+        for (int l = 0; l < Ld; ++l) {
+            CTX_TRY(ctx_alloc(c, &c->qkv_wf[l], (size_t)3 * d * d * e, false));
+            CTX_TRY(ctx_alloc(c, (void**)&c->qkv_c[l], (size_t)3 * d * 4, false));
+            CTX_TRY(ctx_alloc(c, (void**)&c->qkv_bf[l], (size_t)3 * d * 4, false));
+            CTX_TRY(ctx_alloc(c, &c->fc1_wf[l], (size_t)ffn * d * e, false));
+            CTX_TRY(ctx_alloc(c, (void**)&c->fc1_c[l], (size_t)ffn * 4, false));
+            CTX_TRY(ctx_alloc(c, (void**)&c->fc1_bf[l], (size_t)ffn * 4, false));
+            if (c->xlat) {
+                CTX_TRY(ctx_alloc(c, (void**)&c->xlq_c[l], (size_t)H * d * 4, false));
+                CTX_TRY(ctx_alloc(c, (void**)&c->xlq_beff[l], (size_t)d * 4, false));
+            } else {
+                CTX_TRY(ctx_alloc(c, &c->cq_wf[l], (size_t)d * d * e, false));
+                CTX_TRY(ctx_alloc(c, (void**)&c->cq_c[l], (size_t)d * 4, false));
+                CTX_TRY(ctx_alloc(c, (void**)&c->cq_bf[l], (size_t)d * 4, false));
+            }
+        }
     }
     c->pool_layer_stride = (size_t)S * c->pages_per_seq * H * WIPA_PAGE * 64;
     CTX_TRY(ctx_alloc(c, &c->kpool, (size_t)arch->dec_layers * c->pool_layer_stride * e, false));
@@ -819,6 +938,7 @@ extern "C" int wipa_ctx_load_weights(wipa_ctx* c, const wipa_tensor_desc* tensor
     // the weights changed: graphs stay valid (same buffers), cached cross-KV and folded projections do not
     c->n_utts = 0;
     c->xlat_ready = false;
+    c->lnf_ready = false;
     return WIPA_OK;
 }
 
@@ -851,6 +971,7 @@ extern "C" int wipa_encode(wipa_ctx* c, const float* mel, int B, float* enc_out,
     WIPA_TRY(require_weights(c));
     cudaStream_t st = (cudaStream_t)stream;
     WIPA_TRY(xlat_prepare(c, st));
+    WIPA_TRY(lnf_prepare(c, st));
     const size_t mel_clip = (size_t)c->a.n_mels * WIPA_N_FRAMES, enc_clip = (size_t)WIPA_T_ENC * c->a.d_model;
     for (int u0 = 0; u0 < B; u0 += c->enc_mb) {
         const int nb = (B - u0) < c->enc_mb ? (B - u0) : c->enc_mb;
@@ -868,6 +989,7 @@ extern "C" int wipa_set_audio_features(wipa_ctx* c, const float* enc_out, int B,
     cudaStream_t st = (cudaStream_t)stream;
     const size_t enc_clip = (size_t)WIPA_T_ENC * c->a.d_model;
     WIPA_TRY(xlat_prepare(c, st));
+    WIPA_TRY(lnf_prepare(c, st));
     if (c->xlat) WIPA_TRY(launch_convert(enc_out, c->enc_lat, (long long)B * enc_clip, 1.0f, 1, st));
     else for (int u0 = 0; u0 < B; u0 += c->enc_mb) {
         const int nb = (B - u0) < c->enc_mb ? (B - u0) : c->enc_mb;

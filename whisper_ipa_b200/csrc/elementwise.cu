@@ -120,6 +120,38 @@ int launch_embed(const T* tok_emb, const float* pos_emb, const int* tok, const i
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
+// The same for the folded-LayerNorm decode path (common.cuh): besides x it leaves x rounded to h16 (the first GEMM's A
+// operand) and the (mean, M2) of every 32-column piece of the row.  Warp w owns pieces w, w + 8, ...; lane = column in the piece.
+__global__ void __launch_bounds__(256)
+embed_lnf_kernel(const h16* __restrict__ tok_emb, const float* __restrict__ pos_emb, const int* __restrict__ tok,
+                 const int* __restrict__ pos_ptr, float* __restrict__ x, h16* __restrict__ x16, float* __restrict__ stats, int d) {
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    pdl_wait();
+    pdl_launch_dependents();
+    const int p = *pos_ptr;
+    const h16* te = tok_emb + (size_t)tok[b] * d;
+    const float* pe = pos_emb + (size_t)p * d;
+    const int nt = d / WIPA_LN_PIECE;
+    for (int t = warp; t < nt; t += 8) {
+        const int i = t * WIPA_LN_PIECE + lane;
+        const float v = h16_to_f32(te[i]) + pe[i];
+        x[(size_t)b * d + i] = v;
+        x16[(size_t)b * d + i] = f32_to_h16(v);
+        const float mean = warp_sum(v) * (1.0f / WIPA_LN_PIECE);
+        const float dlt = v - mean;
+        const float m2 = warp_sum(dlt * dlt);
+        if (lane == 0) *reinterpret_cast<float2*>(stats + ((size_t)b * nt + t) * 2) = make_float2(mean, m2);
+    }
+}
+
+int launch_embed_lnf(const h16* tok_emb, const float* pos_emb, const int* tok, const int* pos_ptr, float* x, h16* x16, float* stats,
+                     int Bs, int d, cudaStream_t st) {
+    WIPA_CUDA_CHECK(wipa_launch(embed_lnf_kernel, dim3(Bs), dim3(256), (size_t)0, st, tok_emb, pos_emb, tok, pos_ptr, x, x16, stats, d));
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
 template int launch_embed<float>(const float*, const float*, const int*, const int*, float*, int, int, cudaStream_t);
 template int launch_embed<h16>(const h16*, const float*, const int*, const int*, float*, int, int, cudaStream_t);
 

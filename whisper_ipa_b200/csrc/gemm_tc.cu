@@ -213,6 +213,23 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
             for (int i = 0; i < BN; ++i) add[i] = 0.f;
             long long row = 0;
+            // folded LayerNorm, consumer side: this row's (mean, rstd) from the producer's per-piece statistics and the
+            // column sums of the gain-folded weights, all fetched before the accumulator is ready
+            const bool ln = ep.ln_stats != nullptr;
+            float2 mr = make_float2(0.f, 1.f);
+            float lnc[BN];
+#pragma unroll
+            for (int i = 0; i < BN; ++i) lnc[i] = 0.f;
+            if (ln && active) {
+                mr = ln_row_stats(ep.ln_stats + (long long)m * ep.ln_nt * 2, ep.ln_nt);
+                if (fast) {
+#pragma unroll
+                    for (int i = 0; i < BN; i += 4) {
+                        const float4 c4 = *reinterpret_cast<const float4*>(ep.ln_c + n0 + i);
+                        lnc[i] = c4.x; lnc[i + 1] = c4.y; lnc[i + 2] = c4.z; lnc[i + 3] = c4.w;
+                    }
+                }
+            }
             if (active && fast) {
                 if (ep.bias != nullptr) {
 #pragma unroll
@@ -277,12 +294,30 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (!active) {
                     // padding row of the M tile: nothing to store
                 } else if (fast) {
+                    if (ln) {
+#pragma unroll
+                        for (int i = 0; i < BN; ++i) v[i] = mr.y * fmaf(-mr.x, lnc[i], v[i]);
+                    }
 #pragma unroll
                     for (int i = 0; i < BN; ++i) v[i] += add[i];
                     if (mode == EPI_RESADD) {
                         float* o = reinterpret_cast<float*>(ep.out) + row;
 #pragma unroll
                         for (int i = 0; i < BN; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                        if (ep.x16_out != nullptr) {
+                            // folded LayerNorm, producer side: the new residual rounded to h16 (the next GEMM's A operand) and
+                            // the (mean, M2) of this row's 32 columns (BN == WIPA_LN_PIECE)
+                            h16* o16 = reinterpret_cast<h16*>(ep.x16_out) + row;
+#pragma unroll
+                            for (int i = 0; i < BN; i += 8) {
+                                uint4 u;
+                                u.x = pack_h16x2(v[i], v[i + 1]); u.y = pack_h16x2(v[i + 2], v[i + 3]);
+                                u.z = pack_h16x2(v[i + 4], v[i + 5]); u.w = pack_h16x2(v[i + 6], v[i + 7]);
+                                *reinterpret_cast<uint4*>(o16 + i) = u;
+                            }
+                            const float2 st2 = ln_piece_stats(v);
+                            *reinterpret_cast<float2*>(ep.ln_stats_out + ((long long)m * (ep.N / WIPA_LN_PIECE) + blockIdx.x) * 2) = st2;
+                        }
                     } else {
 #pragma unroll
                         for (int i = 0; i < BN; i += 8) epi_group<8, true, MODE>(ep, m, n0 + i, v + i);
@@ -296,12 +331,20 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // the tile's bias goes to shared memory while the main loop runs (weights are static: no dependency), so the
         // column chunks below never wait on a global load
         __shared__ float s_bias[BN];
-        const bool have_bias = ep.bias != nullptr && mode != EPI_ARGMAX;
-        if (have_bias) {
-            for (int i = threadIdx.x - 64; i < BN; i += 128) s_bias[i] = (n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
+        __shared__ float s_lnc[BN];
+        const bool ln = ep.ln_stats != nullptr;
+        const bool have_bias = ep.bias != nullptr && (mode != EPI_ARGMAX || ln);
+        if (have_bias || ln) {
+            for (int i = threadIdx.x - 64; i < BN; i += 128) {
+                s_bias[i] = (have_bias && n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
+                s_lnc[i] = (ln && n0 + i < ep.N) ? ep.ln_c[n0 + i] : 0.f;
+            }
             asm volatile("bar.sync 1, 128;" ::: "memory");
         }
-        const float* bias_tile = have_bias ? s_bias : nullptr;
+        const float* bias_tile = (have_bias && mode != EPI_ARGMAX) ? s_bias : nullptr;
+        // folded LayerNorm, consumer side (see the 32-column path): y = rstd * (acc - mean * c[n]) (+ bias' in the epilogue)
+        float2 mr = make_float2(0.f, 1.f);
+        if (ln && row_ok && !(BOXM == 64 && quarter >= 2)) mr = ln_row_stats(ep.ln_stats + (long long)m * ep.ln_nt * 2, ep.ln_nt);
         ptx::mbar_wait(tmem_full, 0);
         if (threadIdx.x == 64) DBG_STAMP(5);
         ptx::tc_fence_after();
@@ -319,7 +362,8 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int n = n0 + c0 + i;
-                    if (n < ep.N && !vocab_masked(ep, n, begin) && v[i] > best) { best = v[i]; best_n = n; }
+                    const float x = ln ? mr.y * fmaf(-mr.x, s_lnc[c0 + i], v[i]) + s_bias[c0 + i] : v[i];
+                    if (n < ep.N && !vocab_masked(ep, n, begin) && x > best) { best = x; best_n = n; }
                 }
             }
             if (row_ok) {
@@ -332,6 +376,10 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 float v[16];
                 ptx::tmem_ld16(taddr + c0, v);
                 ptx::tmem_ld_wait();
+                if (ln) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = mr.y * fmaf(-mr.x, s_lnc[c0 + i], v[i]);
+                }
                 if (row_ok) {
                     epi_group<8, false, MODE>(ep, m, n0 + c0, v, bias_tile, n0);
                     epi_group<8, false, MODE>(ep, m, n0 + c0 + 8, v + 8, bias_tile, n0);
@@ -441,6 +489,10 @@ int launch_gemm_h16(const AOperand& a, const h16* W, int M, int N, int K, const 
     WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_h16: M != rows_per_batch * batches");
     WIPA_CHECK((reinterpret_cast<uintptr_t>(a.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0, WIPA_EINVAL,
                "gemm_h16: operands must be 16-byte aligned");
+    WIPA_CHECK(ep_in.ln_stats == nullptr || block_n != 32 || (N % 32 == 0 && ep_in.vec_ok), WIPA_EINVAL,
+               "gemm_h16: the folded-LayerNorm epilogue of the 32-column tiles needs N %% 32 == 0");
+    WIPA_CHECK(ep_in.x16_out == nullptr || (block_n == 32 && N % 32 == 0 && ep_in.vec_ok && ep_in.mode == EPI_RESADD), WIPA_EINVAL,
+               "gemm_h16: residual statistics are produced by 32-column EPI_RESADD tiles only");
     const int box_m = (a.a_rpb <= 64 && block_n == 32) ? 64 : 128;
     // WIPA_GEMM_MULTICAST=1: clusters of 4 N tiles with A multicast for the narrow (decode) tiles whenever the N tiles
     // divide evenly.  Parity-tested, but OFF by default: measured on B200 at B=256 the two cluster barriers and the

@@ -28,7 +28,7 @@ constexpr int G2_W_BYTES = G2_BN * G2_BK * 2;                 // 32 KB
 constexpr int G2_LDS = 68;                                    // staging row pitch in floats (64 + 4: conflict-free float4 rows)
 constexpr int G2_STAGE_F = G2_BM * G2_LDS;                    // floats per staging tile (128 rows x 64 columns)
 constexpr int G2_SMEM = G2_STAGES * (G2_A_BYTES + G2_W_BYTES) + 2 * G2_STAGE_F * 4 + 1024 /*align*/ + 256 /*barriers*/ +
-                        1024 /*bias tile*/;
+                        2048 /*bias tile + folded-LayerNorm column sums*/;
 constexpr int G2_THREADS = 64 + 256;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -96,6 +96,7 @@ gemm_h16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
     uint64_t* tmem_empty = tmem_full + 2;                     // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
     float* s_bias = reinterpret_cast<float*>(full) + 64;          // [2 halves][128], after the 256 bytes of barriers
+    float* s_lnc = s_bias + 256;                                  // [2 halves][128] (folded LayerNorm: column sums of W')
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = n_mtiles * n_ntiles;
@@ -202,6 +203,17 @@ gemm_h16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                 const bool begin = (ep.step_ptr != nullptr) && (*ep.step_ptr == 0);
                 float best = -INFINITY;
                 int best_n = 0x7fffffff;
+                // folded final LayerNorm (common.cuh): logits = rstd * (acc - mean * c[n]) + b'[n]; this half's 128 values of
+                // c and b' go through shared memory, the row's (mean, rstd) comes from the producer's per-piece statistics
+                const bool ln = ep.ln_stats != nullptr;
+                float2 mr = make_float2(0.f, 1.f);
+                if (ln) {
+                    named_bar_sync(bar_id, 128);                   // the previous tile's readers are done with s_bias / s_lnc
+                    s_bias[half * 128 + tih] = (n0 + tih < ep.N) ? __ldg(ep.bias + n0 + tih) : 0.f;
+                    s_lnc[half * 128 + tih] = (n0 + tih < ep.N) ? __ldg(ep.ln_c + n0 + tih) : 0.f;
+                    if (t0 + r < ep.M_rows) mr = ln_row_stats(ep.ln_stats + ((long long)batch * a_rpb + t0 + r) * ep.ln_nt * 2, ep.ln_nt);
+                    named_bar_sync(bar_id, 128);
+                }
 #pragma unroll 1
                 for (int c = 0; c < 2; ++c) {
                     float v[64];
@@ -209,6 +221,17 @@ gemm_h16_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid
                     ptx::tmem_ld32(taddr + c * 64 + 32, v + 32);
                     ptx::tmem_ld_wait();
                     const int nc0 = n0 + c * 64;
+                    if (ln) {
+                        const uint32_t sb = ptx::smem_u32(s_bias + half * 128 + c * 64), sc = ptx::smem_u32(s_lnc + half * 128 + c * 64);
+#pragma unroll
+                        for (int i = 0; i < 64; i += 4) {
+                            const float4 b4 = ptx::lds128(sb + i * 4), c4 = ptx::lds128(sc + i * 4);
+                            v[i] = fmaf(mr.y, fmaf(-mr.x, c4.x, v[i]), b4.x);
+                            v[i + 1] = fmaf(mr.y, fmaf(-mr.x, c4.y, v[i + 1]), b4.y);
+                            v[i + 2] = fmaf(mr.y, fmaf(-mr.x, c4.z, v[i + 2]), b4.z);
+                            v[i + 3] = fmaf(mr.y, fmaf(-mr.x, c4.w, v[i + 3]), b4.w);
+                        }
+                    }
 #pragma unroll
                     for (int wd = 0; wd < 2; ++wd) {
                         const int nw = nc0 + wd * 32;              // a multiple of 32: one mask word
@@ -461,6 +484,8 @@ int launch_gemm_h16_persistent(const AOperand& a, const h16* W, int M, int N, in
                "gemm_h16: K / lda / batch stride must be multiples of 8 elements (16 bytes)");
     WIPA_CHECK(M == a.a_rpb * a.n_batch, WIPA_EINVAL, "gemm_h16: M != rows_per_batch * batches");
     WIPA_CHECK(ep_in.mode != EPI_QKV_DEC, WIPA_EINVAL, "gemm_h16_persistent: decode-only epilogue");
+    WIPA_CHECK((ep_in.ln_stats == nullptr || ep_in.mode == EPI_ARGMAX) && ep_in.x16_out == nullptr, WIPA_EINVAL,
+               "gemm_h16_persistent: the folded-LayerNorm epilogue exists for the vocabulary argmax only");
     CUtensorMap tmA, tmW;
     {
         cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)a.a_rpb, (cuuint64_t)a.n_batch};
