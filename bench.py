@@ -441,14 +441,20 @@ def main():
         # latent cross-attention (attn_lat.cu): one pass over the encoder output E [B, 1500, d] per layer serves every head and
         # both the key and the value role.  Timed on its own buffers of the decode shapes; E (0.59 GB at 256 clips) is far
         # larger than L2, so every launch re-streams it from HBM.
+        tiled = bool(int(os.environ.get("WIPA_XL_TILED", "1")))          # the layout the context keeps (default: chunk-tiled)
         E = torch.randn(B, 1500, dm, device=dev).to(tdt)
+        if tiled:
+            Et = torch.zeros(B * lib.wipa_test_lat_tiled_elems(H, 1500), device=dev, dtype=tdt)
+            _lib.check(lib.wipa_test_lat_tile(E.data_ptr(), B, 1500, H, Et.data_ptr(), st), "lat_tile", lib)
+            E = Et
         Qp = (torch.randn(S, H, dm, device=dev) * (1.5 / dm ** 0.5)).to(tdt)
         Cl = torch.empty(S, H, dm, device=dev, dtype=tdt)
         utt = (torch.arange(S, device=dev, dtype=torch.int32) // args.beams).to(torch.int32)
         n_launch = reps * L
 
         def launch():
-            return lib.wipa_test_cross_attn_latent(Qp.data_ptr(), E.data_ptr(), B, utt.data_ptr(), Cl.data_ptr(), S, H, 1500, st)
+            return lib.wipa_test_cross_attn_latent(Qp.data_ptr(), E.data_ptr(), B, utt.data_ptr(), Cl.data_ptr(), S, H, 1500,
+                                                   2 if tiled else 0, st)
         _lib.check(launch(), "cross_attn_latent", lib)
         torch.cuda.synchronize()
         r0.record()

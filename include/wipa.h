@@ -177,7 +177,12 @@ int wipa_test_enc_attention_h16(const void* q, const void* k, const void* v, voi
  * Qp h16 [S, H, 64*H] absorbed queries, E h16 [U, T, 64*H] encoder output, utt_of_seq int32 [S] -> C h16 [S, H, 64*H]
  * = softmax_t(Qp[s,h] . E[u,t]) E[u].  H = 6, 8, 12 or 16 (Whisper tiny .. medium).  All device pointers. */
 int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
-                                void* stream);
+                                int layout, void* stream);
+/* layout of E above: 0 = row-major, fetched as TMA boxes; 1 = row-major in, converted to the chunk-tiled layout inside the
+ * call (not for timing); 2 = already chunk-tiled ([U][chunk][column tile][key][64 swizzled], made by wipa_test_lat_tile into a
+ * zeroed buffer of U * wipa_test_lat_tiled_elems(H, T) h16 elements): what the context keeps and bench.py times. */
+long long wipa_test_lat_tiled_elems(int H, int T);
+int wipa_test_lat_tile(const void* E, int U, int T, int H, void* out, void* stream);
 /* One decode-step self-attention over a caller-built paged KV cache: kpool / vpool [page][H][16][64] (h16 when is_h16,
  * else f32), block_table int32 [B, bt_stride] page ids, *pos_ptr = newest position (length - 1); q f32 [B, H*64];
  * out [B, H*64] in the pool's element type.  All device pointers. */

@@ -219,21 +219,25 @@ def test_cross_attention_streamer(lib, tiny_sd, dtype, tol, monkeypatch):
     m.close()
 
 
-@pytest.mark.parametrize("pipe", [0, 1])
+@pytest.mark.parametrize("layout", [0, 1, 2])
 @pytest.mark.parametrize("H,T,S,U", [(12, 1500, 5, 3), (12, 100, 200, 4), (6, 1500, 3, 3), (16, 333, 4, 2), (8, 48, 2, 1), (12, 1500, 300, 150)])
-def test_cross_attention_latent(lib, h16, H, T, S, U, pipe, monkeypatch):
-    """`pipe` selects the pipelined variant (WIPA_XL_PIPE=1: 32-key chunks, 3-stage ring, one barrier per chunk; up to 12 heads).
+def test_cross_attention_latent(lib, h16, H, T, S, U, layout):
+    """`layout`: how E reaches the kernel - 0 row-major behind a tensor map (TMA boxes), 1 / 2 the chunk-tiled, pre-swizzled
+    image the context keeps (bulk copies; converted inside the call / beforehand by wipa_test_lat_tile).
     Latent cross-attention kernel (mma.sync over TMA-swizzled tiles of the encoder output): C = softmax(Q' E^T) E per
     sequence, sequences mapped to utterances (beams share E), more sequences than SMs, ragged last key chunk, both key
     chunk sizes (48 keys up to 12 heads, 32 above)."""
-    monkeypatch.setenv("WIPA_XL_PIPE", str(pipe))
     d = 64 * H
     g = torch.Generator(device="cuda").manual_seed(H * 1000 + T + S)
     E = torch.randn(U, T, d, device="cuda", generator=g).to(lib.torch_h16(h16))
     Qp = (torch.randn(S, H, d, device="cuda", generator=g) * (1.5 / d ** 0.5)).to(lib.torch_h16(h16))
     utt = (torch.arange(S, device="cuda", dtype=torch.int32) * U // S).to(torch.int32).contiguous()
     C = torch.full((S, H, d), float("nan"), device="cuda", dtype=lib.torch_h16(h16))
-    lib.check(lib.lib(h16).wipa_test_cross_attn_latent(Qp.data_ptr(), E.data_ptr(), U, utt.data_ptr(), C.data_ptr(), S, H, T, _st()),
+    Ein = E
+    if layout == 2:
+        Ein = torch.zeros(U * lib.lib(h16).wipa_test_lat_tiled_elems(H, T), device="cuda", dtype=lib.torch_h16(h16))
+        lib.check(lib.lib(h16).wipa_test_lat_tile(E.data_ptr(), U, T, H, Ein.data_ptr(), _st()), "lat_tile")
+    lib.check(lib.lib(h16).wipa_test_cross_attn_latent(Qp.data_ptr(), Ein.data_ptr(), U, utt.data_ptr(), C.data_ptr(), S, H, T, layout, _st()),
               "cross_attn_latent")
     Eu = E.float()[utt.long()]                                          # [S, T, d]
     scores = torch.einsum("shd,std->sht", Qp.float(), Eu)

@@ -40,6 +40,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn g_encode_xl = nullptr;
 
 constexpr int XL_STAGES = 2;
+constexpr int XL_BULK_SPLIT = 4;              // bulk copies per full chunk (stage bytes are a multiple of 4 * 16)
 constexpr float XL_LOG2E = 1.4426950408889634f;
 
 template <int KEYS>
@@ -186,9 +187,12 @@ __device__ __forceinline__ void xl_finish_segment(int s, int ch0, int ch1, int n
     }
 }
 
-template <int KEYS, int H>
+// TILED: E arrives in the chunk-tiled, pre-swizzled layout (see the header of this file and lat_tile_offset in common.cuh):
+// a chunk is ONE contiguous block of global memory that lands in shared memory with plain bulk copies, exactly as the
+// tensor-map path would have swizzled it.  Otherwise E is row-major [U, T, d] behind a 3-D tensor map (H boxes per chunk).
+template <int KEYS, int H, bool TILED>
 __global__ void __launch_bounds__((H + 1) * 32, 1)
-cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Qp,
+cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Et, const h16* __restrict__ Qp,
                               const int* __restrict__ utt_of_seq, h16* __restrict__ Cout, int S, int T,
                               float* __restrict__ part, int* __restrict__ counters, int slots_per_seq) {
     using Cfg = XlCfg<KEYS>;
@@ -212,11 +216,18 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
     const long long u_lo = n_units * blockIdx.x / gridDim.x, u_hi = n_units * (blockIdx.x + 1) / gridDim.x;
 
     if (threadIdx.x == 0) {
-        ptx::prefetch_tensormap(&tmE);
+        if (!TILED) ptx::prefetch_tensormap(&tmE);
         for (int s = 0; s < XL_STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], (uint32_t)H); }
         ptx::fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 16 * PITCH; i += blockDim.x) Pm[i] = f32_to_h16(0.f);
+    if (TILED) {
+        // the ragged last chunk of a sequence copies only its valid keys; the rest of the stage then holds whatever an
+        // earlier chunk left there (finite values, multiplied by p = 0) - but never uninitialised shared memory
+        uint4* z = reinterpret_cast<uint4*>(sE);
+        for (int i = threadIdx.x; i < (int)(XL_STAGES * stage_bytes / 16); i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        ptx::fence_proxy_async();
+    }
     if (threadIdx.x < 32) alpha[threadIdx.x] = 1.f;
     __syncthreads();
 
@@ -232,10 +243,25 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
             for (int ch = ch0; ch < ch1; ++ch) {
                 ptx::mbar_wait(&empty[st], ph ^ 1);
                 if (ptx::elect_one()) {
-                    ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
                     uint8_t* dst = sE + st * stage_bytes;
-                    for (int h = 0; h < H; ++h)
-                        ptx::tma_load_3d(dst + h * (KEYS * 128), &tmE, &full[st], h * 64, ch * KEYS, u);
+                    if (TILED) {
+                        const uint8_t* src = reinterpret_cast<const uint8_t*>(Et) + ((size_t)u * n_chunks + ch) * stage_bytes;
+                        const int valid = (T - ch * KEYS) < KEYS ? (T - ch * KEYS) : KEYS;
+                        if (valid == KEYS) {                     // the whole chunk: contiguous, a few large bulk copies
+                            constexpr uint32_t piece = stage_bytes / XL_BULK_SPLIT;
+                            ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+#pragma unroll
+                            for (int i = 0; i < XL_BULK_SPLIT; ++i) ptx::bulk_load_1d(dst + i * piece, src + i * piece, piece, &full[st]);
+                        } else {                                 // ragged end of the sequence: the valid rows of each column tile
+                            ptx::mbar_arrive_expect_tx(&full[st], (uint32_t)(H * valid * 128));
+                            for (int h = 0; h < H; ++h)
+                                ptx::bulk_load_1d(dst + h * (KEYS * 128), src + h * (KEYS * 128), (uint32_t)(valid * 128), &full[st]);
+                        }
+                    } else {
+                        ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
+                        for (int h = 0; h < H; ++h)
+                            ptx::tma_load_3d(dst + h * (KEYS * 128), &tmE, &full[st], h * 64, ch * KEYS, u);
+                    }
                 }
                 __syncwarp();
                 if (++st == XL_STAGES) { st = 0; ph ^= 1; }
@@ -384,218 +410,6 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Pipelined variant (UNVALIDATED ON HARDWARE: written after the round's GPU budget was spent; WIPA_XL_PIPE=1 selects it).
-// Same algorithm and scratch protocol; 32-key chunks in a 3-stage ring and ONE named barrier per chunk.  Between two
-// barriers every consumer warp runs, as one instruction stream,
-//     P.E of chunk i-1   (tensor pipe; P[(i-1)&1] and alpha[(i-1)&1] were published before the barrier)
-//     reduction of chunk i (LDS / redux / MUFU latency chain; Sp[i&1] was completed before the barrier)
-//     scores of chunk i+1  (tensor pipe; writes Sp[(i+1)&1])
-// so the reduction's latency hides behind the two MMA phases instead of idling the tensor pipe.
-// ------------------------------------------------------------------------------------------------
-template <int H>
-struct XlPipeCfg {
-    static constexpr int KEYS = 32, STAGES = 3, PITCH = KEYS + 8;
-    static constexpr size_t smem() {
-        return (size_t)STAGES * KEYS * H * 128 + 2 * (size_t)H * H * PITCH * 4 + 2 * 16 * PITCH * 2 + 2 * 16 * 4 + 64 + 1024;
-    }
-};
-
-template <int H>
-__global__ void __launch_bounds__((H + 1) * 32, 1)
-cross_attention_latent_pipe_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Qp,
-                                   const int* __restrict__ utt_of_seq, h16* __restrict__ Cout, int S, int T,
-                                   float* __restrict__ part, int* __restrict__ counters, int slots_per_seq) {
-    using Cfg = XlPipeCfg<H>;
-    constexpr int KEYS = Cfg::KEYS, STAGES = Cfg::STAGES, PITCH = Cfg::PITCH;
-    extern __shared__ uint8_t xl_smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xl_smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr int d = H * 64;
-    constexpr uint32_t stage_bytes = (uint32_t)KEYS * (uint32_t)H * 128u;
-    uint8_t* sE = smem;                                                      // [stage][H tiles][KEYS][128 B], 128B-swizzled
-    float* Sp = reinterpret_cast<float*>(sE + STAGES * stage_bytes);         // [2][warp][head][PITCH]
-    h16* Pm = reinterpret_cast<h16*>(Sp + 2 * H * H * PITCH);              // [2][16][PITCH]
-    float* alpha = reinterpret_cast<float*>(Pm + 2 * 16 * PITCH);            // [2][16]
-    uint64_t* full = reinterpret_cast<uint64_t*>(alpha + 32);
-    uint64_t* empty = full + STAGES;
-    int* last_flag = reinterpret_cast<int*>(empty + STAGES);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_chunks = (T + KEYS - 1) / KEYS;
-    const long long n_units = (long long)S * n_chunks;
-    const long long u_lo = n_units * blockIdx.x / gridDim.x, u_hi = n_units * (blockIdx.x + 1) / gridDim.x;
-
-    if (threadIdx.x == 0) {
-        ptx::prefetch_tensormap(&tmE);
-        for (int s = 0; s < STAGES; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], (uint32_t)H); }
-        ptx::fence_barrier_init();
-    }
-    for (int i = threadIdx.x; i < 2 * 16 * PITCH; i += blockDim.x) Pm[i] = f32_to_h16(0.f);
-    if (threadIdx.x < 32) alpha[threadIdx.x] = 1.f;
-    __syncthreads();
-
-    if (warp == H) {
-        int st = 0;
-        uint32_t ph = 0;
-        for (long long unit = u_lo; unit < u_hi;) {
-            const int s = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)s * n_chunks);
-            const int ch1 = (u_hi - unit) < (long long)(n_chunks - ch0) ? ch0 + (int)(u_hi - unit) : n_chunks;
-            unit += ch1 - ch0;
-            const int u = utt_of_seq[s];
-            for (int ch = ch0; ch < ch1; ++ch) {
-                ptx::mbar_wait(&empty[st], ph ^ 1);
-                if (ptx::elect_one()) {
-                    ptx::mbar_arrive_expect_tx(&full[st], stage_bytes);
-                    uint8_t* dst = sE + st * stage_bytes;
-                    for (int h = 0; h < H; ++h)
-                        ptx::tma_load_3d(dst + h * (KEYS * 128), &tmE, &full[st], h * 64, ch * KEYS, u);
-                }
-                __syncwarp();
-                if (++st == STAGES) { st = 0; ph ^= 1; }
-            }
-        }
-        return;
-    }
-
-    const int w = warp;
-    const int g = lane >> 2, t = lane & 3;
-    constexpr int nthr = H * 32;
-    const bool row_lo = g < H, row_hi = g + 8 < H;
-    pdl_wait();
-    pdl_launch_dependents();
-    const uint32_t sE_s = ptx::smem_u32(sE), Pm_s = ptx::smem_u32(Pm), Sp_s = ptx::smem_u32(Sp);
-    // ring position of the next chunk whose scores start (sc_*) and of the next chunk whose P.E finishes (pv_*): chunks
-    // are consumed in the order the producer loads them
-    int sc_st = 0, pv_st = 0;
-    uint32_t sc_ph = 0;
-
-    for (long long unit = u_lo; unit < u_hi;) {
-        const int s = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)s * n_chunks);
-        const int ch1 = (u_hi - unit) < (long long)(n_chunks - ch0) ? ch0 + (int)(u_hi - unit) : n_chunks;
-        unit += ch1 - ch0;
-        uint32_t qa[4][4];
-        {
-            const uint32_t* q_lo = reinterpret_cast<const uint32_t*>(Qp + ((size_t)s * H + g) * d + w * 64 + 2 * t);
-            const uint32_t* q_hi = reinterpret_cast<const uint32_t*>(Qp + ((size_t)s * H + g + 8) * d + w * 64 + 2 * t);
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-                qa[ks][0] = row_lo ? q_lo[ks * 8] : 0u;
-                qa[ks][1] = row_hi ? q_hi[ks * 8] : 0u;
-                qa[ks][2] = row_lo ? q_lo[ks * 8 + 4] : 0u;
-                qa[ks][3] = row_hi ? q_hi[ks * 8 + 4] : 0u;
-            }
-        }
-        float acc[8][4];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
-        float accl[4] = {0.f, 0.f, 0.f, 0.f};
-        float m_run = -INFINITY;
-
-        // scores of the next chunk in ring order over this warp's columns -> Sp[buf]
-        auto scores = [&](int buf) {
-            ptx::mbar_wait(&full[sc_st], sc_ph);
-            const uint32_t tile = sE_s + (uint32_t)sc_st * stage_bytes + (uint32_t)w * (KEYS * 128);
-            uint32_t bfr[KEYS / 8][2][4];
-#pragma unroll
-            for (int nt = 0; nt < KEYS / 8; ++nt) {
-                const int key = nt * 8 + (lane & 7);
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    const int c16 = half * 4 + (lane >> 3);
-                    ldmatrix_x4(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), bfr[nt][half][0], bfr[nt][half][1],
-                                bfr[nt][half][2], bfr[nt][half][3]);
-                }
-            }
-            float sc[KEYS / 8][4];
-#pragma unroll
-            for (int nt = 0; nt < KEYS / 8; ++nt) { sc[nt][0] = 0.f; sc[nt][1] = 0.f; sc[nt][2] = 0.f; sc[nt][3] = 0.f; }
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-                for (int nt = 0; nt < KEYS / 8; ++nt)
-                    mma_h16(sc[nt], qa[ks], bfr[nt][ks >> 1][(ks & 1) * 2], bfr[nt][ks >> 1][(ks & 1) * 2 + 1]);
-            }
-            const uint32_t base = Sp_s + (uint32_t)(buf * H * H * PITCH) * 4u;
-#pragma unroll
-            for (int nt = 0; nt < KEYS / 8; ++nt) {
-                if (row_lo) sts_f32x2(base + (uint32_t)((w * H + g) * PITCH + nt * 8 + 2 * t) * 4u, sc[nt][0], sc[nt][1]);
-                if (row_hi) sts_f32x2(base + (uint32_t)((w * H + g + 8) * PITCH + nt * 8 + 2 * t) * 4u, sc[nt][2], sc[nt][3]);
-            }
-            if (++sc_st == STAGES) { sc_st = 0; sc_ph ^= 1; }
-        };
-        // head w of chunk ch: sum the partials in Sp[buf], maximum by redux.sync, p -> Pm[buf], rescale factor -> alpha[buf]
-        auto reduce = [&](int ch, int buf) {
-            const uint32_t row = Sp_s + (uint32_t)(buf * H * H * PITCH + w * PITCH + lane) * 4u;
-            float va = 0.f, vb = 0.f;
-#pragma unroll
-            for (int ww = 0; ww < H; ww += 2) {
-                va += lds_f32(row + (uint32_t)(ww * H * PITCH) * 4u);
-                vb += lds_f32(row + (uint32_t)((ww + 1) * H * PITCH) * 4u);
-            }
-            float v = va + vb;
-            if (ch * KEYS + lane >= T) v = -INFINITY;
-            const float m_new = fmaxf(m_run, warp_max_f32(v));       // finite: every chunk holds a valid key
-            const float mb = m_new * XL_LOG2E;
-            const float p = ex2_ftz(fmaf(v, XL_LOG2E, -mb));
-            const float a = ex2_ftz(fmaf(m_run, XL_LOG2E, -mb));
-            m_run = m_new;
-            sts_b16(Pm_s + (uint32_t)(buf * 16 * PITCH + w * PITCH + lane) * 2u, f32_to_h16(p));
-            if (lane == 0) alpha[buf * 16 + w] = a;
-        };
-        // C = alpha * C + P E (and l = alpha * l + P x ones) for the oldest chunk still in the ring, then release its slot
-        auto pv = [&](int buf) {
-            const uint32_t tile = sE_s + (uint32_t)pv_st * stage_bytes + (uint32_t)w * (KEYS * 128);
-            uint32_t vfr[KEYS / 16][4][4];
-#pragma unroll
-            for (int ks = 0; ks < KEYS / 16; ++ks) {
-                const int key = ks * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-#pragma unroll
-                for (int jp = 0; jp < 4; ++jp) {
-                    const int c16 = jp * 2 + (lane >> 4);
-                    ldmatrix_x4_trans(tile + (uint32_t)key * 128u + (uint32_t)((c16 ^ (key & 7)) << 4), vfr[ks][jp][0], vfr[ks][jp][1],
-                                      vfr[ks][jp][2], vfr[ks][jp][3]);
-                }
-            }
-            const float a_lo = alpha[buf * 16 + g], a_hi = alpha[buf * 16 + g + 8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { acc[j][0] *= a_lo; acc[j][1] *= a_lo; acc[j][2] *= a_hi; acc[j][3] *= a_hi; }
-            accl[0] *= a_lo; accl[1] *= a_lo; accl[2] *= a_hi; accl[3] *= a_hi;
-            uint32_t pa[KEYS / 16][4];
-#pragma unroll
-            for (int ks = 0; ks < KEYS / 16; ++ks) {
-                const uint32_t p_lo = Pm_s + (uint32_t)(buf * 16 * PITCH + g * PITCH + ks * 16 + 2 * t) * 2u;
-                const uint32_t p_hi = p_lo + 8u * PITCH * 2u;
-                pa[ks][0] = lds32(p_lo); pa[ks][1] = lds32(p_hi); pa[ks][2] = lds32(p_lo + 16u); pa[ks][3] = lds32(p_hi + 16u);
-            }
-#pragma unroll
-            for (int ks = 0; ks < KEYS / 16; ++ks) {
-#pragma unroll
-                for (int jp = 0; jp < 4; ++jp) {
-                    mma_h16(acc[2 * jp], pa[ks], vfr[ks][jp][0], vfr[ks][jp][1]);
-                    mma_h16(acc[2 * jp + 1], pa[ks], vfr[ks][jp][2], vfr[ks][jp][3]);
-                }
-                mma_h16(accl, pa[ks], WIPA_H16_ONE_X2, WIPA_H16_ONE_X2);
-            }
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&empty[pv_st]);           // the fragments are in registers: the slot can be refilled
-            if (++pv_st == STAGES) pv_st = 0;
-        };
-
-        scores(0);
-        xl_bar(nthr);
-        for (int ch = ch0; ch < ch1; ++ch) {
-            const int b = (ch - ch0) & 1;
-            if (ch > ch0) pv(b ^ 1);
-            reduce(ch, b);
-            if (ch + 1 < ch1) scores(b ^ 1);
-            xl_bar(nthr);
-        }
-        pv((ch1 - 1 - ch0) & 1);
-
-        xl_finish_segment<H>(s, ch0, ch1, n_chunks, n_units, acc, accl, m_run, Cout, part, counters, slots_per_seq, last_flag, w, lane);
-    }
-}
-
 int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) {
     cuuint64_t dims[3] = {(cuuint64_t)d, (cuuint64_t)T, (cuuint64_t)U};
     cuuint64_t strides[2] = {(cuuint64_t)d * 2, (cuuint64_t)T * d * 2};
@@ -611,12 +425,12 @@ int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) 
     return WIPA_OK;
 }
 
-template <int KEYS, int H>
-int xl_launch(const CUtensorMap& tm, const h16* Qp, const int* utt_of_seq, h16* C, int S, int T, int n_sm, float* part,
+template <int KEYS, int H, bool TILED>
+int xl_launch(const CUtensorMap& tm, const h16* Et, const h16* Qp, const int* utt_of_seq, h16* C, int S, int T, int n_sm, float* part,
               size_t part_floats, int* counters, cudaStream_t st) {
     const size_t smem = XlCfg<KEYS>::smem(H);
     static SmemAttr attr;
-    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H>, smem, attr));
+    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H, TILED>, smem, attr));
     const int n_chunks = cdiv(T, KEYS);
     const long long n_units = (long long)S * n_chunks;
     const int grid = n_units < n_sm ? (int)n_units : n_sm;
@@ -624,7 +438,7 @@ int xl_launch(const CUtensorMap& tm, const h16* Qp, const int* utt_of_seq, h16* 
     const int slots_per_seq = n_chunks / (int)(n_units / grid) + 2;
     WIPA_CHECK((size_t)S * slots_per_seq * (H * 1024 + 32) <= part_floats, WIPA_EINVAL,
                "cross_attention_latent: partial scratch too small for %d sequences", S);
-    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Qp,
+    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H, TILED>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Et, Qp,
                                   utt_of_seq, C, S, T, part, counters, slots_per_seq));
     WIPA_LAUNCHED();
     return WIPA_OK;
@@ -635,34 +449,23 @@ int xl_launch(const CUtensorMap& tm, const h16* Qp, const int* utt_of_seq, h16* 
 // one instantiation per Whisper width below large (heads = d / 64): tiny 6, base 8, small 12, medium 16
 int cross_attention_latent_supported(int H) { return H == 6 || H == 8 || H == 12 || H == 16; }
 
-template <int H>
-int xl_launch_pipe(const h16* E, int U, const h16* Qp, const int* utt_of_seq, h16* C, int S, int T, int n_sm, float* part,
-                   size_t part_floats, int* counters, cudaStream_t st) {
-    using Cfg = XlPipeCfg<H>;
-    CUtensorMap tm;
-    WIPA_TRY(xl_make_map(&tm, E, U, T, H * 64, Cfg::KEYS));
-    static SmemAttr attr;
-    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_pipe_kernel<H>, Cfg::smem(), attr));
-    const int n_chunks = cdiv(T, Cfg::KEYS);
-    const long long n_units = (long long)S * n_chunks;
-    const int grid = n_units < n_sm ? (int)n_units : n_sm;
-    const int slots_per_seq = n_chunks / (int)(n_units / grid) + 2;
-    WIPA_CHECK((size_t)S * slots_per_seq * (H * 1024 + 32) <= part_floats, WIPA_EINVAL,
-               "cross_attention_latent: partial scratch too small for %d sequences", S);
-    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_pipe_kernel<H>, dim3(grid), dim3((H + 1) * 32), Cfg::smem(), st, tm, Qp,
-                                  utt_of_seq, C, S, T, part, counters, slots_per_seq));
-    WIPA_LAUNCHED();
-    return WIPA_OK;
-}
-
 // floats of partial scratch that any launch with S <= max_seqs sequences can need on a device with n_sm SMs
 size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm) {
     return (size_t)(2 * n_sm + 3 * max_seqs + 64) * (size_t)(H * 1024 + 32);
 }
 
-// Qp: h16 [S, H, d] absorbed queries; E: h16 [U, T, d] encoder output (d = 64 H); utt_of_seq: int [S]; C: h16 [S, H, d];
+int cross_attention_latent_keys(int H) { return H <= 12 ? 48 : 32; }     // two stages of keys x d x 2 bytes + H x H partial rows must fit 227 KB
+
+// elements of the chunk-tiled image of one utterance's encoder output: whole chunks of `keys` keys (the tail is zero padding)
+size_t cross_attention_latent_tiled_elems(int H, int T) {
+    const int keys = cross_attention_latent_keys(H);
+    return (size_t)cdiv(T, keys) * keys * H * 64;
+}
+
+// Qp: h16 [S, H, d] absorbed queries; E: encoder output (d = 64 H) as h16 [U, T, d] (tiled = 0) or in the chunk-tiled layout
+// (tiled = 1: [U][chunk][h][key][64 swizzled], common.cuh lat_tile_offset); utt_of_seq: int [S]; C: h16 [S, H, d];
 // part / counters: partial scratch (cross_attention_latent_scratch_floats) and int [S] zeroed once (self-resetting)
-int launch_cross_attention_latent(const h16* Qp, const h16* E, int U, const int* utt_of_seq, h16* C, int S, int H, int T,
+int launch_cross_attention_latent(const h16* Qp, const h16* E, int tiled, int U, const int* utt_of_seq, h16* C, int S, int H, int T,
                                   float* part, size_t part_floats, int* counters, cudaStream_t st) {
     WIPA_CHECK(cross_attention_latent_supported(H), WIPA_EUNSUPPORTED, "cross_attention_latent: %d heads (6, 8, 12 or 16)", H);
     WIPA_CHECK(S >= 1 && U >= 1 && T >= 1 && part && counters, WIPA_EINVAL, "cross_attention_latent: bad argument");
@@ -679,21 +482,22 @@ int launch_cross_attention_latent(const h16* Qp, const h16* E, int U, const int*
         WIPA_CUDA_CHECK(cudaGetDevice(&dev));
         WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     }
-    const char* pipe_env = getenv("WIPA_XL_PIPE");              // pipelined variant (unvalidated): 32-key chunks, 3 stages
-    if (pipe_env != nullptr && pipe_env[0] == '1' && H <= 12) {
+    const int keys = cross_attention_latent_keys(H);
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    if (tiled) {
         switch (H) {
-            case 6: return xl_launch_pipe<6>(E, U, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-            case 8: return xl_launch_pipe<8>(E, U, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-            default: return xl_launch_pipe<12>(E, U, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+            case 6: return xl_launch<48, 6, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+            case 8: return xl_launch<48, 8, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+            case 12: return xl_launch<48, 12, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+            default: return xl_launch<32, 16, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
         }
     }
-    const int keys = H <= 12 ? 48 : 32;             // two stages of keys x d x 2 bytes + H x H partial rows must fit 227 KB
-    CUtensorMap tm;
     WIPA_TRY(xl_make_map(&tm, E, U, T, H * 64, keys));
     switch (H) {
-        case 6: return xl_launch<48, 6>(tm, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-        case 8: return xl_launch<48, 8>(tm, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-        case 12: return xl_launch<48, 12>(tm, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-        default: return xl_launch<32, 16>(tm, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        case 6: return xl_launch<48, 6, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        case 8: return xl_launch<48, 8, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        case 12: return xl_launch<48, 12, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        default: return xl_launch<32, 16, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
     }
 }

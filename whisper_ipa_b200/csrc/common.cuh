@@ -484,8 +484,23 @@ int cross_attention_default_split(int elem_bytes, int Bs, int H);
 // attn_lat.cu: cross-attention over the encoder output itself (absorbed k / v projections), h16 only
 int cross_attention_latent_supported(int H);
 size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm);
-int launch_cross_attention_latent(const h16* Qp, const h16* E, int U, const int* utt_of_seq, h16* C, int S, int H, int T,
+int cross_attention_latent_keys(int H);                    // keys per chunk of the kernel instantiation for H heads
+size_t cross_attention_latent_tiled_elems(int H, int T);   // elements per utterance of the chunk-tiled encoder output
+int launch_cross_attention_latent(const h16* Qp, const h16* E, int tiled, int U, const int* utt_of_seq, h16* C, int S, int H, int T,
                                   float* part, size_t part_floats, int* counters, cudaStream_t st);
+// Chunk-tiled layout of one utterance's encoder output E [T, d = 64 H] for the latent cross-attention kernel:
+// [chunk of `keys` keys][column tile h of 64][key][64 columns], the eight 16-byte pieces of every 128-byte row permuted by
+// (piece ^ (key & 7)) - byte for byte what a 128B-swizzled TMA box [keys][64] leaves in shared memory, so that a whole
+// chunk (keys * d * 2 bytes, contiguous) is fetched with plain bulk copies.  Element offset of (t, col):
+__host__ __device__ __forceinline__ size_t lat_tile_offset(int t, int col, int H, int keys) {
+    const int ch = t / keys, key = t - ch * keys, h = col >> 6, e = col & 63;
+    return ((size_t)(ch * H + h) * keys + key) * 64 + (size_t)((((e >> 3) ^ (key & 7)) << 3) | (e & 7));
+}
+// x f32 [rows of T per utterance, d] -> LayerNorm -> chunk-tiled h16 image of utterances u0, u0 + 1, ... (elementwise.cu)
+int launch_layernorm_lat(const float* x, const float* w, const float* b, h16* out_tiled, int M, int d, int T, int u0, int keys,
+                         cudaStream_t st);
+// row-major [U, T, d] (f32 or h16) -> chunk-tiled h16
+int launch_lat_tile(const void* src, int src_is_h16, h16* out_tiled, int U, int T, int H, int keys, cudaStream_t st);
 
 // elementwise.cu
 template <typename T>

@@ -30,6 +30,7 @@ struct Slot {
     int64_t numel;
     int N, C;            // SLOT_CONV
     std::string canon;   // canonical name (aliases share it)
+    float* master;       // fp32 copy (scaled) kept for the folded-LayerNorm weights: W * gain is then rounded ONCE
 };
 
 struct EncLayer {
@@ -38,6 +39,7 @@ struct EncLayer {
     float *qkv_b, *o_b, *fc1_b, *fc2_b;
 };
 struct DecLayer {
+    float *qkv_m, *cq_m, *fc1_m;        // fp32 masters (folded-LayerNorm path), else null
     float *ln1_w, *ln1_b, *ln2_w, *ln2_b, *ln3_w, *ln3_b;
     void *qkv_w, *o_w, *cq_w, *co_w, *fc1_w, *fc2_w;
     float *qkv_b, *o_b, *cq_b, *co_b, *fc1_b, *fc2_b;
@@ -102,6 +104,7 @@ struct wipa_ctx {
     // latent cross-attention (attn_lat.cu): the decoder attends over the encoder output itself, k / v projections folded
     // into the query and output projections.  Default on the h16 path for contexts of >= 128 sequences and <= 16 heads.
     int xlat = 0;
+    int xl_tiled = 1;              // WIPA_XL_TILED: the encoder output is kept chunk-tiled / pre-swizzled (bulk copies) instead of row-major (TMA boxes)
     int bn_xlq = 0;                // WIPA_BN_XLQ: tile width of the absorbed-query GEMM (0: as fc1)
     bool xlat_ready = false;       // folded weights match the loaded weights
     void *enc_lat = nullptr, *dqlat = nullptr, *dclat = nullptr;     // E [max_batch, 1500, d]; Q' and C [S, H*d]
@@ -115,6 +118,7 @@ struct wipa_ctx {
     int lnf = 0;
     bool lnf_ready = false;
     void *dx16 = nullptr, *emb_wf = nullptr;
+    float* emb_master = nullptr;
     float *dstats = nullptr, *emb_c = nullptr, *emb_bf = nullptr;
     std::vector<void*> qkv_wf, cq_wf, fc1_wf;
     std::vector<float*> qkv_c, qkv_bf, cq_c, cq_bf, fc1_c, fc1_bf, xlq_c, xlq_beff;
@@ -158,17 +162,23 @@ struct Carver {
 };
 
 // Lays out both arenas and the name table.  Called twice: once with null bases to measure, once to assign.
-void layout_weights(wipa_ctx* c, char* tbase, char* fbase, size_t* tbytes, size_t* fbytes) {
+void layout_weights(wipa_ctx* c, char* tbase, char* fbase, char* mbase, size_t* tbytes, size_t* fbytes, size_t* mbytes) {
     const wipa_arch& a = c->a;
     const int d = a.d_model, ffn = a.ffn, V = a.vocab;
-    Carver T{tbase, 0, c->esz}, F{fbase, 0, 4};
+    Carver T{tbase, 0, c->esz}, F{fbase, 0, 4}, Mst{mbase, 0, 4};
     const bool assign = tbase != nullptr;
+    float* next_master = nullptr;       // set right before a reg() whose tensor keeps an fp32 master copy
     auto reg = [&](const std::string& name, void* dst, int kind, int64_t numel, float scale = 1.f, int N = 0, int C = 0,
                    const char* canon = nullptr) {
+        float* m = next_master;
+        next_master = nullptr;
         if (!assign) return;
-        Slot s{dst, kind, scale, numel, N, C, canon ? std::string(canon) : name};
+        Slot s{dst, kind, scale, numel, N, C, canon ? std::string(canon) : name, m};
         c->slots[name] = s;
     };
+    // fp32 masters of the weights that consume a LayerNorm output (decoder qkv, cross-attention q, fc1, the tied embedding):
+    // the folded-LayerNorm path multiplies them by the gain and rounds to h16 once (ln_fold_rows)
+    auto master = [&](size_t elems) -> float* { return c->lnf ? (float*)Mst.take(elems) : nullptr; };
     auto ln = [&](const std::string& p, float*& w, float*& b) {
         w = (float*)F.take(d); b = (float*)F.take(d);
         reg(p + ".weight", w, SLOT_F32, d); reg(p + ".bias", b, SLOT_F32, d);
@@ -178,12 +188,15 @@ void layout_weights(wipa_ctx* c, char* tbase, char* fbase, size_t* tbytes, size_
         reg(p + ".weight", w, SLOT_T, (int64_t)N * K); reg(p + ".bias", b, SLOT_F32, N);
     };
     // q|k|v fused: q (and its bias) carry the 64^-0.5 = 0.125 scaling (exact), k has no bias (stays zero)
-    auto qkv = [&](const std::string& p, void*& w, float*& b) {
+    auto qkv = [&](const std::string& p, void*& w, float*& b, float* m = nullptr) {
         w = T.take((size_t)3 * d * d); b = (float*)F.take(3 * d);
         char* wb = (char*)w;
         const size_t blk = (size_t)d * d * c->esz;
+        next_master = m;
         reg(p + ".q_proj.weight", wb, SLOT_T, (int64_t)d * d, 0.125f);
+        next_master = m ? m + (size_t)d * d : nullptr;
         reg(p + ".k_proj.weight", wb ? wb + blk : nullptr, SLOT_T, (int64_t)d * d);
+        next_master = m ? m + (size_t)2 * d * d : nullptr;
         reg(p + ".v_proj.weight", wb ? wb + 2 * blk : nullptr, SLOT_T, (int64_t)d * d);
         reg(p + ".q_proj.bias", b, SLOT_F32, d, 0.125f);
         reg(p + ".v_proj.bias", b ? b + 2 * d : nullptr, SLOT_F32, d);
@@ -215,7 +228,10 @@ void layout_weights(wipa_ctx* c, char* tbase, char* fbase, size_t* tbytes, size_
     ln(pe + "layer_norm", c->enc_ln_w, c->enc_ln_b);
 
     c->tok_emb = T.take((size_t)V * d);
+    c->emb_master = master((size_t)V * d);
+    next_master = c->emb_master;
     reg(pd + "embed_tokens.weight", c->tok_emb, SLOT_T, (int64_t)V * d);
+    next_master = c->emb_master;
     reg("proj_out.weight", c->tok_emb, SLOT_T, (int64_t)V * d, 1.f, 0, 0, "model.decoder.embed_tokens.weight");   // tied head
     c->dec_pos = (float*)F.take((size_t)WIPA_MAX_TGT * d);
     reg(pd + "embed_positions.weight", c->dec_pos, SLOT_F32, (int64_t)WIPA_MAX_TGT * d);
@@ -224,11 +240,14 @@ void layout_weights(wipa_ctx* c, char* tbase, char* fbase, size_t* tbytes, size_
     for (int l = 0; l < a.dec_layers; ++l) {
         const std::string p = pd + "layers." + std::to_string(l) + ".";
         ln(p + "self_attn_layer_norm", D[l].ln1_w, D[l].ln1_b);
-        qkv(p + "self_attn", D[l].qkv_w, D[l].qkv_b);
+        D[l].qkv_m = master((size_t)3 * d * d);
+        qkv(p + "self_attn", D[l].qkv_w, D[l].qkv_b, D[l].qkv_m);
         lin(p + "self_attn.out_proj", D[l].o_w, D[l].o_b, d, d);
         ln(p + "encoder_attn_layer_norm", D[l].ln2_w, D[l].ln2_b);
         // cross-attention: q scaled like self-attention; k / v of all layers fused into one [L*2*d, d] operand
         D[l].cq_w = T.take((size_t)d * d); D[l].cq_b = (float*)F.take(d);
+        D[l].cq_m = (c->lnf && !c->xlat) ? master((size_t)d * d) : nullptr;
+        next_master = D[l].cq_m;
         reg(p + "encoder_attn.q_proj.weight", D[l].cq_w, SLOT_T, (int64_t)d * d, 0.125f);
         reg(p + "encoder_attn.q_proj.bias", D[l].cq_b, SLOT_F32, d, 0.125f);
         char* xw = (char*)c->xkv_w;
@@ -238,12 +257,15 @@ void layout_weights(wipa_ctx* c, char* tbase, char* fbase, size_t* tbytes, size_
         reg(p + "encoder_attn.v_proj.bias", c->xkv_b ? c->xkv_b + (size_t)(2 * l + 1) * d : nullptr, SLOT_F32, d);
         lin(p + "encoder_attn.out_proj", D[l].co_w, D[l].co_b, d, d);
         ln(p + "final_layer_norm", D[l].ln3_w, D[l].ln3_b);
+        D[l].fc1_m = master((size_t)ffn * d);
+        next_master = D[l].fc1_m;
         lin(p + "fc1", D[l].fc1_w, D[l].fc1_b, ffn, d);
         lin(p + "fc2", D[l].fc2_w, D[l].fc2_b, d, ffn);
     }
     ln(pd + "layer_norm", c->dec_ln_w, c->dec_ln_b);
     *tbytes = T.off;
     *fbytes = F.off;
+    *mbytes = Mst.off;
 }
 
 AOperand plainA(const void* p, int M, int K) {
@@ -376,14 +398,15 @@ __global__ void xlat_fold_o_kernel(const h16* __restrict__ Wo, const float* __re
 // folded LayerNorm: W'[n, k] = W[n, k] * gain[k] (one rounding), c[n] = sum_k W'[n, k] (of the ROUNDED values: what the
 // tensor cores will multiply), b'[n] = b[n] + sum_k beta[k] W[n, k].  One warp per output row; any output may be null.
 // ------------------------------------------------------------------------------------------------
+// W is the fp32 master when `Wm` is given (gain-folded weights are then rounded once), else the stored h16 weights.
 __global__ void __launch_bounds__(256)
-ln_fold_rows_kernel(const h16* __restrict__ W, const float* __restrict__ gain, const float* __restrict__ beta,
+ln_fold_rows_kernel(const h16* __restrict__ W, const float* __restrict__ Wm, const float* __restrict__ gain, const float* __restrict__ beta,
                     const float* __restrict__ bias, h16* __restrict__ Wf, float* __restrict__ csum, float* __restrict__ bf, int N, int K) {
     const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (n >= N) return;
     float cs = 0.f, bs = 0.f;
     for (int k = lane; k < K; k += 32) {
-        const float w = h16_to_f32(W[(size_t)n * K + k]);
+        const float w = Wm != nullptr ? Wm[(size_t)n * K + k] : h16_to_f32(W[(size_t)n * K + k]);
         const h16 wf = f32_to_h16(gain != nullptr ? w * gain[k] : w);
         if (Wf != nullptr) Wf[(size_t)n * K + k] = wf;
         cs += h16_to_f32(wf);
@@ -398,8 +421,8 @@ ln_fold_rows_kernel(const h16* __restrict__ W, const float* __restrict__ gain, c
 }
 
 int ln_fold_rows(const void* W, const float* gain, const float* beta, const float* bias, void* Wf, float* csum, float* bf, int N, int K,
-                 cudaStream_t st) {
-    ln_fold_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>((const h16*)W, gain, beta, bias, (h16*)Wf, csum, bf, N, K);
+                 cudaStream_t st, const float* Wm = nullptr) {
+    ln_fold_rows_kernel<<<cdiv(N, 8), 256, 0, st>>>((const h16*)W, Wm, gain, beta, bias, (h16*)Wf, csum, bf, N, K);
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
@@ -436,11 +459,11 @@ int lnf_prepare(wipa_ctx* c, cudaStream_t st) {
     const int d = c->a.d_model, ffn = c->a.ffn, V = c->a.vocab;
     for (int l = 0; l < c->a.dec_layers; ++l) {
         const DecLayer& L = c->dec[l];
-        WIPA_TRY(ln_fold_rows(L.qkv_w, L.ln1_w, L.ln1_b, L.qkv_b, c->qkv_wf[l], c->qkv_c[l], c->qkv_bf[l], 3 * d, d, st));
-        if (!c->xlat) WIPA_TRY(ln_fold_rows(L.cq_w, L.ln2_w, L.ln2_b, L.cq_b, c->cq_wf[l], c->cq_c[l], c->cq_bf[l], d, d, st));
-        WIPA_TRY(ln_fold_rows(L.fc1_w, L.ln3_w, L.ln3_b, L.fc1_b, c->fc1_wf[l], c->fc1_c[l], c->fc1_bf[l], ffn, d, st));
+        WIPA_TRY(ln_fold_rows(L.qkv_w, L.ln1_w, L.ln1_b, L.qkv_b, c->qkv_wf[l], c->qkv_c[l], c->qkv_bf[l], 3 * d, d, st, L.qkv_m));
+        if (!c->xlat) WIPA_TRY(ln_fold_rows(L.cq_w, L.ln2_w, L.ln2_b, L.cq_b, c->cq_wf[l], c->cq_c[l], c->cq_bf[l], d, d, st, L.cq_m));
+        WIPA_TRY(ln_fold_rows(L.fc1_w, L.ln3_w, L.ln3_b, L.fc1_b, c->fc1_wf[l], c->fc1_c[l], c->fc1_bf[l], ffn, d, st, L.fc1_m));
     }
-    WIPA_TRY(ln_fold_rows(c->tok_emb, c->dec_ln_w, c->dec_ln_b, nullptr, c->emb_wf, c->emb_c, c->emb_bf, V, d, st));
+    WIPA_TRY(ln_fold_rows(c->tok_emb, c->dec_ln_w, c->dec_ln_b, nullptr, c->emb_wf, c->emb_c, c->emb_bf, V, d, st, c->emb_master));
     c->lnf_ready = true;
     return WIPA_OK;
 }
@@ -519,6 +542,9 @@ int encode_chunk(wipa_ctx* c, const float* mel, int u0, int nb, float* enc_out, 
     }
     // latent cross-attention keeps the encoder output itself (h16) for the whole batch instead of per-layer K / V
     void* enc_dst = c->xlat ? (void*)((h16*)c->enc_lat + (size_t)u0 * T * d) : c->enc_T;
+    if (c->xlat && c->xl_tiled)
+        WIPA_TRY(launch_layernorm_lat(c->ex, c->enc_ln_w, c->enc_ln_b, (h16*)c->enc_lat, M, d, T, u0, cross_attention_latent_keys(H), st));
+    else
     WIPA_TRY(ln(c, c->ex, c->enc_ln_w, c->enc_ln_b, enc_dst, M, st));
     if (enc_out != nullptr) WIPA_TRY(launch_layernorm<float>(c->ex, c->enc_ln_w, c->enc_ln_b, enc_out, M, d, st));
     if (c->xlat) return WIPA_OK;
@@ -606,7 +632,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
                 if (lnf) consume_ln(ep, c->xlq_c[l], c->xlq_b[l]);          // xlq_w / xlq_b were folded with the gain / beta already
                 if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, c->bn_xlq ? c->bn_xlq : ((S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec), st));
             }
-            if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const h16*)c->dqlat, (const h16*)c->enc_lat, c->max_batch, c->utt_of_seq,
+            if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const h16*)c->dqlat, (const h16*)c->enc_lat, c->xl_tiled, c->max_batch, c->utt_of_seq,
                                                                    (h16*)c->dclat, S, H, WIPA_T_ENC, c->xl_part, c->xl_part_floats,
                                                                    c->ca_counters, st));
             {   // x += C Wo'^T + bo'   (K = H * d is long: split-K)
@@ -752,14 +778,15 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
-    size_t tbytes = 0, fbytes = 0;
-    layout_weights(c, nullptr, nullptr, &tbytes, &fbytes);
-    void *tbase = nullptr, *fbase = nullptr;
+    size_t tbytes = 0, fbytes = 0, mbytes = 0;
+    layout_weights(c, nullptr, nullptr, nullptr, &tbytes, &fbytes, &mbytes);
+    void *tbase = nullptr, *fbase = nullptr, *mbase = nullptr;
     int r = WIPA_OK;
 #define CTX_TRY(expr) do { r = (expr); if (r != WIPA_OK) { wipa_ctx_destroy(c); return r; } } while (0)
     CTX_TRY(ctx_alloc(c, &tbase, tbytes, true));
     CTX_TRY(ctx_alloc(c, &fbase, fbytes, true));
-    layout_weights(c, (char*)tbase, (char*)fbase, &tbytes, &fbytes);
+    if (mbytes > 0) CTX_TRY(ctx_alloc(c, &mbase, mbytes, true));
+    layout_weights(c, (char*)tbase, (char*)fbase, (char*)mbase, &tbytes, &fbytes, &mbytes);
     {
         std::unordered_set<std::string> canon;
         for (auto& kv : c->slots) canon.insert(kv.second.canon);
@@ -779,8 +806,9 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     if (c->xlat) {
         // no per-layer cross-KV: the encoder output itself, plus the folded projections and the [S, H*d] rows around the kernel
         c->xkv = nullptr;
-        c->xkv_bytes = (size_t)max_batch * T * d * e;
-        CTX_TRY(ctx_alloc(c, &c->enc_lat, c->xkv_bytes, false));
+        c->xl_tiled = env_int("WIPA_XL_TILED", 1);
+        c->xkv_bytes = c->xl_tiled ? (size_t)max_batch * cross_attention_latent_tiled_elems(H, (int)T) * e : (size_t)max_batch * T * d * e;
+        CTX_TRY(ctx_alloc(c, &c->enc_lat, c->xkv_bytes, true));          // zeroed: the tiled layout pads every utterance to whole chunks
         CTX_TRY(ctx_alloc(c, &c->dqlat, (size_t)S * H * d * e, false));
         CTX_TRY(ctx_alloc(c, &c->dclat, (size_t)S * H * d * e, false));
         {
@@ -933,6 +961,7 @@ extern "C" int wipa_ctx_load_weights(wipa_ctx* c, const wipa_tensor_desc* tensor
                    (long long)s.numel);
         if (s.kind == SLOT_CONV) WIPA_TRY(launch_conv_weight(t.data, s.dst, s.N, s.C, c->bf, st));
         else WIPA_TRY(launch_convert(t.data, s.dst, s.numel, s.scale, s.kind == SLOT_T ? (int)c->bf : 0, st));
+        if (s.master != nullptr) WIPA_TRY(launch_convert(t.data, s.master, s.numel, s.scale, 0, st));
         c->loaded.insert(s.canon);
     }
     // the weights changed: graphs stay valid (same buffers), cached cross-KV and folded projections do not
@@ -990,7 +1019,8 @@ extern "C" int wipa_set_audio_features(wipa_ctx* c, const float* enc_out, int B,
     const size_t enc_clip = (size_t)WIPA_T_ENC * c->a.d_model;
     WIPA_TRY(xlat_prepare(c, st));
     WIPA_TRY(lnf_prepare(c, st));
-    if (c->xlat) WIPA_TRY(launch_convert(enc_out, c->enc_lat, (long long)B * enc_clip, 1.0f, 1, st));
+    if (c->xlat && c->xl_tiled) WIPA_TRY(launch_lat_tile(enc_out, 0, (h16*)c->enc_lat, B, WIPA_T_ENC, c->a.heads, cross_attention_latent_keys(c->a.heads), st));
+    else if (c->xlat) WIPA_TRY(launch_convert(enc_out, c->enc_lat, (long long)B * enc_clip, 1.0f, 1, st));
     else for (int u0 = 0; u0 < B; u0 += c->enc_mb) {
         const int nb = (B - u0) < c->enc_mb ? (B - u0) : c->enc_mb;
         WIPA_TRY(launch_convert(enc_out + u0 * enc_clip, c->enc_T, (long long)nb * enc_clip, 1.0f, c->bf, st));
@@ -1326,13 +1356,16 @@ extern "C" int wipa_test_logits_argmax(wipa_ctx* c, int S, void* stream) {
 // latent cross-attention kernel alone: Qp h16 [S, H, 64H] absorbed queries, E h16 [U, T, 64H], utt_of_seq int32 [S]
 // -> C h16 [S, H, 64H] = softmax_t(Qp[s, h] . E[u, t]) E[u].  All device pointers.
 extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
-                                           void* stream) {
+                                           int layout, void* stream) {
     WIPA_CHECK(Qp && E && utt_of_seq && C && S >= 1 && cross_attention_latent_supported(H), WIPA_EINVAL,
                "wipa_test_cross_attn_latent: bad argument");
+    WIPA_CHECK(layout >= 0 && layout <= 2, WIPA_EINVAL, "wipa_test_cross_attn_latent: layout 0 (row-major, TMA boxes), 1 (row-major in, "
+               "tiled internally) or 2 (already chunk-tiled)");
     // scratch of the standalone entry point: grow-only, per process (contexts own theirs)
     static float* part = nullptr;
     static int* counters = nullptr;
-    static size_t part_floats = 0;
+    static h16* tiled = nullptr;
+    static size_t part_floats = 0, tiled_elems = 0;
     static int counters_cap = 0;
     int dev = 0, n_sm = 148;
     WIPA_CUDA_CHECK(cudaGetDevice(&dev));
@@ -1351,8 +1384,31 @@ extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U,
         WIPA_CUDA_CHECK(cudaMemset(counters, 0, (size_t)S * 4));
         counters_cap = S;
     }
-    return launch_cross_attention_latent((const h16*)Qp, (const h16*)E, U, utt_of_seq, (h16*)C, S, H, T, part, part_floats, counters,
+    const h16* Ein = (const h16*)E;
+    if (layout == 1) {
+        const size_t elems = (size_t)U * cross_attention_latent_tiled_elems(H, T);
+        if (elems > tiled_elems) {
+            WIPA_CUDA_CHECK(cudaDeviceSynchronize());
+            if (tiled) cudaFree(tiled);
+            WIPA_CUDA_CHECK(cudaMalloc(&tiled, elems * sizeof(h16)));
+            tiled_elems = elems;
+        }
+        WIPA_CUDA_CHECK(cudaMemsetAsync(tiled, 0, elems * sizeof(h16), (cudaStream_t)stream));
+        WIPA_TRY(launch_lat_tile(E, 1, tiled, U, T, H, cross_attention_latent_keys(H), (cudaStream_t)stream));
+        Ein = tiled;
+    }
+    return launch_cross_attention_latent((const h16*)Qp, Ein, layout != 0, U, utt_of_seq, (h16*)C, S, H, T, part, part_floats, counters,
                                          (cudaStream_t)stream);
+}
+
+// row-major h16 encoder output [U, T, 64 H] -> the chunk-tiled layout of the latent kernel (layout 2 above); `out` holds
+// U * wipa_test_lat_tiled_elems(H, T) h16 elements and must be zeroed by the caller once (padding of the last chunk)
+extern "C" long long wipa_test_lat_tiled_elems(int H, int T) {
+    return cross_attention_latent_supported(H) ? (long long)cross_attention_latent_tiled_elems(H, T) : -1;
+}
+extern "C" int wipa_test_lat_tile(const void* E, int U, int T, int H, void* out, void* stream) {
+    WIPA_CHECK(E && out && cross_attention_latent_supported(H), WIPA_EINVAL, "wipa_test_lat_tile: bad argument");
+    return launch_lat_tile(E, 1, (h16*)out, U, T, H, cross_attention_latent_keys(H), (cudaStream_t)stream);
 }
 
 // decoder self-attention step alone over a caller-built paged cache: kpool / vpool [page][H][16][64] (h16 or f32),

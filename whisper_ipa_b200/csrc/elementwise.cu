@@ -43,6 +43,81 @@ layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const
     }
 }
 
+// The encoder's final LayerNorm when the decoder attends over the encoder output itself: same arithmetic, h16 result written in
+// the chunk-tiled, pre-swizzled layout the latent cross-attention kernel streams (common.cuh lat_tile_offset).
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_lat_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b, h16* __restrict__ out,
+                     int M, int T, int u0, int keys, size_t utt_elems) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    constexpr int d = NV * 128;
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
+    float4 v[NV];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        v[i] = xr[i * 32 + lane];
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / d);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, dd = v[i].w - mean;
+        q += (a * a + bb * bb) + (c * c + dd * dd);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / d) + 1e-5f);
+    const int u = row / T, t = row - u * T;
+    h16* base = out + (size_t)(u0 + u) * utt_elems;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c0 = (i * 32 + lane) * 4;
+        const float4 wv = *reinterpret_cast<const float4*>(w + c0);
+        const float4 bv = *reinterpret_cast<const float4*>(b + c0);
+        uint2 pk;
+        pk.x = pack_h16x2((v[i].x - mean) * rstd * wv.x + bv.x, (v[i].y - mean) * rstd * wv.y + bv.y);
+        pk.y = pack_h16x2((v[i].z - mean) * rstd * wv.z + bv.z, (v[i].w - mean) * rstd * wv.w + bv.w);
+        *reinterpret_cast<uint2*>(base + lat_tile_offset(t, c0, d / 64, keys)) = pk;
+    }
+}
+
+int launch_layernorm_lat(const float* x, const float* w, const float* b, h16* out_tiled, int M, int d, int T, int u0, int keys,
+                         cudaStream_t st) {
+    WIPA_CHECK(d % 128 == 0 && d / 128 <= 10, WIPA_EUNSUPPORTED, "layernorm: d=%d must be 128*k, k<=10", d);
+    if (M == 0) return WIPA_OK;
+    const int grid = cdiv(M, 8);
+    const size_t utt = (size_t)cdiv(T, keys) * keys * d;
+    switch (d / 128) {
+#define LN_CASE(NV) case NV: layernorm_lat_kernel<NV><<<grid, 256, 0, st>>>(x, w, b, out_tiled, M, T, u0, keys, utt); break;
+        LN_CASE(1) LN_CASE(2) LN_CASE(3) LN_CASE(4) LN_CASE(5) LN_CASE(6) LN_CASE(7) LN_CASE(8) LN_CASE(9) LN_CASE(10)
+#undef LN_CASE
+    }
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
+// row-major encoder output [U, T, d] (f32 or h16) -> chunk-tiled h16 (audio features handed in from outside; kernel tests)
+__global__ void __launch_bounds__(256)
+lat_tile_kernel(const void* __restrict__ src, int src_is_h16, h16* __restrict__ out, int T, int d, int keys, size_t utt_elems) {
+    const int u = blockIdx.y, t = blockIdx.x;
+    h16* base = out + (size_t)u * utt_elems;
+    const size_t in0 = ((size_t)u * T + t) * d;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const float v = src_is_h16 ? h16_to_f32(reinterpret_cast<const h16*>(src)[in0 + c]) : reinterpret_cast<const float*>(src)[in0 + c];
+        base[lat_tile_offset(t, c, d / 64, keys)] = f32_to_h16(v);
+    }
+}
+
+int launch_lat_tile(const void* src, int src_is_h16, h16* out_tiled, int U, int T, int H, int keys, cudaStream_t st) {
+    if (U == 0) return WIPA_OK;
+    const int d = 64 * H;
+    lat_tile_kernel<<<dim3(T, U), 256, 0, st>>>(src, src_is_h16, out_tiled, T, d, keys, (size_t)cdiv(T, keys) * keys * d);
+    WIPA_LAUNCHED();
+    return WIPA_OK;
+}
+
 template <typename T>
 int launch_layernorm(const float* x, const float* w, const float* b, T* out, int M, int d, cudaStream_t st) {
     WIPA_CHECK(d % 128 == 0 && d / 128 <= 10, WIPA_EUNSUPPORTED, "layernorm: d=%d must be 128*k, k<=10", d);
