@@ -66,8 +66,16 @@ def _ffmpeg() -> Optional[str]:
     return shutil.which("ffmpeg")
 
 
-def read_pcm(path: str, max_seconds: float = 30.0) -> Dict:
-    """One file -> {"pcm": int16 [frames * ch], "frames", "ch", "rate"} (the GPU path) or {"f32": float32 16 kHz mono}."""
+def read_pcm(path: str, max_seconds: float = 30.0, pin=None) -> Dict:
+    """One file -> {"pcm": int16 [frames * ch], "frames", "ch", "rate"} (the GPU path) or {"f32": float32 16 kHz mono}.
+    ``pin(n_elems)`` (optional) hands out a pinned int16 torch buffer: the samples are then copied into it here, in the
+    worker thread, and "pcm" is that buffer (host->device copies start from it without another pass over the data)."""
+    def land(pcm):
+        if pin is None:
+            return pcm
+        buf = pin(pcm.size)
+        np.copyto(buf.numpy()[:pcm.size], pcm)
+        return buf
     try:
         with wave.open(path, "rb") as w:
             ch, width, rate, n = w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()
@@ -77,7 +85,7 @@ def read_pcm(path: str, max_seconds: float = 30.0) -> Dict:
                 n = min(n, need)
                 raw = w.readframes(n)
                 pcm = np.frombuffer(raw, dtype="<i2")
-                return {"pcm": pcm, "frames": len(pcm) // ch, "ch": ch, "rate": rate}
+                return {"pcm": land(pcm), "frames": len(pcm) // ch, "ch": ch, "rate": rate}
     except (wave.Error, EOFError):
         pass                                               # not a RIFF/WAVE file: try ffmpeg below
     exe = _ffmpeg()
@@ -87,14 +95,42 @@ def read_pcm(path: str, max_seconds: float = 30.0) -> Dict:
                str(SAMPLE_RATE), "-"]
         out = subprocess.run(cmd, capture_output=True, check=True).stdout
         pcm = np.frombuffer(out, dtype="<i2")[: int(max_seconds * SAMPLE_RATE)]
-        return {"pcm": pcm, "frames": len(pcm), "ch": 1, "rate": SAMPLE_RATE}
+        return {"pcm": land(pcm), "frames": len(pcm), "ch": 1, "rate": SAMPLE_RATE}
     return {"f32": load_audio(path)[: int(max_seconds * SAMPLE_RATE)]}     # 8- / 32-bit PCM WAV; raises on other containers
 
 
-class AudioIngest:
-    """files -> device f32 [B, 480000], overlapped with whatever runs on the current stream."""
+class _PinnedPool:
+    """Reusable pinned int16 buffers in size classes of 256 Ki samples (pinning is slow, so buffers are recycled; handing one out
+    and taking it back are thread-safe: the pool's workers call get(), the batch loader calls put() once the host->device
+    copy that reads the buffer has been enqueued AND has finished)."""
 
-    def __init__(self, device=None, workers: Optional[int] = None, chunk: int = 32):
+    def __init__(self):
+        import threading
+        self._lock = threading.Lock()
+        self._free: Dict[int, List[torch.Tensor]] = {}
+
+    def get(self, n_elems: int) -> torch.Tensor:
+        size = ((max(n_elems, 1) + 262143) // 262144) * 262144
+        with self._lock:
+            lst = self._free.get(size)
+            if lst:
+                return lst.pop()
+        return torch.empty(size, dtype=torch.int16).pin_memory()
+
+    def put(self, buf: torch.Tensor) -> None:
+        with self._lock:
+            self._free.setdefault(buf.numel(), []).append(buf)
+
+
+class AudioIngest:
+    """files -> device f32 [B, 480000], overlapped with whatever the GPU is doing.
+
+    Worker threads read each file and land its samples in a pinned buffer; the batch loader (the caller's thread for
+    load_batch, a producer thread for iter_batches) enqueues one host->device copy per file and one resampler launch per
+    (rate, channels) group on the ingest stream.  iter_batches keeps one batch in flight: while the caller transcribes batch
+    k, batch k + 1 is read, copied and resampled."""
+
+    def __init__(self, device=None, workers: Optional[int] = None, chunk: int = 64):
         if not torch.cuda.is_available():
             raise RuntimeError("whisper_ipa_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -102,10 +138,9 @@ class AudioIngest:
         self.chunk = int(chunk)
         self.pool = ThreadPoolExecutor(max_workers=self.workers, thread_name_prefix="wipa-ingest")
         self.stream = torch.cuda.Stream(device=self.device)
-        self._staging: List[Optional[torch.Tensor]] = [None, None]
-        self._staging_free: List[Optional[torch.cuda.Event]] = [None, None]
+        self._pinned = _PinnedPool()
         self._taps: Dict[int, torch.Tensor] = {}
-        self._n_chunks = 0
+        self._pending: List[Tuple[torch.cuda.Event, List[torch.Tensor]]] = []    # pinned buffers still being read by a copy
 
     def close(self) -> None:
         self.pool.shutdown(wait=False, cancel_futures=True)
@@ -113,16 +148,19 @@ class AudioIngest:
     # ---- host side -----------------------------------------------------------------------------
     def submit(self, paths: Sequence[str]):
         """Start reading `paths` in the pool; returns the futures (one per file) for load_batch(futures=...)."""
-        return [self.pool.submit(read_pcm, p) for p in paths]
+        return [self.pool.submit(read_pcm, p, 30.0, self._pinned.get) for p in paths]
 
-    def _stage(self, n_elems: int) -> Tuple[torch.Tensor, int]:
-        k = self._n_chunks & 1
-        self._n_chunks += 1
-        if self._staging_free[k] is not None:
-            self._staging_free[k].synchronize()            # the copy that last used this buffer has finished
-        if self._staging[k] is None or self._staging[k].numel() < n_elems:
-            self._staging[k] = torch.empty(max(n_elems, 1), dtype=torch.int16).pin_memory()
-        return self._staging[k], k
+    def _recycle(self, block: bool = False) -> None:
+        keep = []
+        for ev, bufs in self._pending:
+            if block:
+                ev.synchronize()
+            if ev.query():
+                for b in bufs:
+                    self._pinned.put(b)
+            else:
+                keep.append((ev, bufs))
+        self._pending = keep
 
     def _taps_dev(self, rate: int) -> torch.Tensor:
         if rate not in self._taps:
@@ -130,52 +168,52 @@ class AudioIngest:
         return self._taps[rate]
 
     # ---- device side ---------------------------------------------------------------------------
-    def load_batch(self, paths: Optional[Sequence[str]] = None, futures=None) -> Tuple[torch.Tensor, List[Optional[Exception]]]:
-        """-> (audio f32 [B, 480000] on the device, errors[B]).  Work is enqueued on the ingest stream; the CURRENT stream
-        is made to wait for it before this returns, so the result can be consumed right away."""
+    def load_batch(self, paths: Optional[Sequence[str]] = None, futures=None, wait: bool = True
+                   ) -> Tuple[torch.Tensor, List[Optional[Exception]]]:
+        """-> (audio f32 [B, 480000] on the device, errors[B]).  Work is enqueued on the ingest stream; with ``wait`` the CURRENT
+        stream is made to wait for it before this returns, so the result can be consumed right away."""
         futs = futures if futures is not None else self.submit(paths)
         B = len(futs)
-        out = torch.zeros((B, N_SAMPLES), dtype=torch.float32, device=self.device)
         errors: List[Optional[Exception]] = [None] * B
         lib = _lib.lib()
-        self.stream.wait_stream(torch.cuda.current_stream(self.device))        # `out` was zero-filled on the current stream
-        for k0 in range(0, B, self.chunk):
-            items = []
-            for b in range(k0, min(B, k0 + self.chunk)):
-                try:
-                    items.append((b, futs[b].result()))
-                except Exception as e:                                         # unreadable file: silence + the exception
-                    errors[b] = e
-            groups: Dict[Tuple[int, int], List[Tuple[int, Dict]]] = {}
-            for b, it in items:
-                if "f32" in it:
-                    x = torch.from_numpy(np.ascontiguousarray(it["f32"][:N_SAMPLES], dtype=np.float32))
-                    with torch.cuda.stream(self.stream):
+        self._recycle()
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            out = torch.zeros((B, N_SAMPLES), dtype=torch.float32, device=self.device)
+            for k0 in range(0, B, self.chunk):
+                items = []
+                for b in range(k0, min(B, k0 + self.chunk)):
+                    try:
+                        items.append((b, futs[b].result()))
+                    except Exception as e:                                     # unreadable file: silence + the exception
+                        errors[b] = e
+                groups: Dict[Tuple[int, int], List[Tuple[int, Dict]]] = {}
+                for b, it in items:
+                    if "f32" in it:
+                        x = torch.from_numpy(np.ascontiguousarray(it["f32"][:N_SAMPLES], dtype=np.float32))
                         out[b, : x.numel()].copy_(x.pin_memory(), non_blocking=True)
-                else:
-                    groups.setdefault((it["rate"], it["ch"]), []).append((b, it))
-            if not groups:
-                continue
-            total = sum(it["pcm"].size for g in groups.values() for _, it in g)
-            stage, slot = self._stage(total)
-            stage_np = stage.numpy()
-            pos = 0
-            launches = []
-            for (rate, ch), g in groups.items():
-                offs, frames, rows = [], [], []
-                for b, it in g:
-                    n = it["frames"] * ch
-                    stage_np[pos:pos + n] = it["pcm"][:n]
-                    offs.append(pos)
-                    frames.append(it["frames"])
-                    rows.append(b)
-                    pos += n
-                launches.append((rate, ch, offs, frames, rows))
-            with torch.cuda.stream(self.stream):
-                dev_pcm = stage[:max(pos, 1)].to(self.device, non_blocking=True)
+                    else:
+                        groups.setdefault((it["rate"], it["ch"]), []).append((b, it))
+                if not groups:
+                    continue
+                total = sum(it["frames"] * it["ch"] for g in groups.values() for _, it in g)
+                dev_pcm = torch.empty(max(total, 1), dtype=torch.int16, device=self.device)
+                pos, launches, used = 0, [], []
+                for (rate, ch), g in groups.items():
+                    offs, frames, rows = [], [], []
+                    for b, it in g:
+                        n = it["frames"] * ch
+                        src = it["pcm"] if isinstance(it["pcm"], torch.Tensor) else torch.from_numpy(np.ascontiguousarray(it["pcm"])).pin_memory()
+                        if n:
+                            dev_pcm[pos:pos + n].copy_(src[:n], non_blocking=True)       # pinned -> device, one copy per file
+                        used.append(src)
+                        offs.append(pos)
+                        frames.append(it["frames"])
+                        rows.append(b)
+                        pos += n
+                    launches.append((rate, ch, offs, frames, rows))
                 ev = torch.cuda.Event()
                 ev.record(self.stream)
-                self._staging_free[slot] = ev
+                self._pending.append((ev, [u for u in used if u.is_pinned()]))
                 for rate, ch, offs, frames, rows in launches:
                     plan = resample_plan(rate)
                     meta = torch.tensor(offs, dtype=torch.int64).pin_memory().to(self.device, non_blocking=True)
@@ -189,17 +227,44 @@ class AudioIngest:
                                                        self.stream.cuda_stream), "wipa_resample_pcm16")
                     if not contiguous:
                         out.index_copy_(0, torch.tensor(rows, device=self.device), dst)
-                dev_pcm.record_stream(self.stream)
-        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self._last_done = done
+        if wait:
+            torch.cuda.current_stream(self.device).wait_event(done)
+            out.record_stream(torch.cuda.current_stream(self.device))
         return out, errors
 
     def iter_batches(self, paths: Sequence[str], batch_size: int) -> Iterator[Tuple[List[int], torch.Tensor, List[Optional[Exception]]]]:
-        """Yield (indices, audio [b, 480000] on the device, errors) per micro-batch; the files of batch k+1 are being read by
-        the pool while the caller works on batch k."""
+        """Yield (indices, audio [b, 480000] on the device, errors) per micro-batch.  A producer thread stays one batch ahead:
+        while the caller works on batch k, the files of batch k + 1 are read by the pool, copied host->device and resampled on
+        the ingest stream (and the files of batch k + 2 are already being read)."""
+        import queue
+        import threading
         chunks = [list(range(s, min(len(paths), s + batch_size))) for s in range(0, len(paths), batch_size)]
-        nxt = self.submit([paths[i] for i in chunks[0]]) if chunks else None
-        for k, idx in enumerate(chunks):
-            futs = nxt
-            nxt = self.submit([paths[i] for i in chunks[k + 1]]) if k + 1 < len(chunks) else None
-            audio, errors = self.load_batch(futures=futs)
+        if not chunks:
+            return
+        q: "queue.Queue" = queue.Queue(maxsize=1)
+
+        def producer():
+            try:
+                futs = self.submit([paths[i] for i in chunks[0]])
+                for k, idx in enumerate(chunks):
+                    nxt = self.submit([paths[i] for i in chunks[k + 1]]) if k + 1 < len(chunks) else None
+                    audio, errors = self.load_batch(futures=futs, wait=False)
+                    q.put((idx, audio, errors, self._last_done, None))
+                    futs = nxt
+            except BaseException as e:                       # surfaces in the consumer
+                q.put((None, None, None, None, e))
+        t = threading.Thread(target=producer, name="wipa-ingest-producer", daemon=True)
+        t.start()
+        cur = torch.cuda.current_stream(self.device)
+        for _ in chunks:
+            idx, audio, errors, done, exc = q.get()
+            if exc is not None:
+                raise exc
+            cur.wait_event(done)
+            audio.record_stream(cur)
             yield idx, audio, errors
+        t.join()
+        self._recycle(block=True)
