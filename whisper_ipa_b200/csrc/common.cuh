@@ -224,17 +224,26 @@ struct EpiParams {
 // LayerNorm kernel sits between two GEMM nodes of a decode step.
 // ------------------------------------------------------------------------------------------------
 #define WIPA_LN_PIECE 32
-// (mean, rstd) of one row from its `nt` pieces of WIPA_LN_PIECE columns each; eps as HF (1e-5), biased variance
+// (mean, rstd) of one row from its `nt` pieces of WIPA_LN_PIECE columns each; eps as HF (1e-5), biased variance.
+// nt is even and <= WIPA_LN_MAX_NT (d = 1280).  Every piece is fetched up front as independent 16-byte loads - ONE L2 round
+// trip, issued before the accumulator is awaited; a dependent load per piece cost ~9 us per GEMM node.
+#define WIPA_LN_MAX_NT 40
 __device__ __forceinline__ float2 ln_row_stats(const float* __restrict__ stats_row, int nt) {
-    const float2* p = reinterpret_cast<const float2*>(stats_row);
+    const float4* p = reinterpret_cast<const float4*>(stats_row);
+    float4 q[WIPA_LN_MAX_NT / 2];
+#pragma unroll
+    for (int i = 0; i < WIPA_LN_MAX_NT / 2; ++i) q[i] = (2 * i < nt) ? __ldcg(p + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     float ms = 0.f;
-    for (int t = 0; t < nt; ++t) ms += __ldcg(p + t).x;
+#pragma unroll
+    for (int i = 0; i < WIPA_LN_MAX_NT / 2; ++i) ms += q[i].x + q[i].z;        // absent pieces contribute zeros
     const float mean = ms / (float)nt;
     float m2 = 0.f;
-    for (int t = 0; t < nt; ++t) {
-        const float2 q = __ldcg(p + t);
-        const float dlt = q.x - mean;
-        m2 += q.y + (float)WIPA_LN_PIECE * dlt * dlt;
+#pragma unroll
+    for (int i = 0; i < WIPA_LN_MAX_NT / 2; ++i) {
+        if (2 * i < nt) {
+            const float d0 = q[i].x - mean, d1 = q[i].z - mean;
+            m2 += (q[i].y + q[i].w) + (float)WIPA_LN_PIECE * (d0 * d0 + d1 * d1);
+        }
     }
     return make_float2(mean, rsqrtf(m2 / (float)(nt * WIPA_LN_PIECE) + 1e-5f));
 }
