@@ -103,3 +103,87 @@ def test_half_precision_path_on_bench_config(w, arch, n, dtype, monkeypatch):
     assert tf_agree >= lim_agree
     assert agree >= lim_free
     assert lens.cpu().tolist() == [want_ids.shape[1]] * n or want_ids.shape[1] < MAX_NEW
+
+
+# ---- BASELINE configs 4 and 5 at FULL depth ---------------------------------------------------------------------------------
+def _hf_gpu_generate(hf_model, audio, prompt, max_new, n_mels, **kw):
+    """HF fp32 generate on the GPU (TF32 off): ids int64 [B, <= max_new] on the CPU."""
+    import warnings
+    from oracle import hf_reference as hf
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        feats = hf.hf_log_mel(audio, n_mels).cuda()
+        m = hf_model.cuda().float().eval()
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ids = m.generate(feats, decoder_input_ids=torch.tensor([list(prompt)] * len(audio), device="cuda"), max_new_tokens=max_new,
+                             do_sample=False, **kw)
+        return ids.cpu()
+    finally:
+        hf_model.cpu()
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_medium_beam5_full_depth_matches_hf(w):
+    """BASELINE configs[3]: whisper-medium (24 + 24 layers, 16 heads), beam search with 5 beams, length_penalty 1.0.
+    fp32 path: the hypotheses must be HF's own (`_beam_search`); fp16 path: token agreement reported."""
+    from oracle import hf_reference as hf
+    from oracle import whisper_oracle as wo
+    arch = w.ARCHS["medium"]
+    hf_model = hf.build_hf_model("medium", seed=0, init_gain=2.0)          # gain: hypotheses depend on the audio
+    sd = hf.state_dict_f32(hf_model)
+    B, beams, max_new = 2, 5, 16
+    audio = wo.synthetic_audio(B)
+    prompt = arch.prompt("en", "transcribe", True)
+    want = _hf_gpu_generate(hf_model, audio, prompt, max_new, 80, num_beams=beams, length_penalty=1.0, early_stopping=False)
+    feats = w.log_mel_features(audio, 80)
+    for dtype in ("float32", "float16"):
+        m = w.WhisperIPA("medium", dtype=dtype, max_batch=B, max_beams=beams)
+        m.load_state_dict(sd)
+        got = m.generate(feats, decoder_input_ids=torch.tensor([prompt] * B), max_new_tokens=max_new, num_beams=beams,
+                         length_penalty=1.0).cpu()
+        m.close()
+        width = max(got.shape[1], want.shape[1])
+        pad = lambda t: torch.nn.functional.pad(t, (0, width - t.shape[1]), value=arch.eot)
+        agree = (pad(got) == pad(want)).float().mean().item()
+        print(f"\n[medium full depth, beam {beams}, {dtype}] token agreement with HF fp32 beam search {agree:.3f}")
+        if dtype == "float32":
+            assert torch.equal(pad(got), pad(want)), f"beam search differs from HF:\n{got}\n{want}"
+        else:
+            assert agree >= 0.9
+
+
+def test_large_v3_full_depth_greedy_and_per_match_hf(w):
+    """BASELINE configs[4]: whisper-large-v3 (32 + 32 layers, 20 heads, 128 mel bins, vocab 51866): greedy ids of the fp32
+    path equal HF's, PER counts equal the CPU oracle's; the fp16 path (stream-K cross-attention over per-layer K/V: 20 heads
+    have no latent instantiation) reports token agreement."""
+    from oracle import hf_reference as hf
+    from oracle import per_oracle as po
+    from oracle import whisper_oracle as wo
+    from whisper_ipa_b200 import metrics
+    arch = w.ARCHS["large-v3"]
+    hf_model = hf.build_hf_model("large-v3", seed=0, init_gain=1.5)
+    sd = hf.state_dict_f32(hf_model)
+    B, max_new = 2, 16
+    audio = wo.synthetic_audio(B)
+    prompt = arch.prompt("en", "transcribe", True)
+    assert prompt == wo.PROMPT_V3
+    want = _hf_gpu_generate(hf_model, audio, prompt, max_new, 128)
+    feats = w.log_mel_features(audio, 128)
+    refs = wo.synthetic_references(B)
+    for dtype in ("float32", "float16"):
+        m = w.WhisperIPA("large-v3", dtype=dtype, max_batch=B)
+        m.load_state_dict(sd)
+        got = m.generate(feats, decoder_input_ids=torch.tensor([prompt] * B), max_new_tokens=max_new).cpu()
+        m.close()
+        n = min(got.shape[1], want.shape[1])
+        agree = (got[:, :n] == want[:, :n]).float().mean().item()
+        print(f"\n[large-v3 full depth, greedy, {dtype}] token agreement with HF fp32 {agree:.3f}")
+        if dtype == "float32":
+            assert got.shape == want.shape and torch.equal(got, want)
+            counts = metrics.edit_distance_counts(refs, [r.tolist() for r in got]).cpu().numpy()
+            assert (counts[:, 0] == po.levenshtein_batch(refs, [np.asarray(r, np.int32) for r in want.tolist()])).all()
+        else:
+            assert agree >= 0.9

@@ -205,6 +205,7 @@ struct EpiParams {
     float* sk_part;
     int* sk_count;
     int gelu_fast;           // EPI_GELU with a h16 result: A&S-erf GELU (gelu_erf_fast) instead of erff
+    int w_brows;             // batched W (tcgen05 decode kernel): batch b multiplies rows [b * w_brows, b * w_brows + N) of W; 0 = one W
     // ---- LayerNorm folded around the decode GEMMs (16-bit decode path; see "folded LayerNorm" below) ----
     // consumer side: the A operand is the RAW residual stream rounded to h16 and W carries the LayerNorm gain; the epilogue
     // finishes the normalisation per row:  y = rstd * (acc - mean * ln_c[n]) + bias'[n]

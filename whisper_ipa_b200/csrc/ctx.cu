@@ -104,6 +104,10 @@ struct wipa_ctx {
     // latent cross-attention (attn_lat.cu): the decoder attends over the encoder output itself, k / v projections folded
     // into the query and output projections.  Default on the h16 path for contexts of >= 128 sequences and <= 16 heads.
     int xlat = 0;
+    int xl_q2 = 1;                 // WIPA_XL_Q2STEP: absorbed queries in two steps (q = x Wq^T, then q'_h = Wk_h^T q_h per head: 12 x
+                                   // fewer weight bytes and 6 x fewer FLOPs than the one-step GEMM against the folded [H*d, d] matrix)
+    std::vector<void*> xl_wkt;     // per layer [H][d][64]: Wk transposed per head (the per-head GEMM's K-major W operand)
+    void* dq16 = nullptr;          // q rows [S, d] in h16 between the two steps
     int xl_tiled = 1;              // WIPA_XL_TILED: the encoder output is kept chunk-tiled / pre-swizzled (bulk copies) instead of row-major (TMA boxes)
     int bn_xlq = 0;                // WIPA_BN_XLQ: tile width of the absorbed-query GEMM (0: as fc1)
     bool xlat_ready = false;       // folded weights match the loaded weights
@@ -246,7 +250,7 @@ void layout_weights(wipa_ctx* c, char* tbase, char* fbase, char* mbase, size_t* 
         ln(p + "encoder_attn_layer_norm", D[l].ln2_w, D[l].ln2_b);
         // cross-attention: q scaled like self-attention; k / v of all layers fused into one [L*2*d, d] operand
         D[l].cq_w = T.take((size_t)d * d); D[l].cq_b = (float*)F.take(d);
-        D[l].cq_m = (c->lnf && !c->xlat) ? master((size_t)d * d) : nullptr;
+        D[l].cq_m = (c->lnf && (!c->xlat || c->xl_q2)) ? master((size_t)d * d) : nullptr;
         next_master = D[l].cq_m;
         reg(p + "encoder_attn.q_proj.weight", D[l].cq_w, SLOT_T, (int64_t)d * d, 0.125f);
         reg(p + "encoder_attn.q_proj.bias", D[l].cq_b, SLOT_F32, d, 0.125f);
@@ -427,6 +431,12 @@ int ln_fold_rows(const void* W, const float* gain, const float* beta, const floa
     return WIPA_OK;
 }
 
+// WkT[h][n][j] = Wk[64 h + j][n]: the K-major W operand of the per-head step q'_h = Wk_h^T q_h (K = 64)
+__global__ void xlat_wkt_kernel(const h16* __restrict__ Wk, h16* __restrict__ WkT, int d) {
+    const int h = blockIdx.y, n = blockIdx.x * 4 + (threadIdx.x >> 6), j = threadIdx.x & 63;
+    if (n < d) WkT[((size_t)h * d + n) * 64 + j] = Wk[(size_t)(h * 64 + j) * d + n];
+}
+
 int xlat_prepare(wipa_ctx* c, cudaStream_t st) {
     if (!c->xlat || c->xlat_ready) return WIPA_OK;
     const int d = c->a.d_model, H = c->a.heads;
@@ -436,6 +446,13 @@ int xlat_prepare(wipa_ctx* c, cudaStream_t st) {
         const h16* Wk = (const h16*)c->xkv_w + (size_t)(2 * l) * d * d;
         const h16* Wv = (const h16*)c->xkv_w + (size_t)(2 * l + 1) * d * d;
         const float* bv = c->xkv_b + (size_t)(2 * l + 1) * d;
+        if (c->xl_q2) {
+            xlat_wkt_kernel<<<dim3(cdiv(d, 4), H), 256, 0, st>>>(Wk, (h16*)c->xl_wkt[l], d);
+            WIPA_LAUNCHED();
+            xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const h16*)L.co_w, L.co_b, Wv, bv, (h16*)c->xlo_w[l], c->xlo_b[l], d, H);
+            WIPA_LAUNCHED();
+            continue;
+        }
         const float* bq = L.cq_b;
         if (c->lnf) {       // beta of the cross-attention LayerNorm folds into the query bias first: bq + Wq beta
             WIPA_TRY(ln_fold_rows(L.cq_w, nullptr, L.ln2_b, L.cq_b, nullptr, nullptr, c->xlq_beff[l], d, d, st));
@@ -460,7 +477,7 @@ int lnf_prepare(wipa_ctx* c, cudaStream_t st) {
     for (int l = 0; l < c->a.dec_layers; ++l) {
         const DecLayer& L = c->dec[l];
         WIPA_TRY(ln_fold_rows(L.qkv_w, L.ln1_w, L.ln1_b, L.qkv_b, c->qkv_wf[l], c->qkv_c[l], c->qkv_bf[l], 3 * d, d, st, L.qkv_m));
-        if (!c->xlat) WIPA_TRY(ln_fold_rows(L.cq_w, L.ln2_w, L.ln2_b, L.cq_b, c->cq_wf[l], c->cq_c[l], c->cq_bf[l], d, d, st, L.cq_m));
+        if (!c->xlat || c->xl_q2) WIPA_TRY(ln_fold_rows(L.cq_w, L.ln2_w, L.ln2_b, L.cq_b, c->cq_wf[l], c->cq_c[l], c->cq_bf[l], d, d, st, L.cq_m));
         WIPA_TRY(ln_fold_rows(L.fc1_w, L.ln3_w, L.ln3_b, L.fc1_b, c->fc1_wf[l], c->fc1_c[l], c->fc1_bf[l], ffn, d, st, L.fc1_m));
     }
     WIPA_TRY(ln_fold_rows(c->tok_emb, c->dec_ln_w, c->dec_ln_b, nullptr, c->emb_wf, c->emb_c, c->emb_bf, V, d, st, c->emb_master));
@@ -626,6 +643,22 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         if (!lnf && !(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
         if (c->xlat) {
             const int Hd = H * d;
+            if (c->xl_q2) {
+                {   // step 1: q = LN(x) Wq^T + bq (scaled by 2^-3 in the weights) -> h16 [S, d]
+                    EpiParams ep = epi(EPI_STORE, S, d);
+                    ep.bias = L.cq_b; ep.out = c->dq16; ep.out_h16 = 1;
+                    if (lnf) consume_ln(ep, c->cq_c[l], c->cq_bf[l]);
+                    if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->cq_wf[l] : L.cq_w, S, d, d, ep, c->bn_dec, st));
+                }
+                {   // step 2: q'_h = Wk_h^T q_h for every head: H GEMMs [S, 64] x [64, d] in one launch (batch = head; A is the
+                    // 64-column slice of q, W the per-head transposed k-projection) -> h16 [S, H, d]
+                    AOperand A; A.ptr = c->dq16; A.lda = d; A.a_rpb = S; A.a_bstride = WIPA_HEAD_DIM; A.n_batch = H;
+                    EpiParams ep = epi(EPI_STORE, S * H, d);
+                    ep.out = c->dqlat; ep.out_h16 = 1;
+                    ep.o_rpb = S; ep.o_bstride = d; ep.ldo = Hd; ep.w_brows = d;
+                    if (!(skip & 16)) WIPA_TRY(gemm(c, A, c->xl_wkt[l], S * H, d, WIPA_HEAD_DIM, ep, 128, st));
+                }
+            } else
             {   // q' = LN(x) Wq'^T + bq'  -> h16 [S, H, d]
                 EpiParams ep = epi(EPI_STORE, S, Hd);
                 ep.bias = c->xlq_b[l]; ep.out = c->dqlat; ep.out_h16 = 1;
@@ -775,6 +808,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", max_batch * max_beams >= 128 ? 1 : 0) != 0 &&
                cross_attention_latent_supported(arch->heads)) ? 1 : 0;
     c->lnf = (c->bf && env_int("WIPA_LN_FOLD", 1) != 0 && arch->d_model % WIPA_LN_PIECE == 0) ? 1 : 0;
+    c->xl_q2 = (c->xlat && env_int("WIPA_XL_Q2STEP", 1) != 0) ? 1 : 0;
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
@@ -818,12 +852,17 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
             c->xl_part_floats = cross_attention_latent_scratch_floats(H, S, n_sm);
             CTX_TRY(ctx_alloc(c, (void**)&c->xl_part, c->xl_part_floats * 4, false));
         }
-        c->xlq_w.resize(arch->dec_layers); c->xlo_w.resize(arch->dec_layers);
-        c->xlq_b.resize(arch->dec_layers); c->xlo_b.resize(arch->dec_layers);
+        c->xlq_w.assign(arch->dec_layers, nullptr); c->xlo_w.assign(arch->dec_layers, nullptr);
+        c->xlq_b.assign(arch->dec_layers, nullptr); c->xlo_b.assign(arch->dec_layers, nullptr);
+        c->xl_wkt.assign(arch->dec_layers, nullptr);
+        if (c->xl_q2) CTX_TRY(ctx_alloc(c, &c->dq16, (size_t)S * d * e, false));
         for (int l = 0; l < arch->dec_layers; ++l) {
-            CTX_TRY(ctx_alloc(c, &c->xlq_w[l], (size_t)H * d * d * e, false));
+            if (c->xl_q2) CTX_TRY(ctx_alloc(c, &c->xl_wkt[l], (size_t)d * d * e, false));
+            else {
+                CTX_TRY(ctx_alloc(c, &c->xlq_w[l], (size_t)H * d * d * e, false));
+                CTX_TRY(ctx_alloc(c, (void**)&c->xlq_b[l], (size_t)H * d * 4, false));
+            }
             CTX_TRY(ctx_alloc(c, &c->xlo_w[l], (size_t)H * d * d * e, false));
-            CTX_TRY(ctx_alloc(c, (void**)&c->xlq_b[l], (size_t)H * d * 4, false));
             CTX_TRY(ctx_alloc(c, (void**)&c->xlo_b[l], (size_t)d * 4, false));
         }
     } else {
@@ -847,7 +886,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
             CTX_TRY(ctx_alloc(c, &c->fc1_wf[l], (size_t)ffn * d * e, false));
             CTX_TRY(ctx_alloc(c, (void**)&c->fc1_c[l], (size_t)ffn * 4, false));
             CTX_TRY(ctx_alloc(c, (void**)&c->fc1_bf[l], (size_t)ffn * 4, false));
-            if (c->xlat) {
+            if (c->xlat && !c->xl_q2) {
                 CTX_TRY(ctx_alloc(c, (void**)&c->xlq_c[l], (size_t)H * d * 4, false));
                 CTX_TRY(ctx_alloc(c, (void**)&c->xlq_beff[l], (size_t)d * 4, false));
             } else {

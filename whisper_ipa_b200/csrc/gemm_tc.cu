@@ -75,6 +75,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN;
     const int batch = blockIdx.y / tiles_per_batch;
+    const int wn0 = n0 + batch * ep.w_brows;                  // first W row of this tile (batched W: a block of rows per batch)
     const int t0 = (blockIdx.y - batch * tiles_per_batch) * TC_BM;
     // split-K: CTA z of gridDim.z takes k-blocks [kb0, kb0 + num_kb) of the num_kb_total
     const int num_kb_total = num_kb;
@@ -124,7 +125,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 const int nk = (num_kb - g * KPB) < KPB ? (num_kb - g * KPB) : KPB;
                 ptx::mbar_arrive_expect_tx(&full[g], (uint32_t)nk * (Cfg::A_BYTES + Cfg::W_BYTES));
                 for (int i = 0; i < nk; ++i)
-                    ptx::tma_load_2d(sW + g * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[g], (kb0 + g * KPB + i) * TC_BK, n0);
+                    ptx::tma_load_2d(sW + g * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[g], (kb0 + g * KPB + i) * TC_BK, wn0);
             }
             DBG_STAMP(1);
         }
@@ -150,7 +151,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 ptx::mbar_arrive_expect_tx(&full[s], (uint32_t)nk * (Cfg::A_BYTES + Cfg::W_BYTES));
                 for (int i = 0; i < nk; ++i) {
                     load_a(sA + s * Cfg::STAGE_A + i * Cfg::A_BYTES, &full[s], (kb0 + g * KPB + i) * TC_BK);
-                    ptx::tma_load_2d(sW + s * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[s], (kb0 + g * KPB + i) * TC_BK, n0);
+                    ptx::tma_load_2d(sW + s * Cfg::STAGE_W + i * Cfg::W_BYTES, &tmW, &full[s], (kb0 + g * KPB + i) * TC_BK, wn0);
                 }
             }
             __syncwarp();
@@ -508,7 +509,10 @@ int launch_gemm_h16(const AOperand& a, const h16* W, int M, int N, int K, const 
         WIPA_TRY(make_map(&tmA, a.ptr, 3, dims, strides, box));
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+        // batched W: n_batch blocks of w_brows rows; the box of the last n-tile of a block may run into the next block (or past the
+        // end, zero-filled): those columns are >= N and never stored
+        WIPA_CHECK(ep_in.w_brows == 0 || ep_in.w_brows >= N, WIPA_EINVAL, "gemm_h16: w_brows %d < N %d", ep_in.w_brows, N);
+        cuuint64_t dims[2] = {(cuuint64_t)K, ep_in.w_brows > 0 ? (cuuint64_t)ep_in.w_brows * (cuuint64_t)a.n_batch : (cuuint64_t)N};
         cuuint64_t strides[1] = {(cuuint64_t)K * 2};
         cuuint32_t box[2] = {TC_BK, (cuuint32_t)block_n};
         WIPA_TRY(make_map(&tmW, W, 2, dims, strides, box));
