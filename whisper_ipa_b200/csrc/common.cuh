@@ -204,6 +204,7 @@ struct EpiParams {
     // [tile][split][128][BN]; the last one to arrive (ticket in `sk_count[tile]`, self-resetting) sums them in split order
     float* sk_part;
     int* sk_count;
+    int sk_splits;           // K splits when sk_part is given (0: the kernel's default of 3 for 32-column tiles)
     int gelu_fast;           // EPI_GELU with a h16 result: A&S-erf GELU (gelu_erf_fast) instead of erff
     int w_brows;             // batched W (tcgen05 decode kernel): batch b multiplies rows [b * w_brows, b * w_brows + N) of W; 0 = one W
     // ---- LayerNorm folded around the decode GEMMs (16-bit decode path; see "folded LayerNorm" below) ----
@@ -531,6 +532,7 @@ struct DecodeState {       // all device pointers, owned by the context
     int* cur_tok;          // [Bs]
     int* done;             // [Bs]
     int* n_done;           // count of finished rows
+    int* ticket;           // CTA arrival counter of the finalize kernel (zero between launches)
     const int* forced;     // [Bs, n_forced] teacher-forced tokens (the prompt)
     int n_forced;
     int* out_ids;          // [Bs, max_new]

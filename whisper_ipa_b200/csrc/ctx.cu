@@ -97,6 +97,7 @@ struct wipa_ctx {
     int n_logit_tiles;
     int bn_enc, bn_dec, bn_logits, ca_split;
     int splitk = 1;                // WIPA_SPLITK=0 disables the split-K decode fc2
+    int sk_bn = 64, sk_splits = 6; // WIPA_SK_BN / WIPA_SK_SPLITS: tile width and K splits of the long-K decode GEMMs once S needs two M tiles
     int beam_L = 0;                // row length of the beam-search sequence / ancestry arrays of the current decode
     int persistent_min_tiles = 296; // WIPA_PERSISTENT_MIN_TILES: fewer 128x256 tiles than this -> plain 128x128-tile kernel
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
@@ -331,6 +332,7 @@ __global__ void decode_init_kernel(DecodeState ds, int* block_table, int* utt_of
         *ds.pos = 0;
         *ds.step = -(ds.n_forced - 1);
         *ds.n_done = 0;
+        *ds.ticket = 0;
     }
     if (i < Bs) {
         ds.cur_tok[i] = ds.forced[(size_t)i * ds.n_forced];
@@ -592,6 +594,7 @@ int logits_argmax(wipa_ctx* c, int S, int* n_tiles, cudaStream_t st) {
 DecodeState make_state(wipa_ctx* c, int n_forced, int max_new, int eot) {
     DecodeState ds;
     ds.pos = c->d_pos; ds.step = c->d_step; ds.cur_tok = c->d_cur_tok; ds.done = c->d_done; ds.n_done = c->d_n_done;
+    ds.ticket = c->d_pos + 3;
     ds.forced = c->d_forced; ds.n_forced = n_forced; ds.out_ids = c->d_out_ids; ds.out_len = c->d_out_len;
     ds.max_new = max_new; ds.eot = eot;
     return ds;
@@ -607,6 +610,9 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
     // producer of the residual left behind
     const bool lnf = c->lnf != 0;
     const int ln_nt = d / WIPA_LN_PIECE;
+    // long-K GEMMs (folded cross-attention out-projection, fc2): with two or more M tiles the 32-column tiles re-read the
+    // activations 24 times per K split; 64-column tiles and six K splits halve that and still fill one wave
+    const bool wide_sk = c->bf && c->splitk && S > 128 && c->sk_bn == 64 && d % 64 == 0;
     auto consume_ln = [&](EpiParams& ep, const float* csum, const float* bias_f) {
         ep.ln_stats = c->dstats; ep.ln_c = csum; ep.ln_nt = ln_nt; ep.bias = bias_f;
     };
@@ -671,9 +677,9 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             {   // x += C Wo'^T + bo'   (K = H * d is long: split-K)
                 EpiParams ep = epi(EPI_RESADD, S, d);
                 ep.bias = c->xlo_b[l]; ep.out = c->dx; ep.resid = c->dx;
-                if (c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; }
+                if (c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? c->sk_splits : 0; }
                 produce_ln(ep);
-                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dclat, S, Hd), c->xlo_w[l], S, d, Hd, ep, c->bn_dec, st));
+                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dclat, S, Hd), c->xlo_w[l], S, d, Hd, ep, wide_sk ? c->sk_bn : c->bn_dec, st));
             }
         } else {
         {
@@ -709,9 +715,9 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.fc2_b; ep.out = c->dx; ep.resid = c->dx;
-            if (c->bf && c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; }    // K = ffn is long: split-K
+            if (c->bf && c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? c->sk_splits : 0; }    // K = ffn is long: split-K
             produce_ln(ep);
-            if (!(skip & 64)) WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, c->bn_dec, st));
+            if (!(skip & 64)) WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, wide_sk ? c->sk_bn : c->bn_dec, st));
         }
     }
     int n_tiles = 1;
@@ -801,6 +807,8 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->enc_attn_simt = env_int("WIPA_ENC_ATTN_SIMT", 0);
     c->skip_mask = env_int("WIPA_SKIP_MASK", 0);
     c->splitk = env_int("WIPA_SPLITK", 1);
+    c->sk_bn = env_int("WIPA_SK_BN", 64);
+    c->sk_splits = env_int("WIPA_SK_SPLITS", 6);
     c->persistent_min_tiles = env_int("WIPA_PERSISTENT_MIN_TILES", 2 * 148);
     c->bn_xlq = env_int("WIPA_BN_XLQ", 0);
     // latent cross-attention gives every SM whole sequences, so it wants about a wave of them; below that the stream-K
@@ -907,7 +915,9 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     CTX_TRY(ctx_alloc(c, (void**)&c->ca_part, (size_t)S * H * 64 * 66 * 4, false));
     {
         const size_t tiles = (size_t)cdiv(d, 32) * cdiv(S, 64);        // N tiles of 32 columns x M tiles (64-row tiles at S <= 64)
-        CTX_TRY(ctx_alloc(c, (void**)&c->sk_part, tiles * 3 * 128 * 64 * 4, false));
+        // a partial tile is 128 rows x BN fp32 per (n-tile, m-tile, split): d * 512 bytes per (m-tile, split) whatever BN is
+        const size_t sk_bytes = (size_t)d * 512 * cdiv(S, 64) * (size_t)(c->sk_splits > 3 ? c->sk_splits : 3);
+        CTX_TRY(ctx_alloc(c, (void**)&c->sk_part, sk_bytes > tiles * 3 * 128 * 64 * 4 ? sk_bytes : tiles * 3 * 128 * 64 * 4, false));
         CTX_TRY(ctx_alloc(c, (void**)&c->sk_count, tiles * 4, true));
     }
     CTX_TRY(ctx_alloc(c, (void**)&c->ca_counters, (size_t)S * H * 4, true));

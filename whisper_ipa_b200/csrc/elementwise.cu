@@ -325,54 +325,62 @@ int launch_row_argmax(const float* logits, int Bs, int V, const uint32_t* mask_a
 // greedy bookkeeping, one warp per sequence: reduce the per-tile (max, argmax) partials, apply HF's finished-row
 // rule (HF:generation/utils.py:2796-2797: finished rows emit pad = EOT), record the token, feed it back, and
 // advance the shared position.  While *pos + 1 < n_forced the next token is the teacher-forced prompt token.
-// Single CTA (it owns the position counter), so Bs <= 1024 / 32 * loops; rows are strided over the warps.
 // ================================================================================================
-__global__ void __launch_bounds__(1024)
+// One warp per sequence, 8 sequences per CTA.  Every CTA reads the step's position first; the LAST CTA to finish (ticket in
+// *ds.ticket, self-resetting) advances it, so no CTA can see the incremented value.  (A single 1024-thread CTA walking all
+// rows cost 16 us per decode step at 256 sequences x 406 vocabulary pieces.)
+__global__ void __launch_bounds__(256)
 greedy_finalize_kernel(const float* __restrict__ pmax, const int* __restrict__ pidx, int n_tiles, DecodeState ds, int Bs) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     pdl_wait();
     pdl_launch_dependents();                     // only after our own dependency is met: at most two grids overlap
     const int pos = *ds.pos;
     const int i = pos - (ds.n_forced - 1);            // index of the token sampled at this step
-    for (int b = warp; b < Bs; b += 32) {
+    const int b = blockIdx.x * 8 + warp;
+    if (b < Bs) {
         if (i < 0) {
             if (lane == 0) ds.cur_tok[b] = ds.forced[(size_t)b * ds.n_forced + pos + 1];
-            continue;
-        }
-        float best = -INFINITY;
-        int best_n = 0x7fffffff;
-        for (int t = lane; t < n_tiles; t += 32) {
-            const float v = pmax[(size_t)b * n_tiles + t];
-            const int n = pidx[(size_t)b * n_tiles + t];
-            if (v > best || (v == best && n < best_n)) { best = v; best_n = n; }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-            const int on = __shfl_xor_sync(0xffffffffu, best_n, o);
-            if (ov > best || (ov == best && on < best_n)) { best = ov; best_n = on; }
-        }
-        if (lane == 0) {
-            int tok = best_n;
-            if (ds.done[b]) tok = ds.eot;
-            else if (tok == ds.eot) {
-                ds.done[b] = 1;
-                ds.out_len[b] = i;
-                atomicAdd(ds.n_done, 1);
+        } else {
+            float best = -INFINITY;
+            int best_n = 0x7fffffff;
+            for (int t = lane; t < n_tiles; t += 32) {
+                const float v = pmax[(size_t)b * n_tiles + t];
+                const int n = pidx[(size_t)b * n_tiles + t];
+                if (v > best || (v == best && n < best_n)) { best = v; best_n = n; }
             }
-            if (i < ds.max_new) ds.out_ids[(size_t)b * ds.max_new + i] = tok;
-            ds.cur_tok[b] = tok;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int on = __shfl_xor_sync(0xffffffffu, best_n, o);
+                if (ov > best || (ov == best && on < best_n)) { best = ov; best_n = on; }
+            }
+            if (lane == 0) {
+                int tok = best_n;
+                if (ds.done[b]) tok = ds.eot;
+                else if (tok == ds.eot) {
+                    ds.done[b] = 1;
+                    ds.out_len[b] = i;
+                    atomicAdd(ds.n_done, 1);
+                }
+                if (i < ds.max_new) ds.out_ids[(size_t)b * ds.max_new + i] = tok;
+                ds.cur_tok[b] = tok;
+            }
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        *ds.pos = pos + 1;
-        *ds.step = i + 1;
+        __threadfence();
+        const int t = atomicAdd(ds.ticket, 1);
+        if (t == (int)gridDim.x - 1) {               // every CTA has read `pos` and written its rows
+            *ds.ticket = 0;
+            *ds.pos = pos + 1;
+            *ds.step = i + 1;
+        }
     }
 }
 
 int launch_greedy_finalize(const float* pmax, const int* pidx, int n_tiles, DecodeState ds, int Bs, cudaStream_t st) {
-    WIPA_CUDA_CHECK(wipa_launch(greedy_finalize_kernel, dim3(1), dim3(1024), (size_t)0, st, pmax, pidx, n_tiles, ds, Bs));
+    WIPA_CUDA_CHECK(wipa_launch(greedy_finalize_kernel, dim3(cdiv(Bs, 8)), dim3(256), (size_t)0, st, pmax, pidx, n_tiles, ds, Bs));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }

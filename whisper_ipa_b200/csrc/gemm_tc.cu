@@ -204,7 +204,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const int m = batch * a_rpb + t;
         pdl_wait();                                          // the epilogue reads / writes activations of earlier kernels
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        if (BN == 32 && mode != EPI_ARGMAX) {
+        if ((BN == 32 && mode != EPI_ARGMAX) || (BN == 64 && mode == EPI_RESADD)) {
             // Latency-bound decode tiles: fetch bias and residual for the whole BN-column row segment BEFORE the
             // accumulator is ready, so that after the last MMA only tcgen05.ld + adds + stores remain.
             __shared__ int s_last;
@@ -307,7 +307,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         for (int i = 0; i < BN; i += 4) *reinterpret_cast<float4*>(o + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
                         if (ep.x16_out != nullptr) {
                             // folded LayerNorm, producer side: the new residual rounded to h16 (the next GEMM's A operand) and
-                            // the (mean, M2) of this row's 32 columns (BN == WIPA_LN_PIECE)
+                            // the (mean, M2) of every 32-column piece of this row segment
                             h16* o16 = reinterpret_cast<h16*>(ep.x16_out) + row;
 #pragma unroll
                             for (int i = 0; i < BN; i += 8) {
@@ -316,8 +316,12 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                                 u.z = pack_h16x2(v[i + 4], v[i + 5]); u.w = pack_h16x2(v[i + 6], v[i + 7]);
                                 *reinterpret_cast<uint4*>(o16 + i) = u;
                             }
-                            const float2 st2 = ln_piece_stats(v);
-                            *reinterpret_cast<float2*>(ep.ln_stats_out + ((long long)m * (ep.N / WIPA_LN_PIECE) + blockIdx.x) * 2) = st2;
+#pragma unroll
+                            for (int pc = 0; pc < BN / WIPA_LN_PIECE; ++pc) {
+                                const float2 st2 = ln_piece_stats(v + pc * WIPA_LN_PIECE);
+                                *reinterpret_cast<float2*>(ep.ln_stats_out +
+                                                           ((long long)m * (ep.N / WIPA_LN_PIECE) + blockIdx.x * (BN / WIPA_LN_PIECE) + pc) * 2) = st2;
+                            }
                         }
                     } else {
 #pragma unroll
@@ -449,7 +453,7 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int ti
     if constexpr (CL == 1 && BN == 32) {
         switch (ep.mode) { WIPA_TC_CASE(EPI_QKV_DEC); WIPA_TC_CASE(EPI_RESADD); WIPA_TC_CASE(EPI_STORE); default: break; }
     } else if constexpr (CL == 1 && BN == 64) {
-        switch (ep.mode) { WIPA_TC_CASE(EPI_GELU); WIPA_TC_CASE(EPI_STORE); WIPA_TC_CASE(EPI_QKV_DEC); default: break; }
+        switch (ep.mode) { WIPA_TC_CASE(EPI_GELU); WIPA_TC_CASE(EPI_STORE); WIPA_TC_CASE(EPI_QKV_DEC); WIPA_TC_CASE(EPI_RESADD); default: break; }
     } else if constexpr (CL == 1 && BN == 128) {
         switch (ep.mode) { WIPA_TC_CASE(EPI_ARGMAX); WIPA_TC_CASE(EPI_STORE); default: break; }
     }
@@ -492,8 +496,8 @@ int launch_gemm_h16(const AOperand& a, const h16* W, int M, int N, int K, const 
                "gemm_h16: operands must be 16-byte aligned");
     WIPA_CHECK(ep_in.ln_stats == nullptr || block_n != 32 || (N % 32 == 0 && ep_in.vec_ok), WIPA_EINVAL,
                "gemm_h16: the folded-LayerNorm epilogue of the 32-column tiles needs N %% 32 == 0");
-    WIPA_CHECK(ep_in.x16_out == nullptr || (block_n == 32 && N % 32 == 0 && ep_in.vec_ok && ep_in.mode == EPI_RESADD), WIPA_EINVAL,
-               "gemm_h16: residual statistics are produced by 32-column EPI_RESADD tiles only");
+    WIPA_CHECK(ep_in.x16_out == nullptr || ((block_n == 32 || block_n == 64) && N % block_n == 0 && ep_in.vec_ok && ep_in.mode == EPI_RESADD), WIPA_EINVAL,
+               "gemm_h16: residual statistics are produced by 32- / 64-column EPI_RESADD tiles only");
     const int box_m = (a.a_rpb <= 64 && block_n == 32) ? 64 : 128;
     // WIPA_GEMM_MULTICAST=1: clusters of 4 N tiles with A multicast for the narrow (decode) tiles whenever the N tiles
     // divide evenly.  Parity-tested, but OFF by default: measured on B200 at B=256 the two cluster barriers and the
@@ -523,7 +527,10 @@ int launch_gemm_h16(const AOperand& a, const h16* W, int M, int N, int K, const 
     const int tpb = cdiv(a.a_rpb, TC_BM);
     // split-K (3 ways) when the caller provides scratch and K is long: the narrow tiles are bound by how fast ONE SM can
     // stream its 128 x K activations + BN x K weights, so a long K wants more CTAs, not wider ones
-    const int splits = (ep.sk_part != nullptr && block_n == 32 && num_kb >= 24) ? 3 : 1;
+    int splits = 1;
+    if (ep.sk_part != nullptr && num_kb >= 24 && (block_n == 32 || (block_n == 64 && ep.mode == EPI_RESADD && N % 64 == 0 && ep.vec_ok)))
+        splits = ep.sk_splits > 0 ? ep.sk_splits : 3;
+    if (splits > num_kb) splits = num_kb;
     if (splits == 1) { ep.sk_part = nullptr; ep.sk_count = nullptr; }
     switch (block_n) {
         case 32:
