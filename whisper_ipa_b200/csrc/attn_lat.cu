@@ -29,6 +29,8 @@
 //      the softmax denominator l = alpha * l + P x ones rides the same MMAs
 // Rows >= H of the 16-row MMA tile are padding.  Keys beyond 1500 in the last chunk are zero-filled by TMA (3-D map,
 // out-of-bounds rows) and masked to -inf before the softmax.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -39,11 +41,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode_xl = nullptr;
 
-constexpr int XL_STAGES = 2;
 constexpr int XL_BULK_SPLIT = 4;              // bulk copies per full chunk (stage bytes are a multiple of 4 * 16)
 constexpr float XL_LOG2E = 1.4426950408889634f;
 
-template <int KEYS>
+template <int KEYS, int XL_STAGES>
 struct XlCfg {
     static constexpr int PITCH = KEYS + 8;                      // floats per partial-score row / h16 per P row
     static size_t smem(int H) {
@@ -190,12 +191,12 @@ __device__ __forceinline__ void xl_finish_segment(int s, int ch0, int ch1, int n
 // TILED: E arrives in the chunk-tiled, pre-swizzled layout (see the header of this file and lat_tile_offset in common.cuh):
 // a chunk is ONE contiguous block of global memory that lands in shared memory with plain bulk copies, exactly as the
 // tensor-map path would have swizzled it.  Otherwise E is row-major [U, T, d] behind a 3-D tensor map (H boxes per chunk).
-template <int KEYS, int H, bool TILED>
+template <int KEYS, int H, bool TILED, int XL_STAGES>
 __global__ void __launch_bounds__((H + 1) * 32, 1)
 cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Et, const h16* __restrict__ Qp,
                               const int* __restrict__ utt_of_seq, h16* __restrict__ Cout, int S, int T,
                               float* __restrict__ part, int* __restrict__ counters, int slots_per_seq) {
-    using Cfg = XlCfg<KEYS>;
+    using Cfg = XlCfg<KEYS, XL_STAGES>;
     constexpr int PITCH = Cfg::PITCH;
     extern __shared__ uint8_t xl_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(xl_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -425,12 +426,12 @@ int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) 
     return WIPA_OK;
 }
 
-template <int KEYS, int H, bool TILED>
+template <int KEYS, int H, bool TILED, int XL_STAGES = 2>
 int xl_launch(const CUtensorMap& tm, const h16* Et, const h16* Qp, const int* utt_of_seq, h16* C, int S, int T, int n_sm, float* part,
               size_t part_floats, int* counters, cudaStream_t st) {
-    const size_t smem = XlCfg<KEYS>::smem(H);
+    const size_t smem = XlCfg<KEYS, XL_STAGES>::smem(H);
     static SmemAttr attr;
-    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H, TILED>, smem, attr));
+    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H, TILED, XL_STAGES>, smem, attr));
     const int n_chunks = cdiv(T, KEYS);
     const long long n_units = (long long)S * n_chunks;
     const int grid = n_units < n_sm ? (int)n_units : n_sm;
@@ -438,7 +439,7 @@ int xl_launch(const CUtensorMap& tm, const h16* Et, const h16* Qp, const int* ut
     const int slots_per_seq = n_chunks / (int)(n_units / grid) + 2;
     WIPA_CHECK((size_t)S * slots_per_seq * (H * 1024 + 32) <= part_floats, WIPA_EINVAL,
                "cross_attention_latent: partial scratch too small for %d sequences", S);
-    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H, TILED>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Et, Qp,
+    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H, TILED, XL_STAGES>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Et, Qp,
                                   utt_of_seq, C, S, T, part, counters, slots_per_seq));
     WIPA_LAUNCHED();
     return WIPA_OK;
@@ -454,7 +455,22 @@ size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm) {
     return (size_t)(2 * n_sm + 3 * max_seqs + 64) * (size_t)(H * 1024 + 32);
 }
 
-int cross_attention_latent_keys(int H) { return H <= 12 ? 48 : 32; }     // two stages of keys x d x 2 bytes + H x H partial rows must fit 227 KB
+// Chunk size / ring depth: the stages of keys x d x 2 bytes plus H x H partial-score rows must fit 227 KB of shared memory.
+// Default 48 keys x 2 stages up to 12 heads, 32 x 2 at 16 heads; WIPA_XL_KEYS=32 with WIPA_XL_STAGES=3|4 (<= 12 heads) trades
+// chunk size for a deeper ring.  Read once per process: the tiled layout of the encoder output depends on the chunk size.
+static int xl_env(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+int cross_attention_latent_keys(int H) {
+    static const int env_keys = xl_env("WIPA_XL_KEYS", 48);
+    return (H <= 12 && env_keys != 32) ? 48 : 32;
+}
+static int xl_stages(int H) {
+    static const int env_stages = xl_env("WIPA_XL_STAGES", 0);
+    if (H > 12 || cross_attention_latent_keys(H) == 48) return 2;
+    return env_stages == 4 ? 4 : (env_stages == 2 ? 2 : 3);
+}
 
 // elements of the chunk-tiled image of one utterance's encoder output: whole chunks of `keys` keys (the tail is zero padding)
 size_t cross_attention_latent_tiled_elems(int H, int T) {
@@ -485,6 +501,11 @@ int launch_cross_attention_latent(const h16* Qp, const h16* E, int tiled, int U,
     const int keys = cross_attention_latent_keys(H);
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
+    if (tiled && keys == 32 && H <= 12) {
+#define XL_CASE(HH, ST) if (H == HH && xl_stages(H) == ST) return xl_launch<32, HH, true, ST>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st)
+        XL_CASE(6, 2); XL_CASE(6, 3); XL_CASE(6, 4); XL_CASE(8, 2); XL_CASE(8, 3); XL_CASE(8, 4); XL_CASE(12, 2); XL_CASE(12, 3); XL_CASE(12, 4);
+#undef XL_CASE
+    }
     if (tiled) {
         switch (H) {
             case 6: return xl_launch<48, 6, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
@@ -493,6 +514,7 @@ int launch_cross_attention_latent(const h16* Qp, const h16* E, int tiled, int U,
             default: return xl_launch<32, 16, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
         }
     }
+    WIPA_CHECK(keys == (H <= 12 ? 48 : 32), WIPA_EINVAL, "cross_attention_latent: WIPA_XL_KEYS applies to the tiled layout only");
     WIPA_TRY(xl_make_map(&tm, E, U, T, H * 64, keys));
     switch (H) {
         case 6: return xl_launch<48, 6, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
