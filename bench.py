@@ -499,8 +499,9 @@ def main():
     # the whole decode step against the same peak: algorithmic bytes = cross-attention stream + decoder weights (once per step,
     # incl. the folded projections in latent mode) + self-KV read at the mean length + new K/V written
     q2 = bool(int(os.environ.get("WIPA_XL_Q2STEP", "1")))       # two-step absorbed query: Wq + per-head Wk^T instead of the folded [H*d, d]
+    o2 = bool(int(os.environ.get("WIPA_XL_O2STEP", "1")))       # two-step context: per-head Wv + Wo instead of the folded [d, H*d]
     w_dec = ((L * (6 * dm * dm + 2 * dm * ffn) + V * dm) * esz if not latent
-             else (L * (4 * dm * dm + (2 if q2 else H) * dm * dm + H * dm * dm + 2 * dm * ffn) + V * dm) * esz)
+             else (L * (4 * dm * dm + (2 if q2 else H) * dm * dm + (2 if o2 else H) * dm * dm + 2 * dm * ffn) + V * dm) * esz)
     t_mean = P + (args.max_new - 1) / 2.0
     self_kv = S * L * 2 * t_mean * dm * esz + S * L * 2 * dm * esz
     step_bytes = xattn_step_bytes + w_dec + self_kv

@@ -206,7 +206,8 @@ struct EpiParams {
     int* sk_count;
     int sk_splits;           // K splits when sk_part is given (0: the kernel's default of 3 for 32-column tiles)
     int gelu_fast;           // EPI_GELU with a h16 result: A&S-erf GELU (gelu_erf_fast) instead of erff
-    int w_brows;             // batched W (tcgen05 decode kernel): batch b multiplies rows [b * w_brows, b * w_brows + N) of W; 0 = one W
+    int w_brows;             // batched W (tcgen05 decode kernel): batch b multiplies rows [b * w_brows, b * w_brows + N) of W (and takes
+                             // bias[b * w_brows + n]); 0 = one W
     // ---- LayerNorm folded around the decode GEMMs (16-bit decode path; see "folded LayerNorm" below) ----
     // consumer side: the A operand is the RAW residual stream rounded to h16 and W carries the LayerNorm gain; the epilogue
     // finishes the normalisation per row:  y = rstd * (acc - mean * ln_c[n]) + bias'[n]

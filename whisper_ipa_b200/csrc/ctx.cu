@@ -107,6 +107,8 @@ struct wipa_ctx {
     int xlat = 0;
     int xl_q2 = 1;                 // WIPA_XL_Q2STEP: absorbed queries in two steps (q = x Wq^T, then q'_h = Wk_h^T q_h per head: 12 x
                                    // fewer weight bytes and 6 x fewer FLOPs than the one-step GEMM against the folded [H*d, d] matrix)
+    int xl_o2 = 1;                 // WIPA_XL_O2STEP: context rows in two steps as well (ctx_h = Wv_h c_h + bv_h head-batched, then the ordinary
+                                   // out-projection): no folded [d, H*d] matrix, no K = H*d split-K node
     std::vector<void*> xl_wkt;     // per layer [H][d][64]: Wk transposed per head (the per-head GEMM's K-major W operand)
     void* dq16 = nullptr;          // q rows [S, d] in h16 between the two steps
     int xl_tiled = 1;              // WIPA_XL_TILED: the encoder output is kept chunk-tiled / pre-swizzled (bulk copies) instead of row-major (TMA boxes)
@@ -451,8 +453,10 @@ int xlat_prepare(wipa_ctx* c, cudaStream_t st) {
         if (c->xl_q2) {
             xlat_wkt_kernel<<<dim3(cdiv(d, 4), H), 256, 0, st>>>(Wk, (h16*)c->xl_wkt[l], d);
             WIPA_LAUNCHED();
-            xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const h16*)L.co_w, L.co_b, Wv, bv, (h16*)c->xlo_w[l], c->xlo_b[l], d, H);
-            WIPA_LAUNCHED();
+            if (!c->xl_o2) {
+                xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const h16*)L.co_w, L.co_b, Wv, bv, (h16*)c->xlo_w[l], c->xlo_b[l], d, H);
+                WIPA_LAUNCHED();
+            }
             continue;
         }
         const float* bq = L.cq_b;
@@ -465,8 +469,10 @@ int xlat_prepare(wipa_ctx* c, cudaStream_t st) {
         if (c->lnf) {       // column sums of the finished (gain-folded, rounded) weights; beta is all zero here
             WIPA_TRY(ln_fold_rows(c->xlq_w[l], nullptr, nullptr, nullptr, nullptr, c->xlq_c[l], nullptr, H * d, d, st));
         }
-        xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const h16*)L.co_w, L.co_b, Wv, bv, (h16*)c->xlo_w[l], c->xlo_b[l], d, H);
-        WIPA_LAUNCHED();
+        if (!c->xl_o2) {
+            xlat_fold_o_kernel<<<grid, 256, 0, st>>>((const h16*)L.co_w, L.co_b, Wv, bv, (h16*)c->xlo_w[l], c->xlo_b[l], d, H);
+            WIPA_LAUNCHED();
+        }
     }
     c->xlat_ready = true;
     return WIPA_OK;
@@ -674,6 +680,24 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const h16*)c->dqlat, (const h16*)c->enc_lat, c->xl_tiled, c->max_batch, c->utt_of_seq,
                                                                    (h16*)c->dclat, S, H, WIPA_T_ENC, c->xl_part, c->xl_part_floats,
                                                                    c->ca_counters, st));
+            if (c->xl_o2) {
+                {   // ctx_h = Wv_h c_h + bv_h for every head: H GEMMs [S, d] x [d, 64] in one launch (batch = head; A is head h's
+                    // slice of the normalised sums, W the 64 rows of the v-projection that belong to head h) -> h16 [S, d]
+                    AOperand A; A.ptr = c->dclat; A.lda = Hd; A.a_rpb = S; A.a_bstride = d; A.n_batch = H;
+                    EpiParams ep = epi(EPI_STORE, S * H, WIPA_HEAD_DIM);
+                    ep.bias = c->xkv_b + (size_t)(2 * l + 1) * d;
+                    ep.out = c->dattn; ep.out_h16 = 1;
+                    ep.o_rpb = S; ep.o_bstride = WIPA_HEAD_DIM; ep.ldo = d; ep.w_brows = WIPA_HEAD_DIM;
+                    const char* Wv = (const char*)c->xkv_w + (size_t)(2 * l + 1) * d * d * c->esz;
+                    if (!(skip & 16)) WIPA_TRY(gemm(c, A, Wv, S * H, WIPA_HEAD_DIM, d, ep, 32, st));
+                }
+                {   // x += ctx Wo^T + bo: the ordinary out-projection
+                    EpiParams ep = epi(EPI_RESADD, S, d);
+                    ep.bias = L.co_b; ep.out = c->dx; ep.resid = c->dx;
+                    produce_ln(ep);
+                    if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dattn, S, d), L.co_w, S, d, d, ep, c->bn_dec, st));
+                }
+            } else
             {   // x += C Wo'^T + bo'   (K = H * d is long: split-K)
                 EpiParams ep = epi(EPI_RESADD, S, d);
                 ep.bias = c->xlo_b[l]; ep.out = c->dx; ep.resid = c->dx;
@@ -817,6 +841,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
                cross_attention_latent_supported(arch->heads)) ? 1 : 0;
     c->lnf = (c->bf && env_int("WIPA_LN_FOLD", 1) != 0 && arch->d_model % WIPA_LN_PIECE == 0) ? 1 : 0;
     c->xl_q2 = (c->xlat && env_int("WIPA_XL_Q2STEP", 1) != 0) ? 1 : 0;
+    c->xl_o2 = (c->xlat && env_int("WIPA_XL_O2STEP", 1) != 0) ? 1 : 0;
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
     const int d = arch->d_model, H = arch->heads, ffn = arch->ffn, V = arch->vocab, S = c->max_seqs, mb = c->enc_mb;
@@ -870,8 +895,10 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
                 CTX_TRY(ctx_alloc(c, &c->xlq_w[l], (size_t)H * d * d * e, false));
                 CTX_TRY(ctx_alloc(c, (void**)&c->xlq_b[l], (size_t)H * d * 4, false));
             }
-            CTX_TRY(ctx_alloc(c, &c->xlo_w[l], (size_t)H * d * d * e, false));
-            CTX_TRY(ctx_alloc(c, (void**)&c->xlo_b[l], (size_t)d * 4, false));
+            if (!c->xl_o2) {
+                CTX_TRY(ctx_alloc(c, &c->xlo_w[l], (size_t)H * d * d * e, false));
+                CTX_TRY(ctx_alloc(c, (void**)&c->xlo_b[l], (size_t)d * 4, false));
+            }
         }
     } else {
         c->xkv_bytes = (size_t)arch->dec_layers * 2 * c->xkv_which_stride * e;

@@ -235,7 +235,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 if (ep.bias != nullptr) {
 #pragma unroll
                     for (int i = 0; i < BN; i += 4) {
-                        const float4 b = *reinterpret_cast<const float4*>(ep.bias + n0 + i);
+                        const float4 b = *reinterpret_cast<const float4*>(ep.bias + wn0 + i);      // bias is indexed like the rows of W
                         add[i] = b.x; add[i + 1] = b.y; add[i + 2] = b.z; add[i + 3] = b.w;
                     }
                 }
@@ -341,7 +341,7 @@ gemm_h16_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const bool have_bias = ep.bias != nullptr && (mode != EPI_ARGMAX || ln);
         if (have_bias || ln) {
             for (int i = threadIdx.x - 64; i < BN; i += 128) {
-                s_bias[i] = (have_bias && n0 + i < ep.N) ? ep.bias[n0 + i] : 0.f;
+                s_bias[i] = (have_bias && n0 + i < ep.N) ? ep.bias[wn0 + i] : 0.f;                   // indexed like the rows of W
                 s_lnc[i] = (ln && n0 + i < ep.N) ? ep.ln_c[n0 + i] : 0.f;
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");
