@@ -97,7 +97,8 @@ struct wipa_ctx {
     int n_logit_tiles;
     int bn_enc, bn_dec, bn_logits, ca_split;
     int splitk = 1;                // WIPA_SPLITK=0 disables the split-K decode fc2
-    int sk_bn = 32, sk_splits = 6; // WIPA_SK_BN / WIPA_SK_SPLITS: tile width and K splits of the long-K decode GEMMs once S needs two M tiles
+    int sk_bn = 32, sk_splits = 6;
+    int bn_qkv_wide = 64, bn_fc1_wide = 128, bn_xlq2_wide = 256, sk_wide = 1;   // tile widths once S needs more than two M tiles (WIPA_BN_*_WIDE) // WIPA_SK_BN / WIPA_SK_SPLITS: tile width and K splits of the long-K decode GEMMs once S needs two M tiles
     int beam_L = 0;                // row length of the beam-search sequence / ancestry arrays of the current decode
     int persistent_min_tiles = 296; // WIPA_PERSISTENT_MIN_TILES: fewer 128x256 tiles than this -> plain 128x128-tile kernel
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
@@ -618,7 +619,13 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
     const int ln_nt = d / WIPA_LN_PIECE;
     // long-K GEMMs (folded cross-attention out-projection, fc2): with two or more M tiles the 32-column tiles re-read the
     // activations 24 times per K split; 64-column tiles and six K splits halve that and still fill one wave
-    const bool wide_sk = c->bf && c->splitk && S > 128 && c->sk_bn == 64 && d % 64 == 0;
+    const bool many = c->bf && S > 256;               // more than two M tiles: 32-column tiles would need two waves of CTAs
+    const bool wide_sk = c->bf && c->splitk && d % 64 == 0 && ((S > 128 && c->sk_bn == 64) || (many && c->sk_wide));
+    const int sk_splits = (many && c->sk_wide && c->sk_bn != 64) ? 3 : c->sk_splits;
+    const int sk_bn = wide_sk ? 64 : c->bn_dec;
+    const int bn_qkv = many ? c->bn_qkv_wide : c->bn_dec;
+    const int bn_fc1 = many ? c->bn_fc1_wide : ((S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec);
+    const int bn_xlq2 = many ? c->bn_xlq2_wide : 128;
     auto consume_ln = [&](EpiParams& ep, const float* csum, const float* bias_f) {
         ep.ln_stats = c->dstats; ep.ln_c = csum; ep.ln_nt = ln_nt; ep.bias = bias_f;
     };
@@ -638,7 +645,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             ep.bias = L.qkv_b; ep.out = c->dq; ep.out1 = kp; ep.out2 = vp; ep.out_h16 = c->bf;
             ep.H = H; ep.d = d; ep.pos_ptr = c->d_pos; ep.block_table = c->block_table; ep.bt_stride = c->pages_per_seq;
             if (lnf) consume_ln(ep, c->qkv_c[l], c->qkv_bf[l]);
-            if (!(skip & 8)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->qkv_wf[l] : L.qkv_w, S, 3 * d, d, ep, c->bn_dec, st));
+            if (!(skip & 8)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->qkv_wf[l] : L.qkv_w, S, 3 * d, d, ep, bn_qkv, st));
         }
         const int* anc = beam ? c->b_anc : nullptr;            // beam search reads every position from the slot that wrote it
         if (skip & 2) {}
@@ -668,7 +675,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
                     EpiParams ep = epi(EPI_STORE, S * H, d);
                     ep.out = c->dqlat; ep.out_h16 = 1;
                     ep.o_rpb = S; ep.o_bstride = d; ep.ldo = Hd; ep.w_brows = d;
-                    if (!(skip & 16)) WIPA_TRY(gemm(c, A, c->xl_wkt[l], S * H, d, WIPA_HEAD_DIM, ep, 128, st));
+                    if (!(skip & 16)) WIPA_TRY(gemm(c, A, c->xl_wkt[l], S * H, d, WIPA_HEAD_DIM, ep, bn_xlq2, st));
                 }
             } else
             {   // q' = LN(x) Wq'^T + bq'  -> h16 [S, H, d]
@@ -701,9 +708,9 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             {   // x += C Wo'^T + bo'   (K = H * d is long: split-K)
                 EpiParams ep = epi(EPI_RESADD, S, d);
                 ep.bias = c->xlo_b[l]; ep.out = c->dx; ep.resid = c->dx;
-                if (c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? c->sk_splits : 0; }
+                if (c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? sk_splits : 0; }
                 produce_ln(ep);
-                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dclat, S, Hd), c->xlo_w[l], S, d, Hd, ep, wide_sk ? c->sk_bn : c->bn_dec, st));
+                if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dclat, S, Hd), c->xlo_w[l], S, d, Hd, ep, sk_bn, st));
             }
         } else {
         {
@@ -734,14 +741,14 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             ep.bias = L.fc1_b; ep.out = c->dffn; ep.out_h16 = c->bf; ep.gelu_fast = c->bf;
             if (lnf) consume_ln(ep, c->fc1_c[l], c->fc1_bf[l]);
             // N = ffn tiles of 32 columns would not fit one wave once S needs two M tiles: use 64-wide tiles then
-            if (!(skip & 32)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->fc1_wf[l] : L.fc1_w, S, ffn, d, ep, (S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec, st));
+            if (!(skip & 32)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), lnf ? c->fc1_wf[l] : L.fc1_w, S, ffn, d, ep, bn_fc1, st));
         }
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.fc2_b; ep.out = c->dx; ep.resid = c->dx;
-            if (c->bf && c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? c->sk_splits : 0; }    // K = ffn is long: split-K
+            if (c->bf && c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? sk_splits : 0; }    // K = ffn is long: split-K
             produce_ln(ep);
-            if (!(skip & 64)) WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, wide_sk ? c->sk_bn : c->bn_dec, st));
+            if (!(skip & 64)) WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, sk_bn, st));
         }
     }
     int n_tiles = 1;
@@ -833,6 +840,11 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->splitk = env_int("WIPA_SPLITK", 1);
     c->sk_bn = env_int("WIPA_SK_BN", 32);      // 64 x 6 splits measured slower (2704 vs 2406 us per step): the ticketed reduction, not the A re-reads, is what split-K costs
     c->sk_splits = env_int("WIPA_SK_SPLITS", 6);
+    // S > 256 (three or four M tiles): tiles wide enough that every node still fits ONE wave of 148 CTAs
+    c->bn_qkv_wide = env_int("WIPA_BN_QKV_WIDE", 64);
+    c->bn_fc1_wide = env_int("WIPA_BN_FC1_WIDE", 128);
+    c->bn_xlq2_wide = env_int("WIPA_BN_XLQ2_WIDE", 256);
+    c->sk_wide = env_int("WIPA_SK_WIDE", 1);
     c->persistent_min_tiles = env_int("WIPA_PERSISTENT_MIN_TILES", 2 * 148);
     c->bn_xlq = env_int("WIPA_BN_XLQ", 0);
     // latent cross-attention gives every SM whole sequences, so it wants about a wave of them; below that the stream-K

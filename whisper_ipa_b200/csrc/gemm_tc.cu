@@ -455,7 +455,9 @@ int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmW, int num_kb, int ti
     } else if constexpr (CL == 1 && BN == 64) {
         switch (ep.mode) { WIPA_TC_CASE(EPI_GELU); WIPA_TC_CASE(EPI_STORE); WIPA_TC_CASE(EPI_QKV_DEC); WIPA_TC_CASE(EPI_RESADD); default: break; }
     } else if constexpr (CL == 1 && BN == 128) {
-        switch (ep.mode) { WIPA_TC_CASE(EPI_ARGMAX); WIPA_TC_CASE(EPI_STORE); default: break; }
+        switch (ep.mode) { WIPA_TC_CASE(EPI_ARGMAX); WIPA_TC_CASE(EPI_STORE); WIPA_TC_CASE(EPI_GELU); default: break; }
+    } else if constexpr (CL == 1 && BN == 256) {
+        switch (ep.mode) { WIPA_TC_CASE(EPI_STORE); default: break; }
     }
 #undef WIPA_TC_CASE
     return launch_bn_mode<BN, BOXM, CL, -1>(tmA, tmW, num_kb, tiles_per_batch, n_batch, a_rpb, N, ep, st, splits);
