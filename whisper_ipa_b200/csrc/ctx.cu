@@ -98,7 +98,8 @@ struct wipa_ctx {
     int bn_enc, bn_dec, bn_logits, ca_split;
     int splitk = 1;                // WIPA_SPLITK=0 disables the split-K decode fc2
     int sk_bn = 32, sk_splits = 6;
-    int bn_qkv_wide = 64, bn_fc1_wide = 128, bn_xlq2_wide = 256, sk_wide = 1;   // tile widths once S needs more than two M tiles (WIPA_BN_*_WIDE) // WIPA_SK_BN / WIPA_SK_SPLITS: tile width and K splits of the long-K decode GEMMs once S needs two M tiles
+    int bn_qkv_wide = 64, bn_fc1_wide = 64, bn_xlq2_wide = 128, sk_wide = 0;
+    int sk_many = 0;               // WIPA_SPLITK_MANY=1: keep split-K on the long-K nodes when S > 256 (measured slower there)   // tile widths once S needs more than two M tiles (WIPA_BN_*_WIDE) // WIPA_SK_BN / WIPA_SK_SPLITS: tile width and K splits of the long-K decode GEMMs once S needs two M tiles
     int beam_L = 0;                // row length of the beam-search sequence / ancestry arrays of the current decode
     int persistent_min_tiles = 296; // WIPA_PERSISTENT_MIN_TILES: fewer 128x256 tiles than this -> plain 128x128-tile kernel
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
@@ -708,7 +709,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             {   // x += C Wo'^T + bo'   (K = H * d is long: split-K)
                 EpiParams ep = epi(EPI_RESADD, S, d);
                 ep.bias = c->xlo_b[l]; ep.out = c->dx; ep.resid = c->dx;
-                if (c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? sk_splits : 0; }
+                if (c->splitk && (!many || c->sk_many)) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? sk_splits : 0; }
                 produce_ln(ep);
                 if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(c->dclat, S, Hd), c->xlo_w[l], S, d, Hd, ep, sk_bn, st));
             }
@@ -746,7 +747,7 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         {
             EpiParams ep = epi(EPI_RESADD, S, d);
             ep.bias = L.fc2_b; ep.out = c->dx; ep.resid = c->dx;
-            if (c->bf && c->splitk) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? sk_splits : 0; }    // K = ffn is long: split-K
+            if (c->bf && c->splitk && (!many || c->sk_many)) { ep.sk_part = c->sk_part; ep.sk_count = c->sk_count; ep.sk_splits = wide_sk ? sk_splits : 0; }    // K = ffn is long: split-K
             produce_ln(ep);
             if (!(skip & 64)) WIPA_TRY(gemm(c, plainA(c->dffn, S, ffn), L.fc2_w, S, d, ffn, ep, sk_bn, st));
         }
@@ -842,9 +843,12 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->sk_splits = env_int("WIPA_SK_SPLITS", 6);
     // S > 256 (three or four M tiles): tiles wide enough that every node still fits ONE wave of 148 CTAs
     c->bn_qkv_wide = env_int("WIPA_BN_QKV_WIDE", 64);
-    c->bn_fc1_wide = env_int("WIPA_BN_FC1_WIDE", 128);
-    c->bn_xlq2_wide = env_int("WIPA_BN_XLQ2_WIDE", 256);
-    c->sk_wide = env_int("WIPA_SK_WIDE", 1);
+    // measured at small / 512 sequences (us per decode step): qkv 64-column tiles 4036 vs 4074 with 32; fc1 64 / 128 and the
+    // head-batched q' 128 / 256 within noise; fc2 WITHOUT split-K 3936 vs 4018 - 4036 with any split
+    c->bn_fc1_wide = env_int("WIPA_BN_FC1_WIDE", 64);
+    c->bn_xlq2_wide = env_int("WIPA_BN_XLQ2_WIDE", 128);
+    c->sk_wide = env_int("WIPA_SK_WIDE", 0);
+    c->sk_many = env_int("WIPA_SPLITK_MANY", 0);
     c->persistent_min_tiles = env_int("WIPA_PERSISTENT_MIN_TILES", 2 * 148);
     c->bn_xlq = env_int("WIPA_BN_XLQ", 0);
     // latent cross-attention gives every SM whole sequences, so it wants about a wave of them; below that the stream-K
