@@ -84,6 +84,8 @@ def lib(h16: str = "f16") -> C.CDLL:
     handle = _libs.get(h16)
     if handle is None:
         path = LIB_PATH if h16 == "f16" else LIB_PATH_BF16
+        if h16 == "f16" and os.environ.get("WIPA_LIBWIPA"):          # development: an experimental build of the same ABI
+            path = os.environ["WIPA_LIBWIPA"]
         if not os.path.exists(path):
             raise ImportError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(there is no CPU fallback)")

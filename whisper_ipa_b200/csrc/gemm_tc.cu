@@ -31,7 +31,13 @@ template <int BN, int BOXM> struct TcCfg {
     // latency-bound decode GEMMs: their MMAs are short (32 cycles each, bound by the A read from shared memory), so a
     // barrier round trip per 64-wide k-block (~150 cycles of try_wait + commit) would dominate the issue loop.
     static constexpr int KPB = BN == 32 ? (BOXM == 64 ? 4 : 2) : (BN == 64 ? 2 : 1);
-    static constexpr int STAGES = BN == 32 ? (BOXM == 64 ? 3 : 4) : (BN == 64 ? 3 : (BN == 128 ? 3 : 4));
+#ifndef WIPA_TC_STAGES_32
+#define WIPA_TC_STAGES_32 4
+#endif
+#ifndef WIPA_TC_STAGES_64
+#define WIPA_TC_STAGES_64 3
+#endif
+    static constexpr int STAGES = BN == 32 ? (BOXM == 64 ? 3 : WIPA_TC_STAGES_32) : (BN == 64 ? WIPA_TC_STAGES_64 : (BN == 128 ? 3 : 4));
     static constexpr int STAGE_A = KPB * A_BYTES;
     static constexpr int STAGE_W = KPB * W_BYTES;
     static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
