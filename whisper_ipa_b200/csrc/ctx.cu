@@ -105,7 +105,7 @@ struct wipa_ctx {
     int skip_mask = 0;             // WIPA_SKIP_MASK (timing ablation only, results become garbage): see decode_step
     int enc_attn_simt = 0;         // WIPA_ENC_ATTN_SIMT=1: SIMT flash kernel instead of the tcgen05 one (h16 path)
     // latent cross-attention (attn_lat.cu): the decoder attends over the encoder output itself, k / v projections folded
-    // into the query and output projections.  Default on the h16 path for contexts of >= 128 sequences and <= 16 heads.
+    // into the query and output projections.  Default on the h16 path for contexts of >= 96 sequences and <= 16 heads.
     int xlat = 0;
     int xl_q2 = 1;                 // WIPA_XL_Q2STEP: absorbed queries in two steps (q = x Wq^T, then q'_h = Wk_h^T q_h per head: 12 x
                                    // fewer weight bytes and 6 x fewer FLOPs than the one-step GEMM against the folded [H*d, d] matrix)
@@ -853,7 +853,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     c->bn_xlq = env_int("WIPA_BN_XLQ", 0);
     // latent cross-attention gives every SM whole sequences, so it wants about a wave of them; below that the stream-K
     // kernel over per-layer K / V (exactly balanced at any size) is faster.  WIPA_XATTN_LATENT = 1 / 0 forces either.
-    c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", max_batch * max_beams >= 128 ? 1 : 0) != 0 &&
+    c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", max_batch * max_beams >= 96 ? 1 : 0) != 0 &&
                cross_attention_latent_supported(arch->heads)) ? 1 : 0;
     c->lnf = (c->bf && env_int("WIPA_LN_FOLD", 1) != 0 && arch->d_model % WIPA_LN_PIECE == 0) ? 1 : 0;
     c->xl_q2 = (c->xlat && env_int("WIPA_XL_Q2STEP", 1) != 0) ? 1 : 0;
