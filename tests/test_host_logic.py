@@ -350,3 +350,111 @@ def test_cli_flags_match_the_reference():
         assert len(seen["calls"]) == 1 and seen["calls"][0][2] == 100 and seen["calls"][0][3]["n_mels"] == 128
     finally:
         em.evaluate_model = old
+
+
+# ---- long-form windowing on the CPU: a scripted model stands in for the GPU ---------------------------------------------------
+class _ScriptedModel:
+    """decode_begin / decode_next return logits that make a fixed token script the argmax (timestamp rules permitting); the
+    script is chosen per window from the number of windows decoded so far."""
+
+    def __init__(self, scripts, no_speech=0.0):
+        self.arch = w.ARCHS["tiny"]
+        self.device = torch.device("cpu")
+        self.scripts = scripts
+        self.no_speech = no_speech
+        self.window = -1
+        self.prompts = []
+        self.encoded = []
+
+    def encoder(self, mel, return_features=True):
+        self.encoded.append(tuple(mel.shape))
+        return None
+
+    def _logits(self, k):
+        out = torch.full((1, self.arch.vocab), -20.0)
+        script = self.scripts[min(self.window, len(self.scripts) - 1)]
+        out[0, script[k] if k < len(script) else self.arch.eot] = 10.0
+        return out
+
+    def decode_begin(self, tokens):
+        toks = list(tokens[0])
+        if toks[-1] == self.arch.sot and len(toks) == 1 or toks[-1] == self.arch.sot:      # the no-speech probe
+            out = torch.full((1, self.arch.vocab), -20.0)
+            out[0, self.arch.no_speech] = float(np.log(max(self.no_speech, 1e-9) / max(1 - self.no_speech, 1e-9))) - 20.0 + 20.0
+            out[0, 0] = 0.0
+            return out
+        self.window += 1
+        self.prompts.append(toks)
+        self.k = 0
+        return self._logits(0)
+
+    def decode_next(self, tok):
+        self.k += 1
+        return self._logits(self.k)
+
+
+def test_long_form_windows_follow_the_timestamps(monkeypatch):
+    """transcribe(): the seek advances to the last timestamp of a window that ends in a closed pair, the previous window's text
+    conditions the next one behind <|startofprev|>, a window whose no-speech probability is high AND whose log-probability is
+    low is skipped, and the text is the concatenation of the segments' text tokens."""
+    from whisper_ipa_b200 import decoding
+    from whisper_ipa_b200 import transcribe as tr
+    arch = w.ARCHS["tiny"]
+    tb = arch.timestamp_begin
+    monkeypatch.setattr(tr, "log_mel_features", lambda clip, n_mels: torch.zeros(1, n_mels, 3000))
+    decoding.set_detokenizer("ids")
+    try:
+        # window 0: <0.00> 11 12 <10.00><10.00> 13 <20.00><20.00>  -> two segments, seek moves to 20 s (1000 positions * 2 frames)
+        # window 1 (starts at 20 s): <0.00> 21 <5.00> then EOT       -> single closing timestamp: whole window consumed
+        s0 = [tb, 11, 12, tb + 500, tb + 500, 13, tb + 1000, tb + 1000]
+        s1 = [tb, 21, tb + 250]
+        m = _ScriptedModel([s0, s1])
+        audio = np.zeros(16000 * 45, np.float32)                       # 45 s
+        out = tr.transcribe(audio, m, language="en", temperature=0.0, compression_ratio_threshold=None, logprob_threshold=None,
+                            no_speech_threshold=None)
+        segs = out["segments"]
+        assert [(round(s["start"], 2), round(s["end"], 2)) for s in segs] == [(0.0, 10.0), (10.0, 20.0), (20.0, 25.0)]
+        assert [s["seek"] for s in segs] == [0, 0, 2000]
+        assert out["text"] == "11 12 13 21"
+        # the second window was conditioned on the first one's tokens: <|startofprev|> + previous tokens + sot sequence
+        assert m.prompts[0] == [arch.sot, arch.language_token("en"), arch.transcribe]
+        # (the trailing <20.00> opens the next segment and belongs to no slice, as in the reference algorithm)
+        assert m.prompts[1][0] == arch.sot_prev and m.prompts[1][1:-3] == s0[:-1] and m.prompts[1][-3:] == m.prompts[0]
+        assert len(m.encoded) == 2
+        # silence: P(no speech) high and the average log-probability below the threshold -> every window skipped, empty text
+        m2 = _ScriptedModel([[tb, 11, tb + 100]], no_speech=0.99)
+        out2 = tr.transcribe(np.zeros(16000 * 10, np.float32), m2, language="en", temperature=0.0, compression_ratio_threshold=None,
+                             logprob_threshold=0.5, no_speech_threshold=0.6)
+        assert out2["segments"] == [] and out2["text"] == ""
+        # a confident window survives the same no-speech probability (avg_logprob above the threshold)
+        m3 = _ScriptedModel([[tb, 11, tb + 100]], no_speech=0.99)
+        out3 = tr.transcribe(np.zeros(16000 * 10, np.float32), m3, language="en", temperature=0.0, compression_ratio_threshold=None,
+                             logprob_threshold=-1.0, no_speech_threshold=0.6)
+        assert out3["text"] == "11"
+    finally:
+        decoding.set_detokenizer(None)
+
+
+def test_read_pcm_host_side(tmp_path):
+    """ingest.read_pcm (the worker-thread half of the audio ingest, no GPU involved): PCM16 WAVs come back as raw interleaved
+    samples cut to what 30 s of output can need, other sample widths as host-decoded float audio, unreadable files raise."""
+    from whisper_ipa_b200.ingest import read_pcm, resample_plan
+    pcm = (np.arange(48000 * 2 * 2) % 2000 - 1000).astype("<i2").reshape(-1, 2)          # 2 s of 48 kHz stereo
+    p = tmp_path / "s.wav"
+    with wave.open(str(p), "wb") as f:
+        f.setnchannels(2); f.setsampwidth(2); f.setframerate(48000); f.writeframes(pcm.tobytes())
+    it = read_pcm(str(p))
+    assert it["rate"] == 48000 and it["ch"] == 2 and it["frames"] == 96000 and np.array_equal(it["pcm"], pcm.reshape(-1))
+    long = np.zeros((48000 * 40, 1), "<i2")                                              # 40 s mono: only ~30 s are read
+    p2 = tmp_path / "l.wav"
+    with wave.open(str(p2), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(2); f.setframerate(48000); f.writeframes(long.tobytes())
+    it2 = read_pcm(str(p2))
+    assert it2["frames"] == resample_plan(48000).frames_needed(480000) < 48000 * 31
+    p3 = tmp_path / "e.wav"
+    with wave.open(str(p3), "wb") as f:
+        f.setnchannels(1); f.setsampwidth(1); f.setframerate(16000); f.writeframes(bytes(range(256)) * 10)
+    it3 = read_pcm(str(p3))
+    assert "f32" in it3 and it3["f32"].dtype == np.float32 and len(it3["f32"]) == 2560
+    with pytest.raises(Exception):
+        read_pcm(str(tmp_path / "missing.wav"))
