@@ -183,6 +183,12 @@ int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int*
  * zeroed buffer of U * wipa_test_lat_tiled_elems(H, T) h16 elements): what the context keeps and bench.py times. */
 long long wipa_test_lat_tiled_elems(int H, int T);
 int wipa_test_lat_tile(const void* E, int U, int T, int H, void* out, void* stream);
+/* The absorbed queries of the latent cross-attention in one kernel (ctx.cu decode_step runs this per layer; the q rows stay
+ * in shared memory between the two products): A h16 [S, 64*H] (LayerNorm output), Wq / Wk h16 [64*H, 64*H] row-major [out, in]
+ * (HF q_proj / k_proj of WhisperAttention, modeling_whisper.py:241-357), bias f32 [64*H] or NULL, wkt_scratch h16 [H, 64*H, 64]
+ * -> out h16 [S, H, 64*H], out[s, h, :] = Wk_h^T (Wq_h A[s] + bias_h).  H even.  All device pointers. */
+int wipa_test_xlq_fused(const void* A, const void* Wq, const void* Wk, const float* bias, void* wkt_scratch, void* out, int S,
+                        int H, void* stream);
 /* One decode-step self-attention over a caller-built paged KV cache: kpool / vpool [page][H][16][64] (h16 when is_h16,
  * else f32), block_table int32 [B, bt_stride] page ids, *pos_ptr = newest position (length - 1); q f32 [B, H*64];
  * out [B, H*64] in the pool's element type.  All device pointers. */

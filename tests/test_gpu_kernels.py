@@ -247,3 +247,28 @@ def test_cross_attention_latent(lib, h16, H, T, S, U, layout):
     err = (C.float() - ref).abs().max().item()
     # bf16 probabilities (2^-9 relative each, averaged over the keys) + one bf16 rounding of the result
     assert err < _tol(h16, 1.5e-2) * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.parametrize("H,S", [(12, 256), (12, 512), (12, 5), (6, 130), (8, 300), (16, 64), (12, 1000)])
+def test_xlq_fused(lib, h16, H, S):
+    """Absorbed cross-attention queries in one kernel (gemm_q2.cu): out[s, h] = Wk_h^T (Wq_h a_s + b_h), the q rows rounded
+    to 16 bits between the two products exactly like the two-node path (q in h16 through L2).  Ragged last M tile, both
+    chunk widths (128 columns up to 256 sequences, 256 above when d allows), 6 / 8 / 12 / 16 heads."""
+    d = 64 * H
+    dt = lib.torch_h16(h16)
+    g = torch.Generator(device="cuda").manual_seed(H * 100 + S)
+    A = torch.randn(S, d, device="cuda", generator=g).to(dt)
+    Wq = (torch.randn(d, d, device="cuda", generator=g) / d ** 0.5).to(dt)
+    Wk = (torch.randn(d, d, device="cuda", generator=g) / d ** 0.5).to(dt)
+    b = torch.randn(d, device="cuda", generator=g) * 0.1
+    scratch = torch.empty(H * d * 64, device="cuda", dtype=dt)
+    out = torch.full((S, H, d), float("nan"), device="cuda", dtype=dt)
+    lib.check(lib.lib(h16).wipa_test_xlq_fused(A.data_ptr(), Wq.data_ptr(), Wk.data_ptr(), b.data_ptr(), scratch.data_ptr(),
+                                               out.data_ptr(), S, H, _st()), "xlq_fused")
+    q = (A.float() @ Wq.float().T + b).to(dt).float().view(S, H, 64)             # the 16-bit q tile
+    ref = torch.einsum("shi,hij->shj", q, Wk.float().view(H, 64, d))
+    assert not torch.isnan(out.float()).any()
+    err = (out.float() - ref).abs().max().item()
+    # fp32 accumulation over K = d and K = 64; the error is the final 16-bit rounding plus q values that land on the other
+    # side of a rounding boundary (accumulation order differs from torch's)
+    assert err < _tol(h16, 2e-2) * max(1.0, ref.abs().max().item()), f"max err {err}"

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "wipa_test_cross_attn_latent": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wipa_test_lat_tiled_elems": (C.c_longlong, [_i, _i]),
     "wipa_test_lat_tile": (_i, [_vp, _i, _i, _i, _vp, _vp]),
+    "wipa_test_xlq_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "wipa_test_gemm_rows": (_i, [_vp, _i, C.c_longlong, _i, C.c_longlong, _i, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_logits_argmax": (_i, [_vp, _i, _vp]),
     "wipa_test_cross_attn": (_i, [_vp, _i, _i, _vp, _vp, _vp]),

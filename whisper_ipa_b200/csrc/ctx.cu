@@ -111,6 +111,7 @@ struct wipa_ctx {
                                    // fewer weight bytes and 6 x fewer FLOPs than the one-step GEMM against the folded [H*d, d] matrix)
     int xl_o2 = 1;                 // WIPA_XL_O2STEP: context rows in two steps as well (ctx_h = Wv_h c_h + bv_h head-batched, then the ordinary
                                    // out-projection): no folded [d, H*d] matrix, no K = H*d split-K node
+    int xl_qfused = 0;             // WIPA_XL_QFUSED: the two steps above in one kernel (gemm_q2.cu), q never leaves the SM
     std::vector<void*> xl_wkt;     // per layer [H][d][64]: Wk transposed per head (the per-head GEMM's K-major W operand)
     void* dq16 = nullptr;          // q rows [S, d] in h16 between the two steps
     int xl_tiled = 1;              // WIPA_XL_TILED: the encoder output is kept chunk-tiled / pre-swizzled (bulk copies) instead of row-major (TMA boxes)
@@ -663,7 +664,12 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
         if (!lnf && !(skip & 1)) WIPA_TRY(ln(c, c->dx, L.ln2_w, L.ln2_b, c->dh, S, st));
         if (c->xlat) {
             const int Hd = H * d;
-            if (c->xl_q2) {
+            if (c->xl_q2 && c->xl_qfused) {
+                // both steps in one node: the q tile stays in shared memory (gemm_q2.cu)
+                if (!(skip & 16)) WIPA_TRY(launch_xlq_fused((const h16*)(lnf ? c->dx16 : c->dh), (const h16*)(lnf ? c->cq_wf[l] : L.cq_w),
+                                                            (const h16*)c->xl_wkt[l], lnf ? c->cq_bf[l] : L.cq_b, lnf ? c->dstats : nullptr,
+                                                            lnf ? c->cq_c[l] : nullptr, ln_nt, (h16*)c->dqlat, S, H, st));
+            } else if (c->xl_q2) {
                 {   // step 1: q = LN(x) Wq^T + bq (scaled by 2^-3 in the weights) -> h16 [S, d]
                     EpiParams ep = epi(EPI_STORE, S, d);
                     ep.bias = L.cq_b; ep.out = c->dq16; ep.out_h16 = 1;
@@ -857,6 +863,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
                cross_attention_latent_supported(arch->heads)) ? 1 : 0;
     c->lnf = (c->bf && env_int("WIPA_LN_FOLD", 1) != 0 && arch->d_model % WIPA_LN_PIECE == 0) ? 1 : 0;
     c->xl_q2 = (c->xlat && env_int("WIPA_XL_Q2STEP", 1) != 0) ? 1 : 0;
+    c->xl_qfused = (c->xl_q2 && env_int("WIPA_XL_QFUSED", 1) != 0) ? 1 : 0;
     c->xl_o2 = (c->xlat && env_int("WIPA_XL_O2STEP", 1) != 0) ? 1 : 0;
     memset(&c->mel_tables, 0, sizeof(c->mel_tables));
 
@@ -1501,6 +1508,19 @@ extern "C" long long wipa_test_lat_tiled_elems(int H, int T) {
 extern "C" int wipa_test_lat_tile(const void* E, int U, int T, int H, void* out, void* stream) {
     WIPA_CHECK(E && out && cross_attention_latent_supported(H), WIPA_EINVAL, "wipa_test_lat_tile: bad argument");
     return launch_lat_tile(E, 1, (h16*)out, U, T, H, cross_attention_latent_keys(H), (cudaStream_t)stream);
+}
+
+// absorbed cross-attention queries in one node (gemm_q2.cu): A h16 [S, 64 H], Wq / Wk h16 [64 H, 64 H] row-major
+// ([out, in] like nn.Linear), bias f32 [64 H] or NULL -> out h16 [S, H, 64 H] with out[s, h] = Wk_h^T (Wq_h A[s] + bias_h);
+// wkt_scratch: h16 [H, 64 H, 64] (holds the per-head transposed Wk)
+extern "C" int wipa_test_xlq_fused(const void* A, const void* Wq, const void* Wk, const float* bias, void* wkt_scratch, void* out,
+                                   int S, int H, void* stream) {
+    WIPA_CHECK(A && Wq && Wk && wkt_scratch && out && S >= 1 && H >= 1 && H % 2 == 0, WIPA_EINVAL, "wipa_test_xlq_fused: bad argument");
+    const int d = 64 * H;
+    xlat_wkt_kernel<<<dim3(cdiv(d, 4), H), 256, 0, (cudaStream_t)stream>>>((const h16*)Wk, (h16*)wkt_scratch, d);
+    WIPA_LAUNCHED();
+    return launch_xlq_fused((const h16*)A, (const h16*)Wq, (const h16*)wkt_scratch, bias, nullptr, nullptr, 0, (h16*)out, S, H,
+                            (cudaStream_t)stream);
 }
 
 // decoder self-attention step alone over a caller-built paged cache: kpool / vpool [page][H][16][64] (h16 or f32),
