@@ -463,6 +463,8 @@ def main():
         r1.record()
         torch.cuda.synchronize()
         kernel_name, source = "cross_attention_latent_kernel", "whisper_ipa_b200/csrc/attn_lat.cu"
+        if H == 20:                                                       # whisper-large*: two CTAs of 10 heads per key range
+            kernel_name, source = "cross_attention_latent_wide_kernel", "whisper_ipa_b200/csrc/attn_lat_wide.cu"
         bytes_per_launch = B * 1500 * dm * 2 + 2 * S * H * dm * 2       # E once + absorbed queries in + context rows out
         xattn_step_bytes = L * bytes_per_launch
         del E

@@ -175,7 +175,8 @@ int wipa_test_enc_attention_h16(const void* q, const void* k, const void* v, voi
 /* Latent cross-attention kernel alone (the decoder attends over the encoder output itself; k / v projections are folded
  * into the query / output projections, HF:models/whisper/modeling_whisper.py:241-357 WhisperAttention as cross-attention):
  * Qp h16 [S, H, 64*H] absorbed queries, E h16 [U, T, 64*H] encoder output, utt_of_seq int32 [S] -> C h16 [S, H, 64*H]
- * = softmax_t(Qp[s,h] . E[u,t]) E[u].  H = 6, 8, 12 or 16 (Whisper tiny .. medium).  All device pointers. */
+ * = softmax_t(Qp[s,h] . E[u,t]) E[u].  H = 6, 8, 12 or 16 (Whisper tiny .. medium), or 20 (large*: layout 1 or 2 only, two
+ * CTAs of 10 heads per key range, csrc/attn_lat_wide.cu).  All device pointers. */
 int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
                                 int layout, void* stream);
 /* layout of E above: 0 = row-major, fetched as TMA boxes; 1 = row-major in, converted to the chunk-tiled layout inside the

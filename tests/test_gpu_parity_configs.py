@@ -157,10 +157,11 @@ def test_medium_beam5_full_depth_matches_hf(w):
             assert agree >= 0.5
 
 
-def test_large_v3_full_depth_greedy_and_per_match_hf(w):
+def test_large_v3_full_depth_greedy_and_per_match_hf(w, monkeypatch):
     """BASELINE configs[4]: whisper-large-v3 (32 + 32 layers, 20 heads, 128 mel bins, vocab 51866): greedy ids of the fp32
-    path equal HF's, PER counts equal the CPU oracle's; the fp16 path (stream-K cross-attention over per-layer K/V: 20 heads
-    have no latent instantiation) reports token agreement."""
+    path equal HF's, PER counts equal the CPU oracle's; the fp16 path reports token agreement twice - with the stream-K
+    cross-attention over per-layer K/V (what a 2-clip context picks) and with the latent cross-attention forced (what contexts
+    of 96 sequences and more pick: csrc/attn_lat_wide.cu, two CTAs of 10 heads per key range)."""
     from oracle import hf_reference as hf
     from oracle import per_oracle as po
     from oracle import whisper_oracle as wo
@@ -175,14 +176,18 @@ def test_large_v3_full_depth_greedy_and_per_match_hf(w):
     want = _hf_gpu_generate(hf_model, audio, prompt, max_new, 128)
     feats = w.log_mel_features(audio, 128)
     refs = wo.synthetic_references(B)
-    for dtype in ("float32", "float16"):
+    for dtype, latent in (("float32", None), ("float16", "0"), ("float16", "1")):
+        if latent is not None:
+            monkeypatch.setenv("WIPA_XATTN_LATENT", latent)
         m = w.WhisperIPA("large-v3", dtype=dtype, max_batch=B)
+        if latent is not None:
+            assert m.info()["xattn_latent"] == int(latent)
         m.load_state_dict(sd)
         got = m.generate(feats, decoder_input_ids=torch.tensor([prompt] * B), max_new_tokens=max_new).cpu()
         m.close()
         n = min(got.shape[1], want.shape[1])
         agree = (got[:, :n] == want[:, :n]).float().mean().item()
-        print(f"\n[large-v3 full depth, greedy, {dtype}] token agreement with HF fp32 {agree:.3f}")
+        print(f"\n[large-v3 full depth, greedy, {dtype}, latent={latent}] token agreement with HF fp32 {agree:.3f}")
         if dtype == "float32":
             assert got.shape == want.shape and torch.equal(got, want)
             counts = metrics.edit_distance_counts(refs, [r.tolist() for r in got]).cpu().numpy()

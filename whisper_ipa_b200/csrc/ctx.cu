@@ -114,6 +114,7 @@ struct wipa_ctx {
     int xl_qfused = 0;             // WIPA_XL_QFUSED: the two steps above in one kernel (gemm_q2.cu), q never leaves the SM
     std::vector<void*> xl_wkt;     // per layer [H][d][64]: Wk transposed per head (the per-head GEMM's K-major W operand)
     void* dq16 = nullptr;          // q rows [S, d] in h16 between the two steps
+    int xl_wide = 0;               // 20 heads: attn_lat_wide.cu (two CTAs of 10 heads per range) instead of attn_lat.cu
     int xl_tiled = 1;              // WIPA_XL_TILED: the encoder output is kept chunk-tiled / pre-swizzled (bulk copies) instead of row-major (TMA boxes)
     int bn_xlq = 0;                // WIPA_BN_XLQ: tile width of the absorbed-query GEMM (0: as fc1)
     bool xlat_ready = false;       // folded weights match the loaded weights
@@ -691,6 +692,10 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
                 if (lnf) consume_ln(ep, c->xlq_c[l], c->xlq_b[l]);          // xlq_w / xlq_b were folded with the gain / beta already
                 if (!(skip & 16)) WIPA_TRY(gemm(c, plainA(lnf ? c->dx16 : c->dh, S, d), c->xlq_w[l], S, Hd, d, ep, c->bn_xlq ? c->bn_xlq : ((S > 128 && c->bn_dec == 32) ? 64 : c->bn_dec), st));
             }
+            if (c->xl_wide) {
+                if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent_wide((const h16*)c->dqlat, (const h16*)c->enc_lat, c->utt_of_seq, (h16*)c->dclat, S, H,
+                                                                            WIPA_T_ENC, c->xl_part, c->xl_part_floats, c->ca_counters, st));
+            } else
             if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const h16*)c->dqlat, (const h16*)c->enc_lat, c->xl_tiled, c->max_batch, c->utt_of_seq,
                                                                    (h16*)c->dclat, S, H, WIPA_T_ENC, c->xl_part, c->xl_part_floats,
                                                                    c->ca_counters, st));
@@ -860,7 +865,8 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     // latent cross-attention gives every SM whole sequences, so it wants about a wave of them; below that the stream-K
     // kernel over per-layer K / V (exactly balanced at any size) is faster.  WIPA_XATTN_LATENT = 1 / 0 forces either.
     c->xlat = (c->bf && env_int("WIPA_XATTN_LATENT", max_batch * max_beams >= 96 ? 1 : 0) != 0 &&
-               cross_attention_latent_supported(arch->heads)) ? 1 : 0;
+               (cross_attention_latent_supported(arch->heads) || cross_attention_latent_wide_supported(arch->heads))) ? 1 : 0;
+    c->xl_wide = (c->xlat && cross_attention_latent_wide_supported(arch->heads)) ? 1 : 0;
     c->lnf = (c->bf && env_int("WIPA_LN_FOLD", 1) != 0 && arch->d_model % WIPA_LN_PIECE == 0) ? 1 : 0;
     c->xl_q2 = (c->xlat && env_int("WIPA_XL_Q2STEP", 1) != 0) ? 1 : 0;
     c->xl_qfused = (c->xl_q2 && env_int("WIPA_XL_QFUSED", 1) != 0) ? 1 : 0;
@@ -896,7 +902,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
     if (c->xlat) {
         // no per-layer cross-KV: the encoder output itself, plus the folded projections and the [S, H*d] rows around the kernel
         c->xkv = nullptr;
-        c->xl_tiled = env_int("WIPA_XL_TILED", 1);
+        c->xl_tiled = c->xl_wide ? 1 : env_int("WIPA_XL_TILED", 1);     // the 20-head kernel only reads the tiled layout
         c->xkv_bytes = c->xl_tiled ? (size_t)max_batch * cross_attention_latent_tiled_elems(H, (int)T) * e : (size_t)max_batch * T * d * e;
         CTX_TRY(ctx_alloc(c, &c->enc_lat, c->xkv_bytes, true));          // zeroed: the tiled layout pads every utterance to whole chunks
         CTX_TRY(ctx_alloc(c, &c->dqlat, (size_t)S * H * d * e, false));
@@ -905,7 +911,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
             int dev = 0, n_sm = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            c->xl_part_floats = cross_attention_latent_scratch_floats(H, S, n_sm);
+            c->xl_part_floats = c->xl_wide ? cross_attention_latent_wide_scratch_floats(S, n_sm) : cross_attention_latent_scratch_floats(H, S, n_sm);
             CTX_TRY(ctx_alloc(c, (void**)&c->xl_part, c->xl_part_floats * 4, false));
         }
         c->xlq_w.assign(arch->dec_layers, nullptr); c->xlo_w.assign(arch->dec_layers, nullptr);
@@ -1456,8 +1462,10 @@ extern "C" int wipa_test_logits_argmax(wipa_ctx* c, int S, void* stream) {
 // -> C h16 [S, H, 64H] = softmax_t(Qp[s, h] . E[u, t]) E[u].  All device pointers.
 extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
                                            int layout, void* stream) {
-    WIPA_CHECK(Qp && E && utt_of_seq && C && S >= 1 && cross_attention_latent_supported(H), WIPA_EINVAL,
+    const bool wide = cross_attention_latent_wide_supported(H) != 0;
+    WIPA_CHECK(Qp && E && utt_of_seq && C && S >= 1 && (wide || cross_attention_latent_supported(H)), WIPA_EINVAL,
                "wipa_test_cross_attn_latent: bad argument");
+    WIPA_CHECK(!wide || layout != 0, WIPA_EUNSUPPORTED, "wipa_test_cross_attn_latent: 20 heads read the chunk-tiled layout only (layout 1 or 2)");
     WIPA_CHECK(layout >= 0 && layout <= 2, WIPA_EINVAL, "wipa_test_cross_attn_latent: layout 0 (row-major, TMA boxes), 1 (row-major in, "
                "tiled internally) or 2 (already chunk-tiled)");
     // scratch of the standalone entry point: grow-only, per process (contexts own theirs)
@@ -1469,19 +1477,19 @@ extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U,
     int dev = 0, n_sm = 148;
     WIPA_CUDA_CHECK(cudaGetDevice(&dev));
     WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const size_t need = cross_attention_latent_scratch_floats(H, S, n_sm);
+    const size_t need = wide ? cross_attention_latent_wide_scratch_floats(S, n_sm) : cross_attention_latent_scratch_floats(H, S, n_sm);
     if (need > part_floats) {
         WIPA_CUDA_CHECK(cudaDeviceSynchronize());
         if (part) cudaFree(part);
         WIPA_CUDA_CHECK(cudaMalloc(&part, need * 4));
         part_floats = need;
     }
-    if (S > counters_cap) {
+    if (2 * S > counters_cap) {                                  // 20 heads: one counter per (sequence, head group)
         WIPA_CUDA_CHECK(cudaDeviceSynchronize());
         if (counters) cudaFree(counters);
-        WIPA_CUDA_CHECK(cudaMalloc(&counters, (size_t)S * 4));
-        WIPA_CUDA_CHECK(cudaMemset(counters, 0, (size_t)S * 4));
-        counters_cap = S;
+        WIPA_CUDA_CHECK(cudaMalloc(&counters, (size_t)S * 8));
+        WIPA_CUDA_CHECK(cudaMemset(counters, 0, (size_t)S * 8));
+        counters_cap = 2 * S;
     }
     const h16* Ein = (const h16*)E;
     if (layout == 1) {
@@ -1496,6 +1504,7 @@ extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U,
         WIPA_TRY(launch_lat_tile(E, 1, tiled, U, T, H, cross_attention_latent_keys(H), (cudaStream_t)stream));
         Ein = tiled;
     }
+    if (wide) return launch_cross_attention_latent_wide((const h16*)Qp, Ein, utt_of_seq, (h16*)C, S, H, T, part, part_floats, counters, (cudaStream_t)stream);
     return launch_cross_attention_latent((const h16*)Qp, Ein, layout != 0, U, utt_of_seq, (h16*)C, S, H, T, part, part_floats, counters,
                                          (cudaStream_t)stream);
 }
@@ -1503,10 +1512,10 @@ extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U,
 // row-major h16 encoder output [U, T, 64 H] -> the chunk-tiled layout of the latent kernel (layout 2 above); `out` holds
 // U * wipa_test_lat_tiled_elems(H, T) h16 elements and must be zeroed by the caller once (padding of the last chunk)
 extern "C" long long wipa_test_lat_tiled_elems(int H, int T) {
-    return cross_attention_latent_supported(H) ? (long long)cross_attention_latent_tiled_elems(H, T) : -1;
+    return (cross_attention_latent_supported(H) || cross_attention_latent_wide_supported(H)) ? (long long)cross_attention_latent_tiled_elems(H, T) : -1;
 }
 extern "C" int wipa_test_lat_tile(const void* E, int U, int T, int H, void* out, void* stream) {
-    WIPA_CHECK(E && out && cross_attention_latent_supported(H), WIPA_EINVAL, "wipa_test_lat_tile: bad argument");
+    WIPA_CHECK(E && out && (cross_attention_latent_supported(H) || cross_attention_latent_wide_supported(H)), WIPA_EINVAL, "wipa_test_lat_tile: bad argument");
     return launch_lat_tile(E, 1, (h16*)out, U, T, H, cross_attention_latent_keys(H), (cudaStream_t)stream);
 }
 
