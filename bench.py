@@ -454,7 +454,7 @@ def main():
 
         def launch():
             return lib.wipa_test_cross_attn_latent(Qp.data_ptr(), E.data_ptr(), B, utt.data_ptr(), Cl.data_ptr(), S, H, 1500,
-                                                   2 if tiled else 0, st)
+                                                   2 if tiled else 0, args.beams, st)
         _lib.check(launch(), "cross_attn_latent", lib)
         torch.cuda.synchronize()
         r0.record()
@@ -463,7 +463,8 @@ def main():
         r1.record()
         torch.cuda.synchronize()
         kernel_name, source = "cross_attention_latent_kernel", "whisper_ipa_b200/csrc/attn_lat.cu"
-        if H == 20:                                                       # whisper-large*: two CTAs of 10 heads per key range
+        if H == 20 or (H == 16 and tiled and os.environ.get("WIPA_XL_WIDE16", "1") != "0"):
+            # whisper-medium / large*: 128 columns per warp (20 heads: two CTAs of 10 heads per key range)
             kernel_name, source = "cross_attention_latent_wide_kernel", "whisper_ipa_b200/csrc/attn_lat_wide.cu"
         bytes_per_launch = B * 1500 * dm * 2 + 2 * S * H * dm * 2       # E once + absorbed queries in + context rows out
         xattn_step_bytes = L * bytes_per_launch

@@ -178,7 +178,9 @@ int wipa_test_enc_attention_h16(const void* q, const void* k, const void* v, voi
  * = softmax_t(Qp[s,h] . E[u,t]) E[u].  H = 6, 8, 12 or 16 (Whisper tiny .. medium), or 20 (large*: layout 1 or 2 only, two
  * CTAs of 10 heads per key range, csrc/attn_lat_wide.cu).  All device pointers. */
 int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
-                                int layout, void* stream);
+                                int layout, int beams, void* stream);
+/* beams: 1, or the beam count K (2..8) when utt_of_seq[s] = s / K (the K beams of an utterance are adjacent sequences): a group of
+ * K CTAs then walks each (utterance, key range) together so that E leaves HBM once per utterance, not once per beam. */
 /* layout of E above: 0 = row-major, fetched as TMA boxes; 1 = row-major in, converted to the chunk-tiled layout inside the
  * call (not for timing); 2 = already chunk-tiled ([U][chunk][column tile][key][64 swizzled], made by wipa_test_lat_tile into a
  * zeroed buffer of U * wipa_test_lat_tiled_elems(H, T) h16 elements): what the context keeps and bench.py times. */

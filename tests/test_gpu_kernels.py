@@ -241,7 +241,7 @@ def test_cross_attention_latent(lib, h16, H, T, S, U, layout):
     if layout == 2:
         Ein = torch.zeros(U * lib.lib(h16).wipa_test_lat_tiled_elems(H, T), device="cuda", dtype=lib.torch_h16(h16))
         lib.check(lib.lib(h16).wipa_test_lat_tile(E.data_ptr(), U, T, H, Ein.data_ptr(), _st()), "lat_tile")
-    lib.check(lib.lib(h16).wipa_test_cross_attn_latent(Qp.data_ptr(), Ein.data_ptr(), U, utt.data_ptr(), C.data_ptr(), S, H, T, layout, _st()),
+    lib.check(lib.lib(h16).wipa_test_cross_attn_latent(Qp.data_ptr(), Ein.data_ptr(), U, utt.data_ptr(), C.data_ptr(), S, H, T, layout, 1, _st()),
               "cross_attn_latent")
     Eu = E.float()[utt.long()]                                          # [S, T, d]
     scores = torch.einsum("shd,std->sht", Qp.float(), Eu)
@@ -276,3 +276,28 @@ def test_xlq_fused(lib, h16, H, S):
     # fp32 accumulation over K = d and K = 64; the error is the final 16-bit rounding plus q values that land on the other
     # side of a rounding boundary (accumulation order differs from torch's)
     assert err < _tol(h16, 2e-2) * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+@pytest.mark.parametrize("H,T,U,K", [(16, 1500, 64, 5), (12, 1500, 7, 5), (16, 333, 3, 2), (8, 100, 40, 8), (12, 1500, 31, 4)])
+def test_cross_attention_latent_beam_groups(lib, h16, H, T, U, K):
+    """Beam search: the K beams of an utterance are adjacent sequences with the same E.  The kernel then cuts the list of
+    (utterance, chunk) units into ranges walked by GROUPS of K CTAs, one beam per CTA (E leaves HBM once per utterance);
+    results per sequence must not depend on that: compared with the same fp32 reference as the greedy layout."""
+    d = 64 * H
+    S = U * K
+    dt = lib.torch_h16(h16)
+    g = torch.Generator(device="cuda").manual_seed(H * 1000 + T + S)
+    E = torch.randn(U, T, d, device="cuda", generator=g).to(dt)
+    Qp = (torch.randn(S, H, d, device="cuda", generator=g) * (1.5 / d ** 0.5)).to(dt)
+    utt = (torch.arange(S, device="cuda", dtype=torch.int32) // K).to(torch.int32).contiguous()
+    C = torch.full((S, H, d), float("nan"), device="cuda", dtype=dt)
+    Et = torch.zeros(U * lib.lib(h16).wipa_test_lat_tiled_elems(H, T), device="cuda", dtype=dt)
+    lib.check(lib.lib(h16).wipa_test_lat_tile(E.data_ptr(), U, T, H, Et.data_ptr(), _st()), "lat_tile")
+    lib.check(lib.lib(h16).wipa_test_cross_attn_latent(Qp.data_ptr(), Et.data_ptr(), U, utt.data_ptr(), C.data_ptr(), S, H, T, 2, K, _st()),
+              "cross_attn_latent")
+    Eu = E.float()[utt.long()]
+    P = torch.softmax(torch.einsum("shd,std->sht", Qp.float(), Eu), dim=-1)
+    ref = torch.einsum("sht,std->shd", P, Eu)
+    assert not torch.isnan(C.float()).any()
+    err = (C.float() - ref).abs().max().item()
+    assert err < _tol(h16, 1.5e-2) * max(1.0, ref.abs().max().item()), f"max err {err}"

@@ -62,7 +62,7 @@ PROTOTYPES = {
     "wipa_test_gemm_h16": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wipa_test_gemm_f32": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "wipa_test_gemm_epilogue": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "wipa_test_cross_attn_latent": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "wipa_test_cross_attn_latent": (_i, [_vp, _vp, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "wipa_test_lat_tiled_elems": (C.c_longlong, [_i, _i]),
     "wipa_test_lat_tile": (_i, [_vp, _i, _i, _i, _vp, _vp]),
     "wipa_test_xlq_fused": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),

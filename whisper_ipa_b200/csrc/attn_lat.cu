@@ -103,9 +103,10 @@ __device__ __forceinline__ float ex2_ftz(float x) {
 // leaves (m, l, unnormalised C) in this CTA's slot, and the CTA that completes the sequence's chunk count merges the
 // slots in order.  Called by every consumer thread of the CTA (it contains named barriers).
 template <int H>
-__device__ __forceinline__ void xl_finish_segment(int s, int ch0, int ch1, int n_chunks, long long n_units, float (&acc)[8][4],
-                                                  float (&accl)[4], float m_run, h16* __restrict__ Cout, float* __restrict__ part,
-                                                  int* __restrict__ counters, int slots_per_seq, int* last_flag, int w, int lane) {
+__device__ __forceinline__ void xl_finish_segment(int s, int v, int bx, int nx, int ch0, int ch1, int n_chunks, long long n_units,
+                                                  float (&acc)[8][4], float (&accl)[4], float m_run, h16* __restrict__ Cout,
+                                                  float* __restrict__ part, int* __restrict__ counters, int slots_per_seq,
+                                                  int* last_flag, int w, int lane) {
     constexpr int d = H * 64;
     constexpr int nthr = H * 32;
     const int g = lane >> 2, t = lane & 3;
@@ -125,12 +126,12 @@ __device__ __forceinline__ void xl_finish_segment(int s, int ch0, int ch1, int n
     // a part of the sequence: leave (m, l, unnormalised C) in this CTA's slot of the sequence; whoever brings the
     // sequence's chunk count to n_chunks merges the slots in order (deterministic) and stores
     constexpr int SLOT_FLOATS = H * 1024 + 32;                 // [warp][lane][32 accumulators] + m[16] + l[16]
-    const long long first_unit = (long long)s * n_chunks;
-    const int cta_first = (int)(((first_unit + 1) * gridDim.x + n_units - 1) / n_units) - 1;      // CTA holding chunk 0
-    const int cta_last = (int)(((first_unit + n_chunks) * gridDim.x + n_units - 1) / n_units) - 1; // CTA holding the last chunk
+    const long long first_unit = (long long)v * n_chunks;
+    const int cta_first = (int)(((first_unit + 1) * nx + n_units - 1) / n_units) - 1;          // CTA (group) holding chunk 0
+    const int cta_last = (int)(((first_unit + n_chunks) * nx + n_units - 1) / n_units) - 1;   // CTA (group) holding the last chunk
     float* seq_part = part + (size_t)s * slots_per_seq * SLOT_FLOATS;
     {
-        float* slot = seq_part + (size_t)((int)blockIdx.x - cta_first) * SLOT_FLOATS;
+        float* slot = seq_part + (size_t)(bx - cta_first) * SLOT_FLOATS;
         float4* dst = reinterpret_cast<float4*>(slot + (w * 32 + lane) * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dst[j] = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
@@ -195,7 +196,7 @@ template <int KEYS, int H, bool TILED, int XL_STAGES>
 __global__ void __launch_bounds__((H + 1) * 32, 1)
 cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Et, const h16* __restrict__ Qp,
                               const int* __restrict__ utt_of_seq, h16* __restrict__ Cout, int S, int T,
-                              float* __restrict__ part, int* __restrict__ counters, int slots_per_seq) {
+                              float* __restrict__ part, int* __restrict__ counters, int slots_per_seq, int K) {
     using Cfg = XlCfg<KEYS, XL_STAGES>;
     constexpr int PITCH = Cfg::PITCH;
     extern __shared__ uint8_t xl_smem_raw[];
@@ -212,9 +213,13 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_chunks = (T + KEYS - 1) / KEYS;
-    // stream-K: the (sequence, chunk) units form one list cut into equal contiguous ranges, one per CTA
-    const long long n_units = (long long)S * n_chunks;
-    const long long u_lo = n_units * blockIdx.x / gridDim.x, u_hi = n_units * (blockIdx.x + 1) / gridDim.x;
+    // stream-K: the (sequence, chunk) units form one list cut into equal contiguous ranges, one per CTA.  Beam search (K > 1):
+    // the K beams of an utterance (sequences u K .. u K + K - 1) attend over the same E, so the list is over (utterance slot,
+    // chunk) and a GROUP of K CTAs (blockIdx.x = K bx + beam) walks each range, one beam per CTA: the K readers of an E chunk run
+    // within a few hundred cycles of each other and all but the first are served by L2 instead of HBM.
+    const int bx = (int)blockIdx.x / K, beam = (int)blockIdx.x - bx * K, nx = (int)gridDim.x / K;
+    const long long n_units = (long long)(S / K) * n_chunks;
+    const long long u_lo = n_units * bx / nx, u_hi = n_units * (bx + 1) / nx;
 
     if (threadIdx.x == 0) {
         if (!TILED) ptx::prefetch_tensormap(&tmE);
@@ -237,10 +242,10 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
         int st = 0;
         uint32_t ph = 0;
         for (long long unit = u_lo; unit < u_hi;) {
-            const int s = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)s * n_chunks);
+            const int v = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)v * n_chunks);
             const int ch1 = (u_hi - unit) < (long long)(n_chunks - ch0) ? ch0 + (int)(u_hi - unit) : n_chunks;
             unit += ch1 - ch0;
-            const int u = utt_of_seq[s];
+            const int u = utt_of_seq[v * K + beam];
             for (int ch = ch0; ch < ch1; ++ch) {
                 ptx::mbar_wait(&empty[st], ph ^ 1);
                 if (ptx::elect_one()) {
@@ -282,9 +287,10 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
     int st = 0;
     uint32_t ph = 0;
     for (long long unit = u_lo; unit < u_hi;) {
-        const int s = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)s * n_chunks);
+        const int v = (int)(unit / n_chunks), ch0 = (int)(unit - (long long)v * n_chunks);
         const int ch1 = (u_hi - unit) < (long long)(n_chunks - ch0) ? ch0 + (int)(u_hi - unit) : n_chunks;
         unit += ch1 - ch0;
+        const int s = v * K + beam;
         // A fragments of Q': rows g / g + 8 (heads), this warp's 64 columns = 4 k-steps of 16
         uint32_t qa[4][4];
         {
@@ -407,7 +413,7 @@ cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16
             if (lane == 0) ptx::mbar_arrive(&empty[st]);
             if (++st == XL_STAGES) { st = 0; ph ^= 1; }
         }
-        xl_finish_segment<H>(s, ch0, ch1, n_chunks, n_units, acc, accl, m_run, Cout, part, counters, slots_per_seq, last_flag, w, lane);
+        xl_finish_segment<H>(s, v, bx, nx, ch0, ch1, n_chunks, n_units, acc, accl, m_run, Cout, part, counters, slots_per_seq, last_flag, w, lane);
     }
 }
 
@@ -428,19 +434,20 @@ int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) 
 
 template <int KEYS, int H, bool TILED, int XL_STAGES = 2>
 int xl_launch(const CUtensorMap& tm, const h16* Et, const h16* Qp, const int* utt_of_seq, h16* C, int S, int T, int n_sm, float* part,
-              size_t part_floats, int* counters, cudaStream_t st) {
+              size_t part_floats, int* counters, int K, cudaStream_t st) {
     const size_t smem = XlCfg<KEYS, XL_STAGES>::smem(H);
     static SmemAttr attr;
     WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H, TILED, XL_STAGES>, smem, attr));
     const int n_chunks = cdiv(T, KEYS);
-    const long long n_units = (long long)S * n_chunks;
-    const int grid = n_units < n_sm ? (int)n_units : n_sm;
-    // a sequence is cut by at most n_chunks / (shortest CTA range) range boundaries
-    const int slots_per_seq = n_chunks / (int)(n_units / grid) + 2;
+    const long long n_units = (long long)(S / K) * n_chunks;      // per group of K CTAs (K = 1: per CTA)
+    const int groups = n_units < n_sm / K ? (int)n_units : n_sm / K;
+    const int grid = groups * K;
+    // a sequence is cut by at most n_chunks / (shortest range) range boundaries
+    const int slots_per_seq = n_chunks / (int)(n_units / groups) + 2;
     WIPA_CHECK((size_t)S * slots_per_seq * (H * 1024 + 32) <= part_floats, WIPA_EINVAL,
                "cross_attention_latent: partial scratch too small for %d sequences", S);
     WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H, TILED, XL_STAGES>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Et, Qp,
-                                  utt_of_seq, C, S, T, part, counters, slots_per_seq));
+                                  utt_of_seq, C, S, T, part, counters, slots_per_seq, K));
     WIPA_LAUNCHED();
     return WIPA_OK;
 }
@@ -484,9 +491,12 @@ size_t cross_attention_latent_tiled_elems(int H, int T) {
 // (tiled = 1: [U][chunk][h][key][64 swizzled], common.cuh lat_tile_offset); utt_of_seq: int [S]; C: h16 [S, H, d];
 // part / counters: partial scratch (cross_attention_latent_scratch_floats) and int [S] zeroed once (self-resetting)
 int launch_cross_attention_latent(const h16* Qp, const h16* E, int tiled, int U, const int* utt_of_seq, h16* C, int S, int H, int T,
-                                  float* part, size_t part_floats, int* counters, cudaStream_t st) {
+                                  float* part, size_t part_floats, int* counters, cudaStream_t st, int beams) {
     WIPA_CHECK(cross_attention_latent_supported(H), WIPA_EUNSUPPORTED, "cross_attention_latent: %d heads (6, 8, 12 or 16)", H);
     WIPA_CHECK(S >= 1 && U >= 1 && T >= 1 && part && counters, WIPA_EINVAL, "cross_attention_latent: bad argument");
+    // beams > 1: sequences u * beams .. u * beams + beams - 1 share utt_of_seq (the beams of one utterance); they are walked by
+    // a group of `beams` CTAs.  Anything else (or more beams than a tenth of the SMs) falls back to one list of sequences.
+    const int K = (beams >= 2 && beams <= 8 && S % beams == 0) ? beams : 1;
     if (g_encode_xl == nullptr) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
@@ -504,23 +514,23 @@ int launch_cross_attention_latent(const h16* Qp, const h16* E, int tiled, int U,
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
     if (tiled && keys == 32 && H <= 12) {
-#define XL_CASE(HH, ST) if (H == HH && xl_stages(H) == ST) return xl_launch<32, HH, true, ST>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st)
+#define XL_CASE(HH, ST) if (H == HH && xl_stages(H) == ST) return xl_launch<32, HH, true, ST>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st)
         XL_CASE(6, 2); XL_CASE(6, 3); XL_CASE(6, 4); XL_CASE(8, 2); XL_CASE(8, 3); XL_CASE(8, 4); XL_CASE(12, 2); XL_CASE(12, 3); XL_CASE(12, 4);
 #undef XL_CASE
     }
     if (tiled) {
         switch (H) {
-            case 6: return xl_launch<48, 6, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-            case 8: return xl_launch<48, 8, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-            case 12: return xl_launch<48, 12, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-            default: return xl_launch<32, 16, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+            case 6: return xl_launch<48, 6, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+            case 8: return xl_launch<48, 8, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+            case 12: return xl_launch<48, 12, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+            default: return xl_launch<32, 16, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
         }
     }
     WIPA_TRY(xl_make_map(&tm, E, U, T, H * 64, H <= 12 ? 48 : 32));       // the row-major path keeps 48 keys x 2 stages up to 12 heads
     switch (H) {
-        case 6: return xl_launch<48, 6, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-        case 8: return xl_launch<48, 8, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-        case 12: return xl_launch<48, 12, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
-        default: return xl_launch<32, 16, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, st);
+        case 6: return xl_launch<48, 6, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+        case 8: return xl_launch<48, 8, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+        case 12: return xl_launch<48, 12, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+        default: return xl_launch<32, 16, false>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
     }
 }

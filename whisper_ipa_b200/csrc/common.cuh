@@ -499,7 +499,7 @@ size_t cross_attention_latent_scratch_floats(int H, int max_seqs, int n_sm);
 int cross_attention_latent_keys(int H);                    // keys per chunk of the kernel instantiation for H heads
 size_t cross_attention_latent_tiled_elems(int H, int T);   // elements per utterance of the chunk-tiled encoder output
 int launch_cross_attention_latent(const h16* Qp, const h16* E, int tiled, int U, const int* utt_of_seq, h16* C, int S, int H, int T,
-                                  float* part, size_t part_floats, int* counters, cudaStream_t st);
+                                  float* part, size_t part_floats, int* counters, cudaStream_t st, int beams = 1);
 // Chunk-tiled layout of one utterance's encoder output E [T, d = 64 H] for the latent cross-attention kernel:
 // [chunk of `keys` keys][column tile h of 64][key][64 columns], the eight 16-byte pieces of every 128-byte row permuted by
 // (piece ^ (key & 7)) - byte for byte what a 128B-swizzled TMA box [keys][64] leaves in shared memory, so that a whole
@@ -512,11 +512,11 @@ __host__ __device__ __forceinline__ size_t lat_tile_offset(int t, int col, int H
 int launch_layernorm_lat(const float* x, const float* w, const float* b, h16* out_tiled, int M, int d, int T, int u0, int keys,
                          cudaStream_t st);
 // row-major [U, T, d] (f32 or h16) -> chunk-tiled h16
-// 20 heads (whisper-large*): attn_lat_wide.cu, two CTAs per (sequence, chunk) range with 10 heads each; chunk-tiled E only
+// 16 / 20 heads (whisper-medium / large*): attn_lat_wide.cu, 128 columns per warp, 20 heads as two CTAs of 10; chunk-tiled E only
 int cross_attention_latent_wide_supported(int H);
-size_t cross_attention_latent_wide_scratch_floats(int max_seqs, int n_sm);
+size_t cross_attention_latent_wide_scratch_floats(int H, int max_seqs, int n_sm);
 int launch_cross_attention_latent_wide(const h16* Qp, const h16* E, const int* utt_of_seq, h16* C, int S, int H, int T, float* part,
-                                       size_t part_floats, int* counters, cudaStream_t st);
+                                       size_t part_floats, int* counters, cudaStream_t st, int beams = 1);
 int launch_xlq_fused(const h16* A, const h16* Wq, const h16* WkT, const float* bias, const float* ln_stats, const float* ln_c,
                      int ln_nt, h16* out, int S, int H, cudaStream_t st);
 int launch_lat_tile(const void* src, int src_is_h16, h16* out_tiled, int U, int T, int H, int keys, cudaStream_t st);

@@ -114,7 +114,8 @@ struct wipa_ctx {
     int xl_qfused = 0;             // WIPA_XL_QFUSED: the two steps above in one kernel (gemm_q2.cu), q never leaves the SM
     std::vector<void*> xl_wkt;     // per layer [H][d][64]: Wk transposed per head (the per-head GEMM's K-major W operand)
     void* dq16 = nullptr;          // q rows [S, d] in h16 between the two steps
-    int xl_wide = 0;               // 20 heads: attn_lat_wide.cu (two CTAs of 10 heads per range) instead of attn_lat.cu
+    int cur_beams = 1;             // beams of the decode in progress (decode_setup): the latent kernel groups an utterance's beams
+    int xl_wide = 0;               // 16 / 20 heads: attn_lat_wide.cu (128 columns per warp; 20 heads as two CTAs of 10) instead of attn_lat.cu
     int xl_tiled = 1;              // WIPA_XL_TILED: the encoder output is kept chunk-tiled / pre-swizzled (bulk copies) instead of row-major (TMA boxes)
     int bn_xlq = 0;                // WIPA_BN_XLQ: tile width of the absorbed-query GEMM (0: as fc1)
     bool xlat_ready = false;       // folded weights match the loaded weights
@@ -694,11 +695,12 @@ int decode_step(wipa_ctx* c, int S, const DecodeState& ds, int logits_mode, floa
             }
             if (c->xl_wide) {
                 if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent_wide((const h16*)c->dqlat, (const h16*)c->enc_lat, c->utt_of_seq, (h16*)c->dclat, S, H,
-                                                                            WIPA_T_ENC, c->xl_part, c->xl_part_floats, c->ca_counters, st));
+                                                                            WIPA_T_ENC, c->xl_part, c->xl_part_floats, c->ca_counters, st,
+                                                                            beam ? c->cur_beams : 1));
             } else
             if (!(skip & 4)) WIPA_TRY(launch_cross_attention_latent((const h16*)c->dqlat, (const h16*)c->enc_lat, c->xl_tiled, c->max_batch, c->utt_of_seq,
                                                                    (h16*)c->dclat, S, H, WIPA_T_ENC, c->xl_part, c->xl_part_floats,
-                                                                   c->ca_counters, st));
+                                                                   c->ca_counters, st, beam ? c->cur_beams : 1));
             if (c->xl_o2) {
                 {   // ctx_h = Wv_h c_h + bv_h for every head: H GEMMs [S, d] x [d, 64] in one launch (batch = head; A is head h's
                     // slice of the normalised sums, W the 64 rows of the v-projection that belong to head h) -> h16 [S, d]
@@ -798,6 +800,7 @@ int upload_mask(wipa_ctx* c, uint32_t* dmask, const int32_t* ids, int n, cudaStr
 
 int decode_setup(wipa_ctx* c, int S, int beams, const std::vector<int32_t>& forced, int n_forced, int max_new, int eot,
                  DecodeState* ds_out, cudaStream_t st) {
+    c->cur_beams = beams;
     WIPA_CUDA_CHECK(cudaMemcpyAsync(c->d_forced, forced.data(), forced.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     WIPA_CUDA_CHECK(cudaStreamSynchronize(st));
     DecodeState ds = make_state(c, n_forced, max_new, eot);
@@ -911,7 +914,7 @@ extern "C" int wipa_ctx_create(const wipa_arch* arch, int max_batch, int max_bea
             int dev = 0, n_sm = 148;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-            c->xl_part_floats = c->xl_wide ? cross_attention_latent_wide_scratch_floats(S, n_sm) : cross_attention_latent_scratch_floats(H, S, n_sm);
+            c->xl_part_floats = c->xl_wide ? cross_attention_latent_wide_scratch_floats(H, S, n_sm) : cross_attention_latent_scratch_floats(H, S, n_sm);
             CTX_TRY(ctx_alloc(c, (void**)&c->xl_part, c->xl_part_floats * 4, false));
         }
         c->xlq_w.assign(arch->dec_layers, nullptr); c->xlo_w.assign(arch->dec_layers, nullptr);
@@ -1461,8 +1464,9 @@ extern "C" int wipa_test_logits_argmax(wipa_ctx* c, int S, void* stream) {
 // latent cross-attention kernel alone: Qp h16 [S, H, 64H] absorbed queries, E h16 [U, T, 64H], utt_of_seq int32 [S]
 // -> C h16 [S, H, 64H] = softmax_t(Qp[s, h] . E[u, t]) E[u].  All device pointers.
 extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U, const int* utt_of_seq, void* C, int S, int H, int T,
-                                           int layout, void* stream) {
-    const bool wide = cross_attention_latent_wide_supported(H) != 0;
+                                           int layout, int beams, void* stream) {
+    // 16 heads have both kernels: the row-major layout goes to attn_lat.cu, the tiled ones to attn_lat_wide.cu like in a context
+    const bool wide = cross_attention_latent_wide_supported(H) != 0 && (layout != 0 || !cross_attention_latent_supported(H));
     WIPA_CHECK(Qp && E && utt_of_seq && C && S >= 1 && (wide || cross_attention_latent_supported(H)), WIPA_EINVAL,
                "wipa_test_cross_attn_latent: bad argument");
     WIPA_CHECK(!wide || layout != 0, WIPA_EUNSUPPORTED, "wipa_test_cross_attn_latent: 20 heads read the chunk-tiled layout only (layout 1 or 2)");
@@ -1477,7 +1481,7 @@ extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U,
     int dev = 0, n_sm = 148;
     WIPA_CUDA_CHECK(cudaGetDevice(&dev));
     WIPA_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    const size_t need = wide ? cross_attention_latent_wide_scratch_floats(S, n_sm) : cross_attention_latent_scratch_floats(H, S, n_sm);
+    const size_t need = wide ? cross_attention_latent_wide_scratch_floats(H, S, n_sm) : cross_attention_latent_scratch_floats(H, S, n_sm);
     if (need > part_floats) {
         WIPA_CUDA_CHECK(cudaDeviceSynchronize());
         if (part) cudaFree(part);
@@ -1504,9 +1508,9 @@ extern "C" int wipa_test_cross_attn_latent(const void* Qp, const void* E, int U,
         WIPA_TRY(launch_lat_tile(E, 1, tiled, U, T, H, cross_attention_latent_keys(H), (cudaStream_t)stream));
         Ein = tiled;
     }
-    if (wide) return launch_cross_attention_latent_wide((const h16*)Qp, Ein, utt_of_seq, (h16*)C, S, H, T, part, part_floats, counters, (cudaStream_t)stream);
+    if (wide) return launch_cross_attention_latent_wide((const h16*)Qp, Ein, utt_of_seq, (h16*)C, S, H, T, part, part_floats, counters, (cudaStream_t)stream, beams);
     return launch_cross_attention_latent((const h16*)Qp, Ein, layout != 0, U, utt_of_seq, (h16*)C, S, H, T, part, part_floats, counters,
-                                         (cudaStream_t)stream);
+                                         (cudaStream_t)stream, beams);
 }
 
 // row-major h16 encoder output [U, T, 64 H] -> the chunk-tiled layout of the latent kernel (layout 2 above); `out` holds
