@@ -192,11 +192,12 @@ __device__ __forceinline__ void xl_finish_segment(int s, int v, int bx, int nx, 
 // TILED: E arrives in the chunk-tiled, pre-swizzled layout (see the header of this file and lat_tile_offset in common.cuh):
 // a chunk is ONE contiguous block of global memory that lands in shared memory with plain bulk copies, exactly as the
 // tensor-map path would have swizzled it.  Otherwise E is row-major [U, T, d] behind a 3-D tensor map (H boxes per chunk).
-template <int KEYS, int H, bool TILED, int XL_STAGES>
+template <int KEYS, int H, bool TILED, int XL_STAGES, bool BEAMS>
 __global__ void __launch_bounds__((H + 1) * 32, 1)
 cross_attention_latent_kernel(const __grid_constant__ CUtensorMap tmE, const h16* __restrict__ Et, const h16* __restrict__ Qp,
                               const int* __restrict__ utt_of_seq, h16* __restrict__ Cout, int S, int T,
-                              float* __restrict__ part, int* __restrict__ counters, int slots_per_seq, int K) {
+                              float* __restrict__ part, int* __restrict__ counters, int slots_per_seq, int beams) {
+    const int K = BEAMS ? beams : 1;            // a compile-time 1 in the greedy instantiation: its code is that of a plain sequence list
     using Cfg = XlCfg<KEYS, XL_STAGES>;
     constexpr int PITCH = Cfg::PITCH;
     extern __shared__ uint8_t xl_smem_raw[];
@@ -432,12 +433,13 @@ int xl_make_map(CUtensorMap* map, const void* E, int U, int T, int d, int keys) 
     return WIPA_OK;
 }
 
-template <int KEYS, int H, bool TILED, int XL_STAGES = 2>
+template <int KEYS, int H, bool TILED, int XL_STAGES = 2, bool BEAMS = false>
 int xl_launch(const CUtensorMap& tm, const h16* Et, const h16* Qp, const int* utt_of_seq, h16* C, int S, int T, int n_sm, float* part,
               size_t part_floats, int* counters, int K, cudaStream_t st) {
     const size_t smem = XlCfg<KEYS, XL_STAGES>::smem(H);
     static SmemAttr attr;
-    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H, TILED, XL_STAGES>, smem, attr));
+    WIPA_TRY(wipa_ensure_smem(cross_attention_latent_kernel<KEYS, H, TILED, XL_STAGES, BEAMS>, smem, attr));
+    if (!BEAMS) K = 1;
     const int n_chunks = cdiv(T, KEYS);
     const long long n_units = (long long)(S / K) * n_chunks;      // per group of K CTAs (K = 1: per CTA)
     const int groups = n_units < n_sm / K ? (int)n_units : n_sm / K;
@@ -446,7 +448,7 @@ int xl_launch(const CUtensorMap& tm, const h16* Et, const h16* Qp, const int* ut
     const int slots_per_seq = n_chunks / (int)(n_units / groups) + 2;
     WIPA_CHECK((size_t)S * slots_per_seq * (H * 1024 + 32) <= part_floats, WIPA_EINVAL,
                "cross_attention_latent: partial scratch too small for %d sequences", S);
-    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H, TILED, XL_STAGES>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Et, Qp,
+    WIPA_CUDA_CHECK(wipa_launch_c(4, cross_attention_latent_kernel<KEYS, H, TILED, XL_STAGES, BEAMS>, dim3(grid), dim3((H + 1) * 32), smem, st, tm, Et, Qp,
                                   utt_of_seq, C, S, T, part, counters, slots_per_seq, K));
     WIPA_LAUNCHED();
     return WIPA_OK;
@@ -513,6 +515,12 @@ int launch_cross_attention_latent(const h16* Qp, const h16* E, int tiled, int U,
     const int keys = cross_attention_latent_keys(H);
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
+    if (tiled && keys == 32 && H <= 12 && K > 1 && xl_stages(H) == 3) {
+        // beam search on the default layout: groups of K CTAs per key range (other layouts walk one list of sequences)
+        if (H == 6) return xl_launch<32, 6, true, 3, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+        if (H == 8) return xl_launch<32, 8, true, 3, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+        return xl_launch<32, 12, true, 3, true>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st);
+    }
     if (tiled && keys == 32 && H <= 12) {
 #define XL_CASE(HH, ST) if (H == HH && xl_stages(H) == ST) return xl_launch<32, HH, true, ST>(tm, E, Qp, utt_of_seq, C, S, T, n_sm, part, part_floats, counters, K, st)
         XL_CASE(6, 2); XL_CASE(6, 3); XL_CASE(6, 4); XL_CASE(8, 2); XL_CASE(8, 3); XL_CASE(8, 4); XL_CASE(12, 2); XL_CASE(12, 3); XL_CASE(12, 4);
