@@ -11,8 +11,9 @@ from whisper_ipa_b200 import _lib  # noqa: E402
 
 
 def main():
-    B, H, T = 32, 12, 1500
+    B, H = 32, 12
     reps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+    T = int(sys.argv[2]) if len(sys.argv) > 2 else 1500
     g = torch.Generator(device="cuda").manual_seed(0)
     q = (torch.randn(B, H, T, 64, device="cuda", generator=g) * 0.3).half()
     k = torch.randn(B, H, T, 64, device="cuda", generator=g).half()
@@ -29,7 +30,10 @@ def main():
         _lib.check(L.wipa_test_enc_attention_h16(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), B, H, T, 1, st), "fa")
     e1.record()
     torch.cuda.synchronize()
-    print(f"form {os.environ.get('WIPA_FA_FORM', 'default')}: {e0.elapsed_time(e1) / reps * 1e3:.1f} us per launch")
+    us = e0.elapsed_time(e1) / reps * 1e3
+    ctas = ((T + 255) // 256) * B * H
+    print(f"form {os.environ.get('WIPA_FA_FORM', 'default')} T={T}: {us:.1f} us per launch; {ctas} CTAs of {(T + 127) // 128} key blocks: "
+          f"{us * 148 / ctas:.2f} us per CTA")
 
 
 if __name__ == "__main__":
