@@ -128,7 +128,10 @@ logmel_stft_mel_kernel(const float* __restrict__ audio, const float* __restrict_
     }
     __syncthreads();
 
-    // DFT as a [402 x 400] x [400 x 8] product per warp
+    // DFT as a [402 x 400] x [400 x 8] product per warp, at half the multiply-adds: the periodic Hann window is symmetric
+    // (w[n] = w[400 - n], w[0] = 0) and so are the twiddles, dft[400 - n][c] = +dft[n][c] for the cosine components and
+    // -dft[n][c] for the sine components, hence
+    //     X[c] = dft[200][c] x[200] + sum_{n = 1 .. 199} dft[n][c] (x[n] +/- x[400 - n])
     float acc[13][8];
 #pragma unroll
     for (int r = 0; r < 13; ++r)
@@ -136,17 +139,36 @@ logmel_stft_mel_kernel(const float* __restrict__ audio, const float* __restrict_
         for (int f = 0; f < 8; ++f) acc[r][f] = 0.f;
     const float* xs = seg + (warp * 8) * WIPA_HOP;
     const float* wcol = dft + lane;
-#pragma unroll 2
-    for (int n = 0; n < WIPA_N_FFT; ++n) {
+    // component c = lane + 32 r: cosine for c < 201 (r <= 5, and r == 6 for lanes 0 .. 8), sine above
+    const bool r6_cos = lane + 192 < WIPA_N_FREQ;
+    {
+        const float* wr = wcol + (size_t)(WIPA_N_FFT / 2) * LM_NCOMP_PAD;      // n = 200: cos(pi k) = +/-1, the sine row is zero
         float x[8];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) x[f] = xs[f * WIPA_HOP + n];
+        for (int f = 0; f < 8; ++f) x[f] = xs[f * WIPA_HOP + WIPA_N_FFT / 2];
+#pragma unroll
+        for (int r = 0; r < 13; ++r) {
+            const float w = __ldg(wr + 32 * r);
+#pragma unroll
+            for (int f = 0; f < 8; ++f) acc[r][f] = w * x[f];
+        }
+    }
+#pragma unroll 2
+    for (int n = 1; n < WIPA_N_FFT / 2; ++n) {
+        float xa[8], xd[8], x6[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) {
+            const float a = xs[f * WIPA_HOP + n], b = xs[f * WIPA_HOP + WIPA_N_FFT - n];
+            xa[f] = a + b;
+            xd[f] = a - b;
+            x6[f] = r6_cos ? xa[f] : xd[f];
+        }
         const float* wr = wcol + (size_t)n * LM_NCOMP_PAD;
 #pragma unroll
         for (int r = 0; r < 13; ++r) {
             const float w = __ldg(wr + 32 * r);
 #pragma unroll
-            for (int f = 0; f < 8; ++f) acc[r][f] = fmaf(w, x[f], acc[r][f]);
+            for (int f = 0; f < 8; ++f) acc[r][f] = fmaf(w, r < 6 ? xa[f] : (r == 6 ? x6[f] : xd[f]), acc[r][f]);
         }
     }
     __syncthreads();                       // everyone is done reading seg
