@@ -17,8 +17,6 @@
 //
 // Every chunk CTA of a (M tile, head) recomputes the same q tile (d / NC times the phase-1 loads, all from L2): that buys
 // d / NC times the CTAs, i.e. one full wave of 144 CTAs for whisper-small at 256 and 512 sequences.
-#include <stdlib.h>
-
 #define WIPA_PDL_CLASS 8
 #include "common.cuh"
 #include "ptx.cuh"
